@@ -1,0 +1,120 @@
+"""CPU checks that pin the oracle itself: RNG known answers, force = -grad(energy), cell list = brute force."""
+import numpy as np
+import pytest
+
+from oracle import pyoracle
+import clb_testutil as util
+
+
+def test_philox_known_answers():
+    # Random123 kat_vectors for philox4x32-10
+    assert pyoracle.philox([0, 0, 0, 0], [0, 0]) == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    assert pyoracle.philox([0xffffffff] * 4, [0xffffffff] * 2) == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    assert pyoracle.philox([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0]) == \
+        [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+
+
+def _small(seed=3, n_side=9):
+    m = util.melt(n_side, seed=seed)
+    n = len(m["pos"])
+    o = pyoracle.Oracle(n, m["box"], 2.5, 0.3, seed=7)
+    o.set_particles(m["pos"], None, np.ones(n), None, m["type"], np.ones(n, np.int32), m["resid"])
+    return m, o, n
+
+
+def test_cell_list_equals_brute_force():
+    m, o, n = _small()
+    o.set_exclusions(util.exclusions_from(m["bonds"], m["angles"]))
+    a = o.pairs()
+    b = o.pairs_brute()
+    b = b[np.lexsort((b[:, 1], b[:, 0]))]
+    assert len(a) == len(b) and (a == b).all()
+    # exclusions really removed
+    ex = set(map(tuple, util.exclusions_from(m["bonds"], m["angles"])))
+    assert not (ex & set(map(tuple, a)))
+
+
+def _fd_check(o, inters, n, h=1e-6, probes=(0, 5, 17, 100), tol=2e-5):
+    o.compute_forces()
+    st = o.get()
+    x0, f0 = st["pos"].copy(), st["force"].copy()
+    for i in probes:
+        for c in range(3):
+            e = []
+            for s in (+1, -1):
+                x = x0.copy(); x[i, c] += s * h
+                o.set_positions(x); o.rebuild(); o.compute_forces()
+                e.append(sum(o.energy(k) for k in inters))
+            fd = -(e[0] - e[1]) / (2 * h)
+            assert abs(fd - f0[i, c]) <= tol * max(1.0, abs(f0[i, c])), (i, c, fd, f0[i, c])
+    o.set_positions(x0)
+
+
+def test_pair_forces_are_energy_gradient():
+    m, o, n = _small()
+    r, e, f = util.lj_table()
+    # energy/force consistency needs a smooth table: use cubic interpolation for the FD check only
+    tab = o.add_table(r, e, f, 1)
+    nb = o.add_nonbonded(1)
+    for a in (0, 1):
+        for b in (a, 1):
+            o.nb_set_tab(nb, a, b, tab, 2.5)
+    lj = pyoracle.Oracle(n, m["box"], 2.5, 0.3)
+    lj.set_particles(m["pos"], None, np.ones(n), None, m["type"])
+    k = lj.add_nonbonded(2)
+    for a in (0, 1):
+        for b in (a, 1):
+            lj.nb_set_lj(k, a, b, 1.0, 1.0, 2.5, 1)
+    _fd_check(lj, [k], n)
+    # tabulated LJ reproduces analytic LJ to the table's interpolation error
+    o.compute_forces(); lj.compute_forces()
+    assert util.rel_force_err(o.get()["force"], lj.get()["force"]) < 2e-4
+    assert abs(o.energy(nb) - lj.energy(k)) < 1e-4 * abs(lj.energy(k))
+
+
+def test_bonded_forces_are_energy_gradient():
+    m, o, n = _small()
+    rng = np.random.default_rng(0)
+    bl = o.add_list(2); o.list_add(bl, m["bonds"])
+    al = o.add_list(3); o.list_add(al, m["angles"])
+    quads = np.array([(i, i + 1, i + 2, i + 3) for i in range(0, 200, 9)], np.int64)
+    ql = o.add_list(4); o.list_add(ql, quads)
+    ib = o.add_bonded(bl); o.bonded_set_potential(ib, (), 1, (30.0, 0.97))
+    ia = o.add_bonded(al); o.bonded_set_potential(ia, (), 3, (1.25, 2.6))
+    iq = o.add_bonded(ql); o.bonded_set_potential(iq, (), 8, (2.0, 0.7))
+    # tabulated angle + dihedral (cubic so that f = -de/dx holds between knots)
+    th = np.linspace(0.0, np.pi, 361)
+    ta = o.add_table(th, 3.0 * (th - 2.0) ** 2, -6.0 * (th - 2.0), 3)
+    ph = np.linspace(-np.pi, np.pi, 721)
+    td = o.add_table(ph, 1.5 * (1 + np.cos(2 * ph - 0.4)), 3.0 * np.sin(2 * ph - 0.4), 3)
+    al2 = o.add_list(3); o.list_add(al2, m["angles"][:50])
+    ia2 = o.add_bonded(al2); o.bonded_set_potential(ia2, (), 4, (), ta)
+    ql2 = o.add_list(4); o.list_add(ql2, quads)
+    iq2 = o.add_bonded(ql2); o.bonded_set_potential(iq2, (), 5, (), td)
+    # natural-spline end conditions limit the tabulated-angle consistency near theta = pi (straight trimers)
+    _fd_check(o, [ib, ia, iq, ia2, iq2], n, probes=(0, 1, 2, 3, 10, 11), tol=2e-3)
+    o2 = pyoracle.Oracle(n, m["box"], 2.5, 0.3, seed=7)
+    o2.set_particles(m["pos"], None, np.ones(n), None, m["type"])
+    for ar, ids, kind, par in ((2, m["bonds"], 1, (30.0, 0.97)), (3, m["angles"], 3, (1.25, 2.6)), (4, quads, 8, (2.0, 0.7))):
+        l = o2.add_list(ar); o2.list_add(l, ids)
+        o2.bonded_set_potential(o2.add_bonded(l), (), kind, par)
+    _fd_check(o2, [0, 1, 2], n, probes=(0, 1, 2, 3, 10, 11), tol=1e-6)
+    f = o.get()["force"]
+    assert np.abs(f.sum(0)).max() < 1e-9  # Newton's third law
+
+
+def test_akima_and_linear_tables():
+    o = pyoracle.Oracle(1, [10, 10, 10], 1.0, 0.1)
+    x = np.linspace(0.1, 2.0, 96)
+    y = np.sin(3 * x)
+    t1 = o.add_table(x, y, -3 * np.cos(3 * x), 1)
+    t2 = o.add_table(x, y, -3 * np.cos(3 * x), 2)
+    for xv in (0.1, 0.55, 1.234, 1.99):
+        e1, f1, _ = o.table_eval(t1, xv)
+        e2, f2, _ = o.table_eval(t2, xv)
+        i = int((xv - 0.1) / (x[1] - x[0])); i = min(i, 94)
+        b = (xv - x[i]) / (x[1] - x[0])
+        assert abs(e1 - ((1 - b) * y[i] + b * y[i + 1])) < 1e-12
+        assert abs(e2 - np.sin(3 * xv)) < 2e-5       # Akima interpolates a smooth function to O(h^3..4)
+        assert abs(f2 + 3 * np.cos(3 * xv)) < 2e-4
+    assert o.table_eval(t1, 2.5)[2] == 1 and o.table_eval(t1, 0.05)[2] == 1  # out of range flagged
