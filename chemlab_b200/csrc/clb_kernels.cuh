@@ -1,0 +1,399 @@
+// clb_kernels.cuh -- O(N) kernels: cell keys / reorder, Velocity-Verlet + Langevin, resort check,
+// bonded forces (owner-computes CSR), observables.
+#pragma once
+#include "clb_common.cuh"
+
+// ---------------------------------------------------------------- rebuild helpers -----------
+// cell key of every stored particle (storage.decompose(): src/start_simulation.py:171,205,295)
+__global__ void k_cell_keys(int n, const int4* __restrict__ pos, ClbGrid g, int* __restrict__ key, int* __restrict__ val) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int4 p = pos[i];
+    int cx = __umulhi((unsigned)p.x, (unsigned)g.ncx);
+    int cy = __umulhi((unsigned)p.y, (unsigned)g.ncy);
+    int cz = __umulhi((unsigned)p.z, (unsigned)g.ncz);
+    int lz = g.ghost ? wrapi(cz - g.zoff, g.ncz) : cz;
+    key[i] = (lz * g.ncy + cy) * g.ncx + cx;
+    val[i] = i;
+}
+__global__ void k_gather(int n, const int* __restrict__ perm, const int4* __restrict__ pos_in, const float4* __restrict__ vel_in,
+                         const int* __restrict__ slot_in, int4* __restrict__ pos, float4* __restrict__ vel,
+                         int* __restrict__ slot, int4* __restrict__ xref, int* __restrict__ id2idx) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int s = perm[i];
+    int4 p = pos_in[s];
+    pos[i] = p; xref[i] = p;
+    vel[i] = vel_in[s];
+    int sl = slot_in[s];
+    slot[i] = sl;
+    id2idx[sl] = i;
+}
+__global__ void k_cell_start(int n, const int* __restrict__ key, int ncell, int* __restrict__ cell_start) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > n) return;
+    if (n == 0) { if (i == 0) for (int c = 0; c <= ncell; ++c) cell_start[c] = 0; return; }
+    int prev = i == 0 ? -1 : key[i - 1];
+    int cur = i == n ? ncell : key[i];
+    for (int c = prev + 1; c <= cur; ++c) cell_start[c] = i;
+}
+// per-block tile statistics -> dynamic shared memory size and block size of the tile kernels
+__global__ void k_block_stats(ClbGrid g, const int* __restrict__ cell_start, ClbCtl* ctl) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= g.nblocks) return;
+    int row = b / g.nbx, bxi = b - row * g.nbx;
+    int cx0 = bxi * g.bx, bxe = min(g.bx, g.ncx - cx0);
+    int cy = row % g.ncy, zrow = row / g.ncy;
+    int lz = g.ghost ? zrow + 1 : zrow;
+    bool whole = bxe + 2 > g.ncx;
+    int W = whole ? g.ncx : bxe + 2;
+    int T = 0, cmax = 0;
+    for (int k = 0; k < 9; ++k) {
+        int dy = k % 3 - 1, dz = k / 3 - 1;
+        int yy = wrapi(cy + dy, g.ncy);
+        int zz = g.ghost ? lz + dz : wrapi(lz + dz, g.ncz);
+        for (int m = 0; m < W; ++m) {
+            int cx = whole ? m : wrapi(cx0 - 1 + m, g.ncx);
+            int c = (zz * g.ncy + yy) * g.ncx + cx;
+            int cnt = cell_start[c + 1] - cell_start[c];
+            T += cnt; cmax = max(cmax, cnt);
+        }
+    }
+    int c0 = (lz * g.ncy + cy) * g.ncx + cx0;
+    int nh = cell_start[c0 + bxe] - cell_start[c0];
+    atomicMax(&ctl->tile_max, T);
+    atomicMax(&ctl->home_max, nh);
+    atomicMax(&ctl->cell_max, cmax);
+}
+
+// ---------------------------------------------------------------- integrator ----------------
+struct ClbIntegParams {
+    double dt;
+    double invq[3], q[3];
+    int langevin;          // thermostat enabled
+    double pref1, pref2;   // -gamma, sqrt(24 kT gamma / dt)
+    unsigned long long type_mask_lo; // bit t set -> type t thermalised (all ones when add_valid_types unused)
+    uint64_t seed;
+    uint64_t step;         // RNG step key of the half-kick being closed
+    int criterion;
+    int i0, i1;            // owned particle range
+};
+#define CLB_INT_SECOND 1
+#define CLB_INT_FIRST 2
+
+// VelocityVerlet::integrate2 (+ LangevinThermostat::thermalize) and/or integrate1.
+// MODE = SECOND|FIRST fuses the closing half-kick of step i-1 with the opening half-kick and drift
+// of step i (one pass over pos/vel/force instead of two).
+template <int MODE>
+__global__ void __launch_bounds__(256) k_integrate(ClbIntegParams P, int4* __restrict__ pos, float4* __restrict__ vel,
+                                                   double* __restrict__ force, int fstride,
+                                                   const int4* __restrict__ xref, const int* __restrict__ slot,
+                                                   int* __restrict__ image, ClbCtl* ctl) {
+    if (*(volatile int*)&ctl->stall) return;
+    int i = P.i0 + blockIdx.x * blockDim.x + threadIdx.x;
+    float d2 = 0.f;
+    if (i < P.i1) {
+        float4 v4 = vel[i];
+        double m = (double)v4.w;
+        double vx = v4.x, vy = v4.y, vz = v4.z;
+        double fx = force[i], fy = force[i + fstride], fz = force[i + 2 * fstride];
+        int4 p = pos[i];
+        if (MODE & CLB_INT_SECOND) {
+            if (P.langevin && ((P.type_mask_lo >> pw_type(p.w)) & 1ull)) {
+                double u[3];
+                clb_draw3(P.seed, CLB_STREAM_LANGEVIN, P.step, (uint32_t)slot[i], u);
+                double sm = sqrt(m);
+                fx += P.pref1 * m * vx + P.pref2 * sm * (u[0] - 0.5);
+                fy += P.pref1 * m * vy + P.pref2 * sm * (u[1] - 0.5);
+                fz += P.pref1 * m * vz + P.pref2 * sm * (u[2] - 0.5);
+            }
+            if (!(MODE & CLB_INT_FIRST)) { force[i] = fx; force[i + fstride] = fy; force[i + 2 * fstride] = fz; }
+        }
+        double k = ((MODE & CLB_INT_SECOND) && (MODE & CLB_INT_FIRST)) ? P.dt / m : 0.5 * P.dt / m;
+        vx += k * fx; vy += k * fy; vz += k * fz;
+        // stored velocity is fp32: round once, then drift with the STORED value so that a split and a
+        // fused sequence see the same positions up to that rounding
+        float vxf = (float)vx, vyf = (float)vy, vzf = (float)vz;
+        vel[i] = make_float4(vxf, vyf, vzf, v4.w);
+        if (MODE & CLB_INT_FIRST) {
+            double dpx = P.dt * (double)vxf, dpy = P.dt * (double)vyf, dpz = P.dt * (double)vzf;
+            int dx = __double2int_rn(dpx * P.invq[0]), dy = __double2int_rn(dpy * P.invq[1]), dz = __double2int_rn(dpz * P.invq[2]);
+            int nx = p.x + dx, ny = p.y + dy, nz = p.z + dz;
+            int wx = (dx > 0 && (unsigned)nx < (unsigned)p.x) ? 1 : ((dx < 0 && (unsigned)nx > (unsigned)p.x) ? -1 : 0);
+            int wy = (dy > 0 && (unsigned)ny < (unsigned)p.y) ? 1 : ((dy < 0 && (unsigned)ny > (unsigned)p.y) ? -1 : 0);
+            int wz = (dz > 0 && (unsigned)nz < (unsigned)p.z) ? 1 : ((dz < 0 && (unsigned)nz > (unsigned)p.z) ? -1 : 0);
+            if (wx | wy | wz) { int s = slot[i]; image[3 * s] += wx; image[3 * s + 1] += wy; image[3 * s + 2] += wz; }
+            pos[i] = make_int4(nx, ny, nz, p.w);
+            if (P.criterion == 0) d2 = (float)(dpx * dpx + dpy * dpy + dpz * dpz);
+            else {
+                int4 r = xref[i];
+                double ex = (double)(nx - r.x) * P.q[0], ey = (double)(ny - r.y) * P.q[1], ez = (double)(nz - r.z) * P.q[2];
+                d2 = __double2float_ru(ex * ex + ey * ey + ez * ez);
+            }
+        }
+    }
+    if (MODE & CLB_INT_FIRST) {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) d2 = fmaxf(d2, __shfl_xor_sync(0xffffffffu, d2, d));
+        __shared__ float s_m[8];
+        if ((threadIdx.x & 31) == 0) s_m[threadIdx.x >> 5] = d2;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float mm = 0.f;
+            for (int w = 0; w < (blockDim.x >> 5); ++w) mm = fmaxf(mm, s_m[w]);
+            atomicMax(&ctl->maxdisp2_bits, __float_as_uint(mm));
+        }
+    }
+}
+// LangevinThermostat at run entry (recalc1/updateForces/recalc2 with heatUp: pref2 *= sqrt(3))
+__global__ void k_thermalize(ClbIntegParams P, double scale, uint32_t stream, const int4* __restrict__ pos,
+                             const float4* __restrict__ vel, const int* __restrict__ slot, double* __restrict__ force,
+                             int fstride) {
+    int i = P.i0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.i1) return;
+    int4 p = pos[i];
+    if (!((P.type_mask_lo >> pw_type(p.w)) & 1ull)) return;
+    float4 v4 = vel[i];
+    double m = v4.w, sm = sqrt(m), u[3];
+    clb_draw3(P.seed, stream, P.step, (uint32_t)slot[i], u);
+    force[i] += P.pref1 * m * v4.x + P.pref2 * scale * sm * (u[0] - 0.5);
+    force[i + fstride] += P.pref1 * m * v4.y + P.pref2 * scale * sm * (u[1] - 0.5);
+    force[i + 2 * fstride] += P.pref1 * m * v4.z + P.pref2 * scale * sm * (u[2] - 0.5);
+}
+// skin/2 criterion evaluated on the device; sets ctl->stall so that every later kernel of the
+// enqueued chunk becomes a no-op until the host has rebuilt the lists (no per-step host sync).
+__global__ void k_check_resort(ClbCtl* ctl, int criterion, double half_skin, int step_index) {
+    if (ctl->stall) return;
+    float m2 = __uint_as_float(ctl->maxdisp2_bits);
+    ctl->maxdisp2_bits = 0u;
+    bool need;
+    if (criterion == 0) { ctl->accum_maxdist += sqrt((double)m2); need = ctl->accum_maxdist > half_skin; }
+    else need = sqrt((double)m2) > half_skin;
+    if (need || ctl->force_rebuild) { ctl->stall = 1; ctl->stall_step = step_index; }
+    else ctl->steps_ok += 1;
+}
+
+// ---------------------------------------------------------------- bonded --------------------
+struct ClbBondedDesc { int arity, typed, inter, npot, pot_off, active; };
+struct ClbBPot { int t[4]; int kind, table; double p[4]; };
+struct ClbBTabMeta { double x0, invdx, dx; int n, off; };
+
+__device__ __forceinline__ const ClbBPot* bpot_lookup(const ClbBondedDesc& d, const ClbBPot* pots, const int* ty) {
+    if (!d.typed) return d.npot ? pots + d.pot_off : nullptr;
+    for (int k = 0; k < d.npot; ++k) {
+        const ClbBPot* p = pots + d.pot_off + k;
+        bool fwd = true, rev = true;
+        for (int m = 0; m < d.arity; ++m) { fwd &= (p->t[m] == ty[m]); rev &= (p->t[m] == ty[d.arity - 1 - m]); }
+        if (fwd || rev) return p;
+    }
+    return nullptr;
+}
+// returns F = -dU/dx and U for the scalar coordinate x (r, theta or phi)
+__device__ __forceinline__ void bpot_eval(const ClbBPot* p, double x, const ClbBTabMeta* tm, const double4* cf, const double4* ce,
+                                          double& F, double& E, bool want_e, unsigned& err) {
+    switch (p->kind) {
+        case 1: { double d = x - p->p[1]; F = -2.0 * p->p[0] * d; E = p->p[0] * d * d; break; }            // Harmonic
+        case 3: { double d = x - p->p[1]; F = -2.0 * p->p[0] * d; E = p->p[0] * d * d; break; }            // AngularHarmonic
+        case 6: { F = p->p[0] * sin(x - p->p[1]); E = p->p[0] * (1.0 + cos(x - p->p[1])); break; }         // Cosine
+        case 7: { double d = x - p->p[1], xx = d / p->p[2]; F = -p->p[0] * d / (1.0 - xx * xx);
+                  E = -0.5 * p->p[0] * p->p[2] * p->p[2] * log(1.0 - xx * xx); break; }                      // FENE
+        case 8: { double d = x - p->p[1]; d -= 6.283185307179586 * rint(d / 6.283185307179586);
+                  F = -2.0 * p->p[0] * d; E = p->p[0] * d * d; break; }                                      // DihedralHarmonic
+        case 2: case 4: case 5: {                                                                            // tables
+            const ClbBTabMeta t = tm[p->table];
+            double s = (x - t.x0) * t.invdx;
+            int idx = (int)floor(s);
+            if (idx < 0) { idx = 0; err |= CLB_EF_TABLE_RANGE; }
+            if (idx > t.n - 2) { if (x > t.x0 + t.dx * (t.n - 1) * (1.0 + 1e-12)) err |= CLB_EF_TABLE_RANGE; idx = t.n - 2; }
+            double d = x - (t.x0 + idx * t.dx);
+            double4 c = cf[t.off + idx];
+            F = c.x + d * (c.y + d * (c.z + d * c.w));
+            if (want_e) { double4 e = ce[t.off + idx]; E = e.x + d * (e.y + d * (e.z + d * e.w)); }
+            break;
+        }
+        default: F = 0.0; E = 0.0;
+    }
+}
+// Owner-computes bonded forces: thread i evaluates every tuple it is a member of and keeps only its
+// own force -> deterministic, no atomics (each tuple is evaluated arity times; O(N) work).
+// FixedPairList/TripleList/QuadrupleList interaction templates [EXT], SURVEY 8a7-a9, U15.
+template <bool ENERGY>
+__global__ void __launch_bounds__(256) k_bonded(int i0, int i1, const int4* __restrict__ pos, ClbGeom geo,
+                                                const int* __restrict__ rt_off, const int4* __restrict__ rt_mem,
+                                                const int* __restrict__ rt_meta, const ClbBondedDesc* __restrict__ bdesc,
+                                                const ClbBPot* __restrict__ pots, const ClbBTabMeta* __restrict__ btm,
+                                                const double4* __restrict__ cf, const double4* __restrict__ ce,
+                                                double* __restrict__ force, int fstride, int inter,
+                                                double* __restrict__ partial, ClbCtl* ctl) {
+    if (!ENERGY && *(volatile int*)&ctl->stall) return;
+    int i = i0 + blockIdx.x * blockDim.x + threadIdx.x;
+    double ax = 0, ay = 0, az = 0, esum = 0;
+    unsigned err = 0;
+    if (i < i1) {
+        int t0 = rt_off[i - i0], t1 = rt_off[i - i0 + 1];
+        for (int t = t0; t < t1; ++t) {
+            int4 mem = rt_mem[t];
+            int meta = rt_meta[t];
+            int role = meta & 3, li = meta >> 2;
+            const ClbBondedDesc d = bdesc[li];
+            if (ENERGY && (d.inter != inter || role != 0)) continue;
+            int idx[4] = {mem.x, mem.y, mem.z, mem.w};
+            int4 P[4]; int ty[4];
+            for (int m = 0; m < d.arity; ++m) { P[m] = __ldg(pos + idx[m]); ty[m] = pw_type(P[m].w); }
+            const ClbBPot* pp = bpot_lookup(d, pots, ty);
+            if (!pp) continue;
+            double F, E = 0;
+            if (d.arity == 2) {
+                int o = 1 - role;
+                double dx = lat2d(P[role].x - P[o].x) * geo.q[0], dy = lat2d(P[role].y - P[o].y) * geo.q[1], dz = lat2d(P[role].z - P[o].z) * geo.q[2];
+                double r = sqrt(dx * dx + dy * dy + dz * dz);
+                bpot_eval(pp, r, btm, cf, ce, F, E, ENERGY, err);
+                double fr = F / r;
+                ax += fr * dx; ay += fr * dy; az += fr * dz;
+            } else if (d.arity == 3) {
+                double d1[3] = {lat2d(P[0].x - P[1].x) * geo.q[0], lat2d(P[0].y - P[1].y) * geo.q[1], lat2d(P[0].z - P[1].z) * geo.q[2]};
+                double d2[3] = {lat2d(P[2].x - P[1].x) * geo.q[0], lat2d(P[2].y - P[1].y) * geo.q[1], lat2d(P[2].z - P[1].z) * geo.q[2]};
+                double r1 = sqrt(d1[0] * d1[0] + d1[1] * d1[1] + d1[2] * d1[2]);
+                double r2 = sqrt(d2[0] * d2[0] + d2[1] * d2[1] + d2[2] * d2[2]);
+                double c = (d1[0] * d2[0] + d1[1] * d2[1] + d1[2] * d2[2]) / (r1 * r2);
+                c = fmin(1.0, fmax(-1.0, c));
+                double th = acos(c), sn = sqrt(1.0 - c * c);
+                if (sn < 1e-9) sn = 1e-9;
+                bpot_eval(pp, th, btm, cf, ce, F, E, ENERGY, err);
+                double g[3];
+                for (int k = 0; k < 3; ++k) {
+                    double g1 = -(d2[k] / (r1 * r2) - c * d1[k] / (r1 * r1)) / sn;
+                    double g3 = -(d1[k] / (r1 * r2) - c * d2[k] / (r2 * r2)) / sn;
+                    g[k] = role == 0 ? F * g1 : (role == 2 ? F * g3 : -F * (g1 + g3));
+                }
+                ax += g[0]; ay += g[1]; az += g[2];
+            } else {
+                double rij[3] = {lat2d(P[0].x - P[1].x) * geo.q[0], lat2d(P[0].y - P[1].y) * geo.q[1], lat2d(P[0].z - P[1].z) * geo.q[2]};
+                double rkj[3] = {lat2d(P[2].x - P[1].x) * geo.q[0], lat2d(P[2].y - P[1].y) * geo.q[1], lat2d(P[2].z - P[1].z) * geo.q[2]};
+                double rkl[3] = {lat2d(P[2].x - P[3].x) * geo.q[0], lat2d(P[2].y - P[3].y) * geo.q[1], lat2d(P[2].z - P[3].z) * geo.q[2]};
+                double mv[3] = {rij[1] * rkj[2] - rij[2] * rkj[1], rij[2] * rkj[0] - rij[0] * rkj[2], rij[0] * rkj[1] - rij[1] * rkj[0]};
+                double nv[3] = {rkj[1] * rkl[2] - rkj[2] * rkl[1], rkj[2] * rkl[0] - rkj[0] * rkl[2], rkj[0] * rkl[1] - rkj[1] * rkl[0]};
+                double m2 = mv[0] * mv[0] + mv[1] * mv[1] + mv[2] * mv[2];
+                double n2 = nv[0] * nv[0] + nv[1] * nv[1] + nv[2] * nv[2];
+                double rkj2 = rkj[0] * rkj[0] + rkj[1] * rkj[1] + rkj[2] * rkj[2], nrkj = sqrt(rkj2);
+                double cphi = (mv[0] * nv[0] + mv[1] * nv[1] + mv[2] * nv[2]) / sqrt(m2 * n2);
+                cphi = fmin(1.0, fmax(-1.0, cphi));
+                double phi = acos(cphi);
+                if (rij[0] * nv[0] + rij[1] * nv[1] + rij[2] * nv[2] < 0) phi = -phi;
+                bpot_eval(pp, phi, btm, cf, ce, F, E, ENERGY, err);
+                double pq = (rij[0] * rkj[0] + rij[1] * rkj[1] + rij[2] * rkj[2]) / rkj2;
+                double qq = (rkl[0] * rkj[0] + rkl[1] * rkj[1] + rkl[2] * rkj[2]) / rkj2;
+                for (int k = 0; k < 3; ++k) {
+                    double fi = F * (nrkj / m2) * mv[k], fl = -F * (nrkj / n2) * nv[k];
+                    double sv = pq * fi - qq * fl;
+                    double fk = role == 0 ? fi : (role == 1 ? -fi + sv : (role == 2 ? -fl - sv : fl));
+                    if (k == 0) ax += fk; else if (k == 1) ay += fk; else az += fk;
+                }
+            }
+            esum += E;
+        }
+        if (!ENERGY) { force[i] += ax; force[i + fstride] += ay; force[i + 2 * fstride] += az; }
+    }
+    if (err) atomicOr(&ctl->err, err);
+    if (ENERGY) {
+        __shared__ double s_red[8];
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) esum += __shfl_down_sync(0xffffffffu, esum, d);
+        if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = esum;
+        __syncthreads();
+        if (threadIdx.x == 0) { double a = 0; for (int w = 0; w < (blockDim.x >> 5); ++w) a += s_red[w]; partial[blockIdx.x] = a; }
+    }
+}
+// count of bonded terms per owned sorted particle (CSR by slot -> CSR by sorted index)
+__global__ void k_term_counts(int i0, int i1, const int* __restrict__ slot, const int* __restrict__ term_off, int* __restrict__ cnt) {
+    int i = i0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= i1) return;
+    int s = slot[i];
+    cnt[i - i0] = term_off[s + 1] - term_off[s];
+}
+// resolve tuple members (slots) to sorted indices after every re-sort
+__global__ void k_term_resolve(int i0, int i1, const int* __restrict__ slot, const int* __restrict__ term_off,
+                               const int* __restrict__ term_meta, const int* __restrict__ term_tuple,
+                               const int* const* __restrict__ list_tuples, const ClbBondedDesc* __restrict__ bdesc,
+                               const int* __restrict__ id2idx, const int* __restrict__ rt_off, int4* __restrict__ rt_mem,
+                               int* __restrict__ rt_meta, ClbCtl* ctl) {
+    int i = i0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= i1) return;
+    int s = slot[i];
+    int t0 = term_off[s], n = term_off[s + 1] - t0, o = rt_off[i - i0];
+    for (int t = 0; t < n; ++t) {
+        int meta = term_meta[t0 + t], li = meta >> 2, tu = term_tuple[t0 + t];
+        int ar = bdesc[li].arity;
+        const int* ids = list_tuples[li] + (size_t)tu * ar;
+        int m[4] = {0, 0, 0, 0};
+        for (int k = 0; k < ar; ++k) { m[k] = id2idx[ids[k]]; if (m[k] < 0) atomicOr(&ctl->err, CLB_EF_PARTNER_LOST); }
+        rt_mem[o + t] = make_int4(m[0], m[1], m[2], m[3]);
+        rt_meta[o + t] = meta;
+    }
+}
+// expand tuple lists into (member slot, meta, tuple) rows for the CSR-by-slot sort
+__global__ void k_term_expand(int n, int arity, int li, const int* __restrict__ tuples, int base, int* __restrict__ key,
+                              unsigned long long* __restrict__ val) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    for (int r = 0; r < arity; ++r) {
+        key[base + t * arity + r] = tuples[(size_t)t * arity + r];
+        val[base + t * arity + r] = ((unsigned long long)(unsigned)((li << 2) | r) << 32) | (unsigned)t;
+    }
+}
+__global__ void k_term_unpack(int n, const unsigned long long* __restrict__ val, int* __restrict__ meta, int* __restrict__ tuple) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    meta[t] = (int)(val[t] >> 32); tuple[t] = (int)(val[t] & 0xffffffffu);
+}
+// row offsets of a sorted key array: off[s] = lower_bound(keys, s)
+__global__ void k_lower_bounds(int nkeys, const int* __restrict__ keys, int nslots, int* __restrict__ off) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s > nslots) return;
+    int lo = 0, hi = nkeys;
+    while (lo < hi) { int m = (lo + hi) >> 1; if (keys[m] < s) lo = m + 1; else hi = m; }
+    off[s] = lo;
+}
+
+// ---------------------------------------------------------------- observables ---------------
+__global__ void __launch_bounds__(256) k_kinetic(int i0, int i1, const float4* __restrict__ vel, double* __restrict__ partial) {
+    int i = i0 + blockIdx.x * blockDim.x + threadIdx.x;
+    double e = 0;
+    if (i < i1) { float4 v = vel[i]; e = 0.5 * (double)v.w * ((double)v.x * v.x + (double)v.y * v.y + (double)v.z * v.z); }
+    __shared__ double s_red[8];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) e += __shfl_down_sync(0xffffffffu, e, d);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = e;
+    __syncthreads();
+    if (threadIdx.x == 0) { double a = 0; for (int w = 0; w < (blockDim.x >> 5); ++w) a += s_red[w]; partial[blockIdx.x] = a; }
+}
+// fixed-order final reduction of per-block partial sums (bit-reproducible observables)
+__global__ void k_sum_partials(int n, const double* __restrict__ partial, double* __restrict__ out) {
+    __shared__ double s[256];
+    double a = 0;
+    for (int i = threadIdx.x; i < n; i += 256) a += partial[i];
+    s[threadIdx.x] = a;
+    __syncthreads();
+    for (int d = 128; d > 0; d >>= 1) { if (threadIdx.x < d) s[threadIdx.x] += s[threadIdx.x + d]; __syncthreads(); }
+    if (threadIdx.x == 0) *out = s[0];
+}
+__global__ void k_sum_partials_u64(int n, const unsigned long long* __restrict__ partial, unsigned long long* __restrict__ out) {
+    __shared__ unsigned long long s[256];
+    unsigned long long a = 0;
+    for (int i = threadIdx.x; i < n; i += 256) a += partial[i];
+    s[threadIdx.x] = a;
+    __syncthreads();
+    for (int d = 128; d > 0; d >>= 1) { if (threadIdx.x < d) s[threadIdx.x] += s[threadIdx.x + d]; __syncthreads(); }
+    if (threadIdx.x == 0) *out = s[0];
+}
+__global__ void k_count_type(int i0, int i1, const int4* __restrict__ pos, int type, int state, unsigned long long* __restrict__ out) {
+    int i = i0 + blockIdx.x * blockDim.x + threadIdx.x;
+    bool hit = false;
+    if (i < i1) { int w = pos[i].w; hit = pw_type(w) == type && (state < 0 || pw_state(w) == state); }
+    unsigned b = __ballot_sync(0xffffffffu, hit);
+    if ((threadIdx.x & 31) == 0 && b) atomicAdd(out, (unsigned long long)__popc(b));
+}
+__global__ void k_zero_force(int n, double* __restrict__ f, int fstride) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { f[i] = 0; f[i + fstride] = 0; f[i + 2 * fstride] = 0; }
+}

@@ -1,0 +1,1176 @@
+// engine.cu -- host side of the B200 engine: C-ABI (include/chemlab_b200.h), device state,
+// rebuild pipeline, stall-flag step loop.  One engine = one GPU = one stream.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include <cub/cub.cuh>
+
+#include "../../include/chemlab_b200.h"
+#include "clb_common.cuh"
+#include "clb_kernels.cuh"
+#include "clb_tile.cuh"
+#include "engine.h"
+#include "clb_react.cuh"
+
+static std::string g_create_error;
+
+#define CK(call)                                                                                 \
+    do {                                                                                         \
+        cudaError_t _e = (call);                                                                 \
+        if (_e != cudaSuccess) return e->fail(CLB_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+#define TRY(expr)                       \
+    do {                                \
+        int _r = (expr);                \
+        if (_r != CLB_OK) return _r;    \
+    } while (0)
+
+int clb_engine::fail(int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof(buf), fmt, ap); va_end(ap);
+    err = buf;
+    return code;
+}
+
+static inline int ceil_div(long long a, int b) { return (int)((a + b - 1) / b); }
+
+// ------------------------------------------------------------------------------------------
+extern "C" int clb_abi_version(void) { return CLB_ABI_VERSION; }
+
+extern "C" const char* clb_last_error(const clb_engine* e) { return e ? e->err.c_str() : g_create_error.c_str(); }
+
+extern "C" int clb_create(clb_engine** out, int device, const double box[3], double rc_max, double skin, uint64_t seed) {
+    if (!out || !box || rc_max <= 0 || skin < 0) { g_create_error = "clb_create: bad argument"; return CLB_ERR_ARG; }
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0) {
+        g_create_error = std::string("clb_create: no usable CUDA device (") + cudaGetErrorString(ce) + "); this engine has no CPU fallback";
+        return CLB_ERR_CUDA;
+    }
+    if (device < 0 || device >= ndev) { g_create_error = "clb_create: bad device index"; return CLB_ERR_ARG; }
+    clb_engine* e = new clb_engine();
+    e->device = device;
+    if (cudaSetDevice(device) != cudaSuccess) { g_create_error = "cudaSetDevice failed"; delete e; return CLB_ERR_CUDA; }
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, device);
+    e->nsm = prop.multiProcessorCount;
+    e->smem_optin = (int)prop.sharedMemPerBlockOptin;
+    cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking);
+    for (int d = 0; d < 3; ++d) e->box[d] = box[d];
+    e->rc = rc_max; e->skin = skin; e->seed = seed;
+    double rl = rc_max + skin;
+    ClbGrid& g = e->grid;
+    g.ncx = (int)floor(box[0] / rl); g.ncy = (int)floor(box[1] / rl); g.ncz = (int)floor(box[2] / rl);
+    if (g.ncx < 3 || g.ncy < 3 || g.ncz < 3) {
+        g_create_error = "clb_create: the box must hold at least 3 cells of edge rc+skin per dimension";
+        delete e; return CLB_ERR_UNSUPPORTED;
+    }
+    if ((long long)g.ncx * g.ncy * g.ncz > (1ll << 30)) { g_create_error = "too many cells"; delete e; return CLB_ERR_UNSUPPORTED; }
+    g.cz0 = 0; g.nczl = g.ncz; g.zoff = 0; g.nplanes = g.ncz; g.ghost = 0;
+    e->geo.rl2 = rl * rl;
+    for (int d = 0; d < 3; ++d) {
+        e->geo.box[d] = box[d];
+        e->geo.q[d] = box[d] / 4294967296.0;
+        e->geo.cut[d] = (int)std::min(2147483000.0, ceil(rl / e->geo.q[d]) + 1.0);
+    }
+    e->geo.cubic = (box[0] == box[1] && box[1] == box[2]);
+    e->geo.q2 = e->geo.q[0] * e->geo.q[0];
+    e->set_block_cells(8);
+    cudaMalloc(&e->d_ctl, sizeof(ClbCtl));
+    cudaMemset(e->d_ctl, 0, sizeof(ClbCtl));
+    cudaMallocHost(&e->h_ctl, sizeof(ClbCtl));
+    memset(e->h_ctl, 0, sizeof(ClbCtl));
+    cudaMalloc(&e->d_scalar, 64);
+    cudaMallocHost(&e->h_scalar, 64);
+    // opt-in shared memory for the tile kernels
+    int mx = e->smem_optin;
+    cudaFuncSetAttribute(k_build_lists<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+    cudaFuncSetAttribute(k_build_lists<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+    cudaFuncSetAttribute(k_pair_forces<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+    cudaFuncSetAttribute(k_pair_forces<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+    cudaFuncSetAttribute(k_pair_forces<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+    cudaFuncSetAttribute(k_pair_forces<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+    cudaFuncSetAttribute(k_pair_energy<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+    cudaFuncSetAttribute(k_pair_energy<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+    cudaFuncSetAttribute(k_decode_pairs, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+    cudaFuncSetAttribute(k_react_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+    for (int i = 0; i < CLB_NBUCKET; ++i) { cudaEventCreate(&e->ev_a[i]); cudaEventCreate(&e->ev_b[i]); }
+    ce = cudaGetLastError();
+    if (ce != cudaSuccess) { g_create_error = std::string("clb_create: ") + cudaGetErrorString(ce); delete e; return CLB_ERR_CUDA; }
+    *out = e;
+    return CLB_OK;
+}
+
+void clb_engine::set_block_cells(int bx) {
+    bx = std::max(1, std::min(bx, CLB_MAX_BX));
+    grid.bx = bx;
+    grid.nbx = (grid.ncx + bx - 1) / bx;
+    grid.ncell = grid.ncx * grid.ncy * grid.nplanes;
+    grid.nblocks = grid.nbx * grid.ncy * grid.nczl;
+}
+
+extern "C" void clb_destroy(clb_engine* e) {
+    if (!e) return;
+    cudaSetDevice(e->device);
+    cudaStreamSynchronize(e->stream);
+    e->free_all();
+    delete e;
+}
+
+extern "C" int clb_set_option(clb_engine* e, const char* name, double v) {
+    if (!e || !name) return CLB_ERR_ARG;
+    std::string s(name);
+    if (s == "resort_criterion") e->criterion = (int)v;
+    else if (s == "block_cells") { e->set_block_cells((int)v); e->lists_valid = false; }
+    else if (s == "list_capacity") { e->nl_cap_user = (int)v; e->lists_valid = false; }
+    else if (s == "fuse_integrator") e->fuse = (int)v;
+    else if (s == "sync_chunk") e->chunk_user = (int)v;
+    else if (s == "timers") e->timers_on = (int)v;
+    else if (s == "tables_in_smem") e->tabs_smem_user = (int)v;
+    else return e->fail(CLB_ERR_ARG, "unknown option %s", name);
+    return CLB_OK;
+}
+extern "C" int clb_get_option(clb_engine* e, const char* name, double* v) {
+    if (!e || !name || !v) return CLB_ERR_ARG;
+    std::string s(name);
+    if (s == "resort_criterion") *v = e->criterion;
+    else if (s == "block_cells") *v = e->grid.bx;
+    else if (s == "list_capacity") *v = e->nl_cap;
+    else if (s == "fuse_integrator") *v = e->fuse;
+    else if (s == "sync_chunk") *v = e->chunk_user;
+    else if (s == "timers") *v = e->timers_on;
+    else if (s == "tile_max") *v = e->tile_max;
+    else if (s == "home_max") *v = e->home_max;
+    else if (s == "nl_max") *v = e->nl_max;
+    else if (s == "nl_total") *v = (double)e->nl_total;
+    else if (s == "ncx") *v = e->grid.ncx;
+    else if (s == "pair_grid") *v = e->pair_grid;
+    else if (s == "pair_threads") *v = e->pair_threads;
+    else if (s == "pair_smem") *v = e->pair_smem;
+    else if (s == "tables_in_smem") *v = e->tabs_smem;
+    else if (s == "pair_kernel_ms") *v = e->pair_ms;
+    else if (s == "pair_kernel_launches") *v = (double)e->pair_launches;
+    else return e->fail(CLB_ERR_ARG, "unknown option %s", name);
+    return CLB_OK;
+}
+
+// ------------------------------------------------------------------------------------------ particles
+int clb_engine::slot_of(int64_t id) const {
+    auto it = id2slot.find(id);
+    return it == id2slot.end() ? -1 : it->second;
+}
+
+extern "C" int clb_set_particles(clb_engine* e, int64_t n, const int64_t* id, const int32_t* type, const double* pos,
+                                 const double* vel, const double* mass, const double* q, const int32_t* state,
+                                 const int32_t* res_id) {
+    if (!e || n <= 0 || !id || !type || !pos || !mass) return e ? e->fail(CLB_ERR_ARG, "clb_set_particles: bad argument") : CLB_ERR_ARG;
+    if (n >= (1ll << 28)) return e->fail(CLB_ERR_UNSUPPORTED, "more than 2^28 particles");
+    cudaSetDevice(e->device);
+    // slots = rank in ascending id order
+    std::vector<int64_t> order(n);
+    for (int64_t i = 0; i < n; ++i) order[i] = i;
+    std::sort(order.begin(), order.end(), [&](int64_t a, int64_t b) { return id[a] < id[b]; });
+    e->ids.resize(n);
+    e->id2slot.clear();
+    e->id2slot.reserve(n * 2);
+    for (int64_t s = 0; s < n; ++s) {
+        e->ids[s] = id[order[s]];
+        if (s && e->ids[s] == e->ids[s - 1]) return e->fail(CLB_ERR_ARG, "duplicate particle id %lld", (long long)e->ids[s]);
+        e->id2slot[e->ids[s]] = (int)s;
+    }
+    e->n = (int)n;
+    std::vector<int4> hp(n); std::vector<float4> hv(n); std::vector<int> himg(3 * n), hres(n), hslot(n); std::vector<double> hq(n);
+    int maxtype = 0;
+    for (int64_t s = 0; s < n; ++s) {
+        int64_t i = order[s];
+        int xi[3];
+        for (int d = 0; d < 3; ++d) {
+            double fr = pos[3 * i + d] / e->box[d];
+            double fl = floor(fr);
+            double u = rint((fr - fl) * 4294967296.0);
+            int im = (int)fl;
+            if (u >= 4294967296.0) { u -= 4294967296.0; im += 1; }
+            xi[d] = (int)(uint32_t)(uint64_t)u;
+            himg[3 * s + d] = im;
+        }
+        if (type[i] < 0 || type[i] >= CLB_MAX_TYPES) return e->fail(CLB_ERR_ARG, "particle type %d out of range [0,%d)", type[i], CLB_MAX_TYPES);
+        maxtype = std::max(maxtype, (int)type[i]);
+        hp[s] = make_int4(xi[0], xi[1], xi[2], pw_pack(type[i], state ? state[i] : 0));
+        hv[s] = make_float4(vel ? (float)vel[3 * i] : 0.f, vel ? (float)vel[3 * i + 1] : 0.f, vel ? (float)vel[3 * i + 2] : 0.f, (float)mass[i]);
+        hres[s] = res_id ? res_id[i] : 0;
+        hq[s] = q ? q[i] : 0.0;
+        hslot[s] = (int)s;
+    }
+    e->ntypes = std::max(e->ntypes, maxtype + 1);
+    TRY(e->alloc_particles(e->n));
+    CK(cudaMemcpyAsync(e->pos.p, hp.data(), n * sizeof(int4), cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemcpyAsync(e->vel.p, hv.data(), n * sizeof(float4), cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemcpyAsync(e->slot.p, hslot.data(), n * sizeof(int), cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemcpyAsync(e->id2idx.p, hslot.data(), n * sizeof(int), cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemcpyAsync(e->image.p, himg.data(), 3 * n * sizeof(int), cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemcpyAsync(e->resid.p, hres.data(), n * sizeof(int), cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemcpyAsync(e->charge.p, hq.data(), n * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemsetAsync(e->force.p, 0, 3 * (size_t)e->ncap * sizeof(double), e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    e->nstored = e->n; e->own0 = 0; e->own1 = e->n;
+    e->lists_valid = false; e->forces_valid = false; e->excl_dirty = true; e->terms_dirty = true; e->topo_dirty = true;
+    return CLB_OK;
+}
+extern "C" int64_t clb_num_particles(const clb_engine* e) { return e ? e->n : 0; }
+
+int clb_engine::alloc_particles(int n_) {
+    clb_engine* e = this;
+    ncap = n_ + 64;
+    CK(pos.ensure(ncap)); CK(pos2.ensure(ncap)); CK(vel.ensure(ncap)); CK(vel2.ensure(ncap));
+    CK(slot.ensure(ncap)); CK(slot2.ensure(ncap)); CK(xref.ensure(ncap));
+    CK(force.ensure(3 * (size_t)ncap));
+    CK(id2idx.ensure(n_)); CK(image.ensure(3 * (size_t)n_)); CK(resid.ensure(n_)); CK(charge.ensure(n_)); CK(mol.ensure(n_));
+    CK(key.ensure(ncap)); CK(key2.ensure(ncap)); CK(val.ensure(ncap)); CK(val2.ensure(ncap));
+    CK(cell_start.ensure((size_t)grid.ncell + 2));
+    CK(nl_count.ensure(ncap));
+    CK(partial.ensure(65536)); CK(partial_u64.ensure(65536));
+    size_t tb = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tb, key.p, key2.p, val.p, val2.p, ncap, 0, 32, stream);
+    size_t tb2 = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tb2, val.p, val2.p, ncap, stream);
+    CK(cubtmp.ensure(std::max(tb, tb2) + 256));
+    return CLB_OK;
+}
+
+// fetch per-particle state in ascending-id order into host vectors (slot order)
+int clb_engine::download_state(std::vector<int4>& hp, std::vector<float4>& hv, std::vector<int>& hidx) {
+    clb_engine* e = this;
+    hp.resize(nstored); hv.resize(nstored); hidx.resize(n);
+    CK(cudaMemcpyAsync(hp.data(), pos.p, nstored * sizeof(int4), cudaMemcpyDeviceToHost, stream));
+    CK(cudaMemcpyAsync(hv.data(), vel.p, nstored * sizeof(float4), cudaMemcpyDeviceToHost, stream));
+    CK(cudaMemcpyAsync(hidx.data(), id2idx.p, n * sizeof(int), cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    return CLB_OK;
+}
+
+extern "C" int clb_get_particles(clb_engine* e, int64_t n, const int64_t* ids, double* pos, int32_t* image, double* vel,
+                                 double* force, int32_t* type, int32_t* state, double* mass, double* q, int32_t* res_id) {
+    if (!e) return CLB_ERR_ARG;
+    cudaSetDevice(e->device);
+    if (e->nranks > 1) return e->fail(CLB_ERR_UNSUPPORTED, "clb_get_particles on a multi-rank engine: use clb_get_particles on gathered state (not implemented)");
+    std::vector<int4> hp; std::vector<float4> hv; std::vector<int> hidx;
+    TRY(e->download_state(hp, hv, hidx));
+    std::vector<double> hf; std::vector<int> himg, hres; std::vector<double> hq;
+    if (force) { hf.resize(3 * (size_t)e->ncap); CK(cudaMemcpy(hf.data(), e->force.p, hf.size() * 8, cudaMemcpyDeviceToHost)); }
+    if (image) { himg.resize(3 * (size_t)e->n); CK(cudaMemcpy(himg.data(), e->image.p, himg.size() * 4, cudaMemcpyDeviceToHost)); }
+    if (res_id) { hres.resize(e->n); CK(cudaMemcpy(hres.data(), e->resid.p, hres.size() * 4, cudaMemcpyDeviceToHost)); }
+    if (q) { hq.resize(e->n); CK(cudaMemcpy(hq.data(), e->charge.p, hq.size() * 8, cudaMemcpyDeviceToHost)); }
+    int64_t cnt = ids ? n : e->n;
+    for (int64_t k = 0; k < cnt; ++k) {
+        int s = ids ? e->slot_of(ids[k]) : (int)k;
+        if (s < 0) return e->fail(CLB_ERR_ARG, "unknown particle id %lld", (long long)ids[k]);
+        int i = hidx[s];
+        if (pos) { pos[3 * k] = (double)(uint32_t)hp[i].x * e->geo.q[0]; pos[3 * k + 1] = (double)(uint32_t)hp[i].y * e->geo.q[1]; pos[3 * k + 2] = (double)(uint32_t)hp[i].z * e->geo.q[2]; }
+        if (vel) { vel[3 * k] = hv[i].x; vel[3 * k + 1] = hv[i].y; vel[3 * k + 2] = hv[i].z; }
+        if (force) { force[3 * k] = hf[i]; force[3 * k + 1] = hf[i + e->ncap]; force[3 * k + 2] = hf[i + 2 * (size_t)e->ncap]; }
+        if (image) { image[3 * k] = himg[3 * s]; image[3 * k + 1] = himg[3 * s + 1]; image[3 * k + 2] = himg[3 * s + 2]; }
+        if (type) type[k] = pw_type(hp[i].w);
+        if (state) state[k] = pw_state(hp[i].w);
+        if (mass) mass[k] = hv[i].w;
+        if (q) q[k] = hq[s];
+        if (res_id) res_id[k] = hres[s];
+    }
+    return CLB_OK;
+}
+
+static inline int lattice_of(double x, double L, int* im) {
+    double fr = x / L, fl = floor(fr), u = rint((fr - fl) * 4294967296.0);
+    int i = (int)fl;
+    if (u >= 4294967296.0) { u -= 4294967296.0; i += 1; }
+    if (im) *im = i;
+    return (int)(uint32_t)(uint64_t)u;
+}
+
+extern "C" int clb_modify_particle(clb_engine* e, int64_t id, int field, const double* value) {
+    if (!e || !value) return CLB_ERR_ARG;
+    cudaSetDevice(e->device);
+    int s = e->slot_of(id);
+    if (s < 0) return e->fail(CLB_ERR_ARG, "unknown particle id %lld", (long long)id);
+    int i;
+    CK(cudaMemcpy(&i, e->id2idx.p + s, 4, cudaMemcpyDeviceToHost));
+    int4 p; float4 v;
+    CK(cudaMemcpy(&p, e->pos.p + i, sizeof(p), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(&v, e->vel.p + i, sizeof(v), cudaMemcpyDeviceToHost));
+    switch (field) {
+        case 0: { int t = (int)value[0]; if (t < 0 || t >= CLB_MAX_TYPES) return e->fail(CLB_ERR_ARG, "type out of range");
+                  p.w = pw_pack(t, pw_state(p.w)); e->ntypes = std::max(e->ntypes, t + 1); e->pots_dirty = true; break; }
+        case 1: p.w = pw_pack(pw_type(p.w), (int)value[0]); break;
+        case 2: v.w = (float)value[0]; break;
+        case 3: { double qq = value[0]; CK(cudaMemcpy(e->charge.p + s, &qq, 8, cudaMemcpyHostToDevice)); break; }
+        case 4: { int r = (int)value[0]; CK(cudaMemcpy(e->resid.p + s, &r, 4, cudaMemcpyHostToDevice)); break; }
+        case 5: { int im[3]; p.x = lattice_of(value[0], e->box[0], &im[0]); p.y = lattice_of(value[1], e->box[1], &im[1]); p.z = lattice_of(value[2], e->box[2], &im[2]);
+                  CK(cudaMemcpy(e->image.p + 3 * s, im, 12, cudaMemcpyHostToDevice)); e->lists_valid = false; break; }
+        case 6: v.x = (float)value[0]; v.y = (float)value[1]; v.z = (float)value[2]; break;
+        default: return e->fail(CLB_ERR_ARG, "unknown field %d", field);
+    }
+    CK(cudaMemcpy(e->pos.p + i, &p, sizeof(p), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(e->vel.p + i, &v, sizeof(v), cudaMemcpyHostToDevice));
+    e->forces_valid = false;
+    return CLB_OK;
+}
+extern "C" int clb_set_velocities(clb_engine* e, int64_t n, const double* vel) {
+    if (!e || n != e->n || !vel) return e ? e->fail(CLB_ERR_ARG, "clb_set_velocities: n mismatch") : CLB_ERR_ARG;
+    cudaSetDevice(e->device);
+    std::vector<int4> hp; std::vector<float4> hv; std::vector<int> hidx;
+    TRY(e->download_state(hp, hv, hidx));
+    for (int s = 0; s < e->n; ++s) { int i = hidx[s]; hv[i].x = (float)vel[3 * s]; hv[i].y = (float)vel[3 * s + 1]; hv[i].z = (float)vel[3 * s + 2]; }
+    CK(cudaMemcpy(e->vel.p, hv.data(), e->nstored * sizeof(float4), cudaMemcpyHostToDevice));
+    return CLB_OK;
+}
+extern "C" int clb_set_positions(clb_engine* e, int64_t n, const double* pos) {
+    if (!e || n != e->n || !pos) return e ? e->fail(CLB_ERR_ARG, "clb_set_positions: n mismatch") : CLB_ERR_ARG;
+    cudaSetDevice(e->device);
+    std::vector<int4> hp; std::vector<float4> hv; std::vector<int> hidx;
+    TRY(e->download_state(hp, hv, hidx));
+    std::vector<int> himg(3 * (size_t)e->n);
+    for (int s = 0; s < e->n; ++s) {
+        int i = hidx[s];
+        hp[i].x = lattice_of(pos[3 * s], e->box[0], &himg[3 * s]);
+        hp[i].y = lattice_of(pos[3 * s + 1], e->box[1], &himg[3 * s + 1]);
+        hp[i].z = lattice_of(pos[3 * s + 2], e->box[2], &himg[3 * s + 2]);
+    }
+    CK(cudaMemcpy(e->pos.p, hp.data(), e->nstored * sizeof(int4), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(e->image.p, himg.data(), himg.size() * 4, cudaMemcpyHostToDevice));
+    e->lists_valid = false; e->forces_valid = false;
+    return CLB_OK;
+}
+
+// ------------------------------------------------------------------------------------------ exclusions
+extern "C" int clb_set_exclusions(clb_engine* e, int64_t n, const int64_t* pairs) {
+    if (!e || n < 0 || (n && !pairs)) return CLB_ERR_ARG;
+    cudaSetDevice(e->device);
+    std::vector<int2> h; h.reserve(n);
+    for (int64_t k = 0; k < n; ++k) {
+        int a = e->slot_of(pairs[2 * k]), b = e->slot_of(pairs[2 * k + 1]);
+        if (a < 0 || b < 0) return e->fail(CLB_ERR_ARG, "exclusion %lld names an unknown particle", (long long)k);
+        if (a != b) h.push_back(make_int2(std::min(a, b), std::max(a, b)));
+    }
+    std::sort(h.begin(), h.end(), [](const int2& x, const int2& y) { return x.x != y.x ? x.x < y.x : x.y < y.y; });
+    h.erase(std::unique(h.begin(), h.end(), [](const int2& x, const int2& y) { return x.x == y.x && x.y == y.y; }), h.end());
+    e->nexcl = (long long)h.size();
+    CK(e->excl_pairs.ensure(std::max<size_t>(h.size() * 2 + 1024, 1024)));
+    if (!h.empty()) CK(cudaMemcpy(e->excl_pairs.p, h.data(), h.size() * sizeof(int2), cudaMemcpyHostToDevice));
+    e->excl_dirty = true; e->lists_valid = false;
+    return CLB_OK;
+}
+extern "C" int64_t clb_num_exclusions(const clb_engine* e) { return e ? e->nexcl : 0; }
+extern "C" int clb_get_exclusions(clb_engine* e, int64_t cap, int64_t* pairs, int64_t* n_out) {
+    if (!e) return CLB_ERR_ARG;
+    cudaSetDevice(e->device);
+    std::vector<int2> h(e->nexcl);
+    if (e->nexcl) CK(cudaMemcpy(h.data(), e->excl_pairs.p, h.size() * sizeof(int2), cudaMemcpyDeviceToHost));
+    std::sort(h.begin(), h.end(), [](const int2& x, const int2& y) { return x.x != y.x ? x.x < y.x : x.y < y.y; });
+    h.erase(std::unique(h.begin(), h.end(), [](const int2& x, const int2& y) { return x.x == y.x && x.y == y.y; }), h.end());
+    if (n_out) *n_out = (int64_t)h.size();
+    for (size_t k = 0; k < h.size() && (int64_t)k < cap; ++k) { pairs[2 * k] = e->ids[h[k].x]; pairs[2 * k + 1] = e->ids[h[k].y]; }
+    return CLB_OK;
+}
+extern "C" int clb_exclusions_observe(clb_engine* e, int list) {
+    if (!e || list < 0 || list >= (int)e->lists.size()) return e ? e->fail(CLB_ERR_ARG, "bad list handle") : CLB_ERR_ARG;
+    e->lists[list].excl_observed = 1; e->react_dirty = true;
+    return CLB_OK;
+}
+
+__global__ void k_excl_expand(long long n, const int2* __restrict__ pairs, int* __restrict__ key, int* __restrict__ val) {
+    long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    int2 p = pairs[k];
+    key[2 * k] = p.x; val[2 * k] = p.y; key[2 * k + 1] = p.y; val[2 * k + 1] = p.x;
+}
+int clb_engine::build_excl_csr() {
+    clb_engine* e = this;
+    size_t m = (size_t)nexcl * 2;
+    CK(excl_off.ensure((size_t)n + 2));
+    CK(excl_ids.ensure(m + 16));
+    if (m == 0) { CK(cudaMemsetAsync(excl_off.p, 0, ((size_t)n + 2) * 4, stream)); excl_dirty = false; return CLB_OK; }
+    CK(ekey.ensure(m)); CK(ekey2.ensure(m)); CK(eval.ensure(m));
+    k_excl_expand<<<ceil_div(nexcl, 256), 256, 0, stream>>>(nexcl, excl_pairs.p, ekey.p, eval.p);
+    size_t tb = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tb, ekey.p, ekey2.p, eval.p, excl_ids.p, (int)m, 0, 32, stream);
+    CK(cubtmp2.ensure(tb + 256));
+    cub::DeviceRadixSort::SortPairs(cubtmp2.p, tb, ekey.p, ekey2.p, eval.p, excl_ids.p, (int)m, 0, 32, stream);
+    k_lower_bounds<<<ceil_div(n + 1, 256), 256, 0, stream>>>((int)m, ekey2.p, n, excl_off.p);
+    CK(cudaGetLastError());
+    excl_dirty = false;
+    return CLB_OK;
+}
+
+// ------------------------------------------------------------------------------------------ tables & potentials
+static void akima_coeffs(int n, double h, const double* y, std::vector<double>& c) {
+    std::vector<double> m(n + 3);
+    double* mm = m.data() + 2;
+    for (int i = 0; i < n - 1; ++i) mm[i] = (y[i + 1] - y[i]) / h;
+    mm[-1] = 2 * mm[0] - mm[1]; mm[-2] = 2 * mm[-1] - mm[0];
+    mm[n - 1] = 2 * mm[n - 2] - mm[n - 3]; mm[n] = 2 * mm[n - 1] - mm[n - 2];
+    std::vector<double> t(n);
+    for (int i = 0; i < n; ++i) {
+        double w1 = fabs(mm[i + 1] - mm[i]), w2 = fabs(mm[i - 1] - mm[i - 2]);
+        t[i] = (w1 + w2 == 0.0) ? 0.5 * (mm[i - 1] + mm[i]) : (w1 * mm[i - 1] + w2 * mm[i]) / (w1 + w2);
+    }
+    c.assign(4 * (size_t)(n - 1), 0.0);
+    for (int i = 0; i < n - 1; ++i) {
+        c[4 * i] = y[i]; c[4 * i + 1] = t[i];
+        c[4 * i + 2] = (3 * mm[i] - 2 * t[i] - t[i + 1]) / h;
+        c[4 * i + 3] = (t[i] + t[i + 1] - 2 * mm[i]) / (h * h);
+    }
+}
+static void spline_coeffs(int n, double h, const double* y, std::vector<double>& c) {
+    std::vector<double> y2(n, 0.0), u(n, 0.0);
+    for (int i = 1; i < n - 1; ++i) {
+        double p = 0.5 * y2[i - 1] + 2.0;
+        y2[i] = -0.5 / p;
+        u[i] = (y[i + 1] - 2 * y[i] + y[i - 1]) / h;
+        u[i] = (3.0 * u[i] / h - 0.5 * u[i - 1]) / p;
+    }
+    y2[n - 1] = 0;
+    for (int k = n - 2; k >= 0; --k) y2[k] = y2[k] * y2[k + 1] + u[k];
+    c.assign(4 * (size_t)(n - 1), 0.0);
+    for (int i = 0; i < n - 1; ++i) {
+        c[4 * i] = y[i];
+        c[4 * i + 1] = (y[i + 1] - y[i]) / h - h * (2 * y2[i] + y2[i + 1]) / 6.0;
+        c[4 * i + 2] = 0.5 * y2[i];
+        c[4 * i + 3] = (y2[i + 1] - y2[i]) / (6.0 * h);
+    }
+}
+static void linear_coeffs(int n, double h, const double* y, std::vector<double>& c) {
+    c.assign(4 * (size_t)(n - 1), 0.0);
+    for (int i = 0; i < n - 1; ++i) { c[4 * i] = y[i]; c[4 * i + 1] = (y[i + 1] - y[i]) / h; }
+}
+
+extern "C" int clb_add_table(clb_engine* e, int64_t n, const double* x, const double* energy, const double* force, int interp,
+                             int* table_out) {
+    if (!e || n < 2 || !x || !energy || !force || !table_out) return e ? e->fail(CLB_ERR_ARG, "clb_add_table: bad argument") : CLB_ERR_ARG;
+    if (interp < 1 || interp > 3) return e->fail(CLB_ERR_ARG, "interp must be 1 (linear), 2 (Akima) or 3 (cubic)");
+    HostTable t;
+    t.n = (int)n; t.x0 = x[0]; t.dx = (x[n - 1] - x[0]) / (double)(n - 1); t.interp = interp;
+    if (!(t.dx > 0)) return e->fail(CLB_ERR_ARG, "table abscissa must increase");
+    for (int64_t i = 0; i < n; ++i)
+        if (fabs(x[i] - (t.x0 + i * t.dx)) > 1e-6 * t.dx + 1e-9 * fabs(x[i]) + 5e-9)
+            return e->fail(CLB_ERR_ARG, "table abscissa is not uniform at row %lld", (long long)i);
+    t.e.assign(energy, energy + n); t.f.assign(force, force + n);
+    e->tables.push_back(std::move(t));
+    *table_out = (int)e->tables.size() - 1;
+    e->pots_dirty = true;
+    return CLB_OK;
+}
+
+extern "C" int clb_add_nonbonded(clb_engine* e, int kind, int* out) {
+    if (!e || !out || kind < 1 || kind > 3) return e ? e->fail(CLB_ERR_ARG, "bad non-bonded kind") : CLB_ERR_ARG;
+    HostInter it; it.kind = kind; it.bonded = -1;
+    e->inters.push_back(it);
+    *out = (int)e->inters.size() - 1;
+    return CLB_OK;
+}
+static int check_nb(clb_engine* e, int inter, int t1, int t2, int kind, double cutoff) {
+    if (inter < 0 || inter >= (int)e->inters.size() || e->inters[inter].bonded >= 0) return e->fail(CLB_ERR_ARG, "bad non-bonded interaction handle");
+    if (e->inters[inter].kind != kind) return e->fail(CLB_ERR_ARG, "potential kind does not match the interaction kind");
+    if (t1 < 0 || t2 < 0 || t1 >= CLB_MAX_TYPES || t2 >= CLB_MAX_TYPES) return e->fail(CLB_ERR_ARG, "type out of range");
+    if (cutoff > e->rc * (1 + 1e-12)) return e->fail(CLB_ERR_ARG, "potential cutoff %g exceeds the Verlet cutoff %g", cutoff, e->rc);
+    HostPairPot& p = e->pp[t1][t2];
+    if (p.kind != 0 && p.inter != inter) return e->fail(CLB_ERR_UNSUPPORTED, "type pair (%d,%d) already belongs to interaction %d", t1, t2, p.inter);
+    e->ntypes = std::max(e->ntypes, std::max(t1, t2) + 1);
+    return CLB_OK;
+}
+extern "C" int clb_nb_set_tabulated(clb_engine* e, int inter, int t1, int t2, int table, double cutoff) {
+    if (!e) return CLB_ERR_ARG;
+    TRY(check_nb(e, inter, t1, t2, CLB_NB_TABULATED, cutoff));
+    if (table < 0 || table >= (int)e->tables.size()) return e->fail(CLB_ERR_ARG, "bad table handle");
+    if (e->tables[table].interp != 1) return e->fail(CLB_ERR_UNSUPPORTED, "non-bonded tables use linear interpolation (itype=1) as chemlab does (gromacs_topology.py:696-707)");
+    HostPairPot p; p.kind = 1; p.inter = inter; p.tab1 = table; p.tab2 = -1; p.rc = cutoff;
+    e->pp[t1][t2] = e->pp[t2][t1] = p;
+    e->pots_dirty = true; e->forces_valid = false;
+    return CLB_OK;
+}
+extern "C" int clb_nb_set_lj(clb_engine* e, int inter, int t1, int t2, double eps, double sig, double cutoff, int shift_auto) {
+    if (!e) return CLB_ERR_ARG;
+    TRY(check_nb(e, inter, t1, t2, CLB_NB_LENNARD_JONES, cutoff));
+    HostPairPot p; p.kind = 2; p.inter = inter; p.eps = eps; p.sig = sig; p.rc = cutoff;
+    double sr6 = pow(sig / cutoff, 6);
+    p.shift = shift_auto ? 4 * eps * (sr6 * sr6 - sr6) : 0.0;
+    e->pp[t1][t2] = e->pp[t2][t1] = p;
+    e->pots_dirty = true; e->forces_valid = false;
+    return CLB_OK;
+}
+extern "C" int clb_nb_set_mixed(clb_engine* e, int inter, int t1, int t2, int table1, int table2, double mix, int conv_type,
+                                double conv_total, double cutoff) {
+    if (!e) return CLB_ERR_ARG;
+    TRY(check_nb(e, inter, t1, t2, CLB_NB_MIXED_TABULATED, cutoff));
+    if (table1 < 0 || table1 >= (int)e->tables.size() || table2 < 0 || table2 >= (int)e->tables.size()) return e->fail(CLB_ERR_ARG, "bad table handle");
+    const HostTable &a = e->tables[table1], &b = e->tables[table2];
+    if (a.n != b.n || fabs(a.x0 - b.x0) > 1e-12 || fabs(a.dx - b.dx) > 1e-12 || a.interp != 1 || b.interp != 1)
+        return e->fail(CLB_ERR_UNSUPPORTED, "mixed tables must share one grid and use linear interpolation");
+    HostPairPot p; p.kind = 3; p.inter = inter; p.tab1 = table1; p.tab2 = table2; p.mix = mix; p.conv_type = conv_type; p.conv_total = conv_total; p.rc = cutoff;
+    e->pp[t1][t2] = e->pp[t2][t1] = p;
+    e->pots_dirty = true; e->forces_valid = false; e->has_mixed = true;
+    return CLB_OK;
+}
+
+// Upload pair descriptors and tables.  Every type pair with a table gets its own row slot so that
+// mixed tables (x*tab1 + (1-x)*tab2, linear in the rows) are premixed on the host; identical
+// (table, mix) combinations share one slot.
+int clb_engine::upload_potentials() {
+    clb_engine* e = this;
+    int nt = std::max(ntypes, 1);
+    std::vector<ClbPairDesc> pd((size_t)nt * nt); std::vector<ClbPairDescE> pe((size_t)nt * nt);
+    std::vector<ClbTabMeta> tm; std::vector<double2> frows, erows;
+    struct Key { int a, b; double mix; };
+    std::vector<Key> keys;
+    for (int a = 0; a < nt; ++a) for (int b = 0; b < nt; ++b) {
+        const HostPairPot& p = pp[a][b];
+        ClbPairDesc d; memset(&d, 0, sizeof(d)); ClbPairDescE de; memset(&de, 0, sizeof(de));
+        de.inter = p.inter;
+        if (p.kind == 2) {
+            d.kind = 2; d.rc2 = p.rc * p.rc;
+            double s6 = pow(p.sig, 6), s12 = s6 * s6;
+            d.c12 = 48 * p.eps * s12; d.c6 = 24 * p.eps * s6;
+            de.e12 = 4 * p.eps * s12; de.e6 = 4 * p.eps * s6; de.shift = p.shift;
+        } else if (p.kind == 1 || p.kind == 3) {
+            d.kind = 1; d.rc2 = p.rc * p.rc;
+            double mix = p.kind == 3 ? p.mix : 1.0;
+            int t2 = p.kind == 3 ? p.tab2 : -1;
+            int slot_i = -1;
+            for (size_t k = 0; k < keys.size(); ++k) if (keys[k].a == p.tab1 && keys[k].b == t2 && keys[k].mix == mix) slot_i = (int)k;
+            if (slot_i < 0) {
+                const HostTable& A = tables[p.tab1];
+                const HostTable* B = t2 >= 0 ? &tables[t2] : nullptr;
+                ClbTabMeta m; m.x0 = A.x0; m.dx = A.dx; m.invdx = 1.0 / A.dx; m.c_t = -A.x0 / A.dx - 0.5; m.c_idx = 0; m.n = A.n; m.off = (int)frows.size();
+                if (A.x0 + A.dx * (A.n - 1) < p.rc * (1 - 1e-12)) return fail(CLB_ERR_ARG, "table for types (%d,%d) ends at %g before the cutoff %g", a, b, A.x0 + A.dx * (A.n - 1), p.rc);
+                for (int i = 0; i < A.n; ++i) {
+                    auto F = [&](int k) { return B ? mix * A.f[k] + (1 - mix) * B->f[k] : A.f[k]; };
+                    auto E = [&](int k) { return B ? mix * A.e[k] + (1 - mix) * B->e[k] : A.e[k]; };
+                    int i1 = std::min(i + 1, A.n - 1);
+                    double df = F(i1) - F(i), de_ = E(i1) - E(i);
+                    frows.push_back(make_double2(F(i) + 0.5 * df, df));
+                    erows.push_back(make_double2(E(i), de_));
+                }
+                keys.push_back({p.tab1, t2, mix}); tm.push_back(m);
+                slot_i = (int)keys.size() - 1;
+            }
+            d.tab = slot_i;
+        }
+        pd[(size_t)a * nt + b] = d; pe[(size_t)a * nt + b] = de;
+    }
+    nt_dev = nt; ntabs_dev = (int)tm.size(); nrows_dev = (int)frows.size();
+    CK(d_pd.ensure(pd.size())); CK(d_pe.ensure(pe.size()));
+    CK(d_tm.ensure(std::max<size_t>(tm.size(), 1))); CK(d_frows.ensure(std::max<size_t>(frows.size(), 1))); CK(d_erows.ensure(std::max<size_t>(erows.size(), 1)));
+    CK(cudaMemcpyAsync(d_pd.p, pd.data(), pd.size() * sizeof(ClbPairDesc), cudaMemcpyHostToDevice, stream));
+    CK(cudaMemcpyAsync(d_pe.p, pe.data(), pe.size() * sizeof(ClbPairDescE), cudaMemcpyHostToDevice, stream));
+    if (!tm.empty()) {
+        CK(cudaMemcpyAsync(d_tm.p, tm.data(), tm.size() * sizeof(ClbTabMeta), cudaMemcpyHostToDevice, stream));
+        CK(cudaMemcpyAsync(d_frows.p, frows.data(), frows.size() * sizeof(double2), cudaMemcpyHostToDevice, stream));
+        CK(cudaMemcpyAsync(d_erows.p, erows.data(), erows.size() * sizeof(double2), cudaMemcpyHostToDevice, stream));
+    }
+    // bonded descriptors, potentials and tables (cubic coefficients per interval)
+    std::vector<ClbBondedDesc> bd(std::max<size_t>(lists.size(), 1));
+    std::vector<ClbBPot> bp; std::vector<ClbBTabMeta> btm; std::vector<double> cf, cec;
+    std::vector<int> tabmap(tables.size(), -1);
+    for (size_t l = 0; l < lists.size(); ++l) {
+        ClbBondedDesc d; memset(&d, 0, sizeof(d));
+        d.arity = lists[l].arity; d.inter = -1;
+        int bi = lists[l].bonded;
+        if (bi >= 0) {
+            const HostBonded& hb = bondeds[bi];
+            d.typed = hb.typed; d.inter = hb.inter; d.npot = (int)hb.pots.size(); d.pot_off = (int)bp.size(); d.active = d.npot > 0;
+            for (ClbBPot p : hb.pots) {
+                if (p.kind == 2 || p.kind == 4 || p.kind == 5) {
+                    int ht = p.table;
+                    if (tabmap[ht] < 0) {
+                        const HostTable& T = tables[ht];
+                        ClbBTabMeta m; m.x0 = T.x0; m.dx = T.dx; m.invdx = 1.0 / T.dx; m.n = T.n; m.off = (int)(cf.size() / 4);
+                        std::vector<double> c1, c2;
+                        if (T.interp == 1) { linear_coeffs(T.n, T.dx, T.f.data(), c1); linear_coeffs(T.n, T.dx, T.e.data(), c2); }
+                        else if (T.interp == 2) { akima_coeffs(T.n, T.dx, T.f.data(), c1); akima_coeffs(T.n, T.dx, T.e.data(), c2); }
+                        else { spline_coeffs(T.n, T.dx, T.f.data(), c1); spline_coeffs(T.n, T.dx, T.e.data(), c2); }
+                        cf.insert(cf.end(), c1.begin(), c1.end()); cec.insert(cec.end(), c2.begin(), c2.end());
+                        tabmap[ht] = (int)btm.size(); btm.push_back(m);
+                    }
+                    p.table = tabmap[ht];
+                }
+                bp.push_back(p);
+            }
+        }
+        bd[l] = d;
+    }
+    CK(d_bdesc.ensure(bd.size())); CK(d_bpots.ensure(std::max<size_t>(bp.size(), 1))); CK(d_btm.ensure(std::max<size_t>(btm.size(), 1)));
+    CK(d_bcf.ensure(std::max<size_t>(cf.size() / 4, 1))); CK(d_bce.ensure(std::max<size_t>(cec.size() / 4, 1)));
+    CK(cudaMemcpyAsync(d_bdesc.p, bd.data(), bd.size() * sizeof(ClbBondedDesc), cudaMemcpyHostToDevice, stream));
+    if (!bp.empty()) CK(cudaMemcpyAsync(d_bpots.p, bp.data(), bp.size() * sizeof(ClbBPot), cudaMemcpyHostToDevice, stream));
+    if (!btm.empty()) {
+        CK(cudaMemcpyAsync(d_btm.p, btm.data(), btm.size() * sizeof(ClbBTabMeta), cudaMemcpyHostToDevice, stream));
+        CK(cudaMemcpyAsync(d_bcf.p, cf.data(), cf.size() * 8, cudaMemcpyHostToDevice, stream));
+        CK(cudaMemcpyAsync(d_bce.p, cec.data(), cec.size() * 8, cudaMemcpyHostToDevice, stream));
+    }
+    CK(cudaStreamSynchronize(stream));
+    pots_dirty = false;
+    forces_valid = false;
+    return CLB_OK;
+}
+
+// ------------------------------------------------------------------------------------------ tuple lists
+extern "C" int clb_add_list(clb_engine* e, int arity, int* out) {
+    if (!e || !out || arity < 2 || arity > 4) return e ? e->fail(CLB_ERR_ARG, "arity must be 2, 3 or 4") : CLB_ERR_ARG;
+    if (e->lists.size() >= CLB_MAX_LISTS) return e->fail(CLB_ERR_UNSUPPORTED, "too many tuple lists");
+    HostList l; l.arity = arity;
+    e->lists.push_back(std::move(l));
+    *out = (int)e->lists.size() - 1;
+    e->pots_dirty = true; e->terms_dirty = true; e->react_dirty = true;
+    return CLB_OK;
+}
+int clb_engine::list_reserve(int li, long long need) {
+    clb_engine* e = this;
+    HostList& l = lists[li];
+    if ((size_t)need * l.arity <= l.d.n) return CLB_OK;
+    size_t newcap = std::max<size_t>((size_t)need * l.arity * 3 / 2 + 1024, 4096);
+    DevBuf<int> nb;
+    CK(nb.ensure(newcap));
+    if (l.n) CK(cudaMemcpyAsync(nb.p, l.d.p, (size_t)l.n * l.arity * 4, cudaMemcpyDeviceToDevice, stream));
+    CK(cudaStreamSynchronize(stream));
+    l.d.release(); l.d = nb; nb.p = nullptr; nb.n = 0;
+    lists_ptr_dirty = true;
+    return CLB_OK;
+}
+extern "C" int clb_list_add(clb_engine* e, int list, int64_t n, const int64_t* ids) {
+    if (!e || list < 0 || list >= (int)e->lists.size() || n < 0 || (n && !ids)) return e ? e->fail(CLB_ERR_ARG, "clb_list_add: bad argument") : CLB_ERR_ARG;
+    cudaSetDevice(e->device);
+    HostList& l = e->lists[list];
+    std::vector<int> h((size_t)n * l.arity);
+    for (size_t k = 0; k < h.size(); ++k) { int s = e->slot_of(ids[k]); if (s < 0) return e->fail(CLB_ERR_ARG, "tuple names unknown particle id %lld", (long long)ids[k]); h[k] = s; }
+    TRY(e->list_reserve(list, l.n + n));
+    if (n) CK(cudaMemcpy(l.d.p + (size_t)l.n * l.arity, h.data(), h.size() * 4, cudaMemcpyHostToDevice));
+    l.n += n;
+    e->terms_dirty = true; e->forces_valid = false;
+    if (l.arity == 2 && l.tm_observed) e->topo_dirty = true;
+    return CLB_OK;
+}
+extern "C" int64_t clb_list_size(clb_engine* e, int list) {
+    if (!e || list < 0 || list >= (int)e->lists.size()) return -1;
+    return e->lists[list].n;
+}
+extern "C" int clb_list_get(clb_engine* e, int list, int64_t cap, int64_t* ids, int64_t* n_out) {
+    if (!e || list < 0 || list >= (int)e->lists.size()) return e ? e->fail(CLB_ERR_ARG, "bad list handle") : CLB_ERR_ARG;
+    cudaSetDevice(e->device);
+    HostList& l = e->lists[list];
+    if (n_out) *n_out = l.n;
+    long long m = std::min<long long>(l.n, cap);
+    if (m > 0 && ids) {
+        std::vector<int> h((size_t)m * l.arity);
+        CK(cudaMemcpy(h.data(), l.d.p, h.size() * 4, cudaMemcpyDeviceToHost));
+        for (size_t k = 0; k < h.size(); ++k) ids[k] = e->ids[h[k]];
+    }
+    return CLB_OK;
+}
+extern "C" int clb_add_bonded(clb_engine* e, int list, int typed, int* out) {
+    if (!e || !out || list < 0 || list >= (int)e->lists.size()) return e ? e->fail(CLB_ERR_ARG, "bad list handle") : CLB_ERR_ARG;
+    if (e->lists[list].bonded >= 0) return e->fail(CLB_ERR_UNSUPPORTED, "list %d already carries a bonded interaction", list);
+    HostBonded b; b.list = list; b.typed = typed ? 1 : 0;
+    HostInter it; it.kind = 10 + e->lists[list].arity; it.bonded = (int)e->bondeds.size();
+    e->inters.push_back(it);
+    b.inter = (int)e->inters.size() - 1;
+    e->lists[list].bonded = (int)e->bondeds.size();
+    e->bondeds.push_back(b);
+    *out = b.inter;
+    e->pots_dirty = true; e->terms_dirty = true;
+    return CLB_OK;
+}
+extern "C" int clb_bonded_set_potential(clb_engine* e, int inter, int t1, int t2, int t3, int t4, int kind, const double* params,
+                                        int np, int table) {
+    if (!e || inter < 0 || inter >= (int)e->inters.size() || e->inters[inter].bonded < 0) return e ? e->fail(CLB_ERR_ARG, "bad bonded interaction handle") : CLB_ERR_ARG;
+    HostBonded& b = e->bondeds[e->inters[inter].bonded];
+    int ar = e->lists[b.list].arity;
+    bool ok = (ar == 2 && (kind == CLB_POT_HARMONIC || kind == CLB_POT_TABULATED || kind == CLB_POT_FENE)) ||
+              (ar == 3 && (kind == CLB_POT_ANGULAR_HARMONIC || kind == CLB_POT_TABULATED_ANGULAR || kind == CLB_POT_COSINE)) ||
+              (ar == 4 && (kind == CLB_POT_TABULATED_DIHEDRAL || kind == CLB_POT_DIHEDRAL_HARMONIC));
+    if (!ok) return e->fail(CLB_ERR_ARG, "potential kind %d does not fit a list of arity %d", kind, ar);
+    ClbBPot p; memset(&p, 0, sizeof(p));
+    p.kind = kind; p.table = table; p.t[0] = t1; p.t[1] = t2; p.t[2] = t3; p.t[3] = t4;
+    for (int i = 0; i < np && i < 4; ++i) p.p[i] = params[i];
+    if (kind == 2 || kind == 4 || kind == 5) { if (table < 0 || table >= (int)e->tables.size()) return e->fail(CLB_ERR_ARG, "bad table handle"); }
+    if (!b.typed) { b.pots.clear(); b.pots.push_back(p); }
+    else {
+        bool replaced = false;
+        for (auto& o : b.pots) {
+            bool fwd = true, rev = true;
+            for (int m = 0; m < ar; ++m) { fwd &= o.t[m] == p.t[m]; rev &= o.t[m] == p.t[ar - 1 - m]; }
+            if (fwd || rev) { o = p; replaced = true; break; }
+        }
+        if (!replaced) b.pots.push_back(p);
+    }
+    e->pots_dirty = true; e->forces_valid = false;
+    return CLB_OK;
+}
+
+// CSR by slot of all (tuple, role) memberships of lists that carry a bonded interaction.
+int clb_engine::build_term_csr() {
+    clb_engine* e = this;
+    long long total = 0;
+    for (auto& l : lists) if (l.bonded >= 0) total += l.n * l.arity;
+    nterms = total;
+    CK(term_off.ensure((size_t)n + 2));
+    CK(term_meta.ensure((size_t)total + 16)); CK(term_tuple.ensure((size_t)total + 16));
+    if (total == 0) { CK(cudaMemsetAsync(term_off.p, 0, ((size_t)n + 2) * 4, stream)); terms_dirty = false; return CLB_OK; }
+    CK(tkey.ensure(total)); CK(tkey2.ensure(total)); CK(tval.ensure(total)); CK(tval2.ensure(total));
+    long long base = 0;
+    for (size_t li = 0; li < lists.size(); ++li) {
+        HostList& l = lists[li];
+        if (l.bonded < 0 || l.n == 0) continue;
+        k_term_expand<<<ceil_div(l.n, 256), 256, 0, stream>>>((int)l.n, l.arity, (int)li, l.d.p, (int)base, tkey.p, tval.p);
+        base += l.n * l.arity;
+    }
+    size_t tb = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tb, tkey.p, tkey2.p, tval.p, tval2.p, (int)total, 0, 32, stream);
+    CK(cubtmp2.ensure(tb + 256));
+    cub::DeviceRadixSort::SortPairs(cubtmp2.p, tb, tkey.p, tkey2.p, tval.p, tval2.p, (int)total, 0, 32, stream);
+    k_term_unpack<<<ceil_div(total, 256), 256, 0, stream>>>((int)total, tval2.p, term_meta.p, term_tuple.p);
+    k_lower_bounds<<<ceil_div(n + 1, 256), 256, 0, stream>>>((int)total, tkey2.p, n, term_off.p);
+    CK(cudaGetLastError());
+    terms_dirty = false;
+    lists_ptr_dirty = true;
+    rt_valid = false;
+    return CLB_OK;
+}
+int clb_engine::upload_list_ptrs() {
+    clb_engine* e = this;
+    std::vector<const int*> h(CLB_MAX_LISTS, nullptr);
+    for (size_t l = 0; l < lists.size(); ++l) h[l] = lists[l].d.p;
+    CK(d_list_ptrs.ensure(CLB_MAX_LISTS));
+    CK(cudaMemcpyAsync(d_list_ptrs.p, h.data(), CLB_MAX_LISTS * sizeof(int*), cudaMemcpyHostToDevice, stream));
+    CK(cudaStreamSynchronize(stream));
+    lists_ptr_dirty = false;
+    return CLB_OK;
+}
+// resolve memberships to sorted indices (after every re-sort or topology change)
+int clb_engine::resolve_terms() {
+    clb_engine* e = this;
+    int no = own1 - own0;
+    CK(rt_off.ensure((size_t)no + 2)); CK(rt_cnt.ensure((size_t)no + 2));
+    CK(rt_mem.ensure((size_t)nterms + 16)); CK(rt_meta.ensure((size_t)nterms + 16));
+    if (lists_ptr_dirty) TRY(upload_list_ptrs());
+    if (no > 0) {
+        CK(cudaMemsetAsync(rt_cnt.p, 0, ((size_t)no + 2) * 4, stream));
+        k_term_counts<<<ceil_div(no, 256), 256, 0, stream>>>(own0, own1, slot.p, term_off.p, rt_cnt.p);
+        size_t tb = cubtmp.n;
+        cub::DeviceScan::ExclusiveSum(cubtmp.p, tb, rt_cnt.p, rt_off.p, no + 1, stream);
+        if (nterms) k_term_resolve<<<ceil_div(no, 256), 256, 0, stream>>>(own0, own1, slot.p, term_off.p, term_meta.p, term_tuple.p,
+                                                                           (const int* const*)d_list_ptrs.p, d_bdesc.p, id2idx.p, rt_off.p, rt_mem.p, rt_meta.p, d_ctl);
+    }
+    CK(cudaGetLastError());
+    rt_valid = true;
+    return CLB_OK;
+}
+
+// ------------------------------------------------------------------------------------------ rebuild
+int clb_engine::read_ctl() {
+    clb_engine* e = this;
+    CK(cudaMemcpyAsync(h_ctl, d_ctl, sizeof(ClbCtl), cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    return CLB_OK;
+}
+__global__ void k_ctl_reset_stats(ClbCtl* c) { c->tile_max = 0; c->home_max = 0; c->cell_max = 0; c->nl_max = 0; c->nl_total = 0; c->err &= ~CLB_EF_LIST_OVERFLOW; }
+__global__ void k_ctl_after_rebuild(ClbCtl* c) { c->stall = 0; c->accum_maxdist = 0.0; c->maxdisp2_bits = 0u; c->force_rebuild = 0; }
+
+int clb_engine::setup_sync() {
+    if (n <= 0) return fail(CLB_ERR_STATE, "no particles");
+    if (pots_dirty) TRY(upload_potentials());
+    if (excl_dirty) { TRY(build_excl_csr()); lists_valid = false; }
+    if (terms_dirty) TRY(build_term_csr());
+    if (topo_dirty) TRY(build_topology());
+    if (react_dirty) TRY(upload_reactions());
+    return CLB_OK;
+}
+
+int clb_engine::rebuild() {
+    clb_engine* e = this;
+    bucket_begin(CLB_B_NEIGH);
+    if (nranks > 1) TRY(comm_migrate_and_ghosts());
+    int ns = nstored;
+    // 1. sort by cell
+    k_cell_keys<<<ceil_div(ns, 256), 256, 0, stream>>>(ns, pos.p, grid, key.p, val.p);
+    int bits = 1; while ((1ll << bits) < grid.ncell) ++bits;
+    size_t tb = cubtmp.n;
+    cub::DeviceRadixSort::SortPairs(cubtmp.p, tb, key.p, key2.p, val.p, val2.p, ns, 0, bits, stream);
+    k_gather<<<ceil_div(ns, 256), 256, 0, stream>>>(ns, val2.p, pos.p, vel.p, slot.p, pos2.p, vel2.p, slot2.p, xref.p, id2idx.p);
+    std::swap(pos.p, pos2.p); std::swap(vel.p, vel2.p); std::swap(slot.p, slot2.p);
+    k_cell_start<<<ceil_div(ns + 1, 256), 256, 0, stream>>>(ns, key2.p, grid.ncell, cell_start.p);
+    if (nranks > 1) TRY(comm_after_sort());
+    // 2. tile statistics
+    k_ctl_reset_stats<<<1, 1, 0, stream>>>(d_ctl);
+    k_block_stats<<<ceil_div(grid.nblocks, 128), 128, 0, stream>>>(grid, cell_start.p, d_ctl);
+    TRY(read_ctl());
+    tile_max = h_ctl->tile_max; home_max = h_ctl->home_max;
+    if (tile_max > 65535) return fail(CLB_ERR_UNSUPPORTED, "tile of %d particles exceeds 16-bit list entries: lower block_cells", tile_max);
+    // 3. neighbour lists (retry with a larger capacity on overflow)
+    if (nl_cap == 0 || nl_cap_user != nl_cap_user_seen) {
+        double rho = (double)n / (box[0] * box[1] * box[2]);
+        double rl = rc + skin;
+        int expect = (int)(4.18879 * rl * rl * rl * rho);
+        nl_cap = nl_cap_user > 0 ? nl_cap_user : ((expect * 3 / 2 + 32 + 7) / 8) * 8;
+        nl_cap_user_seen = nl_cap_user;
+    }
+    int threads = std::min(512, std::max(64, ((home_max + 31) / 32) * 32));
+    for (int attempt = 0;; ++attempt) {
+        CK(nl_entries.ensure((size_t)ncap * nl_cap));
+        size_t smem = (size_t)tile_max * (sizeof(int4) + sizeof(int)) + 16;
+        if ((int)smem > smem_optin) return fail(CLB_ERR_UNSUPPORTED, "tile needs %zu B of shared memory: lower block_cells", smem);
+        int nb = 0;
+        if (geo.cubic) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_build_lists<true>, threads, smem);
+        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_build_lists<false>, threads, smem);
+        int gridsz = std::min(grid.nblocks, std::max(1, nb) * nsm);
+        if (geo.cubic) k_build_lists<true><<<gridsz, threads, smem, stream>>>(grid, geo, cell_start.p, pos.p, slot.p, excl_off.p, excl_ids.p, nl_entries.p, nl_count.p, nl_cap, d_ctl);
+        else k_build_lists<false><<<gridsz, threads, smem, stream>>>(grid, geo, cell_start.p, pos.p, slot.p, excl_off.p, excl_ids.p, nl_entries.p, nl_count.p, nl_cap, d_ctl);
+        ++launches;
+        TRY(read_ctl());
+        if (!(h_ctl->err & CLB_EF_LIST_OVERFLOW)) break;
+        if (attempt > 6) return fail(CLB_ERR_RANGE, "neighbour list keeps overflowing (max %d entries)", h_ctl->nl_max);
+        nl_cap = ((h_ctl->nl_max * 5 / 4 + 8 + 7) / 8) * 8;
+        k_ctl_reset_stats<<<1, 1, 0, stream>>>(d_ctl);
+    }
+    nl_max = h_ctl->nl_max; nl_total = h_ctl->nl_total;
+    // 4. pair-force launch configuration
+    {
+        size_t fixed = (size_t)nt_dev * nt_dev * sizeof(ClbPairDesc) + (size_t)ntabs_dev * sizeof(ClbTabMeta);
+        size_t rows = (size_t)nrows_dev * sizeof(double2);
+        size_t tile = (size_t)tile_max * sizeof(int4) + 16;
+        bool in_smem = tabs_smem_user != 0 && fixed + rows + tile <= (size_t)std::min(smem_optin, 110 * 1024);
+        if (tabs_smem_user == 2 && fixed + rows + tile <= (size_t)smem_optin) in_smem = true;
+        tabs_smem = in_smem ? 1 : 0;
+        pair_smem = (int)(fixed + (in_smem ? rows : 0) + tile);
+        if (pair_smem > smem_optin) return fail(CLB_ERR_UNSUPPORTED, "pair kernel needs %d B of shared memory: lower block_cells", pair_smem);
+        pair_threads = threads;
+        int nb = 0;
+        if (geo.cubic) { if (in_smem) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_pair_forces<true, true>, threads, pair_smem); else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_pair_forces<true, false>, threads, pair_smem); }
+        else { if (in_smem) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_pair_forces<false, true>, threads, pair_smem); else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_pair_forces<false, false>, threads, pair_smem); }
+        pair_grid = std::min(grid.nblocks, std::max(1, nb) * nsm);
+    }
+    // 5. bonded memberships -> sorted indices
+    TRY(resolve_terms());
+    k_ctl_after_rebuild<<<1, 1, 0, stream>>>(d_ctl);
+    CK(cudaGetLastError());
+    launches += 8;
+    lists_valid = true; forces_valid = false;
+    ++nrebuild;
+    bucket_end(CLB_B_NEIGH);
+    return CLB_OK;
+}
+
+extern "C" int clb_decompose(clb_engine* e) {
+    if (!e) return CLB_ERR_ARG;
+    cudaSetDevice(e->device);
+    TRY(e->setup_sync());
+    TRY(e->rebuild());
+    CK(cudaStreamSynchronize(e->stream));
+    return CLB_OK;
+}
+
+// ------------------------------------------------------------------------------------------ forces
+void clb_engine::enqueue_forces() {
+    bucket_begin(CLB_B_PAIR);
+    if (pair_event_timing) cudaEventRecord(next_pair_event(), stream);
+    if (geo.cubic) {
+        if (tabs_smem) k_pair_forces<true, true><<<pair_grid, pair_threads, pair_smem, stream>>>(grid, geo, cell_start.p, pos.p, nl_entries.p, nl_count.p, nl_cap, d_pd.p, nt_dev, d_tm.p, ntabs_dev, d_frows.p, nrows_dev, force.p, ncap, d_ctl);
+        else k_pair_forces<true, false><<<pair_grid, pair_threads, pair_smem, stream>>>(grid, geo, cell_start.p, pos.p, nl_entries.p, nl_count.p, nl_cap, d_pd.p, nt_dev, d_tm.p, ntabs_dev, d_frows.p, nrows_dev, force.p, ncap, d_ctl);
+    } else {
+        if (tabs_smem) k_pair_forces<false, true><<<pair_grid, pair_threads, pair_smem, stream>>>(grid, geo, cell_start.p, pos.p, nl_entries.p, nl_count.p, nl_cap, d_pd.p, nt_dev, d_tm.p, ntabs_dev, d_frows.p, nrows_dev, force.p, ncap, d_ctl);
+        else k_pair_forces<false, false><<<pair_grid, pair_threads, pair_smem, stream>>>(grid, geo, cell_start.p, pos.p, nl_entries.p, nl_count.p, nl_cap, d_pd.p, nt_dev, d_tm.p, ntabs_dev, d_frows.p, nrows_dev, force.p, ncap, d_ctl);
+    }
+    if (pair_event_timing) cudaEventRecord(next_pair_event(), stream);
+    bucket_end(CLB_B_PAIR);
+    ++launches; ++pair_launches_total;
+    if (nterms > 0) {
+        bucket_begin(CLB_B_BONDED);
+        int no = own1 - own0;
+        k_bonded<false><<<ceil_div(no, 256), 256, 0, stream>>>(own0, own1, pos.p, geo, rt_off.p, rt_mem.p, rt_meta.p, d_bdesc.p, d_bpots.p, d_btm.p,
+                                                                 (const double4*)d_bcf.p, (const double4*)d_bce.p, force.p, ncap, -1, nullptr, d_ctl);
+        bucket_end(CLB_B_BONDED);
+        ++launches;
+    }
+}
+
+int clb_engine::check_device_errors(const char* where) {
+    unsigned er = h_ctl->err;
+    if (er & CLB_EF_TABLE_RANGE) return fail(CLB_ERR_RANGE, "%s: tabulated potential index out of range (fatal in the reference as well)", where);
+    if (er & CLB_EF_PARTNER_LOST) return fail(CLB_ERR_RANGE, "%s: a bonded partner is outside the ghost layer", where);
+    if (er & CLB_EF_DEGREE) return fail(CLB_ERR_RANGE, "%s: more than %d bonds on one particle", where, CLB_MAXDEG);
+    if (er & CLB_EF_TUPLE_OVERFLOW) return fail(CLB_ERR_RANGE, "%s: tuple list overflow", where);
+    return CLB_OK;
+}
+
+extern "C" int clb_compute_forces(clb_engine* e) {
+    if (!e) return CLB_ERR_ARG;
+    cudaSetDevice(e->device);
+    TRY(e->setup_sync());
+    if (!e->lists_valid) TRY(e->rebuild());
+    e->enqueue_forces();
+    TRY(e->read_ctl());
+    CK(cudaGetLastError());
+    e->forces_valid = true;
+    return e->check_device_errors("clb_compute_forces");
+}
+
+extern "C" int clb_energy(clb_engine* e, int inter, double* out) {
+    if (!e || !out || inter < 0 || inter >= (int)e->inters.size()) return e ? e->fail(CLB_ERR_ARG, "bad interaction handle") : CLB_ERR_ARG;
+    cudaSetDevice(e->device);
+    TRY(e->setup_sync());
+    if (!e->lists_valid) TRY(e->rebuild());
+    const HostInter& it = e->inters[inter];
+    if (it.bonded < 0) {
+        size_t smem = (size_t)e->tile_max * sizeof(int4) + 16;
+        int threads = e->pair_threads;
+        int gridsz = std::min(e->grid.nblocks, 4 * e->nsm);
+        gridsz = std::min(gridsz, 65536);
+        if (e->geo.cubic) k_pair_energy<true><<<gridsz, threads, smem, e->stream>>>(e->grid, e->geo, e->cell_start.p, e->pos.p, e->nl_entries.p, e->nl_count.p, e->nl_cap, e->d_pd.p, e->d_pe.p, e->nt_dev, e->d_tm.p, e->d_erows.p, inter, e->partial.p, e->partial_u64.p);
+        else k_pair_energy<false><<<gridsz, threads, smem, e->stream>>>(e->grid, e->geo, e->cell_start.p, e->pos.p, e->nl_entries.p, e->nl_count.p, e->nl_cap, e->d_pd.p, e->d_pe.p, e->nt_dev, e->d_tm.p, e->d_erows.p, inter, e->partial.p, e->partial_u64.p);
+        k_sum_partials<<<1, 256, 0, e->stream>>>(gridsz, e->partial.p, (double*)e->d_scalar);
+        k_sum_partials_u64<<<1, 256, 0, e->stream>>>(gridsz, e->partial_u64.p, (unsigned long long*)e->d_scalar + 1);
+        CK(cudaMemcpyAsync(e->h_scalar, e->d_scalar, 16, cudaMemcpyDeviceToHost, e->stream));
+        CK(cudaStreamSynchronize(e->stream));
+        *out = ((double*)e->h_scalar)[0];
+        e->last_interacting = ((unsigned long long*)e->h_scalar)[1] / 2;
+    } else {
+        int no = e->own1 - e->own0;
+        int nb = ceil_div(no, 256);
+        if (e->nterms == 0 || nb == 0) { *out = 0.0; return CLB_OK; }
+        CK(e->partial.ensure(nb));
+        k_bonded<true><<<nb, 256, 0, e->stream>>>(e->own0, e->own1, e->pos.p, e->geo, e->rt_off.p, e->rt_mem.p, e->rt_meta.p, e->d_bdesc.p, e->d_bpots.p, e->d_btm.p,
+                                                  (const double4*)e->d_bcf.p, (const double4*)e->d_bce.p, e->force.p, e->ncap, inter, e->partial.p, e->d_ctl);
+        k_sum_partials<<<1, 256, 0, e->stream>>>(nb, e->partial.p, (double*)e->d_scalar);
+        CK(cudaMemcpyAsync(e->h_scalar, e->d_scalar, 8, cudaMemcpyDeviceToHost, e->stream));
+        CK(cudaStreamSynchronize(e->stream));
+        *out = ((double*)e->h_scalar)[0];
+    }
+    CK(cudaGetLastError());
+    if (e->nranks > 1) TRY(e->comm_allreduce_sum(out, 1));
+    return CLB_OK;
+}
+
+extern "C" int clb_kinetics(clb_engine* e, double out[3]) {
+    if (!e || !out) return CLB_ERR_ARG;
+    cudaSetDevice(e->device);
+    int no = e->own1 - e->own0, nb = ceil_div(no, 256);
+    CK(e->partial.ensure(std::max(nb, 1)));
+    k_kinetic<<<nb, 256, 0, e->stream>>>(e->own0, e->own1, e->vel.p, e->partial.p);
+    k_sum_partials<<<1, 256, 0, e->stream>>>(nb, e->partial.p, (double*)e->d_scalar);
+    CK(cudaMemcpyAsync(e->h_scalar, e->d_scalar, 8, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    double ek = ((double*)e->h_scalar)[0];
+    if (e->nranks > 1) TRY(e->comm_allreduce_sum(&ek, 1));
+    out[0] = ek; out[1] = 2.0 * ek / (3.0 * e->n); out[2] = (double)e->n;
+    return CLB_OK;
+}
+extern "C" int clb_count_type(clb_engine* e, int type, int state, int64_t* out) {
+    if (!e || !out) return CLB_ERR_ARG;
+    cudaSetDevice(e->device);
+    CK(cudaMemsetAsync(e->d_scalar, 0, 8, e->stream));
+    int no = e->own1 - e->own0;
+    k_count_type<<<ceil_div(no, 256), 256, 0, e->stream>>>(e->own0, e->own1, e->pos.p, type, state, (unsigned long long*)e->d_scalar);
+    CK(cudaMemcpyAsync(e->h_scalar, e->d_scalar, 8, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    double c = (double)((unsigned long long*)e->h_scalar)[0];
+    if (e->nranks > 1) TRY(e->comm_allreduce_sum(&c, 1));
+    *out = (int64_t)c;
+    return CLB_OK;
+}
+
+// ------------------------------------------------------------------------------------------ integrator
+extern "C" int clb_set_dt(clb_engine* e, double dt) { if (!e || dt <= 0) return CLB_ERR_ARG; e->dt = dt; return CLB_OK; }
+extern "C" int clb_set_langevin(clb_engine* e, int enabled, double kT, double gamma, int ntypes, const int32_t* types) {
+    if (!e) return CLB_ERR_ARG;
+    e->lang_on = enabled; e->kT = kT; e->gamma = gamma;
+    if (ntypes <= 0) e->lang_mask = ~0ull;
+    else { e->lang_mask = 0; for (int i = 0; i < ntypes; ++i) if (types[i] >= 0 && types[i] < 64) e->lang_mask |= 1ull << types[i]; }
+    return CLB_OK;
+}
+extern "C" int64_t clb_step(const clb_engine* e) { return e ? e->step : 0; }
+
+ClbIntegParams clb_engine::integ_params(uint64_t key_step) const {
+    ClbIntegParams P;
+    P.dt = dt;
+    for (int d = 0; d < 3; ++d) { P.q[d] = geo.q[d]; P.invq[d] = 1.0 / geo.q[d]; }
+    P.langevin = lang_on; P.pref1 = -gamma; P.pref2 = lang_on ? sqrt(24.0 * kT * gamma / dt) : 0.0;
+    P.type_mask_lo = lang_mask; P.seed = seed; P.step = key_step; P.criterion = criterion; P.i0 = own0; P.i1 = own1;
+    return P;
+}
+void clb_engine::enqueue_integrate(int mode, uint64_t key_step) {
+    bucket_begin(CLB_B_INTEG);
+    ClbIntegParams P = integ_params(key_step);
+    int no = own1 - own0, nb = ceil_div(no, 256);
+    if (mode == (CLB_INT_SECOND | CLB_INT_FIRST)) k_integrate<CLB_INT_SECOND | CLB_INT_FIRST><<<nb, 256, 0, stream>>>(P, pos.p, vel.p, force.p, ncap, xref.p, slot.p, image.p, d_ctl);
+    else if (mode == CLB_INT_SECOND) k_integrate<CLB_INT_SECOND><<<nb, 256, 0, stream>>>(P, pos.p, vel.p, force.p, ncap, xref.p, slot.p, image.p, d_ctl);
+    else k_integrate<CLB_INT_FIRST><<<nb, 256, 0, stream>>>(P, pos.p, vel.p, force.p, ncap, xref.p, slot.p, image.p, d_ctl);
+    ++launches;
+    bucket_end(CLB_B_INTEG);
+}
+
+// integrator.run(n) -- SURVEY 3.2.  Steps are enqueued in chunks without host synchronisation; the
+// skin/2 test runs on the device and stalls the rest of the chunk when a rebuild is due.
+extern "C" int clb_run(clb_engine* e, int64_t nsteps) {
+    if (!e || nsteps < 0) return CLB_ERR_ARG;
+    cudaSetDevice(e->device);
+    TRY(e->setup_sync());
+    if (e->pending_rebuild) { e->lists_valid = false; e->pending_rebuild = false; }
+    if (!e->lists_valid) TRY(e->rebuild());
+    cudaEventRecord(e->ev_a[CLB_B_TOTAL], e->stream);
+    // run entry: recalc forces (+ thermostat heat-up), SURVEY 3.2
+    e->enqueue_forces();
+    if (e->nranks > 1) {}
+    if (e->lang_on) {
+        ClbIntegParams P = e->integ_params((uint64_t)e->step);
+        int no = e->own1 - e->own0;
+        k_thermalize<<<ceil_div(no, 256), 256, 0, e->stream>>>(P, sqrt(3.0), CLB_STREAM_HEATUP, e->pos.p, e->vel.p, e->slot.p, e->force.p, e->ncap);
+        ++e->launches;
+    }
+    const double half_skin = 0.5 * e->skin;
+    int64_t i = 0;
+    bool pend = false;
+    const bool react = e->react_on && !e->reactions.empty();
+    auto boundary_after = [&](int64_t s) { return react && ((e->step + s + 1) % e->react_interval) == 0; };
+    while (i < nsteps) {
+        int chunk = e->chunk_user > 0 ? e->chunk_user : std::max(1, std::min(64, e->last_interval > 0 ? e->last_interval : 4));
+        int64_t j = std::min<int64_t>(nsteps, i + chunk);
+        for (int64_t s = i; s < j; ++s) {
+            if (pend && e->fuse) e->enqueue_integrate(CLB_INT_SECOND | CLB_INT_FIRST, (uint64_t)(e->step + s - 1));
+            else {
+                if (pend) e->enqueue_integrate(CLB_INT_SECOND, (uint64_t)(e->step + s - 1));
+                e->enqueue_integrate(CLB_INT_FIRST, 0);
+            }
+            k_check_resort<<<1, 1, 0, e->stream>>>(e->d_ctl, e->criterion, half_skin, (int)(s - i));
+            ++e->launches;
+            if (e->nranks > 1) TRY(e->comm_halo_positions());
+            e->enqueue_forces();
+            pend = true;
+            if (boundary_after(s)) { j = s + 1; break; }
+        }
+        TRY(e->read_ctl());
+        int64_t done;
+        if (e->h_ctl->stall) {
+            int64_t s = i + e->h_ctl->stall_step;
+            e->last_interval = (int)std::max<int64_t>(1, (e->step + s) - e->last_rebuild_step);
+            e->last_rebuild_step = e->step + s;
+            TRY(e->setup_sync());
+            TRY(e->rebuild());
+            e->pending_rebuild = false;
+            e->enqueue_forces();
+            done = s;
+        } else done = j - 1;
+        if (e->h_ctl->err & ~CLB_EF_LIST_OVERFLOW) { TRY(e->check_device_errors("clb_run")); }
+        pend = true;
+        if (boundary_after(done)) {
+            e->enqueue_integrate(CLB_INT_SECOND, (uint64_t)(e->step + done));
+            pend = false;
+            int64_t keep = e->step;
+            e->step = keep + done + 1;
+            int64_t nev = 0;
+            int rr = e->react_pass(&nev);
+            e->step = keep;
+            if (rr != CLB_OK) return rr;
+        }
+        i = done + 1;
+    }
+    if (pend) e->enqueue_integrate(CLB_INT_SECOND, (uint64_t)(e->step + nsteps - 1));
+    e->step += nsteps;
+    cudaEventRecord(e->ev_b[CLB_B_TOTAL], e->stream);
+    TRY(e->read_ctl());
+    CK(cudaGetLastError());
+    e->collect_timers();
+    e->nsteps_total += nsteps;
+    e->forces_valid = true; // force array holds the thermostatted force of the last step
+    return e->check_device_errors("clb_run");
+}
+
+// ------------------------------------------------------------------------------------------ parity / timers
+extern "C" int clb_get_pairs(clb_engine* e, int64_t cap, int64_t* pairs, int64_t* n_out) {
+    if (!e) return CLB_ERR_ARG;
+    cudaSetDevice(e->device);
+    TRY(e->setup_sync());
+    if (!e->lists_valid) TRY(e->rebuild());
+    size_t outcap = (size_t)e->nl_total / 2 + 1024;
+    DevBuf<int2> out;
+    CK(out.ensure(outcap));
+    CK(cudaMemsetAsync(&e->d_ctl->npairs_out, 0, 8, e->stream));
+    size_t smem = (size_t)e->tile_max * sizeof(int) + 16;
+    k_decode_pairs<<<std::min(e->grid.nblocks, 4 * e->nsm), e->pair_threads, smem, e->stream>>>(e->grid, e->cell_start.p, e->slot.p, e->nl_entries.p, e->nl_count.p, e->nl_cap, out.p, outcap, e->d_ctl);
+    TRY(e->read_ctl());
+    CK(cudaGetLastError());
+    size_t m = (size_t)e->h_ctl->npairs_out;
+    if (m > outcap) { out.release(); return e->fail(CLB_ERR_STATE, "pair list asymmetric: %zu decoded pairs for %llu entries", m, e->nl_total); }
+    std::vector<int2> h(m);
+    if (m) CK(cudaMemcpy(h.data(), out.p, m * sizeof(int2), cudaMemcpyDeviceToHost));
+    out.release();
+    std::sort(h.begin(), h.end(), [](const int2& a, const int2& b) { return a.x != b.x ? a.x < b.x : a.y < b.y; });
+    if (n_out) *n_out = (int64_t)m;
+    for (size_t k = 0; k < m && (int64_t)k < cap; ++k) { pairs[2 * k] = e->ids[h[k].x]; pairs[2 * k + 1] = e->ids[h[k].y]; }
+    return CLB_OK;
+}
+
+void clb_engine::bucket_begin(int b) { if (timers_on) { if (!bucket_open[b]) { cudaEventRecord(ev_a[b], stream); bucket_open[b] = 1; } } }
+void clb_engine::bucket_end(int b) {
+    if (timers_on && bucket_open[b]) {
+        cudaEventRecord(ev_b[b], stream); cudaEventSynchronize(ev_b[b]);
+        float ms = 0; cudaEventElapsedTime(&ms, ev_a[b], ev_b[b]); bucket_s[b] += ms * 1e-3; bucket_open[b] = 0;
+    }
+}
+cudaEvent_t clb_engine::next_pair_event() {
+    if (pair_events.size() <= pair_event_used) { cudaEvent_t ev; cudaEventCreate(&ev); pair_events.push_back(ev); }
+    return pair_events[pair_event_used++];
+}
+void clb_engine::collect_timers() {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, ev_a[CLB_B_TOTAL], ev_b[CLB_B_TOTAL]) == cudaSuccess) bucket_s[CLB_B_TOTAL] += ms * 1e-3;
+    for (size_t k = 0; k + 1 < pair_event_used; k += 2) {
+        float t = 0;
+        if (cudaEventElapsedTime(&t, pair_events[k], pair_events[k + 1]) == cudaSuccess) { pair_ms += t; ++pair_launches; }
+    }
+    pair_event_used = 0;
+}
+extern "C" int clb_timers(clb_engine* e, double out[8], int64_t counters[8]) {
+    if (!e) return CLB_ERR_ARG;
+    if (out) for (int k = 0; k < 8; ++k) out[k] = e->bucket_s[k];
+    if (counters) {
+        counters[0] = e->nsteps_total; counters[1] = e->nrebuild; counters[2] = e->launches; counters[3] = (int64_t)e->nl_total;
+        counters[4] = e->nreact_pass; counters[5] = e->nreact_events; counters[6] = e->nstored - (e->own1 - e->own0); counters[7] = (int64_t)e->last_interacting;
+    }
+    return CLB_OK;
+}
+extern "C" int clb_reset_timers(clb_engine* e) {
+    if (!e) return CLB_ERR_ARG;
+    for (int k = 0; k < 8; ++k) e->bucket_s[k] = 0;
+    e->nsteps_total = 0; e->nrebuild = 0; e->launches = 0; e->nreact_pass = 0; e->nreact_events = 0; e->pair_ms = 0; e->pair_launches = 0;
+    return CLB_OK;
+}
+extern "C" int clb_device_ptr(clb_engine* e, int which, void** ptr, int64_t* n_out) {
+    if (!e || !ptr) return CLB_ERR_ARG;
+    switch (which) {
+        case 0: *ptr = e->pos.p; break;
+        case 1: *ptr = e->vel.p; break;
+        case 2: *ptr = e->force.p; break;
+        default: return e->fail(CLB_ERR_ARG, "unknown buffer");
+    }
+    if (n_out) *n_out = which == 2 ? e->ncap : e->nstored;
+    return CLB_OK;
+}
+extern "C" int clb_stream(clb_engine* e, void** s) { if (!e || !s) return CLB_ERR_ARG; *s = (void*)e->stream; return CLB_OK; }
+
+void clb_engine::free_all() {
+    for (auto& l : lists) l.d.release();
+    for (auto ev : pair_events) cudaEventDestroy(ev);
+    for (int i = 0; i < CLB_NBUCKET; ++i) { cudaEventDestroy(ev_a[i]); cudaEventDestroy(ev_b[i]); }
+    if (d_ctl) cudaFree(d_ctl);
+    if (h_ctl) cudaFreeHost(h_ctl);
+    if (d_scalar) cudaFree(d_scalar);
+    if (h_scalar) cudaFreeHost(h_scalar);
+    comm_destroy();
+    if (stream) cudaStreamDestroy(stream);
+}
+
+#include "engine_react.inl"
+#include "engine_comm.inl"

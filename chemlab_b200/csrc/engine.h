@@ -1,0 +1,193 @@
+// engine.h -- host-side state of one engine (one GPU, one stream).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/chemlab_b200.h"
+#include "clb_common.cuh"
+#include "clb_kernels.cuh"
+
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    // grow-only; contents are NOT preserved
+    cudaError_t ensure(size_t need) {
+        if (need <= n && p) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; n = 0;
+        size_t cap = need ? need : 1;
+        cudaError_t e = cudaMalloc((void**)&p, cap * sizeof(T));
+        if (e == cudaSuccess) n = cap;
+        return e;
+    }
+    // grow and keep the first `keep` elements
+    cudaError_t ensure_keep(size_t need, size_t keep, cudaStream_t st) {
+        if (need <= n && p) return cudaSuccess;
+        T* q = nullptr;
+        size_t cap = need + need / 2 + 16;
+        cudaError_t e = cudaMalloc((void**)&q, cap * sizeof(T));
+        if (e != cudaSuccess) return e;
+        if (p && keep) { e = cudaMemcpyAsync(q, p, keep * sizeof(T), cudaMemcpyDeviceToDevice, st); if (e != cudaSuccess) return e; }
+        e = cudaStreamSynchronize(st);
+        if (p) cudaFree(p);
+        p = q; n = cap;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+};
+
+struct HostTable { int n, interp; double x0, dx; std::vector<double> e, f; };
+struct HostPairPot {
+    int kind = 0, inter = -1, tab1 = -1, tab2 = -1, conv_type = -1;
+    double rc = 0, eps = 0, sig = 0, shift = 0, mix = 1.0, conv_total = 1.0;
+};
+struct HostInter { int kind; int bonded; };
+struct HostList { int arity = 2; long long n = 0; DevBuf<int> d; int bonded = -1; int tm_observed = 0; int excl_observed = 0; };
+struct HostBonded { int list, typed, inter; std::vector<ClbBPot> pots; };
+struct HostChange { int reaction, side, nb_level, old_type, new_type, state_mode, state_value; double new_mass, new_q; };
+struct HostTmReg { int list; int t[4]; };
+
+enum { CLB_B_PAIR = 0, CLB_B_BONDED, CLB_B_NEIGH, CLB_B_INTEG, CLB_B_COMM, CLB_B_REACT, CLB_B_OTHER, CLB_B_TOTAL, CLB_NBUCKET };
+
+struct clb_engine {
+    std::string err;
+    int fail(int code, const char* fmt, ...);
+
+    int device = 0, nsm = 148, smem_optin = 48 * 1024;
+    cudaStream_t stream = nullptr;
+    double box[3], rc, skin, dt = 0.001;
+    uint64_t seed = 0;
+    ClbGrid grid;
+    ClbGeom geo;
+    int criterion = 1, fuse = 1, chunk_user = 0, timers_on = 0, tabs_smem_user = 1;
+
+    // particles
+    int n = 0, nstored = 0, ncap = 0, own0 = 0, own1 = 0, ntypes = 1;
+    std::vector<int64_t> ids;                 // slot -> caller id (ascending)
+    std::unordered_map<int64_t, int> id2slot;
+    int slot_of(int64_t id) const;
+    DevBuf<int4> pos, pos2, xref;
+    DevBuf<float4> vel, vel2;
+    DevBuf<int> slot, slot2, id2idx, image, resid, mol;
+    DevBuf<double> force, charge;
+    DevBuf<int> key, key2, val, val2, cell_start;
+    DevBuf<unsigned char> cubtmp, cubtmp2;
+    DevBuf<double> partial;
+    DevBuf<unsigned long long> partial_u64;
+    ClbCtl *d_ctl = nullptr, *h_ctl = nullptr;
+    void *d_scalar = nullptr, *h_scalar = nullptr;
+
+    // neighbour lists
+    DevBuf<unsigned short> nl_entries;
+    DevBuf<int> nl_count;
+    int nl_cap = 0, nl_cap_user = 0, nl_cap_user_seen = 0, nl_max = 0, tile_max = 0, home_max = 0;
+    unsigned long long nl_total = 0, last_interacting = 0;
+    int pair_grid = 0, pair_threads = 128, pair_smem = 0, tabs_smem = 1;
+    bool lists_valid = false, forces_valid = false;
+
+    // exclusions
+    DevBuf<int2> excl_pairs;
+    long long nexcl = 0;
+    DevBuf<int> excl_off, excl_ids, ekey, ekey2, eval;
+    bool excl_dirty = true;
+
+    // potentials
+    std::vector<HostTable> tables;
+    std::vector<HostInter> inters;
+    HostPairPot pp[CLB_MAX_TYPES][CLB_MAX_TYPES];
+    bool pots_dirty = true, has_mixed = false;
+    int nt_dev = 1, ntabs_dev = 0, nrows_dev = 0;
+    DevBuf<ClbPairDesc> d_pd;
+    DevBuf<ClbPairDescE> d_pe;
+    DevBuf<ClbTabMeta> d_tm;
+    DevBuf<double2> d_frows, d_erows;
+
+    // tuple lists and bonded interactions
+    std::vector<HostList> lists;
+    std::vector<HostBonded> bondeds;
+    DevBuf<ClbBondedDesc> d_bdesc;
+    DevBuf<ClbBPot> d_bpots;
+    DevBuf<ClbBTabMeta> d_btm;
+    DevBuf<double> d_bcf, d_bce;
+    DevBuf<const int*> d_list_ptrs;
+    bool terms_dirty = true, lists_ptr_dirty = true, rt_valid = false;
+    long long nterms = 0;
+    DevBuf<int> term_off, term_meta, term_tuple, tkey, tkey2;
+    DevBuf<unsigned long long> tval, tval2;
+    DevBuf<int> rt_off, rt_cnt, rt_meta;
+    DevBuf<int4> rt_mem;
+
+    // integrator
+    int64_t step = 0;
+    int lang_on = 0;
+    double kT = 1.0, gamma = 1.0;
+    unsigned long long lang_mask = ~0ull;
+    int last_interval = 0;
+    int64_t last_rebuild_step = 0;
+
+    // reactions / topology
+    int react_on = 0, react_interval = 1, react_nearest = 1, react_max_per_interval = 0;
+    std::vector<clb_reaction_spec> reactions;
+    std::vector<HostChange> changes;
+    std::vector<HostTmReg> tmregs;
+    bool react_dirty = true, topo_dirty = true, topo_initialized = false;
+    std::vector<int64_t> react_counters;
+    struct ReactDev;
+    ReactDev* rd = nullptr;
+
+    // timers / counters
+    cudaEvent_t ev_a[CLB_NBUCKET], ev_b[CLB_NBUCKET];
+    int bucket_open[CLB_NBUCKET] = {0};
+    double bucket_s[CLB_NBUCKET] = {0};
+    int64_t nsteps_total = 0, nrebuild = 0, launches = 0, nreact_pass = 0, nreact_events = 0, pair_launches_total = 0;
+    int pair_event_timing = 0;
+    std::vector<cudaEvent_t> pair_events;
+    size_t pair_event_used = 0;
+    double pair_ms = 0;
+    int64_t pair_launches = 0;
+    void bucket_begin(int b);
+    void bucket_end(int b);
+    cudaEvent_t next_pair_event();
+    void collect_timers();
+
+    // multi-GPU
+    int rank = 0, nranks = 1;
+    struct CommDev;
+    CommDev* cd = nullptr;
+    int comm_migrate_and_ghosts();
+    int comm_after_sort();
+    int comm_halo_positions();
+    int comm_allreduce_sum(double* v, int n);
+    int comm_gather_candidates(long long* nc);
+    void comm_destroy();
+
+    // methods
+    void set_block_cells(int bx);
+    int alloc_particles(int n);
+    int download_state(std::vector<int4>& hp, std::vector<float4>& hv, std::vector<int>& hidx);
+    int build_excl_csr();
+    int upload_potentials();
+    int list_reserve(int li, long long need);
+    int build_term_csr();
+    int upload_list_ptrs();
+    int resolve_terms();
+    int read_ctl();
+    int setup_sync();
+    int rebuild();
+    void enqueue_forces();
+    void enqueue_integrate(int mode, uint64_t key_step);
+    ClbIntegParams integ_params(uint64_t key_step) const;
+    int check_device_errors(const char* where);
+    int build_topology();
+    int upload_reactions();
+    int upload_list_descs();
+    bool pending_rebuild = false;
+    int react_pass(int64_t* events_out);
+    int update_mixing();
+    void free_all();
+};

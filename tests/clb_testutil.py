@@ -58,3 +58,85 @@ def rel_force_err(f, fref):
     nr = np.linalg.norm(fref, axis=1)
     rms = np.sqrt((nr ** 2).mean())
     return float((d / np.maximum(nr, rms)).max())
+
+
+class Pair:
+    """The same system set up on the CUDA engine (through the C-ABI) and on the fp64 oracle.
+
+    Positions are pushed to the engine first and read back (the engine stores them on its 2^32
+    lattice); the oracle is fed exactly those values, so both sides see identical inputs."""
+
+    def __init__(self, pos, box, type, mass=None, vel=None, state=None, resid=None, rc=2.5, skin=0.3, seed=11, ids=None):
+        from chemlab_b200 import Engine
+        from oracle import pyoracle
+        n = len(pos)
+        self.n = n
+        self.ids = np.arange(n, dtype=np.int64) if ids is None else np.asarray(ids, np.int64)
+        mass = np.ones(n) if mass is None else np.asarray(mass, float)
+        state = np.zeros(n, np.int32) if state is None else np.asarray(state, np.int32)
+        resid = np.arange(n, dtype=np.int32) if resid is None else np.asarray(resid, np.int32)
+        # oracle index k <-> k-th smallest id: feed both sides in ascending-id order
+        order = np.argsort(self.ids, kind="stable")
+        self.ids = self.ids[order]
+        pos = np.asarray(pos, float)[order]; type = np.asarray(type, np.int32)[order]; mass = mass[order]
+        state = state[order]; resid = resid[order]
+        vel = None if vel is None else np.asarray(vel, float)[order]
+        self.e = Engine(box, rc, skin, seed=seed)
+        self.e.set_particles(self.ids, type, pos, mass, vel=vel, state=state, res_id=resid)
+        st = self.e.get_particles(fields=("pos", "vel", "mass", "image"))
+        self.o = pyoracle.Oracle(n, box, rc, skin, seed=seed)
+        # unfolded position = folded + image * L so that the oracle reproduces the same image counters
+        self.o.set_particles(st["pos"] + st["image"] * np.asarray(box), st["vel"], st["mass"], None, type, state, resid)
+        self.tabs = []
+
+    # every call below is mirrored on both sides
+    def add_table(self, x, e, f, interp=1):
+        a = self.e.add_table(x, e, f, interp); b = self.o.add_table(x, e, f, interp)
+        assert a == b
+        return a
+
+    def nb_tab(self, pairs, tab, rc):
+        a = self.e.add_nonbonded("Tabulated"); b = self.o.add_nonbonded(1)
+        assert a == b
+        for t1, t2 in pairs:
+            self.e.nb_set_tabulated(a, t1, t2, tab, rc); self.o.nb_set_tab(b, t1, t2, tab, rc)
+        return a
+
+    def nb_lj(self, pairs, eps, sig, rc):
+        a = self.e.add_nonbonded("LennardJones"); b = self.o.add_nonbonded(2)
+        assert a == b
+        for t1, t2 in pairs:
+            self.e.nb_set_lj(a, t1, t2, eps, sig, rc, 1); self.o.nb_set_lj(b, t1, t2, eps, sig, rc, 1)
+        return a
+
+    def exclusions(self, ex):
+        self.e.set_exclusions(ex); self.o.set_exclusions(ex)
+
+    def add_list(self, arity, ids):
+        a = self.e.add_list(arity); b = self.o.add_list(arity)
+        assert a == b
+        if len(ids):
+            self.e.list_add(a, ids); self.o.list_add(b, ids)
+        return a
+
+    def add_bonded(self, lst, typed=0):
+        a = self.e.add_bonded(lst, typed); b = self.o.add_bonded(lst, typed)
+        assert a == b
+        return a
+
+    def bonded_pot(self, inter, types, kind, params=(), table=-1):
+        from chemlab_b200.engine import POT
+        self.e.bonded_set_potential(inter, types, kind, params, table)
+        self.o.bonded_set_potential(inter, types, POT[kind], params, table)
+
+    def both(self, name, *a, **k):
+        ra = getattr(self.e, name)(*a, **k)
+        rb = getattr(self.o, name)(*a, **k)
+        return ra, rb
+
+    def close(self):
+        self.e.close()
+
+
+def type_pairs(nt):
+    return [(a, b) for a in range(nt) for b in range(a, nt)]
