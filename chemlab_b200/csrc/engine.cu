@@ -89,6 +89,8 @@ extern "C" int clb_create(clb_engine** out, int device, const double box[3], dou
     cudaMalloc(&e->d_scalar, 64);
     cudaMallocHost(&e->h_scalar, 64);
     // opt-in shared memory for the tile kernels
+    // static shared memory of the tile kernels (offset tables, reaction specs, reduction scratch) stays below 8 KB
+    e->smem_optin -= 8192;
     int mx = e->smem_optin;
     cudaFuncSetAttribute(k_build_lists<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
     cudaFuncSetAttribute(k_build_lists<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);

@@ -979,29 +979,45 @@ void orc_react(orc_sim *s) {
         for (int o = 0; o < s->nobs_excl; ++o) if (s->obs_excl[o] == r->list) excl_push(s, c->a, c->b);
     }
     /* 7. neighbour property changes: particles exactly nb_level bonds from the reactant (BFS on the
-     * updated graph), PostProcessChangeNeighboursProperty (reaction_post_process.py:76-115) */
-    for (int64_t e = 0; e < nev; ++e) {
-        orc_cand *c = &s->cands[ev[e]];
-        for (int side = 1; side <= 2; ++side) {
-            int root = side == 1 ? c->a : c->b;
-            int maxlev = 0;
-            for (int q = 0; q < s->nchg; ++q) if (s->chg[q].reaction == c->r && (s->chg[q].side & side) && s->chg[q].nb_level > maxlev) maxlev = s->chg[q].nb_level;
-            if (!maxlev) continue;
-            int front[256], nf = 1, seen[1024], ns = 1; front[0] = root; seen[0] = root;
-            for (int lev = 1; lev <= maxlev; ++lev) {
-                int nxt[256], nn = 0;
-                for (int a = 0; a < nf; ++a) for (int k = 0; k < s->deg[front[a]]; ++k) {
-                    int y = s->adj[front[a] * ORC_MAXDEG + k], dup = 0;
-                    for (int z = 0; z < ns; ++z) if (seen[z] == y) { dup = 1; break; }
-                    if (!dup && nn < 256 && ns < 1024) { nxt[nn++] = y; seen[ns++] = y; }
+     * updated graph), PostProcessChangeNeighboursProperty (reaction_post_process.py:76-115).
+     * Deterministic, order-independent formulation (the engine runs the events in parallel): every
+     * reached particle whose type -- as it stands after step 6 -- equals a rule's old type files the
+     * claim (event, side, level, rule) with the FIRST matching rule; the smallest claim per particle
+     * is applied. */
+    {
+        uint64_t *claim = malloc(8 * (size_t)s->n);
+        int *touched = malloc(4 * (size_t)s->n); int nt = 0;
+        for (int i = 0; i < s->n; ++i) claim[i] = ~0ull;
+        for (int64_t e = 0; e < nev; ++e) {
+            orc_cand *c = &s->cands[ev[e]];
+            for (int side = 1; side <= 2; ++side) {
+                int root = side == 1 ? c->a : c->b;
+                int maxlev = 0;
+                for (int q = 0; q < s->nchg; ++q) if (s->chg[q].reaction == c->r && (s->chg[q].side & side) && s->chg[q].nb_level > maxlev) maxlev = s->chg[q].nb_level;
+                if (!maxlev) continue;
+                int front[64], nf = 1, seen[192], ns = 1; front[0] = root; seen[0] = root;
+                for (int lev = 1; lev <= maxlev; ++lev) {
+                    int nxt[64], nn = 0;
+                    for (int a = 0; a < nf; ++a) for (int k = 0; k < s->deg[front[a]]; ++k) {
+                        int y = s->adj[front[a] * ORC_MAXDEG + k], dup = 0;
+                        for (int z = 0; z < ns; ++z) if (seen[z] == y) { dup = 1; break; }
+                        if (!dup && nn < 64 && ns < 192) { nxt[nn++] = y; seen[ns++] = y; }
+                    }
+                    for (int a = 0; a < nn; ++a) for (int q = 0; q < s->nchg; ++q) {
+                        orc_change *g = &s->chg[q];
+                        if (g->reaction == c->r && (g->side & side) && g->nb_level == lev && g->old_type == s->type[nxt[a]]) {
+                            uint64_t key = ((uint64_t)e << 24) | ((uint64_t)(side - 1) << 20) | ((uint64_t)lev << 12) | (uint64_t)q;
+                            if (claim[nxt[a]] == ~0ull) touched[nt++] = nxt[a];
+                            if (key < claim[nxt[a]]) claim[nxt[a]] = key;
+                            break;
+                        }
+                    }
+                    memcpy(front, nxt, 4 * nn); nf = nn;
                 }
-                for (int a = 0; a < nn; ++a) for (int q = 0; q < s->nchg; ++q) {
-                    orc_change *g = &s->chg[q];
-                    if (g->reaction == c->r && (g->side & side) && g->nb_level == lev) apply_props(s, g, nxt[a]);
-                }
-                memcpy(front, nxt, 4 * nn); nf = nn;
             }
         }
+        for (int t = 0; t < nt; ++t) apply_props(s, &s->chg[claim[touched[t]] & 0xfff], touched[t]);
+        free(claim); free(touched);
     }
     /* 8. TopologyManager: new angles / dihedrals through the new bond, final types */
     for (int64_t e = 0; e < nev; ++e) {
