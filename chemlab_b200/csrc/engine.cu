@@ -82,12 +82,17 @@ extern "C" int clb_create(clb_engine** out, int device, const double box[3], dou
     e->geo.cubic = (box[0] == box[1] && box[1] == box[2]);
     e->geo.q2 = e->geo.q[0] * e->geo.q[0];
     e->set_block_cells(8);
-    cudaMalloc(&e->d_ctl, sizeof(ClbCtl));
-    cudaMemset(e->d_ctl, 0, sizeof(ClbCtl));
-    cudaMallocHost(&e->h_ctl, sizeof(ClbCtl));
+    (void)cudaGetLastError();   // clear a non-sticky error left by an earlier call in this process
+    ce = cudaMalloc(&e->d_ctl, sizeof(ClbCtl));
+    if (ce == cudaSuccess) ce = cudaMemset(e->d_ctl, 0, sizeof(ClbCtl));
+    if (ce == cudaSuccess) ce = cudaMallocHost(&e->h_ctl, sizeof(ClbCtl));
+    if (ce == cudaSuccess) ce = cudaMalloc(&e->d_scalar, 64);
+    if (ce == cudaSuccess) ce = cudaMallocHost(&e->h_scalar, 64);
+    if (ce != cudaSuccess) {
+        g_create_error = std::string("clb_create: ") + cudaGetErrorString(ce);
+        delete e; return CLB_ERR_CUDA;
+    }
     memset(e->h_ctl, 0, sizeof(ClbCtl));
-    cudaMalloc(&e->d_scalar, 64);
-    cudaMallocHost(&e->h_scalar, 64);
     // opt-in shared memory for the tile kernels
     // static shared memory of the tile kernels (offset tables, reaction specs, reduction scratch) stays below 8 KB
     e->smem_optin -= 8192;
@@ -134,7 +139,8 @@ extern "C" int clb_set_option(clb_engine* e, const char* name, double v) {
     else if (s == "fuse_integrator") e->fuse = (int)v;
     else if (s == "sync_chunk") e->chunk_user = (int)v;
     else if (s == "timers") e->timers_on = (int)v;
-    else if (s == "tables_in_smem") e->tabs_smem_user = (int)v;
+    else if (s == "tables_in_smem") { e->tabs_smem_user = (int)v; if (e->lists_valid) return e->configure_pair_launch(); }
+    else if (s == "pair_event_timing") e->pair_event_timing = (int)v;
     else return e->fail(CLB_ERR_ARG, "unknown option %s", name);
     return CLB_OK;
 }
@@ -605,7 +611,7 @@ int clb_engine::upload_potentials() {
         bd[l] = d;
     }
     CK(d_bdesc.ensure(bd.size())); CK(d_bpots.ensure(std::max<size_t>(bp.size(), 1))); CK(d_btm.ensure(std::max<size_t>(btm.size(), 1)));
-    CK(d_bcf.ensure(std::max<size_t>(cf.size() / 4, 1))); CK(d_bce.ensure(std::max<size_t>(cec.size() / 4, 1)));
+    CK(d_bcf.ensure(std::max<size_t>(cf.size(), 4))); CK(d_bce.ensure(std::max<size_t>(cec.size(), 4)));
     CK(cudaMemcpyAsync(d_bdesc.p, bd.data(), bd.size() * sizeof(ClbBondedDesc), cudaMemcpyHostToDevice, stream));
     if (!bp.empty()) CK(cudaMemcpyAsync(d_bpots.p, bp.data(), bp.size() * sizeof(ClbBPot), cudaMemcpyHostToDevice, stream));
     if (!btm.empty()) {
@@ -616,6 +622,7 @@ int clb_engine::upload_potentials() {
     CK(cudaStreamSynchronize(stream));
     pots_dirty = false;
     forces_valid = false;
+    if (lists_valid) TRY(configure_pair_launch());
     return CLB_OK;
 }
 
@@ -791,6 +798,27 @@ int clb_engine::setup_sync() {
     return CLB_OK;
 }
 
+
+// launch geometry and shared-memory carve-up of the pair-force kernel; depends on the tile size of the
+// last rebuild AND on the potentials, so it is refreshed after either changes
+int clb_engine::configure_pair_launch() {
+    int threads = std::min(512, std::max(64, ((home_max + 31) / 32) * 32));
+        size_t fixed = (size_t)nt_dev * nt_dev * sizeof(ClbPairDesc) + (size_t)ntabs_dev * sizeof(ClbTabMeta);
+        size_t rows = (size_t)nrows_dev * sizeof(double2);
+        size_t tile = (size_t)tile_max * sizeof(int4) + 16;
+        bool in_smem = tabs_smem_user != 0 && fixed + rows + tile <= (size_t)std::min(smem_optin, 110 * 1024);
+        if (tabs_smem_user == 2 && fixed + rows + tile <= (size_t)smem_optin) in_smem = true;
+        tabs_smem = in_smem ? 1 : 0;
+        pair_smem = (int)(fixed + (in_smem ? rows : 0) + tile);
+        if (pair_smem > smem_optin) return fail(CLB_ERR_UNSUPPORTED, "pair kernel needs %d B of shared memory: lower block_cells", pair_smem);
+        pair_threads = threads;
+        int nb = 0;
+        if (geo.cubic) { if (in_smem) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_pair_forces<true, true>, threads, pair_smem); else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_pair_forces<true, false>, threads, pair_smem); }
+        else { if (in_smem) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_pair_forces<false, true>, threads, pair_smem); else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_pair_forces<false, false>, threads, pair_smem); }
+        pair_grid = std::min(grid.nblocks, std::max(1, nb) * nsm);
+        return CLB_OK;
+}
+
 int clb_engine::rebuild() {
     clb_engine* e = this;
     bucket_begin(CLB_B_NEIGH);
@@ -839,21 +867,7 @@ int clb_engine::rebuild() {
     }
     nl_max = h_ctl->nl_max; nl_total = h_ctl->nl_total;
     // 4. pair-force launch configuration
-    {
-        size_t fixed = (size_t)nt_dev * nt_dev * sizeof(ClbPairDesc) + (size_t)ntabs_dev * sizeof(ClbTabMeta);
-        size_t rows = (size_t)nrows_dev * sizeof(double2);
-        size_t tile = (size_t)tile_max * sizeof(int4) + 16;
-        bool in_smem = tabs_smem_user != 0 && fixed + rows + tile <= (size_t)std::min(smem_optin, 110 * 1024);
-        if (tabs_smem_user == 2 && fixed + rows + tile <= (size_t)smem_optin) in_smem = true;
-        tabs_smem = in_smem ? 1 : 0;
-        pair_smem = (int)(fixed + (in_smem ? rows : 0) + tile);
-        if (pair_smem > smem_optin) return fail(CLB_ERR_UNSUPPORTED, "pair kernel needs %d B of shared memory: lower block_cells", pair_smem);
-        pair_threads = threads;
-        int nb = 0;
-        if (geo.cubic) { if (in_smem) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_pair_forces<true, true>, threads, pair_smem); else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_pair_forces<true, false>, threads, pair_smem); }
-        else { if (in_smem) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_pair_forces<false, true>, threads, pair_smem); else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_pair_forces<false, false>, threads, pair_smem); }
-        pair_grid = std::min(grid.nblocks, std::max(1, nb) * nsm);
-    }
+    TRY(configure_pair_launch());
     // 5. bonded memberships -> sorted indices
     TRY(resolve_terms());
     k_ctl_after_rebuild<<<1, 1, 0, stream>>>(d_ctl);
@@ -877,7 +891,7 @@ extern "C" int clb_decompose(clb_engine* e) {
 // ------------------------------------------------------------------------------------------ forces
 void clb_engine::enqueue_forces() {
     bucket_begin(CLB_B_PAIR);
-    if (pair_event_timing) cudaEventRecord(next_pair_event(), stream);
+    if (pair_event_timing) { pair_event_valid.resize(pair_event_used / 2 + 1, 1); pair_event_valid[pair_event_used / 2] = 1; cudaEventRecord(next_pair_event(), stream); }
     if (geo.cubic) {
         if (tabs_smem) k_pair_forces<true, true><<<pair_grid, pair_threads, pair_smem, stream>>>(grid, geo, cell_start.p, pos.p, nl_entries.p, nl_count.p, nl_cap, d_pd.p, nt_dev, d_tm.p, ntabs_dev, d_frows.p, nrows_dev, force.p, ncap, d_ctl);
         else k_pair_forces<true, false><<<pair_grid, pair_threads, pair_smem, stream>>>(grid, geo, cell_start.p, pos.p, nl_entries.p, nl_count.p, nl_cap, d_pd.p, nt_dev, d_tm.p, ntabs_dev, d_frows.p, nrows_dev, force.p, ncap, d_ctl);
@@ -1039,6 +1053,7 @@ extern "C" int clb_run(clb_engine* e, int64_t nsteps) {
     while (i < nsteps) {
         int chunk = e->chunk_user > 0 ? e->chunk_user : std::max(1, std::min(64, e->last_interval > 0 ? e->last_interval : 4));
         int64_t j = std::min<int64_t>(nsteps, i + chunk);
+        const size_t chunk_first_pair = e->pair_event_used / 2;
         for (int64_t s = i; s < j; ++s) {
             if (pend && e->fuse) e->enqueue_integrate(CLB_INT_SECOND | CLB_INT_FIRST, (uint64_t)(e->step + s - 1));
             else {
@@ -1056,6 +1071,8 @@ extern "C" int clb_run(clb_engine* e, int64_t nsteps) {
         int64_t done;
         if (e->h_ctl->stall) {
             int64_t s = i + e->h_ctl->stall_step;
+            // force launches of the stalled step and of every later step of this chunk were no-ops
+            if (e->pair_event_timing) for (int64_t q = s; q < j; ++q) { size_t pi = chunk_first_pair + (size_t)(q - i); if (pi < e->pair_event_valid.size()) e->pair_event_valid[pi] = 0; }
             e->last_interval = (int)std::max<int64_t>(1, (e->step + s) - e->last_rebuild_step);
             e->last_rebuild_step = e->step + s;
             TRY(e->setup_sync());
@@ -1130,9 +1147,11 @@ void clb_engine::collect_timers() {
     if (cudaEventElapsedTime(&ms, ev_a[CLB_B_TOTAL], ev_b[CLB_B_TOTAL]) == cudaSuccess) bucket_s[CLB_B_TOTAL] += ms * 1e-3;
     for (size_t k = 0; k + 1 < pair_event_used; k += 2) {
         float t = 0;
+        if (k / 2 < pair_event_valid.size() && !pair_event_valid[k / 2]) continue;
         if (cudaEventElapsedTime(&t, pair_events[k], pair_events[k + 1]) == cudaSuccess) { pair_ms += t; ++pair_launches; }
     }
     pair_event_used = 0;
+    pair_event_valid.clear();
 }
 extern "C" int clb_timers(clb_engine* e, double out[8], int64_t counters[8]) {
     if (!e) return CLB_ERR_ARG;

@@ -147,6 +147,7 @@ struct clb_engine {
     int64_t nsteps_total = 0, nrebuild = 0, launches = 0, nreact_pass = 0, nreact_events = 0, pair_launches_total = 0;
     int pair_event_timing = 0;
     std::vector<cudaEvent_t> pair_events;
+    std::vector<char> pair_event_valid;
     size_t pair_event_used = 0;
     double pair_ms = 0;
     int64_t pair_launches = 0;
@@ -179,6 +180,7 @@ struct clb_engine {
     int read_ctl();
     int setup_sync();
     int rebuild();
+    int configure_pair_launch();
     void enqueue_forces();
     void enqueue_integrate(int mode, uint64_t key_step);
     ClbIntegParams integ_params(uint64_t key_step) const;

@@ -278,6 +278,15 @@ class Oracle:
         return int(self.L.orc_count_type(self.h, int(t), int(state)))
 
 
+# Engine-compatible method names, so that one set-up routine can drive either side
+Oracle.nb_set_tabulated = Oracle.nb_set_tab
+Oracle.exclusions_observe = Oracle.excl_observe
+Oracle.topology_observe = Oracle.tm_observe
+Oracle.topology_register = Oracle.tm_register
+Oracle.topology_initialize = Oracle.tm_initialize
+Oracle.react_now = Oracle.react
+
+
 def philox(ctr, key):
     c = (C.c_uint32 * 4)(*ctr); k = (C.c_uint32 * 2)(*key); o = (C.c_uint32 * 4)()
     lib().orc_philox(c, k, o)
