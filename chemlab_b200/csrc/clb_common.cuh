@@ -64,12 +64,11 @@ struct ClbGeom {
     double q2;       // q[0]^2 when cubic
 };
 
-struct ClbPairDesc {   // per type pair, 32 bytes
-    double rc2;        // cutoff^2 (real units)
-    double c12, c6;    // LJ: 48 eps sigma^12, 24 eps sigma^6
+struct ClbPairDesc {   // per type pair, 16 bytes: one LDS.128 per listed pair
+    double rc2;        // cutoff^2 (real units); negative when the pair has no potential
     int kind;          // 0 none, 1 table, 2 LJ
-    int tab;           // table slot
-};
+    int tab;           // table slot (general) or first row of the table (uniform-grid fast path)
+};                     // LJ coefficients {48 eps sigma^12, 24 eps sigma^6} live in a parallel double2 array
 struct ClbPairDescE {  // energy-side extras
     double e12, e6, shift; // LJ: 4 eps sigma^12, 4 eps sigma^6, shift
     int inter;             // owning interaction handle

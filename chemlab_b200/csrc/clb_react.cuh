@@ -56,9 +56,9 @@ __global__ void __launch_bounds__(512) k_react_scan(ClbGrid g, ClbGeom geo, cons
             const int4 pi = __ldg(pos + gi);
             const int si = __ldg(slot + gi);
             const int cnt = __ldg(nl_count + gi);
-            const unsigned short* ent = entries + (size_t)t.hs * cap + p;
+            const unsigned short* ent = entries + (size_t)gi * cap;
             for (int k = 0; k < cnt; ++k) {
-                const unsigned e = ent[(size_t)k * t.nh];
+                const unsigned e = ent[k];
                 const int sj = s_slot[e];
                 if (si >= sj) continue;           // every unordered pair once, lower slot first
                 const int4 pj = s_pos[e];

@@ -100,13 +100,16 @@ __device__ __forceinline__ int home_column(const TileCtx& t, const int* s_off, i
 }
 
 // ------------------------------------------------------------------------------------------
-// Neighbour-list build.  One thread per home particle; candidates are the 27 cells around the
-// particle's own cell, read from the shared tile (all lanes of a cell read the same candidate:
-// broadcast).  Inclusion test (U1): r^2 <= (rc+skin)^2 in fp64 on exact lattice differences,
-// after an integer box prefilter.  Exclusions: per-particle sorted partner-slot rows.
-// Entry layout: entries[hs*cap + k*nh + p] (coalesced over p).
+// Neighbour-list build.  One WARP per home particle, lanes = candidates: the 27 cells around the
+// particle's cell are 9 contiguous tile ranges, read 32 at a time (conflict-free LDS.128), tested
+// exactly, compacted with a ballot and appended to the particle's row -> coalesced stores and no
+// divergence.  Inclusion test (U1): r^2 <= (rc+skin)^2.  Cubic boxes: exact unsigned 64-bit integer
+// arithmetic on lattice differences (3 IMAD.WIDE + one compare); otherwise fp64 per-dimension scaling.
+// Exclusions: the particle's partner-slot row is held across the lanes and matched by shuffles.
+// Entry layout: entries[gi*cap + k] (cap % 8 == 0 so the force kernel reads 8 entries per LDG.128).
 template <bool CUBIC>
-__global__ void __launch_bounds__(512) k_build_lists(ClbGrid g, ClbGeom geo, const int* __restrict__ cell_start,
+__global__ void __launch_bounds__(512) k_build_lists(ClbGrid g, ClbGeom geo, unsigned long long rl2_lat,
+                                                     const int* __restrict__ cell_start,
                                                      const int4* __restrict__ pos, const int* __restrict__ slot,
                                                      const int* __restrict__ excl_off, const int* __restrict__ excl_ids,
                                                      unsigned short* __restrict__ entries, int* __restrict__ nl_count,
@@ -114,7 +117,10 @@ __global__ void __launch_bounds__(512) k_build_lists(ClbGrid g, ClbGeom geo, con
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ int s_off[CLB_TILE_CELLS + 1];
     __shared__ int s_src[CLB_TILE_CELLS];
-    __shared__ int s_stat[2];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    int lmax = 0;
+    unsigned long long ltot = 0;
     for (int b = blockIdx.x; b < g.nblocks; b += gridDim.x) {
         TileCtx t;
         tile_geometry(g, b, t);
@@ -123,63 +129,81 @@ __global__ void __launch_bounds__(512) k_build_lists(ClbGrid g, ClbGeom geo, con
         int4* s_pos = reinterpret_cast<int4*>(smem);
         int* s_slot = reinterpret_cast<int*>(s_pos + t.T);
         tile_stage(t, s_off, s_src, pos, s_pos, slot, s_slot, nullptr);
-        if (threadIdx.x == 0) { s_stat[0] = 0; s_stat[1] = 0; }
         __syncthreads();
-        int lmax = 0, ltot = 0;
-        for (int p = threadIdx.x; p < t.nh; p += blockDim.x) {
+        const int mh0 = t.whole ? t.cx0 : 1;
+        const int tbase = s_off[4 * t.W + mh0];
+        for (int p = warp; p < t.nh; p += nw) {
             const int gi = t.hs + p;
+            const int ti = tbase + p;
             const int mh = home_column(t, s_off, p);
-            const int ti = s_off[4 * t.W + (t.whole ? t.cx0 : 1)] + p;   // home cells are consecutive tile cells
             const int4 pi = s_pos[ti];
             const int myslot = s_slot[ti];
-            const int e0 = __ldg(excl_off + myslot), e1 = __ldg(excl_off + myslot + 1);
+            const int e0 = __ldg(excl_off + myslot), nex = __ldg(excl_off + myslot + 1) - e0;
+            int exv = (lane < nex) ? __ldg(excl_ids + e0 + lane) : -1;
+            unsigned short* row = entries + (size_t)gi * cap;
             int cnt = 0;
-            unsigned short* out = entries + (size_t)t.hs * cap + p;
             for (int k = 0; k < CLB_TILE_ROWS; ++k) {
-#pragma unroll
-                for (int dm = -1; dm <= 1; ++dm) {
-                    int m = t.whole ? wrapi(mh + dm, g.ncx) : mh + dm;
-                    int tc = k * t.W + m;
-                    int lo = s_off[tc], hi = s_off[tc + 1];
-                    for (int j = lo; j < hi; ++j) {
-                        int4 pj = s_pos[j];
-                        int dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
-                        if (abs(dx) > geo.cut[0] || abs(dy) > geo.cut[1] || abs(dz) > geo.cut[2]) continue;
-                        double fx = lat2d(dx), fy = lat2d(dy), fz = lat2d(dz), r2;
-                        if (CUBIC) r2 = (fx * fx + fy * fy + fz * fz) * geo.q2;
-                        else { fx *= geo.q[0]; fy *= geo.q[1]; fz *= geo.q[2]; r2 = fx * fx + fy * fy + fz * fz; }
-                        if (r2 > geo.rl2 || j == ti) continue;
-                        int sj = s_slot[j];
-                        bool ex = false;
-                        for (int e = e0; e < e1; ++e) ex |= (__ldg(excl_ids + e) == sj);
-                        if (ex) continue;
-                        if (cnt < cap) out[(size_t)cnt * t.nh] = (unsigned short)j;
-                        ++cnt;
+                // contiguous candidate range(s) of tile row k
+                int nseg = 1, lo[3], hi[3];
+                if (!t.whole) { lo[0] = s_off[k * t.W + mh - 1]; hi[0] = s_off[k * t.W + mh + 2]; }
+                else {
+                    nseg = 3;
+                    for (int dm = -1; dm <= 1; ++dm) { int m = wrapi(mh + dm, g.ncx); lo[dm + 1] = s_off[k * t.W + m]; hi[dm + 1] = s_off[k * t.W + m + 1]; }
+                }
+                for (int sg = 0; sg < nseg; ++sg) {
+                    for (int j0 = lo[sg]; j0 < hi[sg]; j0 += 32) {
+                        const int j = j0 + lane;
+                        bool pass = j < hi[sg];
+                        int sj = -2;
+                        if (pass) {
+                            const int4 pj = s_pos[j];
+                            const int dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
+                            if (CUBIC) {
+                                unsigned long long r2 = (unsigned long long)((long long)dx * dx) + (unsigned long long)((long long)dy * dy) +
+                                                        (unsigned long long)((long long)dz * dz);
+                                pass = r2 <= rl2_lat;
+                            } else {
+                                double fx = lat2d(dx) * geo.q[0], fy = lat2d(dy) * geo.q[1], fz = lat2d(dz) * geo.q[2];
+                                pass = (fx * fx + fy * fy + fz * fz) <= geo.rl2;
+                            }
+                            pass = pass && (j != ti);
+                            if (pass && nex > 0) sj = s_slot[j];
+                        }
+                        if (nex > 0) {
+                            for (int e = 0; e < min(nex, 32); ++e) { int x = __shfl_sync(0xffffffffu, exv, e); if (x == sj) pass = false; }
+                            for (int eb = 32; eb < nex; eb += 32) {   // rows longer than a warp (rare)
+                                int xv = (eb + lane < nex) ? __ldg(excl_ids + e0 + eb + lane) : -1;
+                                for (int e = 0; e < min(nex - eb, 32); ++e) { int x = __shfl_sync(0xffffffffu, xv, e); if (x == sj) pass = false; }
+                            }
+                        }
+                        const unsigned bal = __ballot_sync(0xffffffffu, pass);
+                        if (pass) { int o = cnt + __popc(bal & lt_mask); if (o < cap) row[o] = (unsigned short)j; }
+                        cnt += __popc(bal);
                     }
                 }
             }
-            nl_count[gi] = min(cnt, cap);
-            if (cnt > cap) atomicOr(&ctl->err, CLB_EF_LIST_OVERFLOW);
-            lmax = max(lmax, cnt);
-            ltot += min(cnt, cap);
+            if (lane == 0) {
+                nl_count[gi] = min(cnt, cap);
+                if (cnt > cap) atomicOr(&ctl->err, CLB_EF_LIST_OVERFLOW);
+                lmax = max(lmax, cnt); ltot += (unsigned long long)min(cnt, cap);
+            }
         }
-        // statistics (block reduce through shared atomics: order-independent integers)
-        atomicMax(&s_stat[0], lmax);
-        atomicAdd(&s_stat[1], ltot);
-        __syncthreads();
-        if (threadIdx.x == 0) { atomicMax(&ctl->nl_max, s_stat[0]); atomicAdd(&ctl->nl_total, (unsigned long long)s_stat[1]); }
     }
+    if (lane == 0 && ltot) { atomicMax(&ctl->nl_max, lmax); atomicAdd(&ctl->nl_total, ltot); }
 }
 
 // ------------------------------------------------------------------------------------------
-// Pair forces.  One thread per home particle, full (two-sided) list: no scatter, no atomics,
-// deterministic.  Everything after the integer subtraction is fp64 (B200 has a full-rate fp64
-// pipe that issues beside the fp32/int pipes); no float<->double conversion instructions:
+// Pair forces.  Full (two-sided) list: no scatter, no atomics, deterministic.  Everything after the
+// integer subtraction is fp64 (B200 has a full-rate fp64 pipe that issues beside the fp32/int pipes);
+// no float<->double conversion instructions:
 //   d       exact lattice difference -> double by the 2^52 trick (lat2d)
 //   1/r     MUFU.RSQ seed on the truncated high word + one fp64 Newton step
-//   index   t = (r-x0)/dx ; floor and fraction by the 2^52 rounding trick
-//   F(r)    f[i] + b*(f[i+1]-f[i])  (reference: linear interpolation itype=1)
-// Table rows {f_i + df_i/2, df_i = f_{i+1}-f_i} as double2 live in shared memory (persistent CTAs load them once).
+//   index   u = (r-x0)/dx - 1/2 ; idx = round(u) and fraction b' = u - idx by the 1.5*2^52 trick
+//   F(r)    (f[i] + df[i]/2) + b'*df[i]  (reference: linear interpolation itype=1)
+// Table rows {f_i + df_i/2, df_i} as double2 live in shared memory (persistent CTAs load them once).
+// SPLIT warps share one particle: warp group s takes the 8-entry batches b with b % SPLIT == s, partial
+// sums are combined through shared memory in fixed order (bit-reproducible) -> more resident working
+// warps per SM for the same shared-memory footprint.
 __device__ __forceinline__ double rsqrt_seed(double x) {
     // float with the same value as x truncated to 24 bits, via integer ops only
     int hi = __double2hiint(x), lo = __double2loint(x);
@@ -189,95 +213,118 @@ __device__ __forceinline__ double rsqrt_seed(double x) {
     return __hiloint2double((int)((yb >> 3) + 0x38000000u), (int)(yb << 29));
 }
 
-template <bool CUBIC, bool TABS_SMEM>
-__global__ void __launch_bounds__(512) k_pair_forces(ClbGrid g, ClbGeom geo, const int* __restrict__ cell_start,
-                                                     const int4* __restrict__ pos,
-                                                     const unsigned short* __restrict__ entries,
-                                                     const int* __restrict__ nl_count, int cap,
-                                                     const ClbPairDesc* __restrict__ pdesc, int ntypes,
-                                                     const ClbTabMeta* __restrict__ tmeta, int ntabs,
-                                                     const double2* __restrict__ trows, int nrows_total,
-                                                     double* __restrict__ force, int fstride, ClbCtl* ctl) {
-    if (*(volatile int*)&ctl->stall) return;
+struct ClbPairArgs {
+    const int* cell_start; const int4* pos; const unsigned short* entries; const int* nl_count;
+    const ClbPairDesc* pdesc; const double2* plj; const ClbTabMeta* tmeta; const double2* trows;
+    double* force; ClbCtl* ctl;
+    int cap, ntypes, ntabs, nrows_total, fstride, npw;   // npw = warps per split group
+    ClbTabMeta ugrid;                                      // common grid when UGRID
+};
+
+template <bool CUBIC, bool TABS_SMEM, bool UGRID, int SPLIT>
+__global__ void __launch_bounds__(512) k_pair_forces(ClbGrid g, ClbGeom geo, ClbPairArgs A) {
+    if (*(volatile int*)&A.ctl->stall) return;
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ int s_off[CLB_TILE_CELLS + 1];
     __shared__ int s_src[CLB_TILE_CELLS];
-    // static part of dynamic smem: pair descriptors, table meta, (tables), then the tile
+    const int ntp = A.ntypes * A.ntypes;
     ClbPairDesc* s_pd = reinterpret_cast<ClbPairDesc*>(smem);
-    ClbTabMeta* s_tm = reinterpret_cast<ClbTabMeta*>(s_pd + ntypes * ntypes);
-    double2* s_rows = reinterpret_cast<double2*>(s_tm + ntabs);
-    int4* s_pos = reinterpret_cast<int4*>(s_rows + (TABS_SMEM ? nrows_total : 0));
-    for (int i = threadIdx.x; i < ntypes * ntypes; i += blockDim.x) s_pd[i] = pdesc[i];
-    for (int i = threadIdx.x; i < ntabs; i += blockDim.x) s_tm[i] = tmeta[i];
-    if (TABS_SMEM) for (int i = threadIdx.x; i < nrows_total; i += blockDim.x) s_rows[i] = __ldg(trows + i);
-    const double2* rows = TABS_SMEM ? s_rows : trows;
+    double2* s_lj = reinterpret_cast<double2*>(s_pd + ntp);
+    ClbTabMeta* s_tm = reinterpret_cast<ClbTabMeta*>(s_lj + ntp);
+    double2* s_rows = reinterpret_cast<double2*>(s_tm + A.ntabs);
+    double* s_red = reinterpret_cast<double*>(s_rows + (TABS_SMEM ? A.nrows_total : 0));
+    int4* s_pos = reinterpret_cast<int4*>(s_red + (SPLIT - 1) * 3 * A.npw * 32);
+    for (int i = threadIdx.x; i < ntp; i += blockDim.x) { s_pd[i] = A.pdesc[i]; s_lj[i] = A.plj[i]; }
+    for (int i = threadIdx.x; i < A.ntabs; i += blockDim.x) s_tm[i] = A.tmeta[i];
+    if (TABS_SMEM) for (int i = threadIdx.x; i < A.nrows_total; i += blockDim.x) s_rows[i] = __ldg(A.trows + i);
+    const double2* rows = TABS_SMEM ? s_rows : A.trows;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int sg = SPLIT > 1 ? warp / A.npw : 0;          // split group of this warp
+    const int wp = SPLIT > 1 ? warp - sg * A.npw : warp;  // particle warp inside the group
+    const int nhpass = A.npw * 32;
     unsigned err = 0;
     for (int b = blockIdx.x; b < g.nblocks; b += gridDim.x) {
         TileCtx t;
         tile_geometry(g, b, t);
         __syncthreads();
-        tile_offsets(g, t, cell_start, s_off, s_src);
-        tile_stage(t, s_off, s_src, pos, s_pos, nullptr, nullptr, nullptr);
+        tile_offsets(g, t, A.cell_start, s_off, s_src);
+        tile_stage(t, s_off, s_src, A.pos, s_pos, nullptr, nullptr, nullptr);
         __syncthreads();
-        for (int p0 = 0; p0 < t.nh; p0 += blockDim.x) {
-            const int p = p0 + threadIdx.x;
+        for (int p0 = 0; p0 < t.nh; p0 += nhpass) {
+            const int pl = wp * 32 + lane;                  // particle index inside this pass
+            const int p = p0 + pl;
             const bool act = p < t.nh;
             const int gi = t.hs + (act ? p : 0);
-            const int4 pi = __ldg(pos + gi);
-            const int cnt = act ? __ldg(nl_count + gi) : 0;
-            const ClbPairDesc* pdrow = s_pd + pw_type(pi.w) * ntypes;
-            const unsigned short* ent = entries + (size_t)t.hs * cap + p;
+            const int4 pi = __ldg(A.pos + gi);
+            const int cnt = act ? __ldg(A.nl_count + gi) : 0;
+            const ClbPairDesc* pdrow = s_pd + pw_type(pi.w) * A.ntypes;
+            const uint4* row = reinterpret_cast<const uint4*>(A.entries + (size_t)gi * A.cap);
+            const int nb = (cnt + 7) >> 3;                   // 8-entry batches of this particle
             double ax = 0.0, ay = 0.0, az = 0.0;
-            int kmax = cnt;
-#pragma unroll
-            for (int d = 16; d > 0; d >>= 1) kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, d));
-            unsigned e_next = (0 < cnt) ? ent[0] : 0;
-            for (int k = 0; k < kmax; ++k) {
-                unsigned e = e_next;
-                if (k + 1 < cnt) e_next = ent[(size_t)(k + 1) * t.nh];
-                if (k < cnt) {
+            uint4 ev = make_uint4(0, 0, 0, 0);
+            if (sg < nb) ev = __ldg(row + sg);
+            for (int bi = sg; bi < nb; bi += SPLIT) {
+                uint4 cur = ev;
+                if (bi + SPLIT < nb) ev = __ldg(row + bi + SPLIT);     // prefetch the next batch
+                const int ne = min(8, cnt - bi * 8);
+                for (int u = 0; u < ne; ++u) {
+                    const unsigned e = cur.x & 0xffffu;
+                    cur.x = __funnelshift_r(cur.x, cur.y, 16); cur.y = __funnelshift_r(cur.y, cur.z, 16);
+                    cur.z = __funnelshift_r(cur.z, cur.w, 16); cur.w >>= 16;
                     const int4 pj = s_pos[e];
                     double dx = lat2d(pi.x - pj.x), dy = lat2d(pi.y - pj.y), dz = lat2d(pi.z - pj.z), r2;
                     if (CUBIC) r2 = (dx * dx + dy * dy + dz * dz) * geo.q2;
                     else { dx *= geo.q[0]; dy *= geo.q[1]; dz *= geo.q[2]; r2 = dx * dx + dy * dy + dz * dz; }
-                    const ClbPairDesc pd = pdrow[pw_type(pj.w)];
-                    if (pd.kind != 0 && r2 <= pd.rc2) {
+                    const int tp = pw_type(pj.w);
+                    const ClbPairDesc pd = pdrow[tp];
+                    if (r2 <= pd.rc2) {                         // rc2 < 0 for pairs without a potential (U2)
                         double y = rsqrt_seed(r2);
                         double h = r2 * y;
                         double ee = fma(-h, y, 1.0);
                         y = fma(0.5 * y, ee, y);              // 1/r to ~1e-14
                         double fr;
                         if (pd.kind == 1) {
-                            const ClbTabMeta tm = s_tm[pd.tab];
                             double r = r2 * y;
-                            // u = (r-x0)/dx - 1/2 ; idx = round(u) = floor((r-x0)/dx) ; b' = u - idx in [-1/2,1/2]
-                            double u = fma(r, tm.invdx, tm.c_t);
-                            double ti = u + 6755399441055744.0;            // 1.5 * 2^52: integer in the low word
+                            double invdx, c_t, x0, dxx; int n, off;
+                            if (UGRID) { invdx = A.ugrid.invdx; c_t = A.ugrid.c_t; x0 = A.ugrid.x0; dxx = A.ugrid.dx; n = A.ugrid.n; off = pd.tab; }
+                            else { const ClbTabMeta tm = s_tm[pd.tab]; invdx = tm.invdx; c_t = tm.c_t; x0 = tm.x0; dxx = tm.dx; n = tm.n; off = tm.off; }
+                            double uu = fma(r, invdx, c_t);
+                            double ti = uu + 6755399441055744.0;            // 1.5 * 2^52: integer in the low word
                             int idx = __double2loint(ti);
-                            double bfrac = u - (ti - 6755399441055744.0);
-                            if (idx < 0 || idx > tm.n - 2) {
-                                if (idx < 0 || r > tm.x0 + tm.dx * (tm.n - 1) * (1.0 + 1e-12)) err |= CLB_EF_TABLE_RANGE;
-                                int ic = idx < 0 ? 0 : tm.n - 2;
+                            double bfrac = uu - (ti - 6755399441055744.0);
+                            if ((unsigned)idx > (unsigned)(n - 2)) {
+                                if (idx < 0 || r > x0 + dxx * (n - 1) * (1.0 + 1e-12)) err |= CLB_EF_TABLE_RANGE;
+                                int ic = idx < 0 ? 0 : n - 2;
                                 bfrac += (double)(idx - ic); idx = ic;
                             }
-                            double2 row = rows[tm.off + idx];                // {f_i + df_i/2, df_i}
-                            fr = fma(bfrac, row.y, row.x) * y;
+                            const double2 rw = rows[off + idx];                // {f_i + df_i/2, df_i}
+                            fr = fma(bfrac, rw.y, rw.x) * y;
                         } else {
+                            const double2 lj = s_lj[pw_type(pi.w) * A.ntypes + tp];
                             double y2 = y * y;
                             double y6 = y2 * y2 * y2;
-                            fr = y6 * fma(pd.c12, y6, -pd.c6) * y2;
+                            fr = y6 * fma(lj.x, y6, -lj.y) * y2;
                         }
                         ax = fma(fr, dx, ax); ay = fma(fr, dy, ay); az = fma(fr, dz, az);
                     }
                 }
             }
-            if (act) {
-                if (CUBIC) { ax *= geo.q[0]; ay *= geo.q[0]; az *= geo.q[0]; }
-                force[gi] = ax; force[gi + fstride] = ay; force[gi + 2 * fstride] = az;
+            if (SPLIT > 1) {
+                if (sg > 0) { double* r = s_red + ((sg - 1) * nhpass + pl) * 3; r[0] = ax; r[1] = ay; r[2] = az; }
+                __syncthreads();
+                if (sg == 0) {
+#pragma unroll
+                    for (int s2 = 1; s2 < SPLIT; ++s2) { const double* r = s_red + ((s2 - 1) * nhpass + pl) * 3; ax += r[0]; ay += r[1]; az += r[2]; }
+                }
             }
+            if (act && sg == 0) {
+                if (CUBIC) { ax *= geo.q[0]; ay *= geo.q[0]; az *= geo.q[0]; }
+                A.force[gi] = ax; A.force[gi + A.fstride] = ay; A.force[gi + 2 * A.fstride] = az;
+            }
+            if (SPLIT > 1) __syncthreads();
         }
     }
-    if (err) atomicOr(&ctl->err, err);
+    if (err) atomicOr(&A.ctl->err, err);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -313,15 +360,15 @@ __global__ void __launch_bounds__(512) k_pair_energy(ClbGrid g, ClbGeom geo, con
             const int gi = t.hs + p;
             const int4 pi = __ldg(pos + gi);
             const int cnt = __ldg(nl_count + gi);
-            const unsigned short* ent = entries + (size_t)t.hs * cap + p;
+            const unsigned short* ent = entries + (size_t)gi * cap;
             for (int k = 0; k < cnt; ++k) {
-                const int4 pj = s_pos[ent[(size_t)k * t.nh]];
+                const int4 pj = s_pos[ent[k]];
                 double dx = lat2d(pi.x - pj.x) * geo.q[0], dy = lat2d(pi.y - pj.y) * geo.q[1], dz = lat2d(pi.z - pj.z) * geo.q[2];
                 double r2 = dx * dx + dy * dy + dz * dz;
                 int tp = pw_type(pi.w) * ntypes + pw_type(pj.w);
                 const ClbPairDesc pd = pdesc[tp];
                 const ClbPairDescE pe = pdesce[tp];
-                if (pd.kind == 0 || r2 > pd.rc2) continue;
+                if (pd.kind == 0 || r2 > pd.rc2) continue;   // kind 0 <=> rc2 < 0
                 ++ninter;
                 if (pe.inter != inter) continue;
                 if (pd.kind == 1) {
@@ -378,9 +425,9 @@ __global__ void __launch_bounds__(512) k_decode_pairs(ClbGrid g, const int* __re
             const int gi = t.hs + p;
             const int si = __ldg(slot + gi);
             const int cnt = __ldg(nl_count + gi);
-            const unsigned short* ent = entries + (size_t)t.hs * cap + p;
+            const unsigned short* ent = entries + (size_t)gi * cap;
             for (int k = 0; k < cnt; ++k) {
-                int sj = s_slot[ent[(size_t)k * t.nh]];
+                int sj = s_slot[ent[k]];
                 if (si < sj) {
                     unsigned long long o = atomicAdd(&ctl->npairs_out, 1ull);
                     if (o < outcap) out[o] = make_int2(si, sj);

@@ -1,6 +1,7 @@
 // engine.cu -- host side of the B200 engine: C-ABI (include/chemlab_b200.h), device state,
 // rebuild pipeline, stall-flag step loop.  One engine = one GPU = one stream.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -39,6 +40,18 @@ int clb_engine::fail(int code, const char* fmt, ...) {
 }
 
 static inline int ceil_div(long long a, int b) { return (int)((a + b - 1) / b); }
+
+typedef void (*PairKernel)(ClbGrid, ClbGeom, ClbPairArgs);
+template <bool C, bool S, bool U>
+static PairKernel pair_kernel_split(int split) {
+    switch (split) { case 1: return k_pair_forces<C, S, U, 1>; case 2: return k_pair_forces<C, S, U, 2>; default: return k_pair_forces<C, S, U, 4>; }
+}
+static PairKernel pair_kernel(int cubic, int smem, int ugrid, int split) {
+    if (cubic) { if (smem) return ugrid ? pair_kernel_split<true, true, true>(split) : pair_kernel_split<true, true, false>(split);
+                 return ugrid ? pair_kernel_split<true, false, true>(split) : pair_kernel_split<true, false, false>(split); }
+    if (smem) return ugrid ? pair_kernel_split<false, true, true>(split) : pair_kernel_split<false, true, false>(split);
+    return ugrid ? pair_kernel_split<false, false, true>(split) : pair_kernel_split<false, false, false>(split);
+}
 
 // ------------------------------------------------------------------------------------------
 extern "C" int clb_abi_version(void) { return CLB_ABI_VERSION; }
@@ -99,10 +112,8 @@ extern "C" int clb_create(clb_engine** out, int device, const double box[3], dou
     int mx = e->smem_optin;
     cudaFuncSetAttribute(k_build_lists<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
     cudaFuncSetAttribute(k_build_lists<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
-    cudaFuncSetAttribute(k_pair_forces<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
-    cudaFuncSetAttribute(k_pair_forces<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
-    cudaFuncSetAttribute(k_pair_forces<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
-    cudaFuncSetAttribute(k_pair_forces<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+    for (int c = 0; c < 2; ++c) for (int sm = 0; sm < 2; ++sm) for (int ug = 0; ug < 2; ++ug) for (int sp = 0; sp < 3; ++sp)
+        cudaFuncSetAttribute(pair_kernel(c, sm, ug, 1 << sp), cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
     cudaFuncSetAttribute(k_pair_energy<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
     cudaFuncSetAttribute(k_pair_energy<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
     cudaFuncSetAttribute(k_decode_pairs, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
@@ -141,6 +152,8 @@ extern "C" int clb_set_option(clb_engine* e, const char* name, double v) {
     else if (s == "timers") e->timers_on = (int)v;
     else if (s == "tables_in_smem") { e->tabs_smem_user = (int)v; if (e->lists_valid) return e->configure_pair_launch(); }
     else if (s == "pair_event_timing") e->pair_event_timing = (int)v;
+    else if (s == "pair_split") { e->pair_split_user = (int)v; if (e->lists_valid) return e->configure_pair_launch(); }
+    else if (s == "build_threads") e->build_threads = (int)v;
     else return e->fail(CLB_ERR_ARG, "unknown option %s", name);
     return CLB_OK;
 }
@@ -160,6 +173,8 @@ extern "C" int clb_get_option(clb_engine* e, const char* name, double* v) {
     else if (s == "ncx") *v = e->grid.ncx;
     else if (s == "pair_grid") *v = e->pair_grid;
     else if (s == "pair_threads") *v = e->pair_threads;
+    else if (s == "pair_split") *v = e->pair_split;
+    else if (s == "uniform_grid") *v = e->ugrid_on;
     else if (s == "pair_smem") *v = e->pair_smem;
     else if (s == "tables_in_smem") *v = e->tabs_smem;
     else if (s == "pair_kernel_ms") *v = e->pair_ms;
@@ -530,18 +545,20 @@ extern "C" int clb_nb_set_mixed(clb_engine* e, int inter, int t1, int t2, int ta
 int clb_engine::upload_potentials() {
     clb_engine* e = this;
     int nt = std::max(ntypes, 1);
-    std::vector<ClbPairDesc> pd((size_t)nt * nt); std::vector<ClbPairDescE> pe((size_t)nt * nt);
+    std::vector<ClbPairDesc> pd((size_t)nt * nt); std::vector<ClbPairDescE> pe((size_t)nt * nt); std::vector<double2> plj((size_t)nt * nt);
     std::vector<ClbTabMeta> tm; std::vector<double2> frows, erows;
     struct Key { int a, b; double mix; };
     std::vector<Key> keys;
     for (int a = 0; a < nt; ++a) for (int b = 0; b < nt; ++b) {
         const HostPairPot& p = pp[a][b];
         ClbPairDesc d; memset(&d, 0, sizeof(d)); ClbPairDescE de; memset(&de, 0, sizeof(de));
+        d.rc2 = -1.0;
         de.inter = p.inter;
+        plj[(size_t)a * nt + b] = make_double2(0.0, 0.0);
         if (p.kind == 2) {
             d.kind = 2; d.rc2 = p.rc * p.rc;
             double s6 = pow(p.sig, 6), s12 = s6 * s6;
-            d.c12 = 48 * p.eps * s12; d.c6 = 24 * p.eps * s6;
+            plj[(size_t)a * nt + b] = make_double2(48 * p.eps * s12, 24 * p.eps * s6);
             de.e12 = 4 * p.eps * s12; de.e6 = 4 * p.eps * s6; de.shift = p.shift;
         } else if (p.kind == 1 || p.kind == 3) {
             d.kind = 1; d.rc2 = p.rc * p.rc;
@@ -569,6 +586,16 @@ int clb_engine::upload_potentials() {
         }
         pd[(size_t)a * nt + b] = d; pe[(size_t)a * nt + b] = de;
     }
+    // uniform-grid fast path: every table on the same (x0, dx, n) -> grid constants travel as kernel
+    // arguments and the descriptor carries the first row directly
+    ugrid_on = !tm.empty();
+    for (size_t k = 1; k < tm.size(); ++k) if (tm[k].n != tm[0].n || tm[k].x0 != tm[0].x0 || tm[k].dx != tm[0].dx) ugrid_on = 0;
+    if (!tm.empty()) ugrid_meta = tm[0];
+    CK(d_pd_e.ensure(pd.size()));
+    CK(cudaMemcpyAsync(d_pd_e.p, pd.data(), pd.size() * sizeof(ClbPairDesc), cudaMemcpyHostToDevice, stream));   // energy kernel: slot ids
+    if (ugrid_on) for (auto& d : pd) if (d.kind == 1) d.tab = tm[d.tab].off;
+    CK(d_plj.ensure(plj.size()));
+    CK(cudaMemcpyAsync(d_plj.p, plj.data(), plj.size() * sizeof(double2), cudaMemcpyHostToDevice, stream));
     nt_dev = nt; ntabs_dev = (int)tm.size(); nrows_dev = (int)frows.size();
     CK(d_pd.ensure(pd.size())); CK(d_pe.ensure(pe.size()));
     CK(d_tm.ensure(std::max<size_t>(tm.size(), 1))); CK(d_frows.ensure(std::max<size_t>(frows.size(), 1))); CK(d_erows.ensure(std::max<size_t>(erows.size(), 1)));
@@ -790,6 +817,9 @@ __global__ void k_ctl_after_rebuild(ClbCtl* c) { c->stall = 0; c->accum_maxdist 
 
 int clb_engine::setup_sync() {
     if (n <= 0) return fail(CLB_ERR_STATE, "no particles");
+    const bool trace = getenv("CLB_TRACE") != nullptr && (pots_dirty || excl_dirty || terms_dirty || topo_dirty || react_dirty);
+    auto tr0 = std::chrono::steady_clock::now();
+    struct Fin { bool on; cudaStream_t st; std::chrono::steady_clock::time_point t0; ~Fin() { if (on) { cudaStreamSynchronize(st); fprintf(stderr, "[clb setup_sync] %.3f ms\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count()); } } } fin{trace, stream, tr0};
     if (pots_dirty) TRY(upload_potentials());
     if (excl_dirty) { TRY(build_excl_csr()); lists_valid = false; }
     if (terms_dirty) TRY(build_term_csr());
@@ -802,25 +832,42 @@ int clb_engine::setup_sync() {
 // launch geometry and shared-memory carve-up of the pair-force kernel; depends on the tile size of the
 // last rebuild AND on the potentials, so it is refreshed after either changes
 int clb_engine::configure_pair_launch() {
-    int threads = std::min(512, std::max(64, ((home_max + 31) / 32) * 32));
-        size_t fixed = (size_t)nt_dev * nt_dev * sizeof(ClbPairDesc) + (size_t)ntabs_dev * sizeof(ClbTabMeta);
-        size_t rows = (size_t)nrows_dev * sizeof(double2);
-        size_t tile = (size_t)tile_max * sizeof(int4) + 16;
-        bool in_smem = tabs_smem_user != 0 && fixed + rows + tile <= (size_t)std::min(smem_optin, 110 * 1024);
-        if (tabs_smem_user == 2 && fixed + rows + tile <= (size_t)smem_optin) in_smem = true;
-        tabs_smem = in_smem ? 1 : 0;
-        pair_smem = (int)(fixed + (in_smem ? rows : 0) + tile);
-        if (pair_smem > smem_optin) return fail(CLB_ERR_UNSUPPORTED, "pair kernel needs %d B of shared memory: lower block_cells", pair_smem);
-        pair_threads = threads;
+    const int npw = std::max(1, (home_max + 31) / 32);       // warps that cover the home particles of a block
+    size_t fixed = (size_t)nt_dev * nt_dev * (sizeof(ClbPairDesc) + sizeof(double2)) + (size_t)ntabs_dev * sizeof(ClbTabMeta);
+    size_t rows = (size_t)nrows_dev * sizeof(double2);
+    size_t tile = (size_t)tile_max * sizeof(int4) + 16;
+    bool in_smem = tabs_smem_user != 0 && fixed + rows + tile <= (size_t)std::min(smem_optin, 110 * 1024);
+    if (tabs_smem_user == 2 && fixed + rows + tile <= (size_t)smem_optin) in_smem = true;
+    tabs_smem = in_smem ? 1 : 0;
+    // split factor: as many working warps per SM as registers allow (~32) for the CTAs that fit in shared memory
+    int best_split = 1;
+    double best_warps = 0;
+    for (int sp = 1; sp <= 4; sp *= 2) {
+        if (npw * sp * 32 > 512) break;
+        size_t smem = fixed + (in_smem ? rows : 0) + tile + (size_t)(sp - 1) * 3 * npw * 32 * sizeof(double);
+        if ((int)smem > smem_optin) break;
         int nb = 0;
-        if (geo.cubic) { if (in_smem) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_pair_forces<true, true>, threads, pair_smem); else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_pair_forces<true, false>, threads, pair_smem); }
-        else { if (in_smem) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_pair_forces<false, true>, threads, pair_smem); else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_pair_forces<false, false>, threads, pair_smem); }
-        pair_grid = std::min(grid.nblocks, std::max(1, nb) * nsm);
-        return CLB_OK;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, pair_kernel(geo.cubic, in_smem, ugrid_on, sp), npw * sp * 32, smem);
+        double w = (double)nb * npw * sp;
+        if (w > best_warps * 1.05) { best_warps = w; best_split = sp; }
+    }
+    pair_split = pair_split_user > 0 ? pair_split_user : best_split;
+    if (npw * pair_split * 32 > 512) pair_split = std::max(1, 512 / (npw * 32));
+    if (pair_split == 3) pair_split = 2;
+    pair_npw = npw;
+    pair_threads = npw * pair_split * 32;
+    pair_smem = (int)(fixed + (in_smem ? rows : 0) + tile + (size_t)(pair_split - 1) * 3 * npw * 32 * sizeof(double));
+    if (pair_smem > smem_optin) return fail(CLB_ERR_UNSUPPORTED, "pair kernel needs %d B of shared memory: lower block_cells", pair_smem);
+    int nb = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, pair_kernel(geo.cubic, tabs_smem, ugrid_on, pair_split), pair_threads, pair_smem);
+    pair_grid = std::min(grid.nblocks, std::max(1, nb) * nsm);
+    return CLB_OK;
 }
 
 int clb_engine::rebuild() {
     clb_engine* e = this;
+    const bool trace = getenv("CLB_TRACE") != nullptr;
+    auto tr0 = std::chrono::steady_clock::now();
     bucket_begin(CLB_B_NEIGH);
     if (nranks > 1) TRY(comm_migrate_and_ghosts());
     int ns = nstored;
@@ -847,7 +894,8 @@ int clb_engine::rebuild() {
         nl_cap = nl_cap_user > 0 ? nl_cap_user : ((expect * 3 / 2 + 32 + 7) / 8) * 8;
         nl_cap_user_seen = nl_cap_user;
     }
-    int threads = std::min(512, std::max(64, ((home_max + 31) / 32) * 32));
+    const int threads = build_threads;
+    const unsigned long long rl2_lat = (unsigned long long)floor(geo.rl2 / geo.q2);
     for (int attempt = 0;; ++attempt) {
         CK(nl_entries.ensure((size_t)ncap * nl_cap));
         size_t smem = (size_t)tile_max * (sizeof(int4) + sizeof(int)) + 16;
@@ -856,13 +904,13 @@ int clb_engine::rebuild() {
         if (geo.cubic) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_build_lists<true>, threads, smem);
         else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_build_lists<false>, threads, smem);
         int gridsz = std::min(grid.nblocks, std::max(1, nb) * nsm);
-        if (geo.cubic) k_build_lists<true><<<gridsz, threads, smem, stream>>>(grid, geo, cell_start.p, pos.p, slot.p, excl_off.p, excl_ids.p, nl_entries.p, nl_count.p, nl_cap, d_ctl);
-        else k_build_lists<false><<<gridsz, threads, smem, stream>>>(grid, geo, cell_start.p, pos.p, slot.p, excl_off.p, excl_ids.p, nl_entries.p, nl_count.p, nl_cap, d_ctl);
+        if (geo.cubic) k_build_lists<true><<<gridsz, threads, smem, stream>>>(grid, geo, rl2_lat, cell_start.p, pos.p, slot.p, excl_off.p, excl_ids.p, nl_entries.p, nl_count.p, nl_cap, d_ctl);
+        else k_build_lists<false><<<gridsz, threads, smem, stream>>>(grid, geo, rl2_lat, cell_start.p, pos.p, slot.p, excl_off.p, excl_ids.p, nl_entries.p, nl_count.p, nl_cap, d_ctl);
         ++launches;
         TRY(read_ctl());
         if (!(h_ctl->err & CLB_EF_LIST_OVERFLOW)) break;
         if (attempt > 6) return fail(CLB_ERR_RANGE, "neighbour list keeps overflowing (max %d entries)", h_ctl->nl_max);
-        nl_cap = ((h_ctl->nl_max * 5 / 4 + 8 + 7) / 8) * 8;
+        nl_cap = ((h_ctl->nl_max * 5 / 4 + 8 + 7) / 8) * 8;   // multiple of 8: rows are read as uint4
         k_ctl_reset_stats<<<1, 1, 0, stream>>>(d_ctl);
     }
     nl_max = h_ctl->nl_max; nl_total = h_ctl->nl_total;
@@ -875,6 +923,7 @@ int clb_engine::rebuild() {
     launches += 8;
     lists_valid = true; forces_valid = false;
     ++nrebuild;
+    if (trace) { cudaStreamSynchronize(stream); fprintf(stderr, "[clb rebuild] %.3f ms step=%lld\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tr0).count(), (long long)step); }
     bucket_end(CLB_B_NEIGH);
     return CLB_OK;
 }
@@ -892,12 +941,13 @@ extern "C" int clb_decompose(clb_engine* e) {
 void clb_engine::enqueue_forces() {
     bucket_begin(CLB_B_PAIR);
     if (pair_event_timing) { pair_event_valid.resize(pair_event_used / 2 + 1, 1); pair_event_valid[pair_event_used / 2] = 1; cudaEventRecord(next_pair_event(), stream); }
-    if (geo.cubic) {
-        if (tabs_smem) k_pair_forces<true, true><<<pair_grid, pair_threads, pair_smem, stream>>>(grid, geo, cell_start.p, pos.p, nl_entries.p, nl_count.p, nl_cap, d_pd.p, nt_dev, d_tm.p, ntabs_dev, d_frows.p, nrows_dev, force.p, ncap, d_ctl);
-        else k_pair_forces<true, false><<<pair_grid, pair_threads, pair_smem, stream>>>(grid, geo, cell_start.p, pos.p, nl_entries.p, nl_count.p, nl_cap, d_pd.p, nt_dev, d_tm.p, ntabs_dev, d_frows.p, nrows_dev, force.p, ncap, d_ctl);
-    } else {
-        if (tabs_smem) k_pair_forces<false, true><<<pair_grid, pair_threads, pair_smem, stream>>>(grid, geo, cell_start.p, pos.p, nl_entries.p, nl_count.p, nl_cap, d_pd.p, nt_dev, d_tm.p, ntabs_dev, d_frows.p, nrows_dev, force.p, ncap, d_ctl);
-        else k_pair_forces<false, false><<<pair_grid, pair_threads, pair_smem, stream>>>(grid, geo, cell_start.p, pos.p, nl_entries.p, nl_count.p, nl_cap, d_pd.p, nt_dev, d_tm.p, ntabs_dev, d_frows.p, nrows_dev, force.p, ncap, d_ctl);
+    {
+        ClbPairArgs A;
+        A.cell_start = cell_start.p; A.pos = pos.p; A.entries = nl_entries.p; A.nl_count = nl_count.p;
+        A.pdesc = d_pd.p; A.plj = d_plj.p; A.tmeta = d_tm.p; A.trows = d_frows.p; A.force = force.p; A.ctl = d_ctl;
+        A.cap = nl_cap; A.ntypes = nt_dev; A.ntabs = ntabs_dev; A.nrows_total = nrows_dev; A.fstride = ncap; A.npw = pair_npw;
+        A.ugrid = ugrid_meta;
+        pair_kernel(geo.cubic, tabs_smem, ugrid_on, pair_split)<<<pair_grid, pair_threads, pair_smem, stream>>>(grid, geo, A);
     }
     if (pair_event_timing) cudaEventRecord(next_pair_event(), stream);
     bucket_end(CLB_B_PAIR);
@@ -941,11 +991,11 @@ extern "C" int clb_energy(clb_engine* e, int inter, double* out) {
     const HostInter& it = e->inters[inter];
     if (it.bonded < 0) {
         size_t smem = (size_t)e->tile_max * sizeof(int4) + 16;
-        int threads = e->pair_threads;
+        int threads = 256;
         int gridsz = std::min(e->grid.nblocks, 4 * e->nsm);
         gridsz = std::min(gridsz, 65536);
-        if (e->geo.cubic) k_pair_energy<true><<<gridsz, threads, smem, e->stream>>>(e->grid, e->geo, e->cell_start.p, e->pos.p, e->nl_entries.p, e->nl_count.p, e->nl_cap, e->d_pd.p, e->d_pe.p, e->nt_dev, e->d_tm.p, e->d_erows.p, inter, e->partial.p, e->partial_u64.p);
-        else k_pair_energy<false><<<gridsz, threads, smem, e->stream>>>(e->grid, e->geo, e->cell_start.p, e->pos.p, e->nl_entries.p, e->nl_count.p, e->nl_cap, e->d_pd.p, e->d_pe.p, e->nt_dev, e->d_tm.p, e->d_erows.p, inter, e->partial.p, e->partial_u64.p);
+        if (e->geo.cubic) k_pair_energy<true><<<gridsz, threads, smem, e->stream>>>(e->grid, e->geo, e->cell_start.p, e->pos.p, e->nl_entries.p, e->nl_count.p, e->nl_cap, e->d_pd_e.p, e->d_pe.p, e->nt_dev, e->d_tm.p, e->d_erows.p, inter, e->partial.p, e->partial_u64.p);
+        else k_pair_energy<false><<<gridsz, threads, smem, e->stream>>>(e->grid, e->geo, e->cell_start.p, e->pos.p, e->nl_entries.p, e->nl_count.p, e->nl_cap, e->d_pd_e.p, e->d_pe.p, e->nt_dev, e->d_tm.p, e->d_erows.p, inter, e->partial.p, e->partial_u64.p);
         k_sum_partials<<<1, 256, 0, e->stream>>>(gridsz, e->partial.p, (double*)e->d_scalar);
         k_sum_partials_u64<<<1, 256, 0, e->stream>>>(gridsz, e->partial_u64.p, (unsigned long long*)e->d_scalar + 1);
         CK(cudaMemcpyAsync(e->h_scalar, e->d_scalar, 16, cudaMemcpyDeviceToHost, e->stream));
@@ -1117,7 +1167,7 @@ extern "C" int clb_get_pairs(clb_engine* e, int64_t cap, int64_t* pairs, int64_t
     CK(out.ensure(outcap));
     CK(cudaMemsetAsync(&e->d_ctl->npairs_out, 0, 8, e->stream));
     size_t smem = (size_t)e->tile_max * sizeof(int) + 16;
-    k_decode_pairs<<<std::min(e->grid.nblocks, 4 * e->nsm), e->pair_threads, smem, e->stream>>>(e->grid, e->cell_start.p, e->slot.p, e->nl_entries.p, e->nl_count.p, e->nl_cap, out.p, outcap, e->d_ctl);
+    k_decode_pairs<<<std::min(e->grid.nblocks, 4 * e->nsm), 256, smem, e->stream>>>(e->grid, e->cell_start.p, e->slot.p, e->nl_entries.p, e->nl_count.p, e->nl_cap, out.p, outcap, e->d_ctl);
     TRY(e->read_ctl());
     CK(cudaGetLastError());
     size_t m = (size_t)e->h_ctl->npairs_out;

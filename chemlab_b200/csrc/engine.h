@@ -18,9 +18,10 @@ struct DevBuf {
     // grow-only; contents are NOT preserved
     cudaError_t ensure(size_t need) {
         if (need <= n && p) return cudaSuccess;
+        // regrowth is geometric: cudaFree/cudaMalloc synchronise the device and cost milliseconds
+        size_t cap = p ? need + need / 2 + 64 : (need ? need : 1);
         if (p) cudaFree(p);
         p = nullptr; n = 0;
-        size_t cap = need ? need : 1;
         cudaError_t e = cudaMalloc((void**)&p, cap * sizeof(T));
         if (e == cudaSuccess) n = cap;
         return e;
@@ -87,7 +88,9 @@ struct clb_engine {
     DevBuf<int> nl_count;
     int nl_cap = 0, nl_cap_user = 0, nl_cap_user_seen = 0, nl_max = 0, tile_max = 0, home_max = 0;
     unsigned long long nl_total = 0, last_interacting = 0;
-    int pair_grid = 0, pair_threads = 128, pair_smem = 0, tabs_smem = 1;
+    int pair_grid = 0, pair_threads = 128, pair_smem = 0, tabs_smem = 1, pair_split = 1, pair_split_user = 0, pair_npw = 1, build_threads = 256;
+    int ugrid_on = 0;
+    ClbTabMeta ugrid_meta;
     bool lists_valid = false, forces_valid = false;
 
     // exclusions
@@ -102,7 +105,8 @@ struct clb_engine {
     HostPairPot pp[CLB_MAX_TYPES][CLB_MAX_TYPES];
     bool pots_dirty = true, has_mixed = false;
     int nt_dev = 1, ntabs_dev = 0, nrows_dev = 0;
-    DevBuf<ClbPairDesc> d_pd;
+    DevBuf<ClbPairDesc> d_pd, d_pd_e;
+    DevBuf<double2> d_plj;
     DevBuf<ClbPairDescE> d_pe;
     DevBuf<ClbTabMeta> d_tm;
     DevBuf<double2> d_frows, d_erows;

@@ -170,8 +170,23 @@ int clb_engine::update_mixing() {
 
 // One ChemicalReaction::React pass at the current state; the caller has made `step` the number of
 // completed steps (RNG key).
+#include <chrono>
+struct StageTrace {
+    bool on; cudaStream_t st; std::chrono::steady_clock::time_point t0; std::string log;
+    StageTrace(cudaStream_t s) : on(getenv("CLB_TRACE") != nullptr), st(s), t0(std::chrono::steady_clock::now()) {}
+    void mark(const char* name) {
+        if (!on) return;
+        cudaStreamSynchronize(st);
+        auto t1 = std::chrono::steady_clock::now();
+        char b[128]; snprintf(b, sizeof(b), " %s=%.3fms", name, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        log += b; t0 = t1;
+    }
+    ~StageTrace() { if (on) fprintf(stderr, "[clb react]%s\n", log.c_str()); }
+};
+
 int clb_engine::react_pass(int64_t* events_out) {
     clb_engine* e = this;
+    StageTrace tr(stream);
     if (events_out) *events_out = 0;
     if (reactions.empty()) return CLB_OK;
     bucket_begin(CLB_B_REACT);
@@ -183,12 +198,12 @@ int clb_engine::react_pass(int64_t* events_out) {
     if (R.candcap == 0) { R.candcap = std::max<size_t>(4096, (size_t)n / 4); CK(R.cands.ensure(R.candcap)); }
     size_t smem = (size_t)tile_max * (sizeof(int4) + sizeof(int)) + 16;
     int nb = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_react_scan, pair_threads, smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_react_scan, 256, smem);
     int gridsz = std::min(grid.nblocks, std::max(1, nb) * nsm);
     long long nc = 0;
     for (;;) {
         CK(cudaMemsetAsync(&d_ctl->ncand, 0, 8, stream));
-        k_react_scan<<<gridsz, pair_threads, smem, stream>>>(grid, geo, cell_start.p, pos.p, slot.p, nl_entries.p, nl_count.p, nl_cap, R.specs.p, (int)reactions.size(),
+        k_react_scan<<<gridsz, 256, smem, stream>>>(grid, geo, cell_start.p, pos.p, slot.p, nl_entries.p, nl_count.p, nl_cap, R.specs.p, (int)reactions.size(),
                                                             resid.p, mol.p, seed, (uint64_t)step, R.cands.p, (unsigned long long)R.candcap, d_ctl);
         ++launches;
         TRY(read_ctl());
@@ -198,6 +213,7 @@ int clb_engine::react_pass(int64_t* events_out) {
         CK(R.cands.ensure(R.candcap));
     }
     CK(cudaGetLastError());
+    tr.mark("scan");
     if (nranks > 1) TRY(comm_gather_candidates(&nc));
     R.ncand_last = nc;
     int nev = 0;
@@ -212,6 +228,7 @@ int clb_engine::react_pass(int64_t* events_out) {
         CK(cubtmp2.ensure(tb + 256));
         cub::DeviceRadixSort::SortPairs(cubtmp2.p, tb, R.ckey.p, R.ckey2.p, R.cval.p, R.cval2.p, (int)nc, 0, 64, stream);
         k_cand_gather<<<g1, 256, 0, stream>>>((int)nc, R.cval2.p, R.cands.p, R.cands_sorted.p, R.alive.p);
+        tr.mark("sort");
         // 3. UniqueA then UniqueB (U7)
         for (int role = 0; role < 2; ++role) {
             k_uniq_reset<<<g1, 256, 0, stream>>>((int)nc, R.cands_sorted.p, R.best1.p, R.best2.p, R.asA.p, R.inB.p);
@@ -219,6 +236,7 @@ int clb_engine::react_pass(int64_t* events_out) {
             k_uniq2<<<g1, 256, 0, stream>>>((int)nc, R.cands_sorted.p, R.alive.p, role, react_nearest, R.best1.p, R.best2.p);
             k_uniq3<<<g1, 256, 0, stream>>>((int)nc, R.cands_sorted.p, R.alive.p, role, react_nearest, R.best1.p, R.best2.p);
         }
+        tr.mark("uniq");
         // 4. survivors in canonical order, U8 resolution, event list
         k_iota<<<g1, 256, 0, stream>>>((int)nc, R.iota.p);
         tb = 0;
@@ -235,6 +253,7 @@ int clb_engine::react_pass(int64_t* events_out) {
         }
         launches += 14;
     }
+    tr.mark("resolve");
     // 5..8 apply
     if (nev > 0) {
         TRY(upload_list_descs());
@@ -252,6 +271,7 @@ int clb_engine::react_pass(int64_t* events_out) {
         CK(cudaMemcpyAsync(R.scalars.p + 2, &hx, 8, cudaMemcpyHostToDevice, stream));
         if (!topo_initialized && !R.adj.p) { CK(R.adj.ensure((size_t)n * CLB_MAXDEG)); CK(R.deg.ensure(n)); CK(cudaMemsetAsync(R.deg.p, 0, (size_t)n * 4, stream)); }
         k_apply_bonds<<<ge, 128, 0, stream>>>(nev, R.ev.p, R.cands_sorted.p, R.specs.p, R.lists.p, R.erank.p, R.adj.p, R.deg.p, excl_pairs.p, R.scalars.p + 2, d_ctl);
+        tr.mark("apply_bonds");
         // molecule ids (only needed when some reaction forbids intramolecular bonds)
         bool need_mol = false;
         for (auto& s : reactions) need_mol |= !s.intramolecular;
@@ -283,6 +303,7 @@ int clb_engine::react_pass(int64_t* events_out) {
             if (nt > touchcap) return fail(CLB_ERR_RANGE, "neighbour-change buffer overflow");
             if (nt) k_nb_apply<<<ceil_div((long long)nt, 128), 128, 0, stream>>>((int)nt, R.touched.p, R.claim.p, R.chg.p, id2idx.p, pos.p, vel.p, charge.p);
         }
+        tr.mark("mol_nb");
         // read back the new bond counts
         std::vector<int> hn(CLB_MAX_LISTS);
         CK(cudaMemcpyAsync(hn.data(), R.list_n.p, CLB_MAX_LISTS * 4, cudaMemcpyDeviceToHost, stream));
@@ -330,6 +351,7 @@ int clb_engine::react_pass(int64_t* events_out) {
             }
             k_ev_of_slot<<<ge, 128, 0, stream>>>(nev, R.ev.p, R.cands_sorted.p, R.ev_of_slot.p, 0);
         }
+        tr.mark("topo");
         // counters
         std::vector<unsigned long long> hcnt(CLB_MAX_REACTIONS);
         CK(cudaMemcpyAsync(hcnt.data(), R.counters.p, CLB_MAX_REACTIONS * 8, cudaMemcpyDeviceToHost, stream));
@@ -339,6 +361,7 @@ int clb_engine::react_pass(int64_t* events_out) {
         nreact_events += nev;
         terms_dirty = true; excl_dirty = true; lists_ptr_dirty = true;
         if (has_mixed) TRY(update_mixing());
+        tr.mark("tail");
         // U9: new exclusions / bonds take effect through a forced rebuild at the next resort check
         k_set_force_rebuild<<<1, 1, 0, stream>>>(d_ctl);
         pending_rebuild = true;
