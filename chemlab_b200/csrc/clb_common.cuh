@@ -117,5 +117,8 @@ __host__ __device__ inline void clb_draw_pair(uint64_t seed, uint32_t stream, ui
 __device__ __forceinline__ double lat2d(int d) {
     return __hiloint2double(0x43300000, (int)((unsigned)d ^ 0x80000000u)) - 4503601774854144.0; // 2^52 + 2^31
 }
+// lattice coordinates wrap modulo 2^32: do the arithmetic unsigned (signed overflow is undefined behaviour)
+__host__ __device__ __forceinline__ int wsub(int a, int b) { return (int)((unsigned)a - (unsigned)b); }
+__host__ __device__ __forceinline__ int wadd(int a, int b) { return (int)((unsigned)a + (unsigned)b); }
 __device__ __forceinline__ int wrapi(int c, int n) { return c < 0 ? c + n : (c >= n ? c - n : c); }
 #endif

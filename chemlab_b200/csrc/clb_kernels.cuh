@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(256) k_integrate(ClbIntegParams P, int4* __res
         if (MODE & CLB_INT_FIRST) {
             double dpx = P.dt * (double)vxf, dpy = P.dt * (double)vyf, dpz = P.dt * (double)vzf;
             int dx = __double2int_rn(dpx * P.invq[0]), dy = __double2int_rn(dpy * P.invq[1]), dz = __double2int_rn(dpz * P.invq[2]);
-            int nx = p.x + dx, ny = p.y + dy, nz = p.z + dz;
+            int nx = wadd(p.x, dx), ny = wadd(p.y, dy), nz = wadd(p.z, dz);
             int wx = (dx > 0 && (unsigned)nx < (unsigned)p.x) ? 1 : ((dx < 0 && (unsigned)nx > (unsigned)p.x) ? -1 : 0);
             int wy = (dy > 0 && (unsigned)ny < (unsigned)p.y) ? 1 : ((dy < 0 && (unsigned)ny > (unsigned)p.y) ? -1 : 0);
             int wz = (dz > 0 && (unsigned)nz < (unsigned)p.z) ? 1 : ((dz < 0 && (unsigned)nz > (unsigned)p.z) ? -1 : 0);
@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(256) k_integrate(ClbIntegParams P, int4* __res
             if (P.criterion == 0) d2 = (float)(dpx * dpx + dpy * dpy + dpz * dpz);
             else {
                 int4 r = xref[i];
-                double ex = (double)(nx - r.x) * P.q[0], ey = (double)(ny - r.y) * P.q[1], ez = (double)(nz - r.z) * P.q[2];
+                double ex = (double)wsub(nx, r.x) * P.q[0], ey = (double)wsub(ny, r.y) * P.q[1], ez = (double)wsub(nz, r.z) * P.q[2];
                 d2 = __double2float_ru(ex * ex + ey * ey + ez * ez);
             }
         }
@@ -245,14 +245,14 @@ __global__ void __launch_bounds__(256) k_bonded(int i0, int i1, const int4* __re
             double F, E = 0;
             if (d.arity == 2) {
                 int o = 1 - role;
-                double dx = lat2d(P[role].x - P[o].x) * geo.q[0], dy = lat2d(P[role].y - P[o].y) * geo.q[1], dz = lat2d(P[role].z - P[o].z) * geo.q[2];
+                double dx = lat2d(wsub(P[role].x, P[o].x)) * geo.q[0], dy = lat2d(wsub(P[role].y, P[o].y)) * geo.q[1], dz = lat2d(wsub(P[role].z, P[o].z)) * geo.q[2];
                 double r = sqrt(dx * dx + dy * dy + dz * dz);
                 bpot_eval(pp, r, btm, cf, ce, F, E, ENERGY, err);
                 double fr = F / r;
                 ax += fr * dx; ay += fr * dy; az += fr * dz;
             } else if (d.arity == 3) {
-                double d1[3] = {lat2d(P[0].x - P[1].x) * geo.q[0], lat2d(P[0].y - P[1].y) * geo.q[1], lat2d(P[0].z - P[1].z) * geo.q[2]};
-                double d2[3] = {lat2d(P[2].x - P[1].x) * geo.q[0], lat2d(P[2].y - P[1].y) * geo.q[1], lat2d(P[2].z - P[1].z) * geo.q[2]};
+                double d1[3] = {lat2d(wsub(P[0].x, P[1].x)) * geo.q[0], lat2d(wsub(P[0].y, P[1].y)) * geo.q[1], lat2d(wsub(P[0].z, P[1].z)) * geo.q[2]};
+                double d2[3] = {lat2d(wsub(P[2].x, P[1].x)) * geo.q[0], lat2d(wsub(P[2].y, P[1].y)) * geo.q[1], lat2d(wsub(P[2].z, P[1].z)) * geo.q[2]};
                 double r1 = sqrt(d1[0] * d1[0] + d1[1] * d1[1] + d1[2] * d1[2]);
                 double r2 = sqrt(d2[0] * d2[0] + d2[1] * d2[1] + d2[2] * d2[2]);
                 double c = (d1[0] * d2[0] + d1[1] * d2[1] + d1[2] * d2[2]) / (r1 * r2);
@@ -268,9 +268,9 @@ __global__ void __launch_bounds__(256) k_bonded(int i0, int i1, const int4* __re
                 }
                 ax += g[0]; ay += g[1]; az += g[2];
             } else {
-                double rij[3] = {lat2d(P[0].x - P[1].x) * geo.q[0], lat2d(P[0].y - P[1].y) * geo.q[1], lat2d(P[0].z - P[1].z) * geo.q[2]};
-                double rkj[3] = {lat2d(P[2].x - P[1].x) * geo.q[0], lat2d(P[2].y - P[1].y) * geo.q[1], lat2d(P[2].z - P[1].z) * geo.q[2]};
-                double rkl[3] = {lat2d(P[2].x - P[3].x) * geo.q[0], lat2d(P[2].y - P[3].y) * geo.q[1], lat2d(P[2].z - P[3].z) * geo.q[2]};
+                double rij[3] = {lat2d(wsub(P[0].x, P[1].x)) * geo.q[0], lat2d(wsub(P[0].y, P[1].y)) * geo.q[1], lat2d(wsub(P[0].z, P[1].z)) * geo.q[2]};
+                double rkj[3] = {lat2d(wsub(P[2].x, P[1].x)) * geo.q[0], lat2d(wsub(P[2].y, P[1].y)) * geo.q[1], lat2d(wsub(P[2].z, P[1].z)) * geo.q[2]};
+                double rkl[3] = {lat2d(wsub(P[2].x, P[3].x)) * geo.q[0], lat2d(wsub(P[2].y, P[3].y)) * geo.q[1], lat2d(wsub(P[2].z, P[3].z)) * geo.q[2]};
                 double mv[3] = {rij[1] * rkj[2] - rij[2] * rkj[1], rij[2] * rkj[0] - rij[0] * rkj[2], rij[0] * rkj[1] - rij[1] * rkj[0]};
                 double nv[3] = {rkj[1] * rkl[2] - rkj[2] * rkl[1], rkj[2] * rkl[0] - rkj[0] * rkl[2], rkj[0] * rkl[1] - rkj[1] * rkl[0]};
                 double m2 = mv[0] * mv[0] + mv[1] * mv[1] + mv[2] * mv[2];

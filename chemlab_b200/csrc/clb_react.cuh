@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(512) k_react_scan(ClbGrid g, ClbGeom geo, cons
                 const int sj = s_slot[e];
                 if (si >= sj) continue;           // every unordered pair once, lower slot first
                 const int4 pj = s_pos[e];
-                double dx = lat2d(pi.x - pj.x) * geo.q[0], dy = lat2d(pi.y - pj.y) * geo.q[1], dz = lat2d(pi.z - pj.z) * geo.q[2];
+                double dx = lat2d(wsub(pi.x, pj.x)) * geo.q[0], dy = lat2d(wsub(pi.y, pj.y)) * geo.q[1], dz = lat2d(wsub(pi.z, pj.z)) * geo.q[2];
                 double d2 = dx * dx + dy * dy + dz * dz;
                 for (int ri = 0; ri < nspec; ++ri) {
                     const ClbReactSpec& r = s_spec[ri];

@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(512) k_build_lists(ClbGrid g, ClbGeom geo, uns
                         int sj = -2;
                         if (pass) {
                             const int4 pj = s_pos[j];
-                            const int dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
+                            const int dx = wsub(pi.x, pj.x), dy = wsub(pi.y, pj.y), dz = wsub(pi.z, pj.z);
                             if (CUBIC) {
                                 unsigned long long r2 = (unsigned long long)((long long)dx * dx) + (unsigned long long)((long long)dy * dy) +
                                                         (unsigned long long)((long long)dz * dz);
@@ -205,10 +205,11 @@ __global__ void __launch_bounds__(512) k_build_lists(ClbGrid g, ClbGeom geo, uns
 // sums are combined through shared memory in fixed order (bit-reproducible) -> more resident working
 // warps per SM for the same shared-memory footprint.
 __device__ __forceinline__ double rsqrt_seed(double x) {
-    // float with the same value as x truncated to 24 bits, via integer ops only
+    // float with the same value as x truncated to 24 bits, via integer ops only (no F2F conversions)
     int hi = __double2hiint(x), lo = __double2loint(x);
     unsigned fb = ((unsigned)(hi - 0x38000000) << 3) | ((unsigned)lo >> 29);
-    float y = rsqrtf(__uint_as_float(fb));
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(__uint_as_float(fb)));
     unsigned yb = __float_as_uint(y);
     return __hiloint2double((int)((yb >> 3) + 0x38000000u), (int)(yb << 29));
 }
@@ -220,7 +221,9 @@ struct ClbPairArgs {
     int cap, ntypes, ntabs, nrows_total, fstride, npw;   // npw = warps per split group
     ClbTabMeta ugrid;                                      // common grid when UGRID
 };
-
+// CUBIC boxes work in lattice units end to end: r2 and the cutoffs are lattice^2, the table index uses
+// invdx*q, and F(r)*(1/r_lat)*d_lat is already the real force vector -- no per-pair unit conversion.
+// The host pre-scales ClbPairDesc.rc2, ClbTabMeta.invdx and the LJ coefficients accordingly.
 template <bool CUBIC, bool TABS_SMEM, bool UGRID, int SPLIT>
 __global__ void __launch_bounds__(512) k_pair_forces(ClbGrid g, ClbGeom geo, ClbPairArgs A) {
     if (*(volatile int*)&A.ctl->stall) return;
@@ -242,6 +245,8 @@ __global__ void __launch_bounds__(512) k_pair_forces(ClbGrid g, ClbGeom geo, Clb
     const int sg = SPLIT > 1 ? warp / A.npw : 0;          // split group of this warp
     const int wp = SPLIT > 1 ? warp - sg * A.npw : warp;  // particle warp inside the group
     const int nhpass = A.npw * 32;
+    const double u_invdx = A.ugrid.invdx, u_ct = A.ugrid.c_t;
+    const unsigned u_n = (unsigned)A.ugrid.n;
     unsigned err = 0;
     for (int b = blockIdx.x; b < g.nblocks; b += gridDim.x) {
         TileCtx t;
@@ -256,8 +261,10 @@ __global__ void __launch_bounds__(512) k_pair_forces(ClbGrid g, ClbGeom geo, Clb
             const bool act = p < t.nh;
             const int gi = t.hs + (act ? p : 0);
             const int4 pi = __ldg(A.pos + gi);
+            // bias by 2^31 once so that (pi - pj) is directly the low word of the 2^52 trick
+            const unsigned pix = (unsigned)pi.x + 0x80000000u, piy = (unsigned)pi.y + 0x80000000u, piz = (unsigned)pi.z + 0x80000000u;
             const int cnt = act ? __ldg(A.nl_count + gi) : 0;
-            const ClbPairDesc* pdrow = s_pd + pw_type(pi.w) * A.ntypes;
+            const int trow = pw_type(pi.w) * A.ntypes;
             const uint4* row = reinterpret_cast<const uint4*>(A.entries + (size_t)gi * A.cap);
             const int nb = (cnt + 7) >> 3;                   // 8-entry batches of this particle
             double ax = 0.0, ay = 0.0, az = 0.0;
@@ -267,16 +274,19 @@ __global__ void __launch_bounds__(512) k_pair_forces(ClbGrid g, ClbGeom geo, Clb
                 uint4 cur = ev;
                 if (bi + SPLIT < nb) ev = __ldg(row + bi + SPLIT);     // prefetch the next batch
                 const int ne = min(8, cnt - bi * 8);
+#pragma unroll 1
                 for (int u = 0; u < ne; ++u) {
                     const unsigned e = cur.x & 0xffffu;
                     cur.x = __funnelshift_r(cur.x, cur.y, 16); cur.y = __funnelshift_r(cur.y, cur.z, 16);
                     cur.z = __funnelshift_r(cur.z, cur.w, 16); cur.w >>= 16;
                     const int4 pj = s_pos[e];
-                    double dx = lat2d(pi.x - pj.x), dy = lat2d(pi.y - pj.y), dz = lat2d(pi.z - pj.z), r2;
-                    if (CUBIC) r2 = (dx * dx + dy * dy + dz * dz) * geo.q2;
-                    else { dx *= geo.q[0]; dy *= geo.q[1]; dz *= geo.q[2]; r2 = dx * dx + dy * dy + dz * dz; }
-                    const int tp = pw_type(pj.w);
-                    const ClbPairDesc pd = pdrow[tp];
+                    double dx = __hiloint2double(0x43300000, (int)(pix - (unsigned)pj.x)) - 4503601774854144.0;
+                    double dy = __hiloint2double(0x43300000, (int)(piy - (unsigned)pj.y)) - 4503601774854144.0;
+                    double dz = __hiloint2double(0x43300000, (int)(piz - (unsigned)pj.z)) - 4503601774854144.0;
+                    if (!CUBIC) { dx *= geo.q[0]; dy *= geo.q[1]; dz *= geo.q[2]; }
+                    const double r2 = dx * dx + dy * dy + dz * dz;
+                    const int tp = trow + pw_type(pj.w);
+                    const ClbPairDesc pd = s_pd[tp];
                     if (r2 <= pd.rc2) {                         // rc2 < 0 for pairs without a potential (U2)
                         double y = rsqrt_seed(r2);
                         double h = r2 * y;
@@ -285,22 +295,19 @@ __global__ void __launch_bounds__(512) k_pair_forces(ClbGrid g, ClbGeom geo, Clb
                         double fr;
                         if (pd.kind == 1) {
                             double r = r2 * y;
-                            double invdx, c_t, x0, dxx; int n, off;
-                            if (UGRID) { invdx = A.ugrid.invdx; c_t = A.ugrid.c_t; x0 = A.ugrid.x0; dxx = A.ugrid.dx; n = A.ugrid.n; off = pd.tab; }
-                            else { const ClbTabMeta tm = s_tm[pd.tab]; invdx = tm.invdx; c_t = tm.c_t; x0 = tm.x0; dxx = tm.dx; n = tm.n; off = tm.off; }
+                            double invdx, c_t; unsigned n; int off;
+                            if (UGRID) { invdx = u_invdx; c_t = u_ct; n = u_n; off = pd.tab; }
+                            else { const ClbTabMeta tm = s_tm[pd.tab]; invdx = tm.invdx; c_t = tm.c_t; n = (unsigned)tm.n; off = tm.off; }
                             double uu = fma(r, invdx, c_t);
                             double ti = uu + 6755399441055744.0;            // 1.5 * 2^52: integer in the low word
                             int idx = __double2loint(ti);
                             double bfrac = uu - (ti - 6755399441055744.0);
-                            if ((unsigned)idx > (unsigned)(n - 2)) {
-                                if (idx < 0 || r > x0 + dxx * (n - 1) * (1.0 + 1e-12)) err |= CLB_EF_TABLE_RANGE;
-                                int ic = idx < 0 ? 0 : n - 2;
-                                bfrac += (double)(idx - ic); idx = ic;
-                            }
+                            // row n-1 exists ({f[n-1], 0}) so r == table end is exact; anything else is fatal (U12)
+                            if ((unsigned)idx >= n) { err |= CLB_EF_TABLE_RANGE; idx = 0; }
                             const double2 rw = rows[off + idx];                // {f_i + df_i/2, df_i}
                             fr = fma(bfrac, rw.y, rw.x) * y;
                         } else {
-                            const double2 lj = s_lj[pw_type(pi.w) * A.ntypes + tp];
+                            const double2 lj = s_lj[tp];
                             double y2 = y * y;
                             double y6 = y2 * y2 * y2;
                             fr = y6 * fma(lj.x, y6, -lj.y) * y2;
@@ -317,10 +324,7 @@ __global__ void __launch_bounds__(512) k_pair_forces(ClbGrid g, ClbGeom geo, Clb
                     for (int s2 = 1; s2 < SPLIT; ++s2) { const double* r = s_red + ((s2 - 1) * nhpass + pl) * 3; ax += r[0]; ay += r[1]; az += r[2]; }
                 }
             }
-            if (act && sg == 0) {
-                if (CUBIC) { ax *= geo.q[0]; ay *= geo.q[0]; az *= geo.q[0]; }
-                A.force[gi] = ax; A.force[gi + A.fstride] = ay; A.force[gi + 2 * A.fstride] = az;
-            }
+            if (act && sg == 0) { A.force[gi] = ax; A.force[gi + A.fstride] = ay; A.force[gi + 2 * A.fstride] = az; }
             if (SPLIT > 1) __syncthreads();
         }
     }
@@ -363,7 +367,7 @@ __global__ void __launch_bounds__(512) k_pair_energy(ClbGrid g, ClbGeom geo, con
             const unsigned short* ent = entries + (size_t)gi * cap;
             for (int k = 0; k < cnt; ++k) {
                 const int4 pj = s_pos[ent[k]];
-                double dx = lat2d(pi.x - pj.x) * geo.q[0], dy = lat2d(pi.y - pj.y) * geo.q[1], dz = lat2d(pi.z - pj.z) * geo.q[2];
+                double dx = lat2d(wsub(pi.x, pj.x)) * geo.q[0], dy = lat2d(wsub(pi.y, pj.y)) * geo.q[1], dz = lat2d(wsub(pi.z, pj.z)) * geo.q[2];
                 double r2 = dx * dx + dy * dy + dz * dz;
                 int tp = pw_type(pi.w) * ntypes + pw_type(pj.w);
                 const ClbPairDesc pd = pdesc[tp];

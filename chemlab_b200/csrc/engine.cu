@@ -113,7 +113,8 @@ extern "C" int clb_create(clb_engine** out, int device, const double box[3], dou
     cudaFuncSetAttribute(k_build_lists<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
     cudaFuncSetAttribute(k_build_lists<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
     for (int c = 0; c < 2; ++c) for (int sm = 0; sm < 2; ++sm) for (int ug = 0; ug < 2; ++ug) for (int sp = 0; sp < 3; ++sp)
-        cudaFuncSetAttribute(pair_kernel(c, sm, ug, 1 << sp), cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+    { cudaFuncSetAttribute(pair_kernel(c, sm, ug, 1 << sp), cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+          cudaFuncSetAttribute(pair_kernel(c, sm, ug, 1 << sp), cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); }
     cudaFuncSetAttribute(k_pair_energy<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
     cudaFuncSetAttribute(k_pair_energy<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
     cudaFuncSetAttribute(k_decode_pairs, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
@@ -591,9 +592,22 @@ int clb_engine::upload_potentials() {
     ugrid_on = !tm.empty();
     for (size_t k = 1; k < tm.size(); ++k) if (tm[k].n != tm[0].n || tm[k].x0 != tm[0].x0 || tm[k].dx != tm[0].dx) ugrid_on = 0;
     if (!tm.empty()) ugrid_meta = tm[0];
+    CK(d_tm_e.ensure(std::max<size_t>(tm.size(), 1)));
+    if (!tm.empty()) CK(cudaMemcpyAsync(d_tm_e.p, tm.data(), tm.size() * sizeof(ClbTabMeta), cudaMemcpyHostToDevice, stream));   // real units
     CK(d_pd_e.ensure(pd.size()));
     CK(cudaMemcpyAsync(d_pd_e.p, pd.data(), pd.size() * sizeof(ClbPairDesc), cudaMemcpyHostToDevice, stream));   // energy kernel: slot ids
     if (ugrid_on) for (auto& d : pd) if (d.kind == 1) d.tab = tm[d.tab].off;
+    if (geo.cubic) {
+        // the pair-force kernel of cubic boxes works in lattice units (clb_tile.cuh)
+        const double q = geo.q[0];
+        for (auto& d : pd) if (d.kind) d.rc2 /= geo.q2;
+        for (auto& m : tm) { m.invdx *= q; }
+        for (auto& c : plj) { c.x /= pow(q, 13); c.y /= pow(q, 7); }
+        if (!tm.empty()) ugrid_meta = tm[0];
+    }
+    {   // the last row of every table is read when r equals the table end: {f[n-1], 0}
+        for (auto& m : tm) { frows[m.off + m.n - 1] = make_double2(frows[m.off + m.n - 1].x, 0.0); }
+    }
     CK(d_plj.ensure(plj.size()));
     CK(cudaMemcpyAsync(d_plj.p, plj.data(), plj.size() * sizeof(double2), cudaMemcpyHostToDevice, stream));
     nt_dev = nt; ntabs_dev = (int)tm.size(); nrows_dev = (int)frows.size();
@@ -832,7 +846,9 @@ int clb_engine::setup_sync() {
 // launch geometry and shared-memory carve-up of the pair-force kernel; depends on the tile size of the
 // last rebuild AND on the potentials, so it is refreshed after either changes
 int clb_engine::configure_pair_launch() {
-    const int npw = std::max(1, (home_max + 31) / 32);       // warps that cover the home particles of a block
+    // warps that cover the home particles of a block: mean + 3 sigma (Poisson); rarer, fuller blocks take a second pass
+    const double mean_home = (double)(own1 - own0) / std::max(1, grid.nblocks);
+    const int npw = std::max(1, std::min((home_max + 31) / 32, (int)ceil((mean_home + 3.0 * sqrt(mean_home)) / 32.0)));
     size_t fixed = (size_t)nt_dev * nt_dev * (sizeof(ClbPairDesc) + sizeof(double2)) + (size_t)ntabs_dev * sizeof(ClbTabMeta);
     size_t rows = (size_t)nrows_dev * sizeof(double2);
     size_t tile = (size_t)tile_max * sizeof(int4) + 16;
@@ -994,8 +1010,8 @@ extern "C" int clb_energy(clb_engine* e, int inter, double* out) {
         int threads = 256;
         int gridsz = std::min(e->grid.nblocks, 4 * e->nsm);
         gridsz = std::min(gridsz, 65536);
-        if (e->geo.cubic) k_pair_energy<true><<<gridsz, threads, smem, e->stream>>>(e->grid, e->geo, e->cell_start.p, e->pos.p, e->nl_entries.p, e->nl_count.p, e->nl_cap, e->d_pd_e.p, e->d_pe.p, e->nt_dev, e->d_tm.p, e->d_erows.p, inter, e->partial.p, e->partial_u64.p);
-        else k_pair_energy<false><<<gridsz, threads, smem, e->stream>>>(e->grid, e->geo, e->cell_start.p, e->pos.p, e->nl_entries.p, e->nl_count.p, e->nl_cap, e->d_pd_e.p, e->d_pe.p, e->nt_dev, e->d_tm.p, e->d_erows.p, inter, e->partial.p, e->partial_u64.p);
+        if (e->geo.cubic) k_pair_energy<true><<<gridsz, threads, smem, e->stream>>>(e->grid, e->geo, e->cell_start.p, e->pos.p, e->nl_entries.p, e->nl_count.p, e->nl_cap, e->d_pd_e.p, e->d_pe.p, e->nt_dev, e->d_tm_e.p, e->d_erows.p, inter, e->partial.p, e->partial_u64.p);
+        else k_pair_energy<false><<<gridsz, threads, smem, e->stream>>>(e->grid, e->geo, e->cell_start.p, e->pos.p, e->nl_entries.p, e->nl_count.p, e->nl_cap, e->d_pd_e.p, e->d_pe.p, e->nt_dev, e->d_tm_e.p, e->d_erows.p, inter, e->partial.p, e->partial_u64.p);
         k_sum_partials<<<1, 256, 0, e->stream>>>(gridsz, e->partial.p, (double*)e->d_scalar);
         k_sum_partials_u64<<<1, 256, 0, e->stream>>>(gridsz, e->partial_u64.p, (unsigned long long*)e->d_scalar + 1);
         CK(cudaMemcpyAsync(e->h_scalar, e->d_scalar, 16, cudaMemcpyDeviceToHost, e->stream));

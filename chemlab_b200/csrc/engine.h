@@ -108,7 +108,7 @@ struct clb_engine {
     DevBuf<ClbPairDesc> d_pd, d_pd_e;
     DevBuf<double2> d_plj;
     DevBuf<ClbPairDescE> d_pe;
-    DevBuf<ClbTabMeta> d_tm;
+    DevBuf<ClbTabMeta> d_tm, d_tm_e;
     DevBuf<double2> d_frows, d_erows;
 
     // tuple lists and bonded interactions
