@@ -107,18 +107,24 @@ __device__ __forceinline__ int home_column(const TileCtx& t, const int* s_off, i
 // arithmetic on lattice differences (3 IMAD.WIDE + one compare); otherwise fp64 per-dimension scaling.
 // Exclusions: the particle's partner-slot row is held across the lanes and matched by shuffles.
 // Entry layout: entries[gi*cap + k] (cap % 8 == 0 so the force kernel reads 8 entries per LDG.128).
+#define CLB_BUILD_G 4   // home particles of one cell that share each candidate load
 template <bool CUBIC>
 __global__ void __launch_bounds__(512) k_build_lists(ClbGrid g, ClbGeom geo, unsigned long long rl2_lat,
                                                      const int* __restrict__ cell_start,
                                                      const int4* __restrict__ pos, const int* __restrict__ slot,
                                                      const int* __restrict__ excl_off, const int* __restrict__ excl_ids,
                                                      unsigned short* __restrict__ entries, int* __restrict__ nl_count,
-                                                     int cap, ClbCtl* ctl) {
+                                                     int cap, int tile_cap, ClbCtl* ctl) {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ int s_off[CLB_TILE_CELLS + 1];
     __shared__ int s_src[CLB_TILE_CELLS];
+    __shared__ int s_item[CLB_MAX_BX + 1];      // prefix of (cell, group-of-G) work items over the home cells
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
     const unsigned lt_mask = (1u << lane) - 1u;
+    // dynamic smem: tile positions | tile slots | G staging rows (cap entries each) per warp
+    int4* s_pos = reinterpret_cast<int4*>(smem);
+    int* s_slot = reinterpret_cast<int*>(s_pos + tile_cap);
+    unsigned short* s_rows = reinterpret_cast<unsigned short*>(s_slot + tile_cap) + (size_t)warp * CLB_BUILD_G * cap;
     int lmax = 0;
     unsigned long long ltot = 0;
     for (int b = blockIdx.x; b < g.nblocks; b += gridDim.x) {
@@ -126,67 +132,93 @@ __global__ void __launch_bounds__(512) k_build_lists(ClbGrid g, ClbGeom geo, uns
         tile_geometry(g, b, t);
         __syncthreads();
         tile_offsets(g, t, cell_start, s_off, s_src);
-        int4* s_pos = reinterpret_cast<int4*>(smem);
-        int* s_slot = reinterpret_cast<int*>(s_pos + t.T);
         tile_stage(t, s_off, s_src, pos, s_pos, slot, s_slot, nullptr);
-        __syncthreads();
         const int mh0 = t.whole ? t.cx0 : 1;
+        if (threadIdx.x == 0) {
+            int acc = 0;
+            for (int c = 0; c < t.bxe; ++c) { s_item[c] = acc; acc += (s_off[4 * t.W + mh0 + c + 1] - s_off[4 * t.W + mh0 + c] + CLB_BUILD_G - 1) / CLB_BUILD_G; }
+            s_item[t.bxe] = acc;
+        }
+        __syncthreads();
         const int tbase = s_off[4 * t.W + mh0];
-        for (int p = warp; p < t.nh; p += nw) {
-            const int gi = t.hs + p;
-            const int ti = tbase + p;
-            const int mh = home_column(t, s_off, p);
-            const int4 pi = s_pos[ti];
-            const int myslot = s_slot[ti];
-            const int e0 = __ldg(excl_off + myslot), nex = __ldg(excl_off + myslot + 1) - e0;
-            int exv = (lane < nex) ? __ldg(excl_ids + e0 + lane) : -1;
-            unsigned short* row = entries + (size_t)gi * cap;
-            int cnt = 0;
-            for (int k = 0; k < CLB_TILE_ROWS; ++k) {
-                // contiguous candidate range(s) of tile row k
-                int nseg = 1, lo[3], hi[3];
-                if (!t.whole) { lo[0] = s_off[k * t.W + mh - 1]; hi[0] = s_off[k * t.W + mh + 2]; }
-                else {
-                    nseg = 3;
-                    for (int dm = -1; dm <= 1; ++dm) { int m = wrapi(mh + dm, g.ncx); lo[dm + 1] = s_off[k * t.W + m]; hi[dm + 1] = s_off[k * t.W + m + 1]; }
-                }
-                for (int sg = 0; sg < nseg; ++sg) {
-                    for (int j0 = lo[sg]; j0 < hi[sg]; j0 += 32) {
-                        const int j = j0 + lane;
-                        bool pass = j < hi[sg];
-                        int sj = -2;
-                        if (pass) {
-                            const int4 pj = s_pos[j];
-                            const int dx = wsub(pi.x, pj.x), dy = wsub(pi.y, pj.y), dz = wsub(pi.z, pj.z);
-                            if (CUBIC) {
-                                unsigned long long r2 = (unsigned long long)((long long)dx * dx) + (unsigned long long)((long long)dy * dy) +
-                                                        (unsigned long long)((long long)dz * dz);
-                                pass = r2 <= rl2_lat;
-                            } else {
-                                double fx = lat2d(dx) * geo.q[0], fy = lat2d(dy) * geo.q[1], fz = lat2d(dz) * geo.q[2];
-                                pass = (fx * fx + fy * fy + fz * fz) <= geo.rl2;
-                            }
-                            pass = pass && (j != ti);
-                            if (pass && nex > 0) sj = s_slot[j];
-                        }
-                        if (nex > 0) {
-                            for (int e = 0; e < min(nex, 32); ++e) { int x = __shfl_sync(0xffffffffu, exv, e); if (x == sj) pass = false; }
-                            for (int eb = 32; eb < nex; eb += 32) {   // rows longer than a warp (rare)
-                                int xv = (eb + lane < nex) ? __ldg(excl_ids + e0 + eb + lane) : -1;
-                                for (int e = 0; e < min(nex - eb, 32); ++e) { int x = __shfl_sync(0xffffffffu, xv, e); if (x == sj) pass = false; }
-                            }
+        const int nitems = s_item[t.bxe];
+        const int nsegs = t.whole ? 27 : 9;       // whole-row tiles: the 3 x-neighbours may wrap -> 27 single cells
+#pragma unroll 1
+        for (int item = warp; item < nitems; item += nw) {
+            int c = 0;
+            while (c + 1 < t.bxe && s_item[c + 1] <= item) ++c;
+            const int mh = mh0 + c;                                         // tile column of the home cell
+            const int cell_lo = s_off[4 * t.W + mh], cell_hi = s_off[4 * t.W + mh + 1];
+            const int t0 = cell_lo + (item - s_item[c]) * CLB_BUILD_G;      // tile position of the first particle
+            const int np = min(CLB_BUILD_G, cell_hi - t0);
+            int px[CLB_BUILD_G], py[CLB_BUILD_G], pz[CLB_BUILD_G], cnt[CLB_BUILD_G];
+#pragma unroll
+            for (int q = 0; q < CLB_BUILD_G; ++q) { const int4 v = s_pos[t0 + min(q, np - 1)]; px[q] = v.x; py[q] = v.y; pz[q] = v.z; cnt[q] = 0; }
+            // 1. every candidate is loaded once and tested against the G home particles
+#pragma unroll 1
+            for (int sgm = 0; sgm < nsegs; ++sgm) {
+                int lo, hi;
+                if (!t.whole) { lo = s_off[sgm * t.W + mh - 1]; hi = s_off[sgm * t.W + mh + 2]; }
+                else { int k = sgm / 3, m = wrapi(mh + (sgm - 3 * k) - 1, g.ncx); lo = s_off[k * t.W + m]; hi = s_off[k * t.W + m + 1]; }
+#pragma unroll 1
+                for (int j0 = lo; j0 < hi; j0 += 32) {
+                    const int j = j0 + lane;
+                    const bool valid = j < hi;
+                    const int4 pj = s_pos[valid ? j : lo];
+#pragma unroll
+                    for (int q = 0; q < CLB_BUILD_G; ++q) {
+                        const int dx = wsub(px[q], pj.x), dy = wsub(py[q], pj.y), dz = wsub(pz[q], pj.z);
+                        bool pass;
+                        if (CUBIC) {
+                            unsigned long long r2 = (unsigned long long)((long long)dx * dx) + (unsigned long long)((long long)dy * dy) +
+                                                    (unsigned long long)((long long)dz * dz);
+                            pass = valid && r2 <= rl2_lat;
+                        } else {
+                            double fx = lat2d(dx) * geo.q[0], fy = lat2d(dy) * geo.q[1], fz = lat2d(dz) * geo.q[2];
+                            pass = valid && (fx * fx + fy * fy + fz * fz) <= geo.rl2;
                         }
                         const unsigned bal = __ballot_sync(0xffffffffu, pass);
-                        if (pass) { int o = cnt + __popc(bal & lt_mask); if (o < cap) row[o] = (unsigned short)j; }
-                        cnt += __popc(bal);
+                        if (pass) { int o = cnt[q] + __popc(bal & lt_mask); if (o < cap) s_rows[q * cap + o] = (unsigned short)j; }
+                        cnt[q] += __popc(bal);
                     }
                 }
             }
-            if (lane == 0) {
-                nl_count[gi] = min(cnt, cap);
-                if (cnt > cap) atomicOr(&ctl->err, CLB_EF_LIST_OVERFLOW);
-                lmax = max(lmax, cnt); ltot += (unsigned long long)min(cnt, cap);
+            __syncwarp();
+            // 2./3. per particle: drop itself and its excluded partners (swap-remove), write the row out
+#pragma unroll 1
+            for (int q = 0; q < np; ++q) {
+                unsigned short* s_row = s_rows + q * cap;
+                const int ti = t0 + q;
+                const int gi = t.hs + (ti - tbase);
+                int found = 0;
+#pragma unroll
+                for (int r = 0; r < CLB_BUILD_G; ++r) if (r == q) found = cnt[r];
+                int n = min(found, cap);
+                const int myslot = s_slot[ti];
+                const int e0 = __ldg(excl_off + myslot), nex = __ldg(excl_off + myslot + 1) - e0;
+#pragma unroll 1
+                for (int e = -1; e < nex; ++e) {
+                    const int x = e < 0 ? myslot : __ldg(excl_ids + e0 + e);
+                    int hit = -1;
+                    for (int k = lane; k < n; k += 32) if (s_slot[s_row[k]] == x) hit = k;
+                    const unsigned bal = __ballot_sync(0xffffffffu, hit >= 0);
+                    if (bal) {                                    // a slot appears at most once in a row
+                        const int k = __shfl_sync(0xffffffffu, hit, __ffs(bal) - 1);
+                        if (lane == 0) s_row[k] = s_row[n - 1];
+                        --n;
+                        __syncwarp();
+                    }
+                }
+                const uint4* srow4 = reinterpret_cast<const uint4*>(s_row);
+                uint4* grow4 = reinterpret_cast<uint4*>(entries + (size_t)gi * cap);
+                for (int k = lane; k * 8 < n; k += 32) grow4[k] = srow4[k];
+                if (lane == 0) {
+                    nl_count[gi] = n;
+                    if (found > cap) atomicOr(&ctl->err, CLB_EF_LIST_OVERFLOW);
+                    lmax = max(lmax, found); ltot += (unsigned long long)n;
+                }
             }
+            __syncwarp();
         }
     }
     if (lane == 0 && ltot) { atomicMax(&ctl->nl_max, lmax); atomicAdd(&ctl->nl_total, ltot); }

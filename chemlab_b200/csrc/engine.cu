@@ -41,6 +41,20 @@ int clb_engine::fail(int code, const char* fmt, ...) {
 
 static inline int ceil_div(long long a, int b) { return (int)((a + b - 1) / b); }
 
+// CLB_TRACE=1: host wall-clock per stage (each mark synchronises the stream; debugging aid only)
+struct ClbTrace {
+    bool on; cudaStream_t st; const char* tag; std::chrono::steady_clock::time_point t0; std::string log;
+    ClbTrace(cudaStream_t s, const char* tg, bool enable = true) : on(enable && getenv("CLB_TRACE") != nullptr), st(s), tag(tg), t0(std::chrono::steady_clock::now()) {}
+    void mark(const char* name) {
+        if (!on) return;
+        cudaStreamSynchronize(st);
+        auto t1 = std::chrono::steady_clock::now();
+        char b[128]; snprintf(b, sizeof(b), " %s=%.3fms", name, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        log += b; t0 = t1;
+    }
+    ~ClbTrace() { if (on && !log.empty()) fprintf(stderr, "[clb %s]%s\n", tag, log.c_str()); }
+};
+
 typedef void (*PairKernel)(ClbGrid, ClbGeom, ClbPairArgs);
 template <bool C, bool S, bool U>
 static PairKernel pair_kernel_split(int split) {
@@ -112,6 +126,8 @@ extern "C" int clb_create(clb_engine** out, int device, const double box[3], dou
     int mx = e->smem_optin;
     cudaFuncSetAttribute(k_build_lists<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
     cudaFuncSetAttribute(k_build_lists<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+    cudaFuncSetAttribute(k_build_lists<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(k_build_lists<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     for (int c = 0; c < 2; ++c) for (int sm = 0; sm < 2; ++sm) for (int ug = 0; ug < 2; ++ug) for (int sp = 0; sp < 3; ++sp)
     { cudaFuncSetAttribute(pair_kernel(c, sm, ug, 1 << sp), cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
           cudaFuncSetAttribute(pair_kernel(c, sm, ug, 1 << sp), cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); }
@@ -383,7 +399,7 @@ extern "C" int clb_set_exclusions(clb_engine* e, int64_t n, const int64_t* pairs
     std::sort(h.begin(), h.end(), [](const int2& x, const int2& y) { return x.x != y.x ? x.x < y.x : x.y < y.y; });
     h.erase(std::unique(h.begin(), h.end(), [](const int2& x, const int2& y) { return x.x == y.x && x.y == y.y; }), h.end());
     e->nexcl = (long long)h.size();
-    CK(e->excl_pairs.ensure(std::max<size_t>(h.size() * 2 + 1024, 1024)));
+    CK(e->excl_pairs.ensure(h.size() * 2 + (size_t)e->n + 1024));
     if (!h.empty()) CK(cudaMemcpy(e->excl_pairs.p, h.data(), h.size() * sizeof(int2), cudaMemcpyHostToDevice));
     e->excl_dirty = true; e->lists_valid = false;
     return CLB_OK;
@@ -415,13 +431,14 @@ __global__ void k_excl_expand(long long n, const int2* __restrict__ pairs, int* 
 int clb_engine::build_excl_csr() {
     clb_engine* e = this;
     size_t m = (size_t)nexcl * 2;
+    size_t mcap = std::max(m, excl_pairs.n * 2) + 16;     // sized for the capacity of the pair buffer: no regrowth per reaction pass
     CK(excl_off.ensure((size_t)n + 2));
-    CK(excl_ids.ensure(m + 16));
+    CK(excl_ids.ensure(mcap));
     if (m == 0) { CK(cudaMemsetAsync(excl_off.p, 0, ((size_t)n + 2) * 4, stream)); excl_dirty = false; return CLB_OK; }
-    CK(ekey.ensure(m)); CK(ekey2.ensure(m)); CK(eval.ensure(m));
+    CK(ekey.ensure(mcap)); CK(ekey2.ensure(mcap)); CK(eval.ensure(mcap));
     k_excl_expand<<<ceil_div(nexcl, 256), 256, 0, stream>>>(nexcl, excl_pairs.p, ekey.p, eval.p);
     size_t tb = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, tb, ekey.p, ekey2.p, eval.p, excl_ids.p, (int)m, 0, 32, stream);
+    cub::DeviceRadixSort::SortPairs(nullptr, tb, ekey.p, ekey2.p, eval.p, excl_ids.p, (int)mcap, 0, 32, stream);
     CK(cubtmp2.ensure(tb + 256));
     cub::DeviceRadixSort::SortPairs(cubtmp2.p, tb, ekey.p, ekey2.p, eval.p, excl_ids.p, (int)m, 0, 32, stream);
     k_lower_bounds<<<ceil_div(n + 1, 256), 256, 0, stream>>>((int)m, ekey2.p, n, excl_off.p);
@@ -681,7 +698,8 @@ int clb_engine::list_reserve(int li, long long need) {
     clb_engine* e = this;
     HostList& l = lists[li];
     if ((size_t)need * l.arity <= l.d.n) return CLB_OK;
-    size_t newcap = std::max<size_t>((size_t)need * l.arity * 3 / 2 + 1024, 4096);
+    // generous: cudaMalloc/cudaFree inside a run can stall for 100s of ms, so regrowth must be rare
+    size_t newcap = std::max<size_t>((size_t)need * l.arity * 2 + 1024, (size_t)std::max(n, 4096) * l.arity);
     DevBuf<int> nb;
     CK(nb.ensure(newcap));
     if (l.n) CK(cudaMemcpyAsync(nb.p, l.d.p, (size_t)l.n * l.arity * 4, cudaMemcpyDeviceToDevice, stream));
@@ -769,7 +787,10 @@ int clb_engine::build_term_csr() {
     CK(term_off.ensure((size_t)n + 2));
     CK(term_meta.ensure((size_t)total + 16)); CK(term_tuple.ensure((size_t)total + 16));
     if (total == 0) { CK(cudaMemsetAsync(term_off.p, 0, ((size_t)n + 2) * 4, stream)); terms_dirty = false; return CLB_OK; }
-    CK(tkey.ensure(total)); CK(tkey2.ensure(total)); CK(tval.ensure(total)); CK(tval2.ensure(total));
+    ClbTrace tr(stream, "term_csr");
+    { size_t want = tkey.p ? (size_t)total : (size_t)total * 2 + n;   // headroom: reactions append terms
+      CK(tkey.ensure(want)); CK(tkey2.ensure(want)); CK(tval.ensure(want)); CK(tval2.ensure(want)); CK(term_meta.ensure(want + 16)); CK(term_tuple.ensure(want + 16)); }
+    tr.mark("alloc");
     long long base = 0;
     for (size_t li = 0; li < lists.size(); ++li) {
         HostList& l = lists[li];
@@ -777,12 +798,17 @@ int clb_engine::build_term_csr() {
         k_term_expand<<<ceil_div(l.n, 256), 256, 0, stream>>>((int)l.n, l.arity, (int)li, l.d.p, (int)base, tkey.p, tval.p);
         base += l.n * l.arity;
     }
+    tr.mark("expand");
     size_t tb = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, tb, tkey.p, tkey2.p, tval.p, tval2.p, (int)total, 0, 32, stream);
+    cub::DeviceRadixSort::SortPairs(nullptr, tb, tkey.p, tkey2.p, tval.p, tval2.p, (int)tkey.n, 0, 32, stream);
     CK(cubtmp2.ensure(tb + 256));
+    tr.mark("tmpalloc");
     cub::DeviceRadixSort::SortPairs(cubtmp2.p, tb, tkey.p, tkey2.p, tval.p, tval2.p, (int)total, 0, 32, stream);
+    tr.mark("sort");
     k_term_unpack<<<ceil_div(total, 256), 256, 0, stream>>>((int)total, tval2.p, term_meta.p, term_tuple.p);
+    tr.mark("unpack");
     k_lower_bounds<<<ceil_div(n + 1, 256), 256, 0, stream>>>((int)total, tkey2.p, n, term_off.p);
+    tr.mark("bounds");
     CK(cudaGetLastError());
     terms_dirty = false;
     lists_ptr_dirty = true;
@@ -831,17 +857,14 @@ __global__ void k_ctl_after_rebuild(ClbCtl* c) { c->stall = 0; c->accum_maxdist 
 
 int clb_engine::setup_sync() {
     if (n <= 0) return fail(CLB_ERR_STATE, "no particles");
-    const bool trace = getenv("CLB_TRACE") != nullptr && (pots_dirty || excl_dirty || terms_dirty || topo_dirty || react_dirty);
-    auto tr0 = std::chrono::steady_clock::now();
-    struct Fin { bool on; cudaStream_t st; std::chrono::steady_clock::time_point t0; ~Fin() { if (on) { cudaStreamSynchronize(st); fprintf(stderr, "[clb setup_sync] %.3f ms\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count()); } } } fin{trace, stream, tr0};
-    if (pots_dirty) TRY(upload_potentials());
-    if (excl_dirty) { TRY(build_excl_csr()); lists_valid = false; }
-    if (terms_dirty) TRY(build_term_csr());
-    if (topo_dirty) TRY(build_topology());
-    if (react_dirty) TRY(upload_reactions());
+    ClbTrace tr(stream, "setup_sync", pots_dirty || excl_dirty || terms_dirty || topo_dirty || react_dirty);
+    if (pots_dirty) { TRY(upload_potentials()); tr.mark("pots"); }
+    if (excl_dirty) { TRY(build_excl_csr()); lists_valid = false; tr.mark("excl"); }
+    if (terms_dirty) { TRY(build_term_csr()); tr.mark("terms"); }
+    if (topo_dirty) { TRY(build_topology()); tr.mark("topo"); }
+    if (react_dirty) { TRY(upload_reactions()); tr.mark("react"); }
     return CLB_OK;
 }
-
 
 // launch geometry and shared-memory carve-up of the pair-force kernel; depends on the tile size of the
 // last rebuild AND on the potentials, so it is refreshed after either changes
@@ -882,8 +905,7 @@ int clb_engine::configure_pair_launch() {
 
 int clb_engine::rebuild() {
     clb_engine* e = this;
-    const bool trace = getenv("CLB_TRACE") != nullptr;
-    auto tr0 = std::chrono::steady_clock::now();
+    ClbTrace tr(stream, "rebuild");
     bucket_begin(CLB_B_NEIGH);
     if (nranks > 1) TRY(comm_migrate_and_ghosts());
     int ns = nstored;
@@ -896,12 +918,14 @@ int clb_engine::rebuild() {
     std::swap(pos.p, pos2.p); std::swap(vel.p, vel2.p); std::swap(slot.p, slot2.p);
     k_cell_start<<<ceil_div(ns + 1, 256), 256, 0, stream>>>(ns, key2.p, grid.ncell, cell_start.p);
     if (nranks > 1) TRY(comm_after_sort());
+    tr.mark("sort");
     // 2. tile statistics
     k_ctl_reset_stats<<<1, 1, 0, stream>>>(d_ctl);
     k_block_stats<<<ceil_div(grid.nblocks, 128), 128, 0, stream>>>(grid, cell_start.p, d_ctl);
     TRY(read_ctl());
     tile_max = h_ctl->tile_max; home_max = h_ctl->home_max;
     if (tile_max > 65535) return fail(CLB_ERR_UNSUPPORTED, "tile of %d particles exceeds 16-bit list entries: lower block_cells", tile_max);
+    tr.mark("stats");
     // 3. neighbour lists (retry with a larger capacity on overflow)
     if (nl_cap == 0 || nl_cap_user != nl_cap_user_seen) {
         double rho = (double)n / (box[0] * box[1] * box[2]);
@@ -914,14 +938,15 @@ int clb_engine::rebuild() {
     const unsigned long long rl2_lat = (unsigned long long)floor(geo.rl2 / geo.q2);
     for (int attempt = 0;; ++attempt) {
         CK(nl_entries.ensure((size_t)ncap * nl_cap));
-        size_t smem = (size_t)tile_max * (sizeof(int4) + sizeof(int)) + 16;
+        const int tile_cap = (tile_max + 3) & ~3;     // keeps the per-warp staging rows 16-byte aligned
+        size_t smem = (size_t)tile_cap * (sizeof(int4) + sizeof(int)) + (size_t)(threads / 32) * CLB_BUILD_G * nl_cap * sizeof(unsigned short) + 16;
         if ((int)smem > smem_optin) return fail(CLB_ERR_UNSUPPORTED, "tile needs %zu B of shared memory: lower block_cells", smem);
         int nb = 0;
         if (geo.cubic) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_build_lists<true>, threads, smem);
         else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_build_lists<false>, threads, smem);
         int gridsz = std::min(grid.nblocks, std::max(1, nb) * nsm);
-        if (geo.cubic) k_build_lists<true><<<gridsz, threads, smem, stream>>>(grid, geo, rl2_lat, cell_start.p, pos.p, slot.p, excl_off.p, excl_ids.p, nl_entries.p, nl_count.p, nl_cap, d_ctl);
-        else k_build_lists<false><<<gridsz, threads, smem, stream>>>(grid, geo, rl2_lat, cell_start.p, pos.p, slot.p, excl_off.p, excl_ids.p, nl_entries.p, nl_count.p, nl_cap, d_ctl);
+        if (geo.cubic) k_build_lists<true><<<gridsz, threads, smem, stream>>>(grid, geo, rl2_lat, cell_start.p, pos.p, slot.p, excl_off.p, excl_ids.p, nl_entries.p, nl_count.p, nl_cap, tile_cap, d_ctl);
+        else k_build_lists<false><<<gridsz, threads, smem, stream>>>(grid, geo, rl2_lat, cell_start.p, pos.p, slot.p, excl_off.p, excl_ids.p, nl_entries.p, nl_count.p, nl_cap, tile_cap, d_ctl);
         ++launches;
         TRY(read_ctl());
         if (!(h_ctl->err & CLB_EF_LIST_OVERFLOW)) break;
@@ -930,6 +955,7 @@ int clb_engine::rebuild() {
         k_ctl_reset_stats<<<1, 1, 0, stream>>>(d_ctl);
     }
     nl_max = h_ctl->nl_max; nl_total = h_ctl->nl_total;
+    tr.mark("build");
     // 4. pair-force launch configuration
     TRY(configure_pair_launch());
     // 5. bonded memberships -> sorted indices
@@ -939,7 +965,7 @@ int clb_engine::rebuild() {
     launches += 8;
     lists_valid = true; forces_valid = false;
     ++nrebuild;
-    if (trace) { cudaStreamSynchronize(stream); fprintf(stderr, "[clb rebuild] %.3f ms step=%lld\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tr0).count(), (long long)step); }
+    tr.mark("terms");
     bucket_end(CLB_B_NEIGH);
     return CLB_OK;
 }

@@ -105,6 +105,9 @@ int clb_engine::upload_reactions() {
         rd->slot_arrays_init = true;
     }
     CK(cudaStreamSynchronize(stream));
+    // lists that reactions append to (bond targets, registered angle/dihedral lists): capacity up front
+    for (auto& r : reactions) TRY(list_reserve(r.list, lists[r.list].n + 1));
+    for (auto& g : tmregs) TRY(list_reserve(g.list, lists[g.list].n + 1));
     react_dirty = false;
     return CLB_OK;
 }
@@ -170,23 +173,9 @@ int clb_engine::update_mixing() {
 
 // One ChemicalReaction::React pass at the current state; the caller has made `step` the number of
 // completed steps (RNG key).
-#include <chrono>
-struct StageTrace {
-    bool on; cudaStream_t st; std::chrono::steady_clock::time_point t0; std::string log;
-    StageTrace(cudaStream_t s) : on(getenv("CLB_TRACE") != nullptr), st(s), t0(std::chrono::steady_clock::now()) {}
-    void mark(const char* name) {
-        if (!on) return;
-        cudaStreamSynchronize(st);
-        auto t1 = std::chrono::steady_clock::now();
-        char b[128]; snprintf(b, sizeof(b), " %s=%.3fms", name, std::chrono::duration<double, std::milli>(t1 - t0).count());
-        log += b; t0 = t1;
-    }
-    ~StageTrace() { if (on) fprintf(stderr, "[clb react]%s\n", log.c_str()); }
-};
-
 int clb_engine::react_pass(int64_t* events_out) {
     clb_engine* e = this;
-    StageTrace tr(stream);
+    ClbTrace tr(stream, "react");
     if (events_out) *events_out = 0;
     if (reactions.empty()) return CLB_OK;
     bucket_begin(CLB_B_REACT);
@@ -195,7 +184,7 @@ int clb_engine::react_pass(int64_t* events_out) {
     ReactDev& R = *rd;
     ++nreact_pass;
     // 1. candidate scan (retry on buffer overflow)
-    if (R.candcap == 0) { R.candcap = std::max<size_t>(4096, (size_t)n / 4); CK(R.cands.ensure(R.candcap)); }
+    if (R.candcap == 0) { R.candcap = std::max<size_t>(4096, (size_t)n * 2); CK(R.cands.ensure(R.candcap)); }
     size_t smem = (size_t)tile_max * (sizeof(int4) + sizeof(int)) + 16;
     int nb = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_react_scan, 256, smem);
@@ -219,12 +208,13 @@ int clb_engine::react_pass(int64_t* events_out) {
     int nev = 0;
     if (nc > 0) {
         // 2. canonical order (A, B, r)
-        CK(R.cands_sorted.ensure(nc)); CK(R.ckey.ensure(nc)); CK(R.ckey2.ensure(nc)); CK(R.cval.ensure(nc)); CK(R.cval2.ensure(nc));
-        CK(R.alive.ensure(nc)); CK(R.surv.ensure(nc)); CK(R.status.ensure(nc)); CK(R.ev.ensure(nc)); CK(R.erank.ensure(nc)); CK(R.iota.ensure(nc));
+        { size_t cc = R.candcap;
+          CK(R.cands_sorted.ensure(cc)); CK(R.ckey.ensure(cc)); CK(R.ckey2.ensure(cc)); CK(R.cval.ensure(cc)); CK(R.cval2.ensure(cc));
+          CK(R.alive.ensure(cc)); CK(R.surv.ensure(cc)); CK(R.status.ensure(cc)); CK(R.ev.ensure(cc)); CK(R.erank.ensure(cc)); CK(R.iota.ensure(cc)); }
         int g1 = ceil_div(nc, 256);
         k_cand_keys<<<g1, 256, 0, stream>>>((int)nc, R.cands.p, R.ckey.p, R.cval.p);
         size_t tb = 0;
-        cub::DeviceRadixSort::SortPairs(nullptr, tb, R.ckey.p, R.ckey2.p, R.cval.p, R.cval2.p, (int)nc, 0, 64, stream);
+        cub::DeviceRadixSort::SortPairs(nullptr, tb, R.ckey.p, R.ckey2.p, R.cval.p, R.cval2.p, (int)R.candcap, 0, 64, stream);
         CK(cubtmp2.ensure(tb + 256));
         cub::DeviceRadixSort::SortPairs(cubtmp2.p, tb, R.ckey.p, R.ckey2.p, R.cval.p, R.cval2.p, (int)nc, 0, 64, stream);
         k_cand_gather<<<g1, 256, 0, stream>>>((int)nc, R.cval2.p, R.cands.p, R.cands_sorted.p, R.alive.p);
