@@ -364,6 +364,137 @@ __global__ void __launch_bounds__(512) k_pair_forces(ClbGrid g, ClbGeom geo, Clb
 }
 
 // ------------------------------------------------------------------------------------------
+// Branch-free variant for systems whose pair potentials are ALL tabulated (every shipped chemlab
+// example but atrp_lj).  The 8 entries of a batch are evaluated as straight-line code without any
+// divergent branch (cutoff and list-tail handled by selects), so the compiler interleaves the eight
+// independent fp64 dependency chains -> instruction-level parallelism instead of more resident warps.
+template <bool CUBIC, bool TABS_SMEM, bool UGRID, int SPLIT>
+__global__ void __launch_bounds__(512) k_pair_forces_tab(ClbGrid g, ClbGeom geo, ClbPairArgs A) {
+    if (*(volatile int*)&A.ctl->stall) return;
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ int s_off[CLB_TILE_CELLS + 1];
+    __shared__ int s_src[CLB_TILE_CELLS];
+    const int ntp = A.ntypes * A.ntypes;
+    ClbPairDesc* s_pd = reinterpret_cast<ClbPairDesc*>(smem);
+    double2* s_lj = reinterpret_cast<double2*>(s_pd + ntp);
+    ClbTabMeta* s_tm = reinterpret_cast<ClbTabMeta*>(s_lj + ntp);
+    double2* s_rows = reinterpret_cast<double2*>(s_tm + A.ntabs);
+    double* s_red = reinterpret_cast<double*>(s_rows + (TABS_SMEM ? A.nrows_total : 0));
+    int4* s_pos = reinterpret_cast<int4*>(s_red + (SPLIT - 1) * 3 * A.npw * 32);
+    for (int i = threadIdx.x; i < ntp; i += blockDim.x) s_pd[i] = A.pdesc[i];
+    for (int i = threadIdx.x; i < A.ntabs; i += blockDim.x) s_tm[i] = A.tmeta[i];
+    if (TABS_SMEM) for (int i = threadIdx.x; i < A.nrows_total; i += blockDim.x) s_rows[i] = __ldg(A.trows + i);
+    const double2* rows = TABS_SMEM ? s_rows : A.trows;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int sg = SPLIT > 1 ? warp / A.npw : 0;
+    const int wp = SPLIT > 1 ? warp - sg * A.npw : warp;
+    const int nhpass = A.npw * 32;
+    const double u_invdx = A.ugrid.invdx, u_ct = A.ugrid.c_t;
+    const unsigned u_nm1 = (unsigned)A.ugrid.n - 1u;
+    unsigned err = 0;
+    for (int b = blockIdx.x; b < g.nblocks; b += gridDim.x) {
+        TileCtx t;
+        tile_geometry(g, b, t);
+        __syncthreads();
+        tile_offsets(g, t, A.cell_start, s_off, s_src);
+        tile_stage(t, s_off, s_src, A.pos, s_pos, nullptr, nullptr, nullptr);
+        __syncthreads();
+        for (int p0 = 0; p0 < t.nh; p0 += nhpass) {
+            const int pl = wp * 32 + lane;
+            const int p = p0 + pl;
+            const bool act = p < t.nh;
+            const int gi = t.hs + (act ? p : 0);
+            const int4 pi = __ldg(A.pos + gi);
+            const unsigned pix = (unsigned)pi.x + 0x80000000u, piy = (unsigned)pi.y + 0x80000000u, piz = (unsigned)pi.z + 0x80000000u;
+            const int cnt = act ? __ldg(A.nl_count + gi) : 0;
+            const int trow = pw_type(pi.w) * A.ntypes;
+            const uint4* row = reinterpret_cast<const uint4*>(A.entries + (size_t)gi * A.cap);
+            const int nb = (cnt + 7) >> 3;
+            double ax = 0.0, ay = 0.0, az = 0.0;
+            uint4 ev = make_uint4(0, 0, 0, 0);
+            if (sg < nb) ev = __ldg(row + sg);
+#pragma unroll 1
+            for (int bi = sg; bi < nb; bi += SPLIT) {
+                const uint4 cur = ev;
+                if (bi + SPLIT < nb) ev = __ldg(row + bi + SPLIT);
+                const int ne = cnt - bi * 8;                      // >= 1; entries beyond ne are stale
+                const unsigned wds[4] = {cur.x, cur.y, cur.z, cur.w};
+                // two entries per stage, written stage-major so that the two fp64 chains interleave
+#pragma unroll
+                for (int w = 0; w < 4; ++w) {
+                    bool live[2], in[2];
+                    unsigned e[2], idc[2];
+                    int4 pj[2];
+                    ClbPairDesc pd[2];
+                    double dx[2], dy[2], dz[2], r2[2], y[2], uu[2], ti[2], bfrac[2], fr[2];
+                    double2 rw[2];
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        live[q] = (2 * w + q) < ne;
+                        e[q] = q ? (wds[w] >> 16) : (wds[w] & 0xffffu);
+                        e[q] = live[q] ? e[q] : 0u;
+                        pj[q] = s_pos[e[q]];
+                    }
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        dx[q] = __hiloint2double(0x43300000, (int)(pix - (unsigned)pj[q].x)) - 4503601774854144.0;
+                        dy[q] = __hiloint2double(0x43300000, (int)(piy - (unsigned)pj[q].y)) - 4503601774854144.0;
+                        dz[q] = __hiloint2double(0x43300000, (int)(piz - (unsigned)pj[q].z)) - 4503601774854144.0;
+                        if (!CUBIC) { dx[q] *= geo.q[0]; dy[q] *= geo.q[1]; dz[q] *= geo.q[2]; }
+                        pd[q] = s_pd[trow + pw_type(pj[q].w)];
+                    }
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        r2[q] = dx[q] * dx[q] + dy[q] * dy[q] + dz[q] * dz[q];
+                        in[q] = live[q] && (r2[q] <= pd[q].rc2);   // rc2 < 0: no potential for this type pair
+                        r2[q] = in[q] ? r2[q] : 1.0;                // keeps the masked lanes' arithmetic finite
+                        y[q] = rsqrt_seed(r2[q]);
+                    }
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        const double h = r2[q] * y[q];
+                        const double ee = fma(-h, y[q], 1.0);
+                        y[q] = fma(0.5 * y[q], ee, y[q]);
+                    }
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        const double r = r2[q] * y[q];
+                        double invdx, c_t; unsigned nm1; int off;
+                        if (UGRID) { invdx = u_invdx; c_t = u_ct; nm1 = u_nm1; off = pd[q].tab; }
+                        else { const ClbTabMeta tm = s_tm[pd[q].tab]; invdx = tm.invdx; c_t = tm.c_t; nm1 = (unsigned)tm.n - 1u; off = tm.off; }
+                        uu[q] = fma(r, invdx, c_t);
+                        ti[q] = uu[q] + 6755399441055744.0;
+                        const unsigned idx = (unsigned)__double2loint(ti[q]);
+                        idc[q] = min(idx, nm1);                     // row n-1 = {f[n-1], 0}: r == table end is exact
+                        if (in[q] && idx > nm1) err |= CLB_EF_TABLE_RANGE;   // predicated OR, no divergence (U12)
+                        rw[q] = rows[off + (in[q] ? idc[q] : 0u)];
+                    }
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        bfrac[q] = uu[q] - (ti[q] - 6755399441055744.0);
+                        fr[q] = fma(bfrac[q], rw[q].y, rw[q].x) * y[q];
+                        fr[q] = in[q] ? fr[q] : 0.0;
+                    }
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) { ax = fma(fr[q], dx[q], ax); ay = fma(fr[q], dy[q], ay); az = fma(fr[q], dz[q], az); }
+                }
+            }
+            if (SPLIT > 1) {
+                if (sg > 0) { double* r = s_red + ((sg - 1) * nhpass + pl) * 3; r[0] = ax; r[1] = ay; r[2] = az; }
+                __syncthreads();
+                if (sg == 0) {
+#pragma unroll
+                    for (int s2 = 1; s2 < SPLIT; ++s2) { const double* r = s_red + ((s2 - 1) * nhpass + pl) * 3; ax += r[0]; ay += r[1]; az += r[2]; }
+                }
+            }
+            if (act && sg == 0) { A.force[gi] = ax; A.force[gi + A.fstride] = ay; A.force[gi + 2 * A.fstride] = az; }
+            if (SPLIT > 1) __syncthreads();
+        }
+    }
+    if (err) atomicOr(&A.ctl->err, err);
+}
+
+// ------------------------------------------------------------------------------------------
 // Pair energy of one interaction handle (analysis.PotentialEnergy): fp64 throughout, each pair
 // visited twice (full list) -> factor 1/2.  Per-block partial sums are reduced in a fixed order
 // by k_sum_partials, so the result is bit-reproducible.

@@ -60,6 +60,16 @@ template <bool C, bool S, bool U>
 static PairKernel pair_kernel_split(int split) {
     switch (split) { case 1: return k_pair_forces<C, S, U, 1>; case 2: return k_pair_forces<C, S, U, 2>; default: return k_pair_forces<C, S, U, 4>; }
 }
+template <bool C, bool S, bool U>
+static PairKernel pair_kernel_tab_split(int split) {
+    switch (split) { case 1: return k_pair_forces_tab<C, S, U, 1>; case 2: return k_pair_forces_tab<C, S, U, 2>; default: return k_pair_forces_tab<C, S, U, 4>; }
+}
+static PairKernel pair_kernel_tab(int cubic, int smem, int ugrid, int split) {
+    if (cubic) { if (smem) return ugrid ? pair_kernel_tab_split<true, true, true>(split) : pair_kernel_tab_split<true, true, false>(split);
+                 return ugrid ? pair_kernel_tab_split<true, false, true>(split) : pair_kernel_tab_split<true, false, false>(split); }
+    if (smem) return ugrid ? pair_kernel_tab_split<false, true, true>(split) : pair_kernel_tab_split<false, true, false>(split);
+    return ugrid ? pair_kernel_tab_split<false, false, true>(split) : pair_kernel_tab_split<false, false, false>(split);
+}
 static PairKernel pair_kernel(int cubic, int smem, int ugrid, int split) {
     if (cubic) { if (smem) return ugrid ? pair_kernel_split<true, true, true>(split) : pair_kernel_split<true, true, false>(split);
                  return ugrid ? pair_kernel_split<true, false, true>(split) : pair_kernel_split<true, false, false>(split); }
@@ -129,7 +139,9 @@ extern "C" int clb_create(clb_engine** out, int device, const double box[3], dou
     cudaFuncSetAttribute(k_build_lists<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     cudaFuncSetAttribute(k_build_lists<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     for (int c = 0; c < 2; ++c) for (int sm = 0; sm < 2; ++sm) for (int ug = 0; ug < 2; ++ug) for (int sp = 0; sp < 3; ++sp)
-    { cudaFuncSetAttribute(pair_kernel(c, sm, ug, 1 << sp), cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+    { cudaFuncSetAttribute(pair_kernel_tab(c, sm, ug, 1 << sp), cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+          cudaFuncSetAttribute(pair_kernel_tab(c, sm, ug, 1 << sp), cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+          cudaFuncSetAttribute(pair_kernel(c, sm, ug, 1 << sp), cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
           cudaFuncSetAttribute(pair_kernel(c, sm, ug, 1 << sp), cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); }
     cudaFuncSetAttribute(k_pair_energy<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
     cudaFuncSetAttribute(k_pair_energy<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
@@ -171,6 +183,7 @@ extern "C" int clb_set_option(clb_engine* e, const char* name, double v) {
     else if (s == "pair_event_timing") e->pair_event_timing = (int)v;
     else if (s == "pair_split") { e->pair_split_user = (int)v; if (e->lists_valid) return e->configure_pair_launch(); }
     else if (s == "build_threads") e->build_threads = (int)v;
+    else if (s == "pair_branchfree") { e->branchfree_user = (int)v; if (e->lists_valid) return e->configure_pair_launch(); }
     else return e->fail(CLB_ERR_ARG, "unknown option %s", name);
     return CLB_OK;
 }
@@ -606,6 +619,8 @@ int clb_engine::upload_potentials() {
     }
     // uniform-grid fast path: every table on the same (x0, dx, n) -> grid constants travel as kernel
     // arguments and the descriptor carries the first row directly
+    all_tab = !tm.empty();
+    for (auto& d : pd) if (d.kind == 2) all_tab = 0;
     ugrid_on = !tm.empty();
     for (size_t k = 1; k < tm.size(); ++k) if (tm[k].n != tm[0].n || tm[k].x0 != tm[0].x0 || tm[k].dx != tm[0].dx) ugrid_on = 0;
     if (!tm.empty()) ugrid_meta = tm[0];
@@ -868,6 +883,10 @@ int clb_engine::setup_sync() {
 
 // launch geometry and shared-memory carve-up of the pair-force kernel; depends on the tile size of the
 // last rebuild AND on the potentials, so it is refreshed after either changes
+PairKernel clb_engine_pair_fn(const clb_engine* e, int in_smem, int split) {
+    return (e->all_tab && e->branchfree_user) ? pair_kernel_tab(e->geo.cubic, in_smem, e->ugrid_on, split) : pair_kernel(e->geo.cubic, in_smem, e->ugrid_on, split);
+}
+
 int clb_engine::configure_pair_launch() {
     // warps that cover the home particles of a block: mean + 3 sigma (Poisson); rarer, fuller blocks take a second pass
     const double mean_home = (double)(own1 - own0) / std::max(1, grid.nblocks);
@@ -886,11 +905,13 @@ int clb_engine::configure_pair_launch() {
         size_t smem = fixed + (in_smem ? rows : 0) + tile + (size_t)(sp - 1) * 3 * npw * 32 * sizeof(double);
         if ((int)smem > smem_optin) break;
         int nb = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, pair_kernel(geo.cubic, in_smem, ugrid_on, sp), npw * sp * 32, smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, clb_engine_pair_fn(this, in_smem, sp), npw * sp * 32, smem);
         double w = (double)nb * npw * sp;
         if (w > best_warps * 1.05) { best_warps = w; best_split = sp; }
     }
-    pair_split = pair_split_user > 0 ? pair_split_user : best_split;
+    // measured on B200 (1M-bead melt): the kernel is shared-memory-pipe bound, extra split warps do not pay -> default 1
+    (void)best_split;
+    pair_split = pair_split_user > 0 ? pair_split_user : 1;
     if (npw * pair_split * 32 > 512) pair_split = std::max(1, 512 / (npw * 32));
     if (pair_split == 3) pair_split = 2;
     pair_npw = npw;
@@ -898,7 +919,7 @@ int clb_engine::configure_pair_launch() {
     pair_smem = (int)(fixed + (in_smem ? rows : 0) + tile + (size_t)(pair_split - 1) * 3 * npw * 32 * sizeof(double));
     if (pair_smem > smem_optin) return fail(CLB_ERR_UNSUPPORTED, "pair kernel needs %d B of shared memory: lower block_cells", pair_smem);
     int nb = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, pair_kernel(geo.cubic, tabs_smem, ugrid_on, pair_split), pair_threads, pair_smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, clb_engine_pair_fn(this, tabs_smem, pair_split), pair_threads, pair_smem);
     pair_grid = std::min(grid.nblocks, std::max(1, nb) * nsm);
     return CLB_OK;
 }
@@ -989,7 +1010,7 @@ void clb_engine::enqueue_forces() {
         A.pdesc = d_pd.p; A.plj = d_plj.p; A.tmeta = d_tm.p; A.trows = d_frows.p; A.force = force.p; A.ctl = d_ctl;
         A.cap = nl_cap; A.ntypes = nt_dev; A.ntabs = ntabs_dev; A.nrows_total = nrows_dev; A.fstride = ncap; A.npw = pair_npw;
         A.ugrid = ugrid_meta;
-        pair_kernel(geo.cubic, tabs_smem, ugrid_on, pair_split)<<<pair_grid, pair_threads, pair_smem, stream>>>(grid, geo, A);
+        clb_engine_pair_fn(this, tabs_smem, pair_split)<<<pair_grid, pair_threads, pair_smem, stream>>>(grid, geo, A);
     }
     if (pair_event_timing) cudaEventRecord(next_pair_event(), stream);
     bucket_end(CLB_B_PAIR);

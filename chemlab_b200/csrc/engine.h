@@ -89,7 +89,7 @@ struct clb_engine {
     int nl_cap = 0, nl_cap_user = 0, nl_cap_user_seen = 0, nl_max = 0, tile_max = 0, home_max = 0;
     unsigned long long nl_total = 0, last_interacting = 0;
     int pair_grid = 0, pair_threads = 128, pair_smem = 0, tabs_smem = 1, pair_split = 1, pair_split_user = 0, pair_npw = 1, build_threads = 256;
-    int ugrid_on = 0;
+    int ugrid_on = 0, all_tab = 0, branchfree_user = 1;
     ClbTabMeta ugrid_meta;
     bool lists_valid = false, forces_valid = false;
 
