@@ -1,0 +1,150 @@
+"""espressopp.analysis.* observables chemlab registers with its SystemMonitor (src/start_simulation.py:446-569)."""
+import numpy as np
+
+from ._context import not_in_scope
+
+
+class _Obs:
+    def __init__(self, system, *a, **k):
+        self._system = system
+        self._ctx = system._ctx
+
+
+class Temperature(_Obs):
+    """analysis.Temperature(system).compute(): T = 2 Ekin / (3 N) in energy units (kB folded into the thermostat value)."""
+    def add_type(self, t):
+        pass
+
+    def compute(self):
+        return float(self._ctx.require_engine().kinetics()[1])
+
+
+class KineticEnergy(_Obs):
+    def __init__(self, system, temperature=None):
+        super().__init__(system)
+
+    def compute(self):
+        return float(self._ctx.require_engine().kinetics()[0])
+
+
+class PotentialEnergy(_Obs):
+    """analysis.PotentialEnergy(system, interaction): src/start_simulation.py:470-480."""
+    def __init__(self, system, interaction):
+        super().__init__(system)
+        self._inter = interaction
+
+    def compute(self):
+        e = self._ctx.require_engine()
+        if getattr(self._inter, "_h", None) is None:
+            self._inter._attach(e)
+        return float(e.energy(self._inter._h))
+
+
+class NPart(_Obs):
+    def compute(self):
+        return len(self._ctx.pid)
+
+
+class MaxPID(_Obs):
+    def compute(self):
+        return max(self._ctx.pid)
+
+
+class _NEntries(_Obs):
+    def __init__(self, system, flist):
+        super().__init__(system)
+        self._list = flist
+
+    def compute(self):
+        return int(self._list.totalSize())
+
+
+NFixedPairListEntries = NFixedTripleListEntries = NFixedQuadrupleListEntries = _NEntries
+
+
+class NExcludeListEntries(_Obs):
+    def __init__(self, system, vl):
+        super().__init__(system)
+
+    def compute(self):
+        e = self._ctx.engine
+        return len(self._ctx.exclusions) if e is None else len(e.get_exclusions())
+
+
+class ChemicalConversion(_Obs):
+    """ChemicalConversion(system, type, total): N(type)/total (gromacs_topology.py:574-583; tools.py:102-180)."""
+    def __init__(self, system, type_id, total=None):
+        super().__init__(system)
+        self.type_id, self.total = int(type_id), (float(total) if total else 1.0)
+
+    def compute(self):
+        return self._ctx.require_engine().count_type(self.type_id) / self.total
+
+
+class ChemicalConversionTypeState(_Obs):
+    def __init__(self, system, type_id, state, total=None):
+        super().__init__(system)
+        self.type_id, self.state, self.total = int(type_id), int(state), (float(total) if total else 1.0)
+
+    def compute(self):
+        return self._ctx.require_engine().count_type(self.type_id, self.state) / self.total
+
+
+class CMVelocity(_Obs):
+    """analysis.CMVelocity(system).reset(): removes the centre-of-mass velocity (src/start_simulation.py:680-682)."""
+    def compute(self):
+        e = self._ctx.require_engine()
+        g = e.get_particles(fields=("vel", "mass"))
+        return tuple((g["vel"] * g["mass"][:, None]).sum(0) / g["mass"].sum())
+
+    def reset(self):
+        e = self._ctx.require_engine()
+        g = e.get_particles(fields=("vel", "mass"))
+        v = g["vel"] - (g["vel"] * g["mass"][:, None]).sum(0) / g["mass"].sum()
+        e.set_velocities(v)
+
+
+class SystemMonitorOutputCSV:
+    def __init__(self, filename, delimiter="\t"):
+        self.filename, self.delimiter = filename, delimiter
+        self._fh = None
+
+    def write(self, header, row):
+        if self._fh is None:
+            self._fh = open(self.filename, "w")
+            self._fh.write(self.delimiter.join(header) + "\n")
+        self._fh.write(self.delimiter.join("%.10g" % v if isinstance(v, float) else str(v) for v in row) + "\n")
+        self._fh.flush()
+
+
+class SystemMonitor:
+    """SystemMonitor(system, integrator, output) + add_observable / info / dump: src/start_simulation.py:446-569,729."""
+    def __init__(self, system, integrator_, output):
+        self._system, self._integrator, self._out = system, integrator_, output
+        self._obs = []
+        self.potential_energy = 0.0
+        self._last = None
+
+    def add_observable(self, name, obs, visible=True):
+        self._obs.append((name, obs, visible))
+
+    def perform_action(self):
+        step = self._integrator.step
+        vals = [obs.compute() for _, obs, _ in self._obs]
+        self.potential_energy = float(sum(v for (n, o, _), v in zip(self._obs, vals) if isinstance(o, PotentialEnergy)))
+        self._last = (step, vals)
+        self._out.write(["step", "time"] + [n for n, _, _ in self._obs], [step, step * self._integrator.dt] + vals)
+
+    dump = perform_action
+
+    def info(self):
+        if self._last is None:
+            return
+        step, vals = self._last
+        cols = ["%s=%.6g" % (n, v) for (n, _, vis), v in zip(self._obs, vals) if vis]
+        print("step %d: %s" % (step, " ".join(cols)))
+
+
+for _n in ("Pressure", "BoxSize", "ResolutionFixedPairList", "NParticlePairScalingEntries", "NumFixDistances", "MaxForce"):
+    globals()[_n] = not_in_scope("analysis." + _n)
+del _n

@@ -1,0 +1,93 @@
+"""Host-side driver layer (no GPU needed): the reference's own two unit tests re-expressed, the shipped exclusion
+list of examples/atrp_lj as a known answer for exclusion generation, type-id assignment from the shipped run log,
+and the espressopp surface's constructibility rules."""
+import os
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = os.path.join(HERE, "golden")
+
+
+def test_parse_exchange_reaction():
+    # src/tests/test_reaction_parser.py:29-51
+    from chemlab_b200.chemlab import reaction_parser as rp
+    r, kind = rp.parse_exchange_equation("C(0,1):E(0,1) + W(0,1) -> A(1):Z(1) + E(1)")
+    assert kind == rp.REACTION_EXCHANGE
+    assert (r["type_1"]["name"], r["type_1"]["new_type"], r["type_1"]["min"], r["type_1"]["max"], r["type_1"]["delta"]) == ("C", "A", "0", "1", "1")
+    assert (r["type_2"]["name"], r["type_2"]["new_type"], r["type_2"]["min"], r["type_2"]["max"], r["type_2"]["delta"]) == ("E", "E", "0", "1", "1")
+    assert (r["type_3"]["name"], r["type_3"]["new_type"], r["type_3"]["min"], r["type_3"]["max"], r["type_3"]["delta"]) == ("W", "Z", "0", "1", "1")
+
+
+def test_replicated_molecules():
+    # src/tests/test_topology_reader.py:34-69 on the reference's own fixture (topol.top + diol_cg.itp + ter_cg.itp)
+    from chemlab_b200.chemlab.gromacs_topology import GromacsTopology
+    gt = GromacsTopology(os.path.join(GOLD, "parser", "topol.top"), generate_exclusions=True).read()
+    for name, store in (("atoms", gt.atoms), ("bonds", gt.bonds), ("angles", gt.angles), ("dihedrals", gt.dihedrals), ("pairs", gt.pairs)):
+        expected = sum(n * len(gt.gt.molecules_data[mol].get(name, [])) for mol, n in gt.gt.molecules)
+        assert len(store) == expected, name
+    assert len(gt.atoms) > 0 and len(gt.bonds) > 0
+
+
+def test_atrp_lj_topology_and_exclusions_match_shipped_artefacts():
+    from chemlab_b200.chemlab.gromacs_topology import GromacsTopology, gen_particle_list
+    from chemlab_b200.chemlab.files_io import GROFile
+    d = os.path.join(GOLD, "atrp_lj")
+    gt = GromacsTopology(os.path.join(d, "topol.top")).read()
+    # counts logged by the reference run (examples/atrp_lj/single:37,43-45): 6000 particles, 4000 bonds, 2000 angles
+    assert (len(gt.atoms), len(gt.bonds), len(gt.angles)) == (6000, 4000, 2000)
+    # exclusion_topol.list is what src/start_simulation.py:182-187 wrote from gt.exclusions
+    want = sorted(tuple(int(x) for x in l.split()) for l in open(os.path.join(d, "exclusion_topol.list")) if l.strip())
+    assert sorted(gt.exclusions) == want
+    # type ids: MA ML first (molecule order), then the remaining [atomtypes] (run log :199-205: MA0 ML1 DA2 FA3 PA4 RA5 PL6)
+    ids = gt.atomsym_atomtype
+    assert ids["MA"] == 0 and ids["ML"] == 1 and set(ids) == {"MA", "ML", "DA", "FA", "PA", "RA", "PL"} and sorted(ids.values()) == list(range(7))
+    conf = GROFile(os.path.join(d, "conf.gro")); conf.read()
+    assert len(conf.atoms) == 6000 and abs(conf.box[0] - 28.11442) < 1e-5
+    props, rows = gen_particle_list(conf, gt)
+    assert props[:3] == ["id", "type", "pos"] and len(rows) == 6000 and rows[0][0] == 1
+    # [atomstate] gives the initial chemical state per type (files_io.py:682-687)
+    assert {r[6] for r in rows if r[1] == ids["MA"]} == {gt.gt.atomtypes["MA"].get("state", 0)}
+
+
+def test_arg_file_convention(tmp_path):
+    from chemlab_b200.chemlab import app_args
+    f = tmp_path / "params"
+    f.write_text("conf=conf.gro\ntop=topol.top\n# comment\nrun=2000 ; trailing\nskin=0.4\nkb=1.0\nreactions=atrp.cfg\n")
+    a = app_args._args().parse_args(["@%s" % f])
+    assert a.run == 2000 and float(a.skin) == 0.4 and a.kb == 1.0 and a.reactions == "atrp.cfg" and a.thermostat == "lv"
+    shipped = app_args._args().parse_args(["@%s" % os.path.join(GOLD, "atrp_lj", "params")])
+    assert shipped.lj_cutoff == 2.5 and shipped.dt == 0.0025 and shipped.maximum_conversion == "PL(1):1200:2000"
+
+
+def test_reaction_config_of_atrp_lj():
+    from chemlab_b200.chemlab import reaction_parser as rp
+    c = rp.parse_config(os.path.join(GOLD, "atrp_lj", "atrp.cfg"))
+    assert c["general"]["interval"] == 200 and c["general"]["nearest"] is True      # bool('0') quirk preserved
+    g = c["reactions"]["reaction_1"]
+    assert g["potential"] == "Harmonic" and g["potential_options"] == {"K": "30.0", "r0": "0.97"}
+    assert [r["equation"].split()[0] for r in g["reaction_list"]] == ["FA(3,", "DA(3,", "FA(3,", "DA(3,"]
+    assert g["extensions"]["atrp"]["class"] == "ATRPActivator" and g["extensions"]["change_neighbour_type"]["class"] == "ChangeNeighboursProperty"
+
+
+def test_out_of_scope_names_are_constructible_but_refuse_to_run():
+    import chemlab_b200.espressopp as es
+    s = es.System()
+    s.rng = es.esutil.RNG(1); s.bc = es.bc.OrthorhombicBC(s.rng, (10, 10, 10)); s.skin = 0.3
+    s.storage = es.storage.DomainDecomposition(s, (1, 1, 1), (3, 3, 3))
+    integ = es.integrator.VelocityVerlet(s)
+    vl = es.VerletList(s, cutoff=2.5, exclusionlist=es.DynamicExcludeList(integ, []))
+    capped = es.interaction.VerletListTabulatedCapped(vl)            # gromacs_topology.py:513 builds it unconditionally
+    with pytest.raises(NotImplementedError):
+        capped.setPotential(type1=0, type2=0, potential=None)
+    with pytest.raises(NotImplementedError):
+        es.io.DumpH5MD(s, integ).dump()
+
+
+def test_molecule_exclusions_nrexcl():
+    from chemlab_b200.chemlab.gromacs_topology import GromacsTopology as G
+    chain = [(1, 2), (2, 3), (3, 4), (4, 5)]
+    assert G.molecule_exclusions(chain, 1) == {(1, 2), (2, 3), (3, 4), (4, 5)}
+    assert G.molecule_exclusions(chain, 2) == {(1, 2), (2, 3), (3, 4), (4, 5), (1, 3), (2, 4), (3, 5)}
+    assert (1, 4) in G.molecule_exclusions(chain, 3) and (1, 5) not in G.molecule_exclusions(chain, 3)
