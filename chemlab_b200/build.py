@@ -15,20 +15,18 @@ def _newest_source():
 
 
 def nccl_flags():
-    """Locate the NCCL that torch bundles (same library torch.distributed uses)."""
+    """nccl.h is needed for the types only: libnccl is resolved with dlopen at clb_comm_init time
+    (csrc/engine_comm.inl), so the engine neither links against it nor needs it for single-GPU use."""
+    if os.path.exists("/usr/include/nccl.h"):
+        return ["-ldl"]
     try:
         import nvidia.nccl as m
-        base = os.path.dirname(m.__file__)
-        inc, lib = os.path.join(base, "include"), os.path.join(base, "lib")
+        inc = os.path.join(os.path.dirname(m.__file__), "include")
         if os.path.exists(os.path.join(inc, "nccl.h")):
-            so = [f for f in os.listdir(lib) if f.startswith("libnccl.so")]
-            if so:
-                return ["-I" + inc, "-L" + lib, "-l:" + so[0], "-Xlinker", "-rpath," + lib, "-DCLB_WITH_NCCL=1"]
+            return ["-I" + inc, "-ldl"]
     except Exception:
         pass
-    if os.path.exists("/usr/include/nccl.h"):
-        return ["-lnccl", "-DCLB_WITH_NCCL=1"]
-    return []
+    raise RuntimeError("nccl.h not found")
 
 
 def build(force=False, verbose=False):

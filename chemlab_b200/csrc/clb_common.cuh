@@ -18,7 +18,7 @@
 #define CLB_EF_TUPLE_OVERFLOW 16u
 #define CLB_EF_PARTNER_LOST 32u // bonded partner not resolvable (outside ghost layer)
 
-// pos.w packing: type in bits 0..7, chemical state in bits 8..23 (signed 16 bit), bit 31 = ghost
+// pos.w packing: type in bits 0..7, chemical state in bits 8..23 (signed 16 bit)
 __host__ __device__ inline int pw_type(int w) { return w & 0xff; }
 __host__ __device__ inline int pw_state(int w) { return (int)((int16_t)((w >> 8) & 0xffff)); }
 __host__ __device__ inline int pw_pack(int type, int state) { return (type & 0xff) | ((state & 0xffff) << 8); }
@@ -49,8 +49,10 @@ struct ClbGrid {
     int nbx;     // blocks per row
     int nblocks; // nbx * ncy * nczl
     int cz0, nczl; // owned z-plane range [cz0, cz0+nczl) of this rank (single GPU: 0, ncz)
-    int zoff;      // local plane index = (cz - zoff) mod ncz ; local planes = nczl + 2 ghosts when nranks>1
-    int nplanes;   // number of locally stored planes
+    int zoff;      // = cz0.  Local plane of global plane cz: l = (cz - zoff) mod ncz; owned planes are l in [0,nczl),
+                   // the upper ghost plane (cz0+nczl) is local plane nczl, the lower ghost plane (cz0-1, l = ncz-1) is
+                   // stored as local plane nczl+1 -> plane arithmetic is periodic modulo nplanes on every rank
+    int nplanes;   // number of locally stored planes: ncz (single GPU) or nczl + 2
     int ghost;     // 1 when ghost planes are present (multi-GPU)
 };
 
@@ -121,4 +123,11 @@ __device__ __forceinline__ double lat2d(int d) {
 __host__ __device__ __forceinline__ int wsub(int a, int b) { return (int)((unsigned)a - (unsigned)b); }
 __host__ __device__ __forceinline__ int wadd(int a, int b) { return (int)((unsigned)a + (unsigned)b); }
 __device__ __forceinline__ int wrapi(int c, int n) { return c < 0 ? c + n : (c >= n ? c - n : c); }
+// local plane index of global plane cz (see ClbGrid::zoff); planes that are neither owned nor ghost map to -1
+__device__ __forceinline__ int local_plane(const ClbGrid& g, int cz) {
+    if (!g.ghost) return cz;
+    int l = wrapi(cz - g.zoff, g.ncz);
+    if (l <= g.nczl) return l;
+    return l == g.ncz - 1 ? g.nczl + 1 : -1;
+}
 #endif

@@ -12,8 +12,10 @@ __global__ void k_cell_keys(int n, const int4* __restrict__ pos, ClbGrid g, int*
     int cx = __umulhi((unsigned)p.x, (unsigned)g.ncx);
     int cy = __umulhi((unsigned)p.y, (unsigned)g.ncy);
     int cz = __umulhi((unsigned)p.z, (unsigned)g.ncz);
-    int lz = g.ghost ? wrapi(cz - g.zoff, g.ncz) : cz;
-    key[i] = (lz * g.ncy + cy) * g.ncx + cx;
+    int lz = local_plane(g, cz);
+    // a particle outside the owned+ghost planes cannot occur between rebuilds (displacement < skin/2); park it in
+    // the last cell so that the sort stays well defined
+    key[i] = lz < 0 ? g.ncell - 1 : (lz * g.ncy + cy) * g.ncx + cx;
     val[i] = i;
 }
 __global__ void k_gather(int n, const int* __restrict__ perm, const int4* __restrict__ pos_in, const float4* __restrict__ vel_in,
@@ -44,14 +46,14 @@ __global__ void k_block_stats(ClbGrid g, const int* __restrict__ cell_start, Clb
     int row = b / g.nbx, bxi = b - row * g.nbx;
     int cx0 = bxi * g.bx, bxe = min(g.bx, g.ncx - cx0);
     int cy = row % g.ncy, zrow = row / g.ncy;
-    int lz = g.ghost ? zrow + 1 : zrow;
+    int lz = zrow;
     bool whole = bxe + 2 > g.ncx;
     int W = whole ? g.ncx : bxe + 2;
     int T = 0, cmax = 0;
     for (int k = 0; k < 9; ++k) {
         int dy = k % 3 - 1, dz = k / 3 - 1;
         int yy = wrapi(cy + dy, g.ncy);
-        int zz = g.ghost ? lz + dz : wrapi(lz + dz, g.ncz);
+        int zz = wrapi(lz + dz, g.nplanes);
         for (int m = 0; m < W; ++m) {
             int cx = whole ? m : wrapi(cx0 - 1 + m, g.ncx);
             int c = (zz * g.ncy + yy) * g.ncx + cx;

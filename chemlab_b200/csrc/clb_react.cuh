@@ -198,18 +198,22 @@ __global__ void __launch_bounds__(1024) k_resolve(int ns, const int* __restrict_
     if (threadIdx.x == 0) { ctl->nev = max_per_interval > 0 ? min(s_base, max_per_interval) : s_base; ctl->rounds = rounds; }
 }
 
-__device__ __forceinline__ void apply_props(const ClbChange& g, int idx, int s, int4* pos, float4* vel, double* charge) {
-    int w = pos[idx].w;
+// Particle properties during a reaction pass: the type|state word of EVERY particle lives in the replicated
+// per-slot array `wslot` (identical on all ranks, so every rank takes identical decisions); the copy inside
+// pos[].w, the mass (vel[].w) and the charge are updated when the particle is stored locally (idx >= 0).
+__device__ __forceinline__ void apply_props(const ClbChange& g, int idx, int s, int* wslot, int4* pos, float4* vel, double* charge) {
+    int w = wslot[s];
     if (pw_type(w) != g.old_type) return;
     int st = pw_state(w);
     if (g.state_mode == 1) st = g.state_value; else if (g.state_mode == 2) st += g.state_value;
-    pos[idx].w = pw_pack(g.new_type, st);
-    if (g.new_mass > 0) vel[idx].w = (float)g.new_mass;
+    w = pw_pack(g.new_type, st);
+    wslot[s] = w;
+    if (idx >= 0) { pos[idx].w = w; if (g.new_mass > 0) vel[idx].w = (float)g.new_mass; }
     if (g.new_q == g.new_q) charge[s] = g.new_q;
 }
 // phase 5: reactant changes (nb_level 0) in rule order, then state deltas; per-list bond ranks
 __global__ void k_apply_reactants(int nev, const int* __restrict__ ev, const ClbCand* __restrict__ c, const ClbReactSpec* __restrict__ specs,
-                                  const ClbChange* __restrict__ chg, int nchg, const int* __restrict__ id2idx, int4* pos, float4* vel,
+                                  const ClbChange* __restrict__ chg, int nchg, const int* __restrict__ id2idx, int* wslot, int4* pos, float4* vel,
                                   double* charge, unsigned long long* __restrict__ counters) {
     int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= nev) return;
@@ -219,12 +223,15 @@ __global__ void k_apply_reactants(int nev, const int* __restrict__ ev, const Clb
     for (int q = 0; q < nchg; ++q) {
         const ClbChange g = chg[q];
         if (g.reaction != x.r || g.nb_level != 0) continue;
-        if (g.side & 1) apply_props(g, ia, x.a, pos, vel, charge);
-        if (g.side & 2) apply_props(g, ib, x.b, pos, vel, charge);
+        if (g.side & 1) apply_props(g, ia, x.a, wslot, pos, vel, charge);
+        if (g.side & 2) apply_props(g, ib, x.b, wslot, pos, vel, charge);
     }
-    int wa = pos[ia].w, wb = pos[ib].w;
-    pos[ia].w = pw_pack(pw_type(wa), pw_state(wa) + r.delta_1);
-    pos[ib].w = pw_pack(pw_type(wb), pw_state(wb) + r.delta_2);
+    int wa = wslot[x.a], wb = wslot[x.b];
+    wa = pw_pack(pw_type(wa), pw_state(wa) + r.delta_1);
+    wb = pw_pack(pw_type(wb), pw_state(wb) + r.delta_2);
+    wslot[x.a] = wa; wslot[x.b] = wb;
+    if (ia >= 0) pos[ia].w = wa;
+    if (ib >= 0) pos[ib].w = wb;
     atomicAdd(counters + x.r, 1ull);
 }
 // phase 6: bonds -> tuple lists (slot at list_n[list] + rank in event order), graph, exclusions
@@ -288,8 +295,8 @@ __global__ void k_apply_bonds(int nev, const int* __restrict__ ev, const ClbCand
 // whose CURRENT type equals the rule's old type files a claim (event, side, level, rule); the smallest
 // claim per particle wins (deterministic stand-in for the sequential event order of the reference).
 __global__ void k_nb_claims(int nev, const int* __restrict__ ev, const ClbCand* __restrict__ c, const ClbChange* __restrict__ chg, int nchg,
-                            const int* __restrict__ adj, const int* __restrict__ deg, const int* __restrict__ id2idx,
-                            const int4* __restrict__ pos, unsigned long long* __restrict__ claim, int* __restrict__ touched,
+                            const int* __restrict__ adj, const int* __restrict__ deg, const int* __restrict__ wslot,
+                            unsigned long long* __restrict__ claim, int* __restrict__ touched,
                             unsigned long long* __restrict__ ntouched, unsigned long long touchcap) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= 2 * nev) return;
@@ -310,7 +317,7 @@ __global__ void k_nb_claims(int nev, const int* __restrict__ ev, const ClbCand* 
             if (!dup && nn < 64 && ns < 192) { nxt[nn++] = y; seen[ns++] = y; }
         }
         for (int a = 0; a < nn; ++a) {
-            int ty = pw_type(pos[id2idx[nxt[a]]].w);
+            int ty = pw_type(wslot[nxt[a]]);
             for (int q = 0; q < nchg; ++q) {
                 const ClbChange& g = chg[q];
                 if (g.reaction == x.r && (g.side & side) && g.nb_level == lev && g.old_type == ty) {
@@ -326,13 +333,13 @@ __global__ void k_nb_claims(int nev, const int* __restrict__ ev, const ClbCand* 
     }
 }
 __global__ void k_nb_apply(int ntouched, const int* __restrict__ touched, unsigned long long* __restrict__ claim, const ClbChange* __restrict__ chg,
-                           const int* __restrict__ id2idx, int4* pos, float4* vel, double* charge) {
+                           const int* __restrict__ id2idx, int* wslot, int4* pos, float4* vel, double* charge) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= ntouched) return;
     int s = touched[t];
     unsigned long long key = claim[s];
     claim[s] = ~0ull;
-    apply_props(chg[key & 0xfff], id2idx[s], s, pos, vel, charge);
+    apply_props(chg[key & 0xfff], id2idx[s], s, wslot, pos, vel, charge);
 }
 // phase 8: TopologyManager -- angles/dihedrals through each new bond whose (final) type tuple is
 // registered.  A tuple containing several bonds of this pass is emitted by the LAST of them in event
@@ -346,11 +353,11 @@ __device__ __forceinline__ int find_event_of_bond(int nev, const int* ev, const 
     if (specs[x.r].is_virtual) return -1;
     return ((x.a == a && x.b == b) || (x.a == b && x.b == a)) ? e : -1;
 }
-__device__ __forceinline__ void tm_emit(int mode, int ar, const int* ids, const int* id2idx, const int4* pos, const ClbTmReg* regs, int nreg,
+__device__ __forceinline__ void tm_emit(int mode, int ar, const int* ids, const int* wslot, const ClbTmReg* regs, int nreg,
                                         const ClbListDev* lists, int* list_cursor, int* list_count, int2* excl_pairs,
                                         unsigned long long* nexcl, unsigned long long* nexcl_count) {
     int ty[4];
-    for (int m = 0; m < ar; ++m) ty[m] = pw_type(pos[id2idx[ids[m]]].w);
+    for (int m = 0; m < ar; ++m) ty[m] = pw_type(wslot[ids[m]]);
     for (int k = 0; k < nreg; ++k) {
         const ClbTmReg& g = regs[k];
         if (g.arity != ar) continue;
@@ -377,8 +384,8 @@ __global__ void k_ev_of_slot(int nev, const int* __restrict__ ev, const ClbCand*
 template <int MODE>
 __global__ void k_topo_tuples(int nev, const int* __restrict__ ev, const ClbCand* __restrict__ c, const ClbReactSpec* __restrict__ specs,
                               const ClbListDev* __restrict__ lists, const ClbTmReg* __restrict__ regs, int nreg, const int* __restrict__ adj,
-                              const int* __restrict__ deg, const int* __restrict__ ev_of_slot, const int* __restrict__ id2idx,
-                              const int4* __restrict__ pos, int* list_cursor, int* list_count, int2* excl_pairs, unsigned long long* nexcl,
+                              const int* __restrict__ deg, const int* __restrict__ ev_of_slot, const int* __restrict__ wslot,
+                              int* list_cursor, int* list_count, int2* excl_pairs, unsigned long long* nexcl,
                               unsigned long long* nexcl_count) {
     int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= nev) return;
@@ -393,13 +400,13 @@ __global__ void k_topo_tuples(int nev, const int* __restrict__ ev, const ClbCand
             if (xx == o) continue;
             if (find_event_of_bond(nev, ev, c, specs, ev_of_slot, xx, p) > e) continue;
             int t3[3] = {xx, p, o};
-            tm_emit(MODE, 3, t3, id2idx, pos, regs, nreg, lists, list_cursor, list_count, excl_pairs, nexcl, nexcl_count);
+            tm_emit(MODE, 3, t3, wslot, regs, nreg, lists, list_cursor, list_count, excl_pairs, nexcl, nexcl_count);
             for (int k2 = 0; k2 < deg[xx]; ++k2) {
                 int y = adj[xx * CLB_MAXDEG + k2];
                 if (y == p || y == o) continue;
                 if (find_event_of_bond(nev, ev, c, specs, ev_of_slot, y, xx) > e) continue;
                 int t4[4] = {y, xx, p, o};
-                tm_emit(MODE, 4, t4, id2idx, pos, regs, nreg, lists, list_cursor, list_count, excl_pairs, nexcl, nexcl_count);
+                tm_emit(MODE, 4, t4, wslot, regs, nreg, lists, list_cursor, list_count, excl_pairs, nexcl, nexcl_count);
             }
         }
     }
@@ -411,7 +418,7 @@ __global__ void k_topo_tuples(int nev, const int* __restrict__ ev, const ClbCand
             if (y == a || y == xx) continue;
             if (find_event_of_bond(nev, ev, c, specs, ev_of_slot, xx, a) > e || find_event_of_bond(nev, ev, c, specs, ev_of_slot, b, y) > e) continue;
             int t4[4] = {xx, a, b, y};
-            tm_emit(MODE, 4, t4, id2idx, pos, regs, nreg, lists, list_cursor, list_count, excl_pairs, nexcl, nexcl_count);
+            tm_emit(MODE, 4, t4, wslot, regs, nreg, lists, list_cursor, list_count, excl_pairs, nexcl, nexcl_count);
         }
     }
 }

@@ -30,7 +30,7 @@ __device__ __forceinline__ void tile_geometry(const ClbGrid& g, int b, TileCtx& 
     t.bxe = min(g.bx, g.ncx - t.cx0);
     t.cy = row % g.ncy;
     int zrow = row / g.ncy;                 // 0..nczl-1 : owned plane index
-    t.lz = g.ghost ? zrow + 1 : zrow;
+    t.lz = zrow;
     t.whole = (t.bxe + 2 > g.ncx);
     t.W = t.whole ? g.ncx : t.bxe + 2;
 }
@@ -38,7 +38,7 @@ __device__ __forceinline__ void tile_geometry(const ClbGrid& g, int b, TileCtx& 
 __device__ __forceinline__ int tile_cell(const ClbGrid& g, const TileCtx& t, int k, int m) {
     int dy = k % 3 - 1, dz = k / 3 - 1;
     int cy = wrapi(t.cy + dy, g.ncy);
-    int lz = g.ghost ? t.lz + dz : wrapi(t.lz + dz, g.ncz);
+    int lz = wrapi(t.lz + dz, g.nplanes);   // owned planes first, then upper ghost, then lower ghost (ClbGrid::zoff)
     int cx = t.whole ? m : wrapi(t.cx0 - 1 + m, g.ncx);
     return (lz * g.ncy + cy) * g.ncx + cx;
 }

@@ -261,29 +261,54 @@ extern "C" int clb_set_particles(clb_engine* e, int64_t n, const int64_t* id, co
         hslot[s] = (int)s;
     }
     e->ntypes = std::max(e->ntypes, maxtype + 1);
-    TRY(e->alloc_particles(e->n));
-    CK(cudaMemcpyAsync(e->pos.p, hp.data(), n * sizeof(int4), cudaMemcpyHostToDevice, e->stream));
-    CK(cudaMemcpyAsync(e->vel.p, hv.data(), n * sizeof(float4), cudaMemcpyHostToDevice, e->stream));
-    CK(cudaMemcpyAsync(e->slot.p, hslot.data(), n * sizeof(int), cudaMemcpyHostToDevice, e->stream));
-    CK(cudaMemcpyAsync(e->id2idx.p, hslot.data(), n * sizeof(int), cudaMemcpyHostToDevice, e->stream));
+    std::vector<int> hw(n);
+    for (int64_t s = 0; s < n; ++s) hw[s] = hp[s].w;
+    // multi-GPU: every rank receives the full set and keeps the particles of its own cell planes; the per-slot
+    // arrays (image, res_id, charge, type|state word, id2idx) stay full size
+    std::vector<int> hid2idx(n, -1);
+    int64_t nloc = n;
+    if (e->nranks > 1) {
+        const ClbGrid& g = e->grid;
+        nloc = 0;
+        for (int64_t s = 0; s < n; ++s) {
+            int cz = (int)(((uint64_t)(uint32_t)hp[s].z * (uint64_t)g.ncz) >> 32);
+            int l = cz - g.cz0; if (l < 0) l += g.ncz;
+            if (l >= g.nczl) continue;
+            hp[nloc] = hp[s]; hv[nloc] = hv[s]; hslot[nloc] = (int)s; hid2idx[s] = (int)nloc;
+            ++nloc;
+        }
+        double frac = (double)(g.nczl + 2) / g.ncz;
+        int64_t cap = std::min<int64_t>(n, (int64_t)(n * frac * 1.5) + 16384);
+        TRY(e->alloc_particles((int)std::max<int64_t>(cap, nloc)));
+    } else {
+        for (int64_t s = 0; s < n; ++s) hid2idx[s] = (int)s;
+        TRY(e->alloc_particles(e->n));
+    }
+    if (nloc) {
+        CK(cudaMemcpyAsync(e->pos.p, hp.data(), nloc * sizeof(int4), cudaMemcpyHostToDevice, e->stream));
+        CK(cudaMemcpyAsync(e->vel.p, hv.data(), nloc * sizeof(float4), cudaMemcpyHostToDevice, e->stream));
+        CK(cudaMemcpyAsync(e->slot.p, hslot.data(), nloc * sizeof(int), cudaMemcpyHostToDevice, e->stream));
+    }
+    CK(cudaMemcpyAsync(e->id2idx.p, hid2idx.data(), n * sizeof(int), cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemcpyAsync(e->wslot.p, hw.data(), n * sizeof(int), cudaMemcpyHostToDevice, e->stream));
     CK(cudaMemcpyAsync(e->image.p, himg.data(), 3 * n * sizeof(int), cudaMemcpyHostToDevice, e->stream));
     CK(cudaMemcpyAsync(e->resid.p, hres.data(), n * sizeof(int), cudaMemcpyHostToDevice, e->stream));
     CK(cudaMemcpyAsync(e->charge.p, hq.data(), n * sizeof(double), cudaMemcpyHostToDevice, e->stream));
     CK(cudaMemsetAsync(e->force.p, 0, 3 * (size_t)e->ncap * sizeof(double), e->stream));
     CK(cudaStreamSynchronize(e->stream));
-    e->nstored = e->n; e->own0 = 0; e->own1 = e->n;
+    e->nstored = (int)nloc; e->own0 = 0; e->own1 = (int)nloc;
     e->lists_valid = false; e->forces_valid = false; e->excl_dirty = true; e->terms_dirty = true; e->topo_dirty = true;
     return CLB_OK;
 }
 extern "C" int64_t clb_num_particles(const clb_engine* e) { return e ? e->n : 0; }
 
-int clb_engine::alloc_particles(int n_) {
+int clb_engine::alloc_particles(int nlocal_cap) {
     clb_engine* e = this;
-    ncap = n_ + 64;
+    ncap = nlocal_cap + 64;
     CK(pos.ensure(ncap)); CK(pos2.ensure(ncap)); CK(vel.ensure(ncap)); CK(vel2.ensure(ncap));
     CK(slot.ensure(ncap)); CK(slot2.ensure(ncap)); CK(xref.ensure(ncap));
     CK(force.ensure(3 * (size_t)ncap));
-    CK(id2idx.ensure(n_)); CK(image.ensure(3 * (size_t)n_)); CK(resid.ensure(n_)); CK(charge.ensure(n_)); CK(mol.ensure(n_));
+    CK(id2idx.ensure(n)); CK(image.ensure(3 * (size_t)n)); CK(resid.ensure(n)); CK(charge.ensure(n)); CK(mol.ensure(n)); CK(wslot.ensure(n));
     CK(key.ensure(ncap)); CK(key2.ensure(ncap)); CK(val.ensure(ncap)); CK(val2.ensure(ncap));
     CK(cell_start.ensure((size_t)grid.ncell + 2));
     CK(nl_count.ensure(ncap));
@@ -311,7 +336,7 @@ extern "C" int clb_get_particles(clb_engine* e, int64_t n, const int64_t* ids, d
                                  double* force, int32_t* type, int32_t* state, double* mass, double* q, int32_t* res_id) {
     if (!e) return CLB_ERR_ARG;
     cudaSetDevice(e->device);
-    if (e->nranks > 1) return e->fail(CLB_ERR_UNSUPPORTED, "clb_get_particles on a multi-rank engine: use clb_get_particles on gathered state (not implemented)");
+    if (e->nranks > 1) return e->get_particles_gathered(n, ids, pos, image, vel, force, type, state, mass, q, res_id);
     std::vector<int4> hp; std::vector<float4> hv; std::vector<int> hidx;
     TRY(e->download_state(hp, hv, hidx));
     std::vector<double> hf; std::vector<int> himg, hres; std::vector<double> hq;
@@ -337,6 +362,60 @@ extern "C" int clb_get_particles(clb_engine* e, int64_t n, const int64_t* ids, d
     return CLB_OK;
 }
 
+// multi-rank read-back: every rank fills the rows of the particles it owns, the rows are summed over the ranks
+// (exact: one non-zero contribution per row), so all ranks return the full, identical state
+int clb_engine::get_particles_gathered(int64_t nq, const int64_t* ids, double* pos_o, int32_t* image_o, double* vel_o, double* force_o,
+                                       int32_t* type_o, int32_t* state_o, double* mass_o, double* q_o, int32_t* res_o) {
+    clb_engine* e = this;
+    const int K = 15;
+    const int no = own1;
+    std::vector<int4> hp(no); std::vector<float4> hv(no); std::vector<int> hs(no), himg(3 * (size_t)n); std::vector<double> hf(3 * (size_t)ncap);
+    if (no) {
+        CK(cudaMemcpyAsync(hp.data(), this->pos.p, no * sizeof(int4), cudaMemcpyDeviceToHost, stream));
+        CK(cudaMemcpyAsync(hv.data(), this->vel.p, no * sizeof(float4), cudaMemcpyDeviceToHost, stream));
+        CK(cudaMemcpyAsync(hs.data(), slot.p, no * sizeof(int), cudaMemcpyDeviceToHost, stream));
+    }
+    CK(cudaMemcpyAsync(himg.data(), image.p, himg.size() * 4, cudaMemcpyDeviceToHost, stream));
+    CK(cudaMemcpyAsync(hf.data(), this->force.p, hf.size() * 8, cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    std::vector<double> M((size_t)n * K, 0.0);
+    for (int i = 0; i < no; ++i) {
+        double* r = &M[(size_t)hs[i] * K];
+        r[0] = (double)(uint32_t)hp[i].x; r[1] = (double)(uint32_t)hp[i].y; r[2] = (double)(uint32_t)hp[i].z;
+        r[3] = hv[i].x; r[4] = hv[i].y; r[5] = hv[i].z;
+        r[6] = hf[i]; r[7] = hf[i + ncap]; r[8] = hf[i + 2 * (size_t)ncap];
+        r[9] = himg[3 * hs[i]]; r[10] = himg[3 * hs[i] + 1]; r[11] = himg[3 * hs[i] + 2];
+        r[12] = pw_type(hp[i].w); r[13] = pw_state(hp[i].w); r[14] = hv[i].w;
+    }
+    DevBuf<double> d;
+    CK(d.ensure(M.size()));
+    CK(cudaMemcpyAsync(d.p, M.data(), M.size() * 8, cudaMemcpyHostToDevice, stream));
+    int rr = comm_allreduce_sum_dev(d.p, M.size());
+    if (rr != CLB_OK) { d.release(); return rr; }
+    CK(cudaMemcpyAsync(M.data(), d.p, M.size() * 8, cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    d.release();
+    std::vector<int> hres; std::vector<double> hq;
+    if (res_o) { hres.resize(n); CK(cudaMemcpy(hres.data(), resid.p, (size_t)n * 4, cudaMemcpyDeviceToHost)); }
+    if (q_o) { hq.resize(n); CK(cudaMemcpy(hq.data(), charge.p, (size_t)n * 8, cudaMemcpyDeviceToHost)); }
+    int64_t cnt = ids ? nq : n;
+    for (int64_t k = 0; k < cnt; ++k) {
+        int s = ids ? slot_of(ids[k]) : (int)k;
+        if (s < 0) return fail(CLB_ERR_ARG, "unknown particle id %lld", (long long)ids[k]);
+        const double* r = &M[(size_t)s * K];
+        if (pos_o) for (int d3 = 0; d3 < 3; ++d3) pos_o[3 * k + d3] = r[d3] * geo.q[d3];
+        if (vel_o) for (int d3 = 0; d3 < 3; ++d3) vel_o[3 * k + d3] = r[3 + d3];
+        if (force_o) for (int d3 = 0; d3 < 3; ++d3) force_o[3 * k + d3] = r[6 + d3];
+        if (image_o) for (int d3 = 0; d3 < 3; ++d3) image_o[3 * k + d3] = (int)r[9 + d3];
+        if (type_o) type_o[k] = (int)r[12];
+        if (state_o) state_o[k] = (int)r[13];
+        if (mass_o) mass_o[k] = r[14];
+        if (q_o) q_o[k] = hq[s];
+        if (res_o) res_o[k] = hres[s];
+    }
+    return CLB_OK;
+}
+
 static inline int lattice_of(double x, double L, int* im) {
     double fr = x / L, fl = floor(fr), u = rint((fr - fl) * 4294967296.0);
     int i = (int)fl;
@@ -352,24 +431,35 @@ extern "C" int clb_modify_particle(clb_engine* e, int64_t id, int field, const d
     if (s < 0) return e->fail(CLB_ERR_ARG, "unknown particle id %lld", (long long)id);
     int i;
     CK(cudaMemcpy(&i, e->id2idx.p + s, 4, cudaMemcpyDeviceToHost));
+    if (e->nranks > 1 && (field == 5)) return e->fail(CLB_ERR_UNSUPPORTED, "moving a particle on a multi-rank engine is not supported");
+    // replicated per-slot properties first (all ranks make the same call), then the local copy if the particle is stored here
+    int w;
+    CK(cudaMemcpy(&w, e->wslot.p + s, 4, cudaMemcpyDeviceToHost));
+    switch (field) {
+        case 0: { int t = (int)value[0]; if (t < 0 || t >= CLB_MAX_TYPES) return e->fail(CLB_ERR_ARG, "type out of range");
+                  w = pw_pack(t, pw_state(w)); e->ntypes = std::max(e->ntypes, t + 1); e->pots_dirty = true; break; }
+        case 1: w = pw_pack(pw_type(w), (int)value[0]); break;
+        case 3: { double qq = value[0]; CK(cudaMemcpy(e->charge.p + s, &qq, 8, cudaMemcpyHostToDevice)); break; }
+        case 4: { int r = (int)value[0]; CK(cudaMemcpy(e->resid.p + s, &r, 4, cudaMemcpyHostToDevice)); break; }
+        case 2: case 5: case 6: break;
+        default: return e->fail(CLB_ERR_ARG, "unknown field %d", field);
+    }
+    CK(cudaMemcpy(e->wslot.p + s, &w, 4, cudaMemcpyHostToDevice));
+    e->forces_valid = false;
+    if (i < 0) return CLB_OK;
     int4 p; float4 v;
     CK(cudaMemcpy(&p, e->pos.p + i, sizeof(p), cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(&v, e->vel.p + i, sizeof(v), cudaMemcpyDeviceToHost));
+    p.w = w;
     switch (field) {
-        case 0: { int t = (int)value[0]; if (t < 0 || t >= CLB_MAX_TYPES) return e->fail(CLB_ERR_ARG, "type out of range");
-                  p.w = pw_pack(t, pw_state(p.w)); e->ntypes = std::max(e->ntypes, t + 1); e->pots_dirty = true; break; }
-        case 1: p.w = pw_pack(pw_type(p.w), (int)value[0]); break;
         case 2: v.w = (float)value[0]; break;
-        case 3: { double qq = value[0]; CK(cudaMemcpy(e->charge.p + s, &qq, 8, cudaMemcpyHostToDevice)); break; }
-        case 4: { int r = (int)value[0]; CK(cudaMemcpy(e->resid.p + s, &r, 4, cudaMemcpyHostToDevice)); break; }
         case 5: { int im[3]; p.x = lattice_of(value[0], e->box[0], &im[0]); p.y = lattice_of(value[1], e->box[1], &im[1]); p.z = lattice_of(value[2], e->box[2], &im[2]);
                   CK(cudaMemcpy(e->image.p + 3 * s, im, 12, cudaMemcpyHostToDevice)); e->lists_valid = false; break; }
         case 6: v.x = (float)value[0]; v.y = (float)value[1]; v.z = (float)value[2]; break;
-        default: return e->fail(CLB_ERR_ARG, "unknown field %d", field);
+        default: break;
     }
     CK(cudaMemcpy(e->pos.p + i, &p, sizeof(p), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(e->vel.p + i, &v, sizeof(v), cudaMemcpyHostToDevice));
-    e->forces_valid = false;
     return CLB_OK;
 }
 extern "C" int clb_set_velocities(clb_engine* e, int64_t n, const double* vel) {
@@ -377,12 +467,13 @@ extern "C" int clb_set_velocities(clb_engine* e, int64_t n, const double* vel) {
     cudaSetDevice(e->device);
     std::vector<int4> hp; std::vector<float4> hv; std::vector<int> hidx;
     TRY(e->download_state(hp, hv, hidx));
-    for (int s = 0; s < e->n; ++s) { int i = hidx[s]; hv[i].x = (float)vel[3 * s]; hv[i].y = (float)vel[3 * s + 1]; hv[i].z = (float)vel[3 * s + 2]; }
+    for (int s = 0; s < e->n; ++s) { int i = hidx[s]; if (i < 0) continue; hv[i].x = (float)vel[3 * s]; hv[i].y = (float)vel[3 * s + 1]; hv[i].z = (float)vel[3 * s + 2]; }
     CK(cudaMemcpy(e->vel.p, hv.data(), e->nstored * sizeof(float4), cudaMemcpyHostToDevice));
     return CLB_OK;
 }
 extern "C" int clb_set_positions(clb_engine* e, int64_t n, const double* pos) {
     if (!e || n != e->n || !pos) return e ? e->fail(CLB_ERR_ARG, "clb_set_positions: n mismatch") : CLB_ERR_ARG;
+    if (e->nranks > 1) return e->fail(CLB_ERR_UNSUPPORTED, "clb_set_positions on a multi-rank engine: call clb_set_particles again");
     cudaSetDevice(e->device);
     std::vector<int4> hp; std::vector<float4> hv; std::vector<int> hidx;
     TRY(e->download_state(hp, hv, hidx));
@@ -928,17 +1019,26 @@ int clb_engine::rebuild() {
     clb_engine* e = this;
     ClbTrace tr(stream, "rebuild");
     bucket_begin(CLB_B_NEIGH);
-    if (nranks > 1) TRY(comm_migrate_and_ghosts());
-    int ns = nstored;
-    // 1. sort by cell
-    k_cell_keys<<<ceil_div(ns, 256), 256, 0, stream>>>(ns, pos.p, grid, key.p, val.p);
+    if (nranks > 1) {
+        // ghosts are dropped, owned particles that left the slab move to the neighbour ranks (engine_comm.inl)
+        CK(cudaMemsetAsync(id2idx.p, 0xff, (size_t)n * sizeof(int), stream));
+        TRY(comm_migrate());
+    }
+    int ns = own1;
+    // 1. sort the owned particles by cell
+    k_cell_keys<<<ceil_div(std::max(ns, 1), 256), 256, 0, stream>>>(ns, pos.p, grid, key.p, val.p);
     int bits = 1; while ((1ll << bits) < grid.ncell) ++bits;
     size_t tb = cubtmp.n;
     cub::DeviceRadixSort::SortPairs(cubtmp.p, tb, key.p, key2.p, val.p, val2.p, ns, 0, bits, stream);
-    k_gather<<<ceil_div(ns, 256), 256, 0, stream>>>(ns, val2.p, pos.p, vel.p, slot.p, pos2.p, vel2.p, slot2.p, xref.p, id2idx.p);
+    k_gather<<<ceil_div(std::max(ns, 1), 256), 256, 0, stream>>>(ns, val2.p, pos.p, vel.p, slot.p, pos2.p, vel2.p, slot2.p, xref.p, id2idx.p);
     std::swap(pos.p, pos2.p); std::swap(vel.p, vel2.p); std::swap(slot.p, slot2.p);
+    if (nranks > 1) {
+        // boundary planes of the sorted owned range -> neighbours' ghost planes, appended behind the owned range
+        k_cell_start<<<ceil_div(ns + 1, 256), 256, 0, stream>>>(ns, key2.p, grid.ncell, cell_start.p);
+        TRY(comm_exchange_ghosts());
+        ns = nstored;
+    }
     k_cell_start<<<ceil_div(ns + 1, 256), 256, 0, stream>>>(ns, key2.p, grid.ncell, cell_start.p);
-    if (nranks > 1) TRY(comm_after_sort());
     tr.mark("sort");
     // 2. tile statistics
     k_ctl_reset_stats<<<1, 1, 0, stream>>>(d_ctl);
@@ -1151,7 +1251,6 @@ extern "C" int clb_run(clb_engine* e, int64_t nsteps) {
     cudaEventRecord(e->ev_a[CLB_B_TOTAL], e->stream);
     // run entry: recalc forces (+ thermostat heat-up), SURVEY 3.2
     e->enqueue_forces();
-    if (e->nranks > 1) {}
     if (e->lang_on) {
         ClbIntegParams P = e->integ_params((uint64_t)e->step);
         int no = e->own1 - e->own0;
@@ -1173,6 +1272,7 @@ extern "C" int clb_run(clb_engine* e, int64_t nsteps) {
                 if (pend) e->enqueue_integrate(CLB_INT_SECOND, (uint64_t)(e->step + s - 1));
                 e->enqueue_integrate(CLB_INT_FIRST, 0);
             }
+            if (e->nranks > 1) TRY(e->comm_max_displacement());
             k_check_resort<<<1, 1, 0, e->stream>>>(e->d_ctl, e->criterion, half_skin, (int)(s - i));
             ++e->launches;
             if (e->nranks > 1) TRY(e->comm_halo_positions());
@@ -1225,7 +1325,8 @@ extern "C" int clb_get_pairs(clb_engine* e, int64_t cap, int64_t* pairs, int64_t
     cudaSetDevice(e->device);
     TRY(e->setup_sync());
     if (!e->lists_valid) TRY(e->rebuild());
-    size_t outcap = (size_t)e->nl_total / 2 + 1024;
+    // single GPU: every pair sits in two rows; with ghosts a row entry may be the only local copy of its pair
+    size_t outcap = (e->nranks > 1 ? (size_t)e->nl_total : (size_t)e->nl_total / 2) + 1024;
     DevBuf<int2> out;
     CK(out.ensure(outcap));
     CK(cudaMemsetAsync(&e->d_ctl->npairs_out, 0, 8, e->stream));
@@ -1236,7 +1337,15 @@ extern "C" int clb_get_pairs(clb_engine* e, int64_t cap, int64_t* pairs, int64_t
     size_t m = (size_t)e->h_ctl->npairs_out;
     if (m > outcap) { out.release(); return e->fail(CLB_ERR_STATE, "pair list asymmetric: %zu decoded pairs for %llu entries", m, e->nl_total); }
     std::vector<int2> h(m);
-    if (m) CK(cudaMemcpy(h.data(), out.p, m * sizeof(int2), cudaMemcpyDeviceToHost));
+    if (e->nranks > 1) {
+        // every unordered pair is decoded by the rank that owns its lower slot (U16): the union is the global pair set
+        void* all = nullptr; size_t tot = 0;
+        int rr = e->comm_allgatherv(out.p, m * sizeof(int2), &all, &tot);
+        if (rr != CLB_OK) { out.release(); return rr; }
+        m = tot / sizeof(int2);
+        h.resize(m);
+        if (m) CK(cudaMemcpy(h.data(), all, tot, cudaMemcpyDeviceToHost));
+    } else if (m) CK(cudaMemcpy(h.data(), out.p, m * sizeof(int2), cudaMemcpyDeviceToHost));
     out.release();
     std::sort(h.begin(), h.end(), [](const int2& a, const int2& b) { return a.x != b.x ? a.x < b.x : a.y < b.y; });
     if (n_out) *n_out = (int64_t)m;

@@ -75,6 +75,7 @@ struct clb_engine {
     DevBuf<int4> pos, pos2, xref;
     DevBuf<float4> vel, vel2;
     DevBuf<int> slot, slot2, id2idx, image, resid, mol;
+    DevBuf<int> wslot;                        // replicated per-slot type|state word (reaction decisions; clb_react.cuh)
     DevBuf<double> force, charge;
     DevBuf<int> key, key2, val, val2, cell_start;
     DevBuf<unsigned char> cubtmp, cubtmp2;
@@ -164,16 +165,21 @@ struct clb_engine {
     int rank = 0, nranks = 1;
     struct CommDev;
     CommDev* cd = nullptr;
-    int comm_migrate_and_ghosts();
-    int comm_after_sort();
+    int comm_migrate();
+    int comm_exchange_ghosts();
     int comm_halo_positions();
+    int comm_max_displacement();
     int comm_allreduce_sum(double* v, int n);
+    int comm_allreduce_sum_dev(double* d, size_t n);
+    int comm_allgatherv(const void* dsend, size_t bytes, void** dout, size_t* total);
     int comm_gather_candidates(long long* nc);
     void comm_destroy();
 
     // methods
     void set_block_cells(int bx);
-    int alloc_particles(int n);
+    int alloc_particles(int nlocal_cap);
+    int get_particles_gathered(int64_t nq, const int64_t* ids, double* pos, int32_t* image, double* vel, double* force, int32_t* type,
+                               int32_t* state, double* mass, double* q, int32_t* res_id);
     int download_state(std::vector<int4>& hp, std::vector<float4>& hv, std::vector<int>& hidx);
     int build_excl_csr();
     int upload_potentials();

@@ -1,20 +1,352 @@
-// engine_comm.inl -- multi-GPU slab decomposition over NCCL (included by engine.cu)
-struct clb_engine::CommDev { int dummy; };
+// engine_comm.inl -- multi-GPU slab decomposition over NCCL (included by engine.cu).
+//
+// Replaces storage.DomainDecomposition's MPI node grid + ghost exchange (src/start_simulation.py:152-163;
+// [EXT] storage/DomainDecomposition.cpp): one engine per GPU/process, the box is cut into slabs of whole cell
+// planes along z.  Rank r owns planes [cz0, cz0+nczl) and stores one ghost plane on either side:
+//
+//      sorted particle arrays:   [ owned (cell-sorted) | upper ghost plane | lower ghost plane ]
+//                                  0 ............ own1   own1 ...... +n_hi   ........ nstored
+//
+//   * positions are lattice integers modulo 2^32, so ghosts need no coordinate shift;
+//   * a neighbour's boundary plane is ONE contiguous range of its sorted arrays, and it arrives in the
+//     sender's cell order, so the per-step halo is two contiguous ncclSend/ncclRecv pairs per rank and
+//     the ghost planes never need sorting;
+//   * forces are owner-computes over full lists -> there is no reverse (force) halo;
+//   * the resort criterion is the global maximum displacement: one 4-byte ncclAllReduce(max) per step,
+//     so every rank stalls at the same step and the host-side chunk loop stays in lock-step;
+//   * topology (tuple lists, bond graph, exclusions, molecule ids, type|state words) is replicated; the
+//     reaction candidates of all ranks are all-gathered and every rank runs the same deterministic
+//     conflict pass (replaces the reference's three neighbour-rank multimap exchanges).
+//
+// NCCL is resolved with dlopen at clb_comm_init time (inside a torch process this is torch's own
+// libnccl.so.2), so the library loads on machines without NCCL and single-GPU use never touches it.
+#include <dlfcn.h>
+#include <nccl.h>
+
+struct NcclApi {
+    void* h = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    std::string err;
+    bool load() {
+        if (h) return true;
+        const char* names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char* nm : names) { h = dlopen(nm, RTLD_NOW | RTLD_GLOBAL); if (h) break; }
+        if (!h) { err = std::string("cannot load libnccl: ") + dlerror(); return false; }
+#define CLB_NCCL_SYM(field, sym) *(void**)(&field) = dlsym(h, sym); if (!field) { err = std::string("libnccl lacks ") + sym; h = nullptr; return false; }
+        CLB_NCCL_SYM(GetUniqueId, "ncclGetUniqueId") CLB_NCCL_SYM(CommInitRank, "ncclCommInitRank") CLB_NCCL_SYM(CommDestroy, "ncclCommDestroy")
+        CLB_NCCL_SYM(Send, "ncclSend") CLB_NCCL_SYM(Recv, "ncclRecv") CLB_NCCL_SYM(AllReduce, "ncclAllReduce") CLB_NCCL_SYM(AllGather, "ncclAllGather")
+        CLB_NCCL_SYM(Broadcast, "ncclBroadcast") CLB_NCCL_SYM(GroupStart, "ncclGroupStart") CLB_NCCL_SYM(GroupEnd, "ncclGroupEnd")
+        CLB_NCCL_SYM(GetErrorString, "ncclGetErrorString")
+#undef CLB_NCCL_SYM
+        return true;
+    }
+};
+static NcclApi g_nccl;
+
+#define NC(call)                                                                                              \
+    do {                                                                                                      \
+        ncclResult_t _r = (call);                                                                             \
+        if (_r != ncclSuccess) return e->fail(CLB_ERR_COMM, "%s failed: %s", #call, g_nccl.GetErrorString(_r)); \
+    } while (0)
+
+// migrating particle: everything that is stored per sorted index plus the owner-only per-slot image counters
+struct ClbMig { int4 p; float4 v; int slot, ix, iy, iz; };
+
+struct clb_engine::CommDev {
+    ncclComm_t comm = nullptr;
+    int up = 0, dn = 0;                        // ranks owning the planes above / below
+    int n_hi = 0, n_lo = 0;                    // ghost counts: upper plane (from `up`), lower plane (from `dn`)
+    int send_lo0 = 0, send_lo1 = 0;            // my bottom plane [send_lo0, send_lo1) -> dn's upper ghost
+    int send_hi0 = 0, send_hi1 = 0;            // my top plane                         -> up's lower ghost
+    DevBuf<int> cnt;                           // small device scratch for count exchanges
+    int* h_cnt = nullptr;                      // pinned mirror
+    DevBuf<ClbMig> mig_send, mig_recv;
+    DevBuf<int> mkey, mkey2, mval, mval2, moff;
+    DevBuf<unsigned char> gat;                 // all-gather staging
+    DevBuf<double> red;                        // host-value reductions
+    DevBuf<long long> sizes;
+    std::vector<int> plane0, planes;           // cz0 and nczl of every rank
+};
 
 extern "C" int clb_nccl_unique_id(void* id128_out) {
-    (void)id128_out;
-    g_create_error = "multi-GPU support is not built yet";
-    return CLB_ERR_UNSUPPORTED;
+    if (!id128_out) return CLB_ERR_ARG;
+    if (!g_nccl.load()) { g_create_error = g_nccl.err; return CLB_ERR_COMM; }
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    ncclUniqueId id;
+    ncclResult_t r = g_nccl.GetUniqueId(&id);
+    if (r != ncclSuccess) { g_create_error = std::string("ncclGetUniqueId: ") + g_nccl.GetErrorString(r); return CLB_ERR_COMM; }
+    memcpy(id128_out, &id, 128);
+    return CLB_OK;
 }
+
+// planes owned by rank r of nr: ncz/nr each, the first ncz%nr ranks one more (host and tests share this rule:
+// chemlab_b200/engine.py::slab_planes)
+static void slab_planes(int ncz, int nr, int r, int* cz0, int* nczl) {
+    int base = ncz / nr, rem = ncz % nr;
+    *nczl = base + (r < rem ? 1 : 0);
+    *cz0 = r * base + std::min(r, rem);
+}
+
 extern "C" int clb_comm_init(clb_engine* e, int rank, int nranks, const void* nccl_id128) {
-    (void)rank; (void)nccl_id128;
-    if (!e) return CLB_ERR_ARG;
+    if (!e || nranks < 1 || rank < 0 || rank >= nranks) return e ? e->fail(CLB_ERR_ARG, "clb_comm_init: bad rank/nranks") : CLB_ERR_ARG;
     if (nranks == 1) return CLB_OK;
-    return e->fail(CLB_ERR_UNSUPPORTED, "multi-GPU support is not built yet");
+    if (!nccl_id128) return e->fail(CLB_ERR_ARG, "clb_comm_init: NULL nccl id");
+    if (e->n > 0) return e->fail(CLB_ERR_STATE, "clb_comm_init must precede clb_set_particles");
+    if (e->cd) return e->fail(CLB_ERR_STATE, "clb_comm_init called twice");
+    cudaSetDevice(e->device);
+    if (!g_nccl.load()) return e->fail(CLB_ERR_COMM, "%s", g_nccl.err.c_str());
+    ClbGrid& g = e->grid;
+    auto* cd = new clb_engine::CommDev();
+    cd->plane0.resize(nranks); cd->planes.resize(nranks);
+    for (int r = 0; r < nranks; ++r) {
+        slab_planes(g.ncz, nranks, r, &cd->plane0[r], &cd->planes[r]);
+        // a rank must not see the same foreign plane as both its upper and its lower ghost
+        if (cd->planes[r] < 1 || g.ncz - cd->planes[r] < 2) {
+            delete cd;
+            return e->fail(CLB_ERR_UNSUPPORTED, "%d cell planes along z cannot be split over %d ranks (every rank needs >= 1 owned and >= 2 foreign planes)", g.ncz, nranks);
+        }
+    }
+    ncclUniqueId id; memcpy(&id, nccl_id128, 128);
+    ncclResult_t r = g_nccl.CommInitRank(&cd->comm, nranks, id, rank);
+    if (r != ncclSuccess) { delete cd; return e->fail(CLB_ERR_COMM, "ncclCommInitRank: %s", g_nccl.GetErrorString(r)); }
+    cd->up = (rank + 1) % nranks; cd->dn = (rank + nranks - 1) % nranks;
+    e->cd = cd; e->rank = rank; e->nranks = nranks;
+    g.cz0 = cd->plane0[rank]; g.nczl = cd->planes[rank]; g.zoff = g.cz0; g.nplanes = g.nczl + 2; g.ghost = 1;
+    e->set_block_cells(g.bx);
+    CK(cd->cnt.ensure(64));
+    CK(cudaMallocHost(&cd->h_cnt, 64 * sizeof(int)));
+    return CLB_OK;
 }
-int clb_engine::comm_migrate_and_ghosts() { return CLB_OK; }
-int clb_engine::comm_after_sort() { return CLB_OK; }
-int clb_engine::comm_halo_positions() { return CLB_OK; }
-int clb_engine::comm_allreduce_sum(double*, int) { return CLB_OK; }
-int clb_engine::comm_gather_candidates(long long*) { return CLB_OK; }
-void clb_engine::comm_destroy() {}
+
+void clb_engine::comm_destroy() {
+    if (!cd) return;
+    if (cd->comm) g_nccl.CommDestroy(cd->comm);
+    if (cd->h_cnt) cudaFreeHost(cd->h_cnt);
+    delete cd; cd = nullptr;
+}
+
+// ---- migration (before the owned sort) ------------------------------------------------------------------
+// destination of every owned particle after the drift: 0 stay, 1 -> up, 2 -> dn
+__global__ void k_mig_classify(int n, const int4* __restrict__ pos, ClbGrid g, int* __restrict__ key, int* __restrict__ val, ClbCtl* ctl) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int cz = __umulhi((unsigned)pos[i].z, (unsigned)g.ncz);
+    int l = local_plane(g, cz);
+    if (l < 0) { atomicOr(&ctl->err, CLB_EF_PARTNER_LOST); l = 0; }   // moved more than one plane: cannot happen with skin/2
+    key[i] = l < g.nczl ? 0 : (l == g.nczl ? 1 : 2);
+    val[i] = i;
+}
+__global__ void k_mig_pack(int n, const int* __restrict__ perm, const int4* __restrict__ pos, const float4* __restrict__ vel,
+                           const int* __restrict__ slot, const int* __restrict__ image, int* __restrict__ id2idx, ClbMig* __restrict__ out) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    int i = perm[k];
+    ClbMig m; m.p = pos[i]; m.v = vel[i]; m.slot = slot[i];
+    m.ix = image[3 * m.slot]; m.iy = image[3 * m.slot + 1]; m.iz = image[3 * m.slot + 2];
+    out[k] = m;
+}
+// new owned set = stayers (in their previous order) followed by the immigrants
+__global__ void k_mig_compact(int nstay, const int* __restrict__ perm, const int4* __restrict__ pos_in, const float4* __restrict__ vel_in,
+                              const int* __restrict__ slot_in, int4* __restrict__ pos, float4* __restrict__ vel, int* __restrict__ slot) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nstay) return;
+    int i = perm[k];
+    pos[k] = pos_in[i]; vel[k] = vel_in[i]; slot[k] = slot_in[i];
+}
+__global__ void k_mig_unpack(int n, const ClbMig* __restrict__ in, int base, int4* __restrict__ pos, float4* __restrict__ vel,
+                             int* __restrict__ slot, int* __restrict__ image) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    ClbMig m = in[k];
+    pos[base + k] = m.p; vel[base + k] = m.v; slot[base + k] = m.slot;
+    image[3 * m.slot] = m.ix; image[3 * m.slot + 1] = m.iy; image[3 * m.slot + 2] = m.iz;
+}
+__global__ void k_store4(int* dst, int a, int b, int c, int d) { dst[0] = a; dst[1] = b; dst[2] = c; dst[3] = d; }
+__global__ void k_mig_counts(const int* __restrict__ off, int* __restrict__ cnt) {   // off = lower bounds of keys 0,1,2,3
+    cnt[0] = off[1];            // stayers
+    cnt[1] = off[2] - off[1];   // to up
+    cnt[2] = off[3] - off[2];   // to dn
+}
+
+int clb_engine::comm_migrate() {
+    clb_engine* e = this;
+    CommDev& c = *cd;
+    const int no = own1;
+    CK(c.mkey.ensure(ncap)); CK(c.mkey2.ensure(ncap)); CK(c.mval.ensure(ncap)); CK(c.mval2.ensure(ncap)); CK(c.moff.ensure(8));
+    k_mig_classify<<<ceil_div(std::max(no, 1), 256), 256, 0, stream>>>(no, pos.p, grid, c.mkey.p, c.mval.p, d_ctl);
+    size_t tb = cubtmp.n;
+    cub::DeviceRadixSort::SortPairs(cubtmp.p, tb, c.mkey.p, c.mkey2.p, c.mval.p, c.mval2.p, no, 0, 2, stream);
+    k_lower_bounds<<<1, 32, 0, stream>>>(no, c.mkey2.p, 3, c.moff.p);
+    k_mig_counts<<<1, 1, 0, stream>>>(c.moff.p, c.cnt.p);
+    // exchange the counts: cnt[1] (to up) -> up's cnt[4] (from dn); cnt[2] (to dn) -> dn's cnt[5] (from up)
+    NC(g_nccl.GroupStart());
+    NC(g_nccl.Send(c.cnt.p + 1, 1, ncclInt32, c.up, c.comm, stream));
+    NC(g_nccl.Send(c.cnt.p + 2, 1, ncclInt32, c.dn, c.comm, stream));
+    NC(g_nccl.Recv(c.cnt.p + 4, 1, ncclInt32, c.dn, c.comm, stream));
+    NC(g_nccl.Recv(c.cnt.p + 5, 1, ncclInt32, c.up, c.comm, stream));
+    NC(g_nccl.GroupEnd());
+    CK(cudaMemcpyAsync(c.h_cnt, c.cnt.p, 8 * sizeof(int), cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    const int nstay = c.h_cnt[0], to_up = c.h_cnt[1], to_dn = c.h_cnt[2], from_dn = c.h_cnt[4], from_up = c.h_cnt[5];
+    const int nnew = nstay + from_dn + from_up;
+    if (nnew + 64 > ncap) return fail(CLB_ERR_RANGE, "rank %d: %d owned particles exceed the local capacity %d", rank, nnew, ncap);
+    CK(c.mig_send.ensure((size_t)to_up + to_dn + 1)); CK(c.mig_recv.ensure((size_t)from_dn + from_up + 1));
+    if (to_up + to_dn > 0)
+        k_mig_pack<<<ceil_div(to_up + to_dn, 256), 256, 0, stream>>>(to_up + to_dn, c.mval2.p + nstay, pos.p, vel.p, slot.p, image.p, id2idx.p, c.mig_send.p);
+    NC(g_nccl.GroupStart());
+    if (to_up) NC(g_nccl.Send(c.mig_send.p, (size_t)to_up * sizeof(ClbMig), ncclChar, c.up, c.comm, stream));
+    if (to_dn) NC(g_nccl.Send(c.mig_send.p + to_up, (size_t)to_dn * sizeof(ClbMig), ncclChar, c.dn, c.comm, stream));
+    if (from_dn) NC(g_nccl.Recv(c.mig_recv.p, (size_t)from_dn * sizeof(ClbMig), ncclChar, c.dn, c.comm, stream));
+    if (from_up) NC(g_nccl.Recv(c.mig_recv.p + from_dn, (size_t)from_up * sizeof(ClbMig), ncclChar, c.up, c.comm, stream));
+    NC(g_nccl.GroupEnd());
+    if (nstay > 0) k_mig_compact<<<ceil_div(nstay, 256), 256, 0, stream>>>(nstay, c.mval2.p, pos.p, vel.p, slot.p, pos2.p, vel2.p, slot2.p);
+    if (from_dn + from_up > 0)
+        k_mig_unpack<<<ceil_div(from_dn + from_up, 256), 256, 0, stream>>>(from_dn + from_up, c.mig_recv.p, nstay, pos2.p, vel2.p, slot2.p, image.p);
+    std::swap(pos.p, pos2.p); std::swap(vel.p, vel2.p); std::swap(slot.p, slot2.p);
+    own0 = 0; own1 = nnew; nstored = nnew;
+    CK(cudaGetLastError());
+    launches += 6;
+    return CLB_OK;
+}
+
+// ---- ghost planes (after the owned sort) ----------------------------------------------------------------
+__global__ void k_ghost_finish(int n0, int n1, const int4* __restrict__ pos, const int* __restrict__ slot, ClbGrid g,
+                               int* __restrict__ key, int* __restrict__ id2idx) {
+    int i = n0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n1) return;
+    int4 p = pos[i];
+    int cx = __umulhi((unsigned)p.x, (unsigned)g.ncx), cy = __umulhi((unsigned)p.y, (unsigned)g.ncy), cz = __umulhi((unsigned)p.z, (unsigned)g.ncz);
+    int lz = local_plane(g, cz);
+    key[i] = lz < 0 ? g.ncell - 1 : (lz * g.ncy + cy) * g.ncx + cx;
+    id2idx[slot[i]] = i;
+}
+__global__ void k_plane_bounds(const int* __restrict__ cell_start, int plane_cells, int nczl, int nown, int* __restrict__ cnt) {
+    cnt[0] = 0; cnt[1] = cell_start[plane_cells];                 // bottom owned plane
+    cnt[2] = cell_start[(nczl - 1) * plane_cells]; cnt[3] = nown; // top owned plane
+    cnt[8] = cnt[1] - cnt[0]; cnt[9] = cnt[3] - cnt[2];
+}
+
+// called by rebuild() after the owned particles are cell-sorted (keys in key2, cell_start over the owned part)
+int clb_engine::comm_exchange_ghosts() {
+    clb_engine* e = this;
+    CommDev& c = *cd;
+    const int no = own1;
+    k_plane_bounds<<<1, 1, 0, stream>>>(cell_start.p, grid.ncx * grid.ncy, grid.nczl, no, c.cnt.p);
+    // my bottom-plane count -> dn (its n_hi); my top-plane count -> up (its n_lo)
+    NC(g_nccl.GroupStart());
+    NC(g_nccl.Send(c.cnt.p + 8, 1, ncclInt32, c.dn, c.comm, stream));
+    NC(g_nccl.Send(c.cnt.p + 9, 1, ncclInt32, c.up, c.comm, stream));
+    NC(g_nccl.Recv(c.cnt.p + 10, 1, ncclInt32, c.up, c.comm, stream));
+    NC(g_nccl.Recv(c.cnt.p + 11, 1, ncclInt32, c.dn, c.comm, stream));
+    NC(g_nccl.GroupEnd());
+    CK(cudaMemcpyAsync(c.h_cnt, c.cnt.p, 12 * sizeof(int), cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    c.send_lo0 = c.h_cnt[0]; c.send_lo1 = c.h_cnt[1]; c.send_hi0 = c.h_cnt[2]; c.send_hi1 = c.h_cnt[3];
+    c.n_hi = c.h_cnt[10]; c.n_lo = c.h_cnt[11];
+    const int ns = no + c.n_hi + c.n_lo;
+    if (ns + 64 > ncap) return fail(CLB_ERR_RANGE, "rank %d: %d stored particles (owned + ghosts) exceed the local capacity %d", rank, ns, ncap);
+    NC(g_nccl.GroupStart());
+    NC(g_nccl.Send(pos.p + c.send_lo0, (size_t)(c.send_lo1 - c.send_lo0) * sizeof(int4), ncclChar, c.dn, c.comm, stream));
+    NC(g_nccl.Send(pos.p + c.send_hi0, (size_t)(c.send_hi1 - c.send_hi0) * sizeof(int4), ncclChar, c.up, c.comm, stream));
+    NC(g_nccl.Recv(pos.p + no, (size_t)c.n_hi * sizeof(int4), ncclChar, c.up, c.comm, stream));
+    NC(g_nccl.Recv(pos.p + no + c.n_hi, (size_t)c.n_lo * sizeof(int4), ncclChar, c.dn, c.comm, stream));
+    NC(g_nccl.Send(slot.p + c.send_lo0, (size_t)(c.send_lo1 - c.send_lo0), ncclInt32, c.dn, c.comm, stream));
+    NC(g_nccl.Send(slot.p + c.send_hi0, (size_t)(c.send_hi1 - c.send_hi0), ncclInt32, c.up, c.comm, stream));
+    NC(g_nccl.Recv(slot.p + no, (size_t)c.n_hi, ncclInt32, c.up, c.comm, stream));
+    NC(g_nccl.Recv(slot.p + no + c.n_hi, (size_t)c.n_lo, ncclInt32, c.dn, c.comm, stream));
+    NC(g_nccl.GroupEnd());
+    nstored = ns;
+    if (ns > no) k_ghost_finish<<<ceil_div(ns - no, 256), 256, 0, stream>>>(no, ns, pos.p, slot.p, grid, key2.p, id2idx.p);
+    CK(cudaGetLastError());
+    launches += 4;
+    return CLB_OK;
+}
+
+// per-step forward halo: boundary-plane positions (with their type|state word) -> the neighbours' ghost planes
+int clb_engine::comm_halo_positions() {
+    clb_engine* e = this;
+    CommDev& c = *cd;
+    NC(g_nccl.GroupStart());
+    NC(g_nccl.Send(pos.p + c.send_lo0, (size_t)(c.send_lo1 - c.send_lo0) * sizeof(int4), ncclChar, c.dn, c.comm, stream));
+    NC(g_nccl.Send(pos.p + c.send_hi0, (size_t)(c.send_hi1 - c.send_hi0) * sizeof(int4), ncclChar, c.up, c.comm, stream));
+    NC(g_nccl.Recv(pos.p + own1, (size_t)c.n_hi * sizeof(int4), ncclChar, c.up, c.comm, stream));
+    NC(g_nccl.Recv(pos.p + own1 + c.n_hi, (size_t)c.n_lo * sizeof(int4), ncclChar, c.dn, c.comm, stream));
+    NC(g_nccl.GroupEnd());
+    ++launches;
+    return CLB_OK;
+}
+// global maximum displacement of this step (float bits of a non-negative number order like unsigned integers)
+int clb_engine::comm_max_displacement() {
+    clb_engine* e = this;
+    NC(g_nccl.AllReduce(&d_ctl->maxdisp2_bits, &d_ctl->maxdisp2_bits, 1, ncclUint32, ncclMax, cd->comm, stream));
+    ++launches;
+    return CLB_OK;
+}
+
+// sum of host doubles over the ranks (observables)
+int clb_engine::comm_allreduce_sum(double* v, int nv) {
+    clb_engine* e = this;
+    if (nranks == 1) return CLB_OK;
+    CK(cd->red.ensure(nv));
+    CK(cudaMemcpyAsync(cd->red.p, v, nv * sizeof(double), cudaMemcpyHostToDevice, stream));
+    NC(g_nccl.AllReduce(cd->red.p, cd->red.p, nv, ncclDouble, ncclSum, cd->comm, stream));
+    CK(cudaMemcpyAsync(v, cd->red.p, nv * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    return CLB_OK;
+}
+// in-place sum of a device array of doubles over the ranks
+int clb_engine::comm_allreduce_sum_dev(double* d, size_t nv) {
+    clb_engine* e = this;
+    if (nranks == 1) return CLB_OK;
+    NC(g_nccl.AllReduce(d, d, nv, ncclDouble, ncclSum, cd->comm, stream));
+    return CLB_OK;
+}
+
+// variable-size all-gather of device bytes: every rank ends with the concatenation (rank order) in cd->gat
+int clb_engine::comm_allgatherv(const void* dsend, size_t bytes, void** dout, size_t* total) {
+    clb_engine* e = this;
+    CommDev& c = *cd;
+    CK(c.sizes.ensure(2 * (size_t)nranks));
+    long long mine = (long long)bytes;
+    CK(cudaMemcpyAsync(c.sizes.p + nranks + rank, &mine, 8, cudaMemcpyHostToDevice, stream));
+    NC(g_nccl.AllGather(c.sizes.p + nranks + rank, c.sizes.p, 1, ncclInt64, c.comm, stream));
+    std::vector<long long> hs(nranks);
+    CK(cudaMemcpyAsync(hs.data(), c.sizes.p, nranks * 8, cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    size_t tot = 0;
+    for (int r = 0; r < nranks; ++r) tot += (size_t)hs[r];
+    CK(c.gat.ensure(tot + 16));
+    size_t off = 0;
+    NC(g_nccl.GroupStart());
+    for (int r = 0; r < nranks; ++r) {
+        if (hs[r] > 0) NC(g_nccl.Broadcast(r == rank ? dsend : (const void*)(c.gat.p + off), c.gat.p + off, (size_t)hs[r], ncclChar, r, c.comm, stream));
+        off += (size_t)hs[r];
+    }
+    NC(g_nccl.GroupEnd());
+    CK(cudaStreamSynchronize(stream));   // callers read the result with plain (legacy-stream) copies
+    *dout = c.gat.p; *total = tot;
+    return CLB_OK;
+}
+
+// reaction handshake: concatenate the candidates of all ranks into R.cands (every rank then sorts them canonically)
+int clb_engine::comm_gather_candidates(long long* nc) {
+    clb_engine* e = this;
+    ReactDev& R = *rd;
+    void* all = nullptr; size_t tot = 0;
+    TRY(comm_allgatherv(R.cands.p, (size_t)*nc * sizeof(ClbCand), &all, &tot));
+    size_t m = tot / sizeof(ClbCand);
+    if (m > R.candcap) { R.candcap = m * 5 / 4 + 1024; CK(R.cands.ensure(R.candcap)); }
+    if (m) CK(cudaMemcpyAsync(R.cands.p, all, tot, cudaMemcpyDeviceToDevice, stream));
+    *nc = (long long)m;
+    return CLB_OK;
+}

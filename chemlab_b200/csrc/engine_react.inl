@@ -255,7 +255,7 @@ int clb_engine::react_pass(int64_t* events_out) {
         for (size_t l = 0; l < lists.size(); ++l) if (add[l]) TRY(list_reserve((int)l, lists[l].n + add[l]));
         CK(excl_pairs.ensure_keep((size_t)nexcl + nev + 1024, (size_t)nexcl, stream));
         TRY(upload_list_descs());
-        k_apply_reactants<<<ge, 128, 0, stream>>>(nev, R.ev.p, R.cands_sorted.p, R.specs.p, R.chg.p, (int)changes.size(), id2idx.p, pos.p, vel.p, charge.p, R.counters.p);
+        k_apply_reactants<<<ge, 128, 0, stream>>>(nev, R.ev.p, R.cands_sorted.p, R.specs.p, R.chg.p, (int)changes.size(), id2idx.p, wslot.p, pos.p, vel.p, charge.p, R.counters.p);
         k_event_ranks<<<1, 1024, 0, stream>>>(nev, R.ev.p, R.cands_sorted.p, R.specs.p, (int)lists.size(), R.erank.p, R.list_n.p);
         unsigned long long hx = (unsigned long long)nexcl;
         CK(cudaMemcpyAsync(R.scalars.p + 2, &hx, 8, cudaMemcpyHostToDevice, stream));
@@ -285,13 +285,13 @@ int clb_engine::react_pass(int64_t* events_out) {
             size_t touchcap = (size_t)nev * 2 * 64;
             CK(R.touched.ensure(touchcap));
             CK(cudaMemsetAsync(R.scalars.p + 4, 0, 8, stream));
-            k_nb_claims<<<ceil_div(2 * nev, 128), 128, 0, stream>>>(nev, R.ev.p, R.cands_sorted.p, R.chg.p, (int)changes.size(), R.adj.p, R.deg.p, id2idx.p, pos.p,
+            k_nb_claims<<<ceil_div(2 * nev, 128), 128, 0, stream>>>(nev, R.ev.p, R.cands_sorted.p, R.chg.p, (int)changes.size(), R.adj.p, R.deg.p, wslot.p,
                                                                    R.claim.p, R.touched.p, R.scalars.p + 4, (unsigned long long)touchcap);
             unsigned long long nt = 0;
             CK(cudaMemcpyAsync(&nt, R.scalars.p + 4, 8, cudaMemcpyDeviceToHost, stream));
             CK(cudaStreamSynchronize(stream));
             if (nt > touchcap) return fail(CLB_ERR_RANGE, "neighbour-change buffer overflow");
-            if (nt) k_nb_apply<<<ceil_div((long long)nt, 128), 128, 0, stream>>>((int)nt, R.touched.p, R.claim.p, R.chg.p, id2idx.p, pos.p, vel.p, charge.p);
+            if (nt) k_nb_apply<<<ceil_div((long long)nt, 128), 128, 0, stream>>>((int)nt, R.touched.p, R.claim.p, R.chg.p, id2idx.p, wslot.p, pos.p, vel.p, charge.p);
         }
         tr.mark("mol_nb");
         // read back the new bond counts
@@ -308,7 +308,7 @@ int clb_engine::react_pass(int64_t* events_out) {
             CK(cudaMemsetAsync(R.list_cnt.p, 0, CLB_MAX_LISTS * 4, stream));
             CK(cudaMemsetAsync(R.scalars.p + 6, 0, 8, stream));
             k_topo_tuples<0><<<ge, 128, 0, stream>>>(nev, R.ev.p, R.cands_sorted.p, R.specs.p, R.lists.p, R.regs.p, (int)tmregs.size(), R.adj.p, R.deg.p, R.ev_of_slot.p,
-                                                     id2idx.p, pos.p, R.list_n.p, R.list_cnt.p, excl_pairs.p, R.scalars.p + 2, R.scalars.p + 6);
+                                                     wslot.p, R.list_n.p, R.list_cnt.p, excl_pairs.p, R.scalars.p + 2, R.scalars.p + 6);
             std::vector<int> hc(CLB_MAX_LISTS);
             unsigned long long nx = 0;
             CK(cudaMemcpyAsync(hc.data(), R.list_cnt.p, CLB_MAX_LISTS * 4, cudaMemcpyDeviceToHost, stream));
@@ -322,7 +322,7 @@ int clb_engine::react_pass(int64_t* events_out) {
                 hx = (unsigned long long)nexcl;
                 CK(cudaMemcpyAsync(R.scalars.p + 2, &hx, 8, cudaMemcpyHostToDevice, stream));
                 k_topo_tuples<1><<<ge, 128, 0, stream>>>(nev, R.ev.p, R.cands_sorted.p, R.specs.p, R.lists.p, R.regs.p, (int)tmregs.size(), R.adj.p, R.deg.p, R.ev_of_slot.p,
-                                                         id2idx.p, pos.p, R.list_n.p, R.list_cnt.p, excl_pairs.p, R.scalars.p + 2, R.scalars.p + 6);
+                                                         wslot.p, R.list_n.p, R.list_cnt.p, excl_pairs.p, R.scalars.p + 2, R.scalars.p + 6);
                 CK(cudaStreamSynchronize(stream));
                 // deterministic order of the appended tuples: sort each new segment on the host
                 for (size_t l = 0; l < lists.size(); ++l) if (hc[l]) {

@@ -37,6 +37,25 @@ POT = dict(Harmonic=1, Tabulated=2, AngularHarmonic=3, TabulatedAngular=4, Tabul
 NB = dict(Tabulated=1, LennardJones=2, MixedTabulated=3)
 
 
+def slab_planes(ncz, nranks):
+    """[(cz0, nczl)] per rank: the cell planes along z are dealt out contiguously, the first ncz % nranks ranks
+    get one more (same rule as slab_planes() in csrc/engine_comm.inl)."""
+    base, rem = divmod(int(ncz), int(nranks))
+    out = []
+    for r in range(nranks):
+        out.append((r * base + min(r, rem), base + (1 if r < rem else 0)))
+    return out
+
+
+def slab_owner(z, box_z, rc_plus_skin, nranks):
+    """Rank that owns coordinate(s) z: plane = floor(frac(z / Lz) * ncz) with ncz = floor(Lz / (rc + skin))."""
+    ncz = int(np.floor(box_z / rc_plus_skin))
+    fr = np.asarray(z, float) / box_z
+    cz = np.minimum((np.floor((fr - np.floor(fr)) * ncz)).astype(np.int64), ncz - 1)
+    bounds = np.array([c0 for c0, _ in slab_planes(ncz, nranks)] + [ncz])
+    return np.searchsorted(bounds, cz, side="right") - 1
+
+
 class Engine:
     def __init__(self, box, rc_max, skin, seed=0, device=0):
         self.L = _lib.load()
@@ -307,6 +326,23 @@ class Engine:
     def comm_init(self, rank, nranks, nccl_id):
         buf = (C.c_char * 128).from_buffer_copy(bytes(nccl_id))
         self._ck(self.L.clb_comm_init(self.h, int(rank), int(nranks), buf))
+
+    def join(self, group=None):
+        """Make this engine one slab of a multi-GPU run: rank 0 creates the NCCL id, torch.distributed broadcasts
+        the 128 bytes (torch is plumbing only), every rank calls clb_comm_init.  Replaces the MPI node grid of
+        storage.DomainDecomposition (src/start_simulation.py:152-163).  Must precede set_particles."""
+        import torch
+        import torch.distributed as dist
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        if world == 1:
+            return rank, world
+        dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+        buf = torch.zeros(128, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            buf.copy_(torch.frombuffer(bytearray(self.nccl_unique_id()), dtype=torch.uint8))
+        dist.broadcast(buf, src=0, group=group)
+        self.comm_init(rank, world, bytes(buf.cpu().numpy().tobytes()))
+        return rank, world
 
     @staticmethod
     def nccl_unique_id():

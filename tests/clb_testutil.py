@@ -66,7 +66,7 @@ class Pair:
     Positions are pushed to the engine first and read back (the engine stores them on its 2^32
     lattice); the oracle is fed exactly those values, so both sides see identical inputs."""
 
-    def __init__(self, pos, box, type, mass=None, vel=None, state=None, resid=None, rc=2.5, skin=0.3, seed=11, ids=None):
+    def __init__(self, pos, box, type, mass=None, vel=None, state=None, resid=None, rc=2.5, skin=0.3, seed=11, ids=None, join=False, device=0):
         from chemlab_b200 import Engine
         from oracle import pyoracle
         n = len(pos)
@@ -81,7 +81,9 @@ class Pair:
         pos = np.asarray(pos, float)[order]; type = np.asarray(type, np.int32)[order]; mass = mass[order]
         state = state[order]; resid = resid[order]
         vel = None if vel is None else np.asarray(vel, float)[order]
-        self.e = Engine(box, rc, skin, seed=seed)
+        self.e = Engine(box, rc, skin, seed=seed, device=device)
+        if join:
+            self.e.join()       # multi-GPU: this engine becomes one slab (torch.distributed must be initialised)
         self.e.set_particles(self.ids, type, pos, mass, vel=vel, state=state, res_id=resid)
         st = self.e.get_particles(fields=("pos", "vel", "mass", "image"))
         self.o = pyoracle.Oracle(n, box, rc, skin, seed=seed)
