@@ -186,21 +186,13 @@ def main():
 
     sysd = synthetic.trimer_melt(a.n_side, rho=RHO, seed=12345, kT=KT)
     n = sysd["n"]
-    from chemlab_b200 import Engine
-    if world > 1:
-        # one engine per rank, slab decomposition over z; rank 0 creates the NCCL id
-        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
-        if rank == 0:
-            idt = torch.tensor(list(Engine.nccl_unique_id()), dtype=torch.uint8, device="cuda")
-        dist.broadcast(idt, 0)
-        nccl_id = bytes(idt.cpu().tolist())
     from chemlab_b200 import Engine as _E
     e = _E(sysd["box"], RC, SKIN, seed=SEED, device=device)
     for kv in a.option:
         k, v = kv.split("=")
         e.set_option(k, float(v))
     if world > 1:
-        e.comm_init(rank, world, nccl_id)
+        e.join()          # one engine per rank = one z-slab; torch.distributed only carries the NCCL id
     e.set_particles(sysd["ids"], sysd["type"], sysd["pos"], sysd["mass"], vel=sysd["vel"], state=sysd["state"], res_id=sysd["resid"])
     h = synthetic.setup_reactive_melt(e, sysd, rc=RC, dt=DT, kT=KT, gamma=GAMMA, interval=INTERVAL, p_accept=P_ACCEPT)
 
@@ -216,7 +208,8 @@ def main():
     e.reaction_general(1, INTERVAL, 1, 0)
     if a.warmup > 0:
         e.run(a.warmup)
-    snap = snapshot(e, sysd, h) if (world == 1 and rank == 0 and not (a.no_e2e and a.no_cpu_baseline)) else None
+    # the read-back is collective on a multi-rank engine: every rank takes the snapshot
+    snap = snapshot(e, sysd, h) if not (a.no_e2e and (a.no_cpu_baseline or world > 1)) else None
 
     e.reset_timers()
     e.set_option("pair_event_timing", 1)
@@ -231,12 +224,16 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     tm, cn = e.timers()
     t_dev = tm["total"]
-    if dist is not None:
-        tt = torch.tensor([t_dev, t_wall], dtype=torch.float64, device="cuda")
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        t_dev, t_wall = float(tt[0]), float(tt[1])
     pair_ms = e.get_option("pair_kernel_ms")
     pair_launches = e.get_option("pair_kernel_launches")
+    if dist is not None:
+        # timing = max over ranks; extensive counters = sum over ranks
+        tt = torch.tensor([t_dev, t_wall, pair_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_dev, t_wall, pair_ms = float(tt[0]), float(tt[1]), float(tt[2])
+        cc = torch.tensor([cn["list_entries"], cn["launches"], cn["ghosts"]], dtype=torch.float64, device="cuda")
+        dist.all_reduce(cc, op=dist.ReduceOp.SUM)
+        cn["list_entries"], cn["launches"], cn["ghosts"] = int(cc[0]), int(cc[1]), int(cc[2])
     e.set_option("pair_event_timing", 0)
     e.energy(h["nb"])                       # also counts the pairs inside the force cutoff
     _, cn2 = e.timers()
@@ -265,13 +262,20 @@ def main():
                 "pair_interactions_per_s": interacting * steps_per_s, "interacting_pairs_per_step": interacting,
                 "list_pairs_per_particle": cn["list_entries"] / 2.0 / n, "ns_per_day_at_dt_ps": steps_per_s * DT * 86.4,
                 "rebuilds": cn["rebuilds"], "reaction_passes": cn["reaction_passes"], "reaction_events": cn["reaction_events"],
-                "new_bonds_total": nbonds_new, "temperature": float(kin[1]), "wall_s": t_wall, "equil_steps": a.equil}
+                "new_bonds_total": nbonds_new, "temperature": float(kin[1]), "wall_s": t_wall, "equil_steps": a.equil,
+                "ghost_beads_total": cn["ghosts"], "pair_threads": e.get_option("pair_threads"), "pair_grid": e.get_option("pair_grid"),
+                "home_max": e.get_option("home_max"), "tile_max": e.get_option("tile_max"),
+                "buckets_s": {k: v for k, v in tm.items() if v > 0} if e.get_option("timers") else None}
 
-    # e2e: public API with HOST buffers (N=1: a fresh engine restarted from the host snapshot)
-    if world == 1 and rank == 0 and not a.no_e2e:
+    # e2e: public API with HOST buffers -- a fresh engine (one per rank when N > 1) restarted from the host snapshot:
+    # upload of the particle state, run in chunks with observables read back, final state download
+    if not a.no_e2e:
         chunk = INTERVAL
+        barrier()
         t0 = time.perf_counter()
         e2 = _E(snap["box"], RC, SKIN, seed=SEED, device=device)
+        if world > 1:
+            e2.join()
         e2.set_particles(snap["ids"], snap["type"], snap["pos"], snap["mass"], vel=snap["vel"], state=snap["state"], res_id=snap["resid"])
         h2 = synthetic.setup_reactive_melt(e2, snap, rc=RC, dt=DT, kT=KT, gamma=GAMMA, interval=INTERVAL, p_accept=P_ACCEPT)
         restore_into(e2, snap, h2)
@@ -283,11 +287,17 @@ def main():
             e2.run(m); done += m
             obs.append((e2.kinetics()[1], e2.energy(h2["nb"]), e2.energy(h2["bonds"]), e2.energy(h2["angles"]), e2.energy(h2["react_bonds"])))
         out = e2.get_particles(fields=("pos", "vel", "type", "state", "image"))
+        barrier()
         t_e2e = time.perf_counter() - t0
+        if dist is not None:
+            tt = torch.tensor([t_e2e], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            t_e2e = float(tt[0])
         h2d = n * (8 + 4 + 24 + 24 + 8 + 4 + 4) + snap["bonds"].size * 8 + snap["angles_now"].size * 8 + snap["excl_now"].size * 8 + 3 * 1500 * 8
         d2h = n * (24 + 24 + 4 + 4 + 12) + len(obs) * 5 * 8
-        line["e2e"] = {"value": a.steps / t_e2e, "unit": "steps/s", "h2d_bytes_per_step": h2d / a.steps, "d2h_bytes_per_step": d2h / a.steps,
-                       "seconds": t_e2e, "what": "Engine create + full state upload + run in %d-step chunks with T/Epot read back per chunk + final state download" % chunk}
+        if rank == 0:
+            line["e2e"] = {"value": a.steps / t_e2e, "unit": "steps/s", "h2d_bytes_per_step": h2d / a.steps, "d2h_bytes_per_step": d2h / a.steps,
+                           "seconds": t_e2e, "what": "Engine create%s + full state upload + run in %d-step chunks with T/Epot read back per chunk + final state download (N > 1: every rank uploads and downloads the full state)" % (" + NCCL join" if world > 1 else "", chunk)}
         e2.close()
     elif rank == 0:
         line["e2e"] = None

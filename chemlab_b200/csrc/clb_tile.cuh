@@ -495,6 +495,140 @@ __global__ void __launch_bounds__(512) k_pair_forces_tab(ClbGrid g, ClbGeom geo,
 }
 
 // ------------------------------------------------------------------------------------------
+// Third generation of the all-tabulated kernel (cubic box + one common table grid; the benchmark melt and every
+// shipped chemlab example with a cubic box).  Same algorithm and results as k_pair_forces_tab, fewer instructions:
+//   * 16 fp64 operations per listed pair instead of 20:
+//       1/r   : y0 = MUFU.RSQ seed, yh = y0/2 by an exponent decrement (free), h = r2*y0, e = fma(-h, yh, 1/2),
+//               y = fma(y0, e, y0), r = fma(h, e, h)                                  (4 instead of 5)
+//       table : rows are stored as {A_i, B_i} with F(r) = A_i + r*B_i on [r_i, r_i+1) -- the SAME straight line as
+//               the reference's (1-b) f_i + b f_i+1 (U12) -- and the index comes from the low word of
+//               fma.rd(r, 1/dx, 1.5*2^52 - x0/dx) = floor((r-x0)/dx): no fraction, no back-subtraction (2 instead of 5)
+//   * one 64-bit select per pair (on the final force factor; the row index of a masked pair is merely clamped) instead of two;
+//   * ONEPD: when every type pair shares one table and one cutoff the descriptor lives in registers -> one
+//     shared-memory gather less per pair (the kernel is shared-memory-pipe bound);
+//   * NI entries are evaluated in lock step (stage-major source) so that their dependency chains interleave.
+struct ClbPairArgs2 {
+    const int* cell_start; const int4* pos; const unsigned short* entries; const int* nl_count;
+    const double2* pd2;      // per type pair {rc2 (lattice^2; < 0: no potential), 1.5*2^52 + first row (row = low word)}
+    const double2* trows;    // {A_i, B_i} rows of all tables, lattice units
+    double* force; ClbCtl* ctl;
+    int cap, ntypes, nrows_total, fstride, npw;
+    double invdx, cmagic;    // 1/dx (lattice units) and 1.5*2^52 - x0/dx (x0/dx integral: checked by the host)
+    unsigned nm1;            // rows - 1 of every table
+    double one_rc2; int one_off;   // ONEPD descriptor
+};
+__device__ __forceinline__ void rsqrt_seed2(double x, double& y0, double& yh) {
+    int hi = __double2hiint(x), lo = __double2loint(x);
+    unsigned fb = ((unsigned)(hi - 0x38000000) << 3) | ((unsigned)lo >> 29);
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(__uint_as_float(fb)));
+    unsigned yb = __float_as_uint(y);
+    int h = (int)((yb >> 3) + 0x38000000u), l = (int)(yb << 29);
+    y0 = __hiloint2double(h, l);
+    yh = __hiloint2double(h - 0x00100000, l);      // y0 / 2
+}
+template <bool TABS_SMEM, bool ONEPD, int NI>
+__global__ void __launch_bounds__(512) k_pair_forces_tab2(ClbGrid g, ClbPairArgs2 A) {
+    if (*(volatile int*)&A.ctl->stall) return;
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ int s_off[CLB_TILE_CELLS + 1];
+    __shared__ int s_src[CLB_TILE_CELLS];
+    const int ntp = A.ntypes * A.ntypes;
+    double2* s_pd = reinterpret_cast<double2*>(smem);
+    double2* s_rows = s_pd + (ONEPD ? 0 : ntp);
+    int4* s_pos = reinterpret_cast<int4*>(s_rows + (TABS_SMEM ? A.nrows_total : 0));
+    if (!ONEPD) for (int i = threadIdx.x; i < ntp; i += blockDim.x) s_pd[i] = A.pd2[i];
+    if (TABS_SMEM) for (int i = threadIdx.x; i < A.nrows_total; i += blockDim.x) s_rows[i] = __ldg(A.trows + i);
+    const double2* rows = TABS_SMEM ? s_rows : A.trows;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nhpass = A.npw * 32;
+    const double invdx = A.invdx, cmagic = A.cmagic;
+    const unsigned nm1 = A.nm1;
+    unsigned err = 0;
+    for (int b = blockIdx.x; b < g.nblocks; b += gridDim.x) {
+        TileCtx t;
+        tile_geometry(g, b, t);
+        __syncthreads();
+        tile_offsets(g, t, A.cell_start, s_off, s_src);
+        tile_stage(t, s_off, s_src, A.pos, s_pos, nullptr, nullptr, nullptr);
+        __syncthreads();
+        for (int p0 = 0; p0 < t.nh; p0 += nhpass) {
+            const int p = p0 + warp * 32 + lane;
+            const bool act = p < t.nh;
+            const int gi = t.hs + (act ? p : 0);
+            const int4 pi = __ldg(A.pos + gi);
+            const unsigned pix = (unsigned)pi.x + 0x80000000u, piy = (unsigned)pi.y + 0x80000000u, piz = (unsigned)pi.z + 0x80000000u;
+            const int cnt = act ? __ldg(A.nl_count + gi) : 0;
+            const int trow = pw_type(pi.w) * A.ntypes;
+            const uint4* row = reinterpret_cast<const uint4*>(A.entries + (size_t)gi * A.cap);
+            const int nb = (cnt + 7) >> 3;
+            double ax = 0.0, ay = 0.0, az = 0.0;
+            uint4 ev = make_uint4(0, 0, 0, 0);
+            if (nb > 0) ev = __ldg(row);
+#pragma unroll 1
+            for (int bi = 0; bi < nb; ++bi) {
+                const uint4 cur = ev;
+                if (bi + 1 < nb) ev = __ldg(row + bi + 1);
+                const int ne = cnt - bi * 8;                      // >= 1; entries beyond ne are stale
+                const unsigned wds[4] = {cur.x, cur.y, cur.z, cur.w};
+#pragma unroll
+                for (int s0 = 0; s0 < 8; s0 += NI) {
+                    bool in[NI];
+                    int4 pj[NI];
+                    double dx[NI], dy[NI], dz[NI], r2[NI], y0[NI], yh[NI], y[NI], r[NI], rc2[NI], ti[NI], F[NI];
+                    int off[NI];
+                    double2 rw[NI];
+#pragma unroll
+                    for (int q = 0; q < NI; ++q) {
+                        const int k = s0 + q;
+                        unsigned e = (k & 1) ? (wds[k >> 1] >> 16) : (wds[k >> 1] & 0xffffu);
+                        in[q] = k < ne;
+                        e = in[q] ? e : 0u;
+                        pj[q] = s_pos[e];
+                    }
+#pragma unroll
+                    for (int q = 0; q < NI; ++q) {
+                        dx[q] = __hiloint2double(0x43300000, (int)(pix - (unsigned)pj[q].x)) - 4503601774854144.0;
+                        dy[q] = __hiloint2double(0x43300000, (int)(piy - (unsigned)pj[q].y)) - 4503601774854144.0;
+                        dz[q] = __hiloint2double(0x43300000, (int)(piz - (unsigned)pj[q].z)) - 4503601774854144.0;
+                        if (ONEPD) { rc2[q] = A.one_rc2; off[q] = A.one_off; }
+                        else { const double2 d = s_pd[trow + pw_type(pj[q].w)]; rc2[q] = d.x; off[q] = __double2loint(d.y); }
+                    }
+#pragma unroll
+                    for (int q = 0; q < NI; ++q) r2[q] = fma(dz[q], dz[q], fma(dy[q], dy[q], dx[q] * dx[q]));
+#pragma unroll
+                    for (int q = 0; q < NI; ++q) { in[q] = in[q] && (r2[q] <= rc2[q]); rsqrt_seed2(r2[q], y0[q], yh[q]); }
+#pragma unroll
+                    for (int q = 0; q < NI; ++q) {
+                        const double h = r2[q] * y0[q];
+                        const double ee = fma(-h, yh[q], 0.5);
+                        y[q] = fma(y0[q], ee, y0[q]);             // 1/r
+                        r[q] = fma(h, ee, h);                     // r
+                    }
+#pragma unroll
+                    for (int q = 0; q < NI; ++q) {
+                        ti[q] = __fma_rd(r[q], invdx, cmagic);    // round down: the low word is floor((r - x0)/dx) exactly
+                        const unsigned idx = (unsigned)__double2loint(ti[q]);
+                        if (in[q] && idx > nm1) err |= CLB_EF_TABLE_RANGE;       // fatal in the reference (U12)
+                        rw[q] = rows[off[q] + (int)min(idx, nm1)];
+                    }
+#pragma unroll
+                    for (int q = 0; q < NI; ++q) {
+                        // outside the cutoff / list tail: whatever was computed from the (clamped) row is discarded here
+                        F[q] = fma(r[q], rw[q].y, rw[q].x) * y[q];
+                        F[q] = in[q] ? F[q] : 0.0;
+                    }
+#pragma unroll
+                    for (int q = 0; q < NI; ++q) { ax = fma(F[q], dx[q], ax); ay = fma(F[q], dy[q], ay); az = fma(F[q], dz[q], az); }
+                }
+            }
+            if (act) { A.force[gi] = ax; A.force[gi + A.fstride] = ay; A.force[gi + 2 * A.fstride] = az; }
+        }
+    }
+    if (err) atomicOr(&A.ctl->err, err);
+}
+
+// ------------------------------------------------------------------------------------------
 // Pair energy of one interaction handle (analysis.PotentialEnergy): fp64 throughout, each pair
 // visited twice (full list) -> factor 1/2.  Per-block partial sums are reduced in a fixed order
 // by k_sum_partials, so the result is bit-reproducible.

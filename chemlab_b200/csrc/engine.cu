@@ -70,6 +70,13 @@ static PairKernel pair_kernel_tab(int cubic, int smem, int ugrid, int split) {
     if (smem) return ugrid ? pair_kernel_tab_split<false, true, true>(split) : pair_kernel_tab_split<false, true, false>(split);
     return ugrid ? pair_kernel_tab_split<false, false, true>(split) : pair_kernel_tab_split<false, false, false>(split);
 }
+typedef void (*PairKernel2)(ClbGrid, ClbPairArgs2);
+static PairKernel2 pair_kernel_tab2(int smem, int onepd, int ni) {
+    if (ni >= 4) { if (smem) return onepd ? k_pair_forces_tab2<true, true, 4> : k_pair_forces_tab2<true, false, 4>;
+                   return onepd ? k_pair_forces_tab2<false, true, 4> : k_pair_forces_tab2<false, false, 4>; }
+    if (smem) return onepd ? k_pair_forces_tab2<true, true, 2> : k_pair_forces_tab2<true, false, 2>;
+    return onepd ? k_pair_forces_tab2<false, true, 2> : k_pair_forces_tab2<false, false, 2>;
+}
 static PairKernel pair_kernel(int cubic, int smem, int ugrid, int split) {
     if (cubic) { if (smem) return ugrid ? pair_kernel_split<true, true, true>(split) : pair_kernel_split<true, true, false>(split);
                  return ugrid ? pair_kernel_split<true, false, true>(split) : pair_kernel_split<true, false, false>(split); }
@@ -143,6 +150,10 @@ extern "C" int clb_create(clb_engine** out, int device, const double box[3], dou
           cudaFuncSetAttribute(pair_kernel_tab(c, sm, ug, 1 << sp), cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
           cudaFuncSetAttribute(pair_kernel(c, sm, ug, 1 << sp), cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
           cudaFuncSetAttribute(pair_kernel(c, sm, ug, 1 << sp), cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); }
+    for (int sm = 0; sm < 2; ++sm) for (int op = 0; op < 2; ++op) for (int ni = 2; ni <= 4; ni += 2) {
+        cudaFuncSetAttribute(pair_kernel_tab2(sm, op, ni), cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+        cudaFuncSetAttribute(pair_kernel_tab2(sm, op, ni), cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    }
     cudaFuncSetAttribute(k_pair_energy<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
     cudaFuncSetAttribute(k_pair_energy<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
     cudaFuncSetAttribute(k_decode_pairs, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
@@ -183,6 +194,9 @@ extern "C" int clb_set_option(clb_engine* e, const char* name, double v) {
     else if (s == "pair_event_timing") e->pair_event_timing = (int)v;
     else if (s == "pair_split") { e->pair_split_user = (int)v; if (e->lists_valid) return e->configure_pair_launch(); }
     else if (s == "build_threads") e->build_threads = (int)v;
+    else if (s == "pair_warps") { e->pair_warps_user = (int)v; if (e->lists_valid) return e->configure_pair_launch(); }
+    else if (s == "pair_kernel") { e->pair_kernel_user = (int)v; if (e->lists_valid) return e->configure_pair_launch(); }
+    else if (s == "pair_ni") { e->pair_ni = (int)v >= 4 ? 4 : 2; if (e->lists_valid) return e->configure_pair_launch(); }
     else if (s == "pair_branchfree") { e->branchfree_user = (int)v; if (e->lists_valid) return e->configure_pair_launch(); }
     else return e->fail(CLB_ERR_ARG, "unknown option %s", name);
     return CLB_OK;
@@ -204,6 +218,8 @@ extern "C" int clb_get_option(clb_engine* e, const char* name, double* v) {
     else if (s == "pair_grid") *v = e->pair_grid;
     else if (s == "pair_threads") *v = e->pair_threads;
     else if (s == "pair_split") *v = e->pair_split;
+    else if (s == "pair_kernel") *v = e->pair_kernel_active;
+    else if (s == "pair_onepd") *v = e->tab2_onepd;
     else if (s == "uniform_grid") *v = e->ugrid_on;
     else if (s == "pair_smem") *v = e->pair_smem;
     else if (s == "tables_in_smem") *v = e->tabs_smem;
@@ -731,6 +747,34 @@ int clb_engine::upload_potentials() {
     {   // the last row of every table is read when r equals the table end: {f[n-1], 0}
         for (auto& m : tm) { frows[m.off + m.n - 1] = make_double2(frows[m.off + m.n - 1].x, 0.0); }
     }
+    // third-generation kernel (k_pair_forces_tab2): rows {A_i, B_i} with F = A_i + r_lat * B_i, descriptors {rc2, first row}
+    tab2_ok = 0; tab2_onepd = 0;
+    if (geo.cubic && ugrid_on && all_tab) {
+        const ClbTabMeta& m0 = tm[0];
+        const double k0 = m0.x0 / m0.dx;
+        if (fabs(k0 - rint(k0)) < 1e-9 && rint(k0) < 1e6) {
+            const double q = geo.q[0];
+            std::vector<double2> rows2(frows.size()), pd2(pd.size());
+            for (auto& m : tm)
+                for (int i = 0; i < m.n; ++i) {
+                    const double2 fr = frows[m.off + i];               // {f_i + df_i/2, df_i}
+                    const double fi = fr.x - 0.5 * fr.y, sl = fr.y / m.dx, xi = m.x0 + i * m.dx;
+                    rows2[m.off + i] = make_double2(fi - xi * sl, q * sl);
+                }
+            bool one = true;
+            for (size_t k = 0; k < pd.size(); ++k) {
+                pd2[k] = make_double2(pd[k].kind ? pd[k].rc2 : -1.0, 6755399441055744.0 + (double)pd[k].tab);   // rc2 in lattice^2; first row in the LOW WORD (1.5*2^52 + n)
+                one = one && pd[k].kind == 1 && pd[k].rc2 == pd[0].rc2 && pd[k].tab == pd[0].tab;
+            }
+            CK(d_rows2.ensure(rows2.size())); CK(d_pd2.ensure(pd2.size()));
+            CK(cudaMemcpyAsync(d_rows2.p, rows2.data(), rows2.size() * sizeof(double2), cudaMemcpyHostToDevice, stream));
+            CK(cudaMemcpyAsync(d_pd2.p, pd2.data(), pd2.size() * sizeof(double2), cudaMemcpyHostToDevice, stream));
+            CK(cudaStreamSynchronize(stream));
+            tab2_ok = 1; tab2_onepd = one ? 1 : 0;
+            tab2_invdx = q / m0.dx; tab2_cmagic = 6755399441055744.0 - rint(k0); tab2_nm1 = (unsigned)m0.n - 1u;
+            tab2_one_rc2 = pd[0].rc2; tab2_one_off = pd[0].tab;
+        }
+    }
     CK(d_plj.ensure(plj.size()));
     CK(cudaMemcpyAsync(d_plj.p, plj.data(), plj.size() * sizeof(double2), cudaMemcpyHostToDevice, stream));
     nt_dev = nt; ntabs_dev = (int)tm.size(); nrows_dev = (int)frows.size();
@@ -979,9 +1023,33 @@ PairKernel clb_engine_pair_fn(const clb_engine* e, int in_smem, int split) {
 }
 
 int clb_engine::configure_pair_launch() {
+    pair_kernel_active = (tab2_ok && branchfree_user && pair_kernel_user != 1) ? 2 : 1;
+    if (pair_kernel_active == 2) {
+        const double mean_home = (double)(own1 - own0) / std::max(1, grid.nblocks);
+        int npw = std::max(1, std::min((home_max + 31) / 32, (int)ceil((mean_home + 3.0 * sqrt(mean_home)) / 32.0)));
+        if (pair_warps_user > 0) npw = pair_warps_user;
+        npw = std::min(npw, 16);
+        size_t fixed = tab2_onepd ? 0 : (size_t)nt_dev * nt_dev * sizeof(double2);
+        size_t rows = (size_t)nrows_dev * sizeof(double2);
+        size_t tile = (size_t)tile_max * sizeof(int4) + 16;
+        bool in_smem = tabs_smem_user != 0 && fixed + rows + tile <= (size_t)std::min(smem_optin, 110 * 1024);
+        if (tabs_smem_user == 2 && fixed + rows + tile <= (size_t)smem_optin) in_smem = true;
+        tabs_smem = in_smem ? 1 : 0;
+        pair_split = 1; pair_npw = npw; pair_threads = npw * 32;
+        pair_smem = (int)(fixed + (in_smem ? rows : 0) + tile);
+        if (pair_smem > smem_optin) return fail(CLB_ERR_UNSUPPORTED, "pair kernel needs %d B of shared memory: lower block_cells", pair_smem);
+        int nb = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, pair_kernel_tab2(tabs_smem, tab2_onepd, pair_ni), pair_threads, pair_smem);
+        pair_grid = std::min(grid.nblocks, std::max(1, nb) * nsm);
+        return CLB_OK;
+    }
     // warps that cover the home particles of a block: mean + 3 sigma (Poisson); rarer, fuller blocks take a second pass
     const double mean_home = (double)(own1 - own0) / std::max(1, grid.nblocks);
-    const int npw = std::max(1, std::min((home_max + 31) / 32, (int)ceil((mean_home + 3.0 * sqrt(mean_home)) / 32.0)));
+    // warps that cover the home particles of a block in one pass: mean + 3 sigma (a 1 x 1 x bx row of cells has a large
+    // surface, its occupancy fluctuates almost like a Poisson variable); measured on B200: sizing for the mean (5 warps
+    // at 148 beads/block) forces a second pass on ~1/4 of the blocks and costs 22 %
+    int npw = std::max(1, std::min((home_max + 31) / 32, (int)ceil((mean_home + 3.0 * sqrt(mean_home)) / 32.0)));
+    if (pair_warps_user > 0) npw = pair_warps_user;
     size_t fixed = (size_t)nt_dev * nt_dev * (sizeof(ClbPairDesc) + sizeof(double2)) + (size_t)ntabs_dev * sizeof(ClbTabMeta);
     size_t rows = (size_t)nrows_dev * sizeof(double2);
     size_t tile = (size_t)tile_max * sizeof(int4) + 16;
@@ -1104,7 +1172,14 @@ extern "C" int clb_decompose(clb_engine* e) {
 void clb_engine::enqueue_forces() {
     bucket_begin(CLB_B_PAIR);
     if (pair_event_timing) { pair_event_valid.resize(pair_event_used / 2 + 1, 1); pair_event_valid[pair_event_used / 2] = 1; cudaEventRecord(next_pair_event(), stream); }
-    {
+    if (pair_kernel_active == 2) {
+        ClbPairArgs2 A;
+        A.cell_start = cell_start.p; A.pos = pos.p; A.entries = nl_entries.p; A.nl_count = nl_count.p;
+        A.pd2 = d_pd2.p; A.trows = d_rows2.p; A.force = force.p; A.ctl = d_ctl;
+        A.cap = nl_cap; A.ntypes = nt_dev; A.nrows_total = nrows_dev; A.fstride = ncap; A.npw = pair_npw;
+        A.invdx = tab2_invdx; A.cmagic = tab2_cmagic; A.nm1 = tab2_nm1; A.one_rc2 = tab2_one_rc2; A.one_off = tab2_one_off;
+        pair_kernel_tab2(tabs_smem, tab2_onepd, pair_ni)<<<pair_grid, pair_threads, pair_smem, stream>>>(grid, A);
+    } else {
         ClbPairArgs A;
         A.cell_start = cell_start.p; A.pos = pos.p; A.entries = nl_entries.p; A.nl_count = nl_count.p;
         A.pdesc = d_pd.p; A.plj = d_plj.p; A.tmeta = d_tm.p; A.trows = d_frows.p; A.force = force.p; A.ctl = d_ctl;
@@ -1164,7 +1239,13 @@ extern "C" int clb_energy(clb_engine* e, int inter, double* out) {
         CK(cudaMemcpyAsync(e->h_scalar, e->d_scalar, 16, cudaMemcpyDeviceToHost, e->stream));
         CK(cudaStreamSynchronize(e->stream));
         *out = ((double*)e->h_scalar)[0];
-        e->last_interacting = ((unsigned long long*)e->h_scalar)[1] / 2;
+        // full lists visit every interacting pair twice (once per owner, possibly on two ranks)
+        double both[2] = {*out, (double)((unsigned long long*)e->h_scalar)[1]};
+        if (e->nranks > 1) TRY(e->comm_allreduce_sum(both, 2));
+        *out = both[0];
+        e->last_interacting = (unsigned long long)(both[1] + 0.5) / 2;
+        CK(cudaGetLastError());
+        return CLB_OK;
     } else {
         int no = e->own1 - e->own0;
         int nb = ceil_div(no, 256);

@@ -90,7 +90,7 @@ struct clb_engine {
     int nl_cap = 0, nl_cap_user = 0, nl_cap_user_seen = 0, nl_max = 0, tile_max = 0, home_max = 0;
     unsigned long long nl_total = 0, last_interacting = 0;
     int pair_grid = 0, pair_threads = 128, pair_smem = 0, tabs_smem = 1, pair_split = 1, pair_split_user = 0, pair_npw = 1, build_threads = 256;
-    int ugrid_on = 0, all_tab = 0, branchfree_user = 1;
+    int ugrid_on = 0, all_tab = 0, branchfree_user = 1, pair_warps_user = 0;
     ClbTabMeta ugrid_meta;
     bool lists_valid = false, forces_valid = false;
 
@@ -110,7 +110,10 @@ struct clb_engine {
     DevBuf<double2> d_plj;
     DevBuf<ClbPairDescE> d_pe;
     DevBuf<ClbTabMeta> d_tm, d_tm_e;
-    DevBuf<double2> d_frows, d_erows;
+    DevBuf<double2> d_frows, d_erows, d_rows2, d_pd2;
+    int tab2_ok = 0, tab2_onepd = 0, tab2_one_off = 0, pair_kernel_user = 0, pair_kernel_active = 1, pair_ni = 4;
+    unsigned tab2_nm1 = 0;
+    double tab2_invdx = 0, tab2_cmagic = 0, tab2_one_rc2 = 0;
 
     // tuple lists and bonded interactions
     std::vector<HostList> lists;

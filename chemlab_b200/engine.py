@@ -56,6 +56,21 @@ def slab_owner(z, box_z, rc_plus_skin, nranks):
     return np.searchsorted(bounds, cz, side="right") - 1
 
 
+def broadcast_nccl_id(group=None):
+    """128-byte ncclUniqueId created on rank 0 and broadcast over the torch.distributed group (nccl or gloo backend)."""
+    import torch
+    import torch.distributed as dist
+    rank = dist.get_rank(group)
+    on_gpu = dist.get_backend(group) == "nccl"
+    dev = torch.device("cuda", torch.cuda.current_device()) if on_gpu else torch.device("cpu")
+    buf = torch.zeros(128, dtype=torch.uint8)
+    if rank == 0:
+        buf = torch.frombuffer(bytearray(Engine.nccl_unique_id()), dtype=torch.uint8).clone()
+    buf = buf.to(dev)
+    dist.broadcast(buf, src=0, group=group)
+    return bytes(buf.cpu().numpy().tobytes())
+
+
 class Engine:
     def __init__(self, box, rc_max, skin, seed=0, device=0):
         self.L = _lib.load()
@@ -331,17 +346,11 @@ class Engine:
         """Make this engine one slab of a multi-GPU run: rank 0 creates the NCCL id, torch.distributed broadcasts
         the 128 bytes (torch is plumbing only), every rank calls clb_comm_init.  Replaces the MPI node grid of
         storage.DomainDecomposition (src/start_simulation.py:152-163).  Must precede set_particles."""
-        import torch
         import torch.distributed as dist
         rank, world = dist.get_rank(group), dist.get_world_size(group)
         if world == 1:
             return rank, world
-        dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
-        buf = torch.zeros(128, dtype=torch.uint8, device=dev)
-        if rank == 0:
-            buf.copy_(torch.frombuffer(bytearray(self.nccl_unique_id()), dtype=torch.uint8))
-        dist.broadcast(buf, src=0, group=group)
-        self.comm_init(rank, world, bytes(buf.cpu().numpy().tobytes()))
+        self.comm_init(rank, world, broadcast_nccl_id(group))
         return rank, world
 
     @staticmethod

@@ -1,0 +1,13 @@
+#!/bin/bash
+timeout 100 python -m pytest tests/test_gpu_reactions.py -x -q 2>&1 | tail -n 2
+for opt in "--option block_cells=12" "--option block_cells=16" "--option block_cells=16 --option pair_ni=2" "--option block_cells=6"; do
+  echo "== $opt"
+  timeout 120 python bench.py --steps 400 --warmup 100 --equil 500 --no_cpu_baseline --no_e2e $opt --option timers=0 2>&1 | python -c "
+import sys,json
+for l in sys.stdin:
+    if l.startswith('{'):
+        d=json.loads(l); r=d['roofline']
+        print('steps/s %.1f ms/step %.4f pair_ms %.4f share %.3f threads %s grid %s home_max %s tile_max %s rebuilds %s T %.4f'%(d['value'],d['ms_per_step'],r['kernel_ms'],r['kernel_share_of_step'],d.get('pair_threads'),d.get('pair_grid'),d.get('home_max'),d.get('tile_max'),d['rebuilds'],d['temperature']))
+    elif 'rror' in l: print(l.strip())
+"
+done
