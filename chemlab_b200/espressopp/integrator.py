@@ -364,11 +364,13 @@ class ATRPActivator:
         if not hits:
             return
         sel = self._rng.permutation(len(hits))[: self.num_particles]
-        n_act = n_deact = 0
+        n_activated = n_deactivated = 0
         for j in sel:
             i, k = hits[j]
-            t, s, act, prop, ds = self._centers[k]
-            p = (self.k_activate * self.ratio_activator) if act else (self.k_deactivate * self.ratio_deactivator)
+            t, s, needs_deactivator, prop, ds = self._centers[k]
+            # flag "A" (is_activator=False in chemlab's call, reaction_post_process.py:411): a dormant end that meets the
+            # ACTIVATOR catalyst, rate k_activate * ratio_activator; flag "DA": an active end that meets the DEACTIVATOR
+            p = (self.k_deactivate * self.ratio_deactivator) if needs_deactivator else (self.k_activate * self.ratio_activator)
             if self._rng.random() >= p:
                 continue
             pid = int(pids[i])
@@ -377,8 +379,10 @@ class ATRPActivator:
                 e.modify_particle(pid, "type", int(prop.type))
             if prop.mass is not None:
                 e.modify_particle(pid, "mass", float(prop.mass))
-            n_act += act; n_deact += (not act)
-        d = self.delta_catalyst * (n_act - n_deact) / max(1, self.num_particles)
+            n_deactivated += needs_deactivator; n_activated += (not needs_deactivator)
+        n_act, n_deact = n_activated, n_deactivated
+        # an activation turns one activator complex into a deactivator complex and vice versa
+        d = self.delta_catalyst * (n_activated - n_deactivated) / max(1, self.num_particles)
         self.ratio_activator = min(1.0, max(0.0, self.ratio_activator - d))
         self.ratio_deactivator = min(1.0, max(0.0, self.ratio_deactivator + d))
         if self.stats_filename:

@@ -1,0 +1,280 @@
+#!/usr/bin/env python
+"""start_simulation.py -- chemlab's driver on the B200 engine:  python -m chemlab_b200.start_simulation @params
+
+Same command line, same input files (`params` arg-file, GROMACS-like .top/.itp, .gro, INI reaction file, optional
+hooks.py) and same output files as the reference driver (src/start_simulation.py), re-authored for Python 3 on
+top of `chemlab_b200.espressopp`.  Stages follow the reference one to one:
+
+  setup     :77-197   units, topology, coordinates, System / storage / integrator, exclusions, VerletList
+  topology  :211-212  TopologyManager
+  hooks     :214-228  hooks.py from the working directory (hook_init_reaction, hook_at_step, ...)
+  reactions :241-272  reaction_parser + SetupReactions
+  forces    :298-310  non-bonded, bonds, angles, dihedrals
+  thermostat:326-376  Langevin only (others are outside the engine's scope and raise)
+  observers :446-569  SystemMonitor CSV
+  main loop :728-797  integrator.run(integrator_step) with reaction start/stop and the conversion stop criterion
+  outputs   :800-1081 final .gro, bond/angle/dihedral lists, reaction counters, benchmark record
+"""
+import os
+import random
+import sys
+import time
+
+import numpy as np
+
+from . import espressopp
+from .chemlab import app_args, files_io, gromacs_topology, reaction_parser, reaction_setup, tools
+
+
+def _load_hooks(path="hooks.py"):
+    """hooks.py is executed in the driver's namespace (reference: execfile, :220-228)."""
+    hooks = {}
+    if os.path.exists(path):
+        ns = {"espressopp": espressopp, "__name__": "hooks"}
+        with open(path) as f:
+            exec(compile(f.read(), path, "exec"), ns)
+        for name in ("hook_init_reaction", "hook_at_step", "hook_postsetup_interaction", "hook_setup_interactions", "hook_end"):
+            if callable(ns.get(name)):
+                hooks[name] = ns[name]
+        print("Loaded hooks: %s" % ", ".join(sorted(hooks)))
+    return hooks
+
+
+def main(argv=None):
+    args = app_args._args().parse_args(argv)
+    prefix_dir = os.path.dirname(args.output_prefix)
+    if prefix_dir:
+        os.makedirs(prefix_dir, exist_ok=True)
+    app_args._args().save_to_file("%sparams.out" % args.output_prefix, args)
+
+    kb = args.kb if args.kb else 0.0083144621                   # :53-61 (GROMACS units unless overridden)
+    mass_factor = args.mass_factor if args.mass_factor else 1.6605402
+    lj_cutoff, cg_cutoff = args.lj_cutoff, args.cg_cutoff
+    max_cutoff = max(lj_cutoff, cg_cutoff)                      # :77-80
+    dt = args.dt
+    time0 = time.time()
+
+    has_excl_file = args.exclusion_list is not None and os.path.exists(args.exclusion_list)
+    gt = gromacs_topology.GromacsTopology(args.top, generate_exclusions=not has_excl_file).read()
+    conf = files_io.GROFile(args.conf)
+    conf.read()
+    box = conf.box
+
+    integrator_step = args.int_step
+    if args.trj_collect > 0:
+        integrator_step = min(args.int_step, args.trj_collect)  # :100-103
+    skin = 0.16 if args.skin == "auto" else float(args.skin)
+    rng_seed = args.rng_seed
+    if not rng_seed or rng_seed == -1:
+        rng_seed = random.randint(10, 1000000)
+        args.rng_seed = rng_seed
+    prefix = "%s_%s" % (args.output_prefix, rng_seed)
+    print("Skin: %s\nRNG Seed: %s\nBoltzmann constant: %s" % (skin, rng_seed, kb))
+
+    part_prop, particle_list = gromacs_topology.gen_particle_list(conf, gt)
+    npart = len(particle_list)
+    print("Reads %d particles with properties %s" % (npart, part_prop))
+    if args.temperature is None:
+        raise RuntimeError("Temperature not defined!")
+    temperature = args.temperature * kb                          # :135
+
+    # ---- System / storage / integrator (:148-171)
+    system = espressopp.System()
+    system.rng = espressopp.esutil.RNG(rng_seed)
+    system.skin = skin
+    node_grid = (tuple(int(x) for x in args.node_grid.split(",")) if getattr(args, "node_grid", None)
+                 else espressopp.tools.decomp.nodeGrid(1))
+    cell_grid = espressopp.tools.decomp.cellGrid(box, node_grid, max_cutoff, skin)
+    print("Cell grid: %s, node grid: %s" % (cell_grid, node_grid))
+    system.bc = espressopp.bc.OrthorhombicBC(system.rng, box)
+    system.storage = espressopp.storage.DomainDecomposition(system, node_grid, cell_grid)
+    integrator = espressopp.integrator.VelocityVerlet(system)
+    integrator.dt = dt
+    system.integrator = integrator
+    part_prop = list(part_prop)
+    mi = part_prop.index("mass")
+    masses = [p[mi] * mass_factor for p in particle_list]
+    has_vel = all(a.velocity is not None for a in conf.atoms.values())
+    if getattr(args, "gen_velocity", False) or not has_vel:    # :136-146
+        vx, vy, vz = espressopp.tools.velocities.gaussian(temperature, npart, masses, kb=1.0, seed=rng_seed)
+        vel = [espressopp.Real3D(a, b, c) for a, b, c in zip(vx, vy, vz)]
+        print("Generated Maxwell-Boltzmann velocities at T*kB = %s" % temperature)
+    else:
+        vel = [espressopp.Real3D(*conf.atoms[p[0]].velocity) for p in particle_list]
+    particle_list = [tuple(p[:mi]) + (m,) + tuple(p[mi + 1:]) + (v,) for p, m, v in zip(particle_list, masses, vel)]
+    part_prop.append("v")
+    system.storage.addParticles(particle_list, *part_prop)
+    system.storage.decompose()
+
+    # ---- exclusions + Verlet list (:174-197)
+    if has_excl_file:
+        exclusions = [tuple(int(x) for x in l.split()) for l in open(args.exclusion_list) if l.strip()]
+        print("Read exclusion list from %s (%d pairs)" % (args.exclusion_list, len(exclusions)))
+    else:
+        exclusions = sorted(gt.exclusions)
+        with open("exclusion_%s.list" % os.path.basename(args.top).split(".")[0], "w") as f:
+            f.writelines("%d %d\n" % p for p in exclusions)
+    print("Excluded pairs from LJ interaction: %d" % len(exclusions))
+    dynamic_exclude = espressopp.DynamicExcludeList(integrator, exclusions)
+    verletlist = espressopp.VerletList(system, cutoff=max_cutoff, exclusionlist=dynamic_exclude)
+
+    # ---- topology manager, hooks, reactions (:211-272)
+    topology_manager = espressopp.integrator.TopologyManager(system)
+    system.topology_manager = topology_manager
+    hooks = _load_hooks()
+    ar = None
+    chem_fpls, reactions, ext_to_integrator = [], [], []
+    sc = None
+    ar_interval = 0
+    if args.reactions:
+        if not os.path.exists(args.reactions):
+            raise RuntimeError("Reaction config %s not found" % args.reactions)
+        cfg = reaction_parser.parse_config(args.reactions)
+        sc = reaction_setup.SetupReactions(system, verletlist, gt, topology_manager, cfg, args)
+        ar, chem_fpls, reactions, ext_to_integrator = sc.setup_reactions()
+        ar_interval = sc.ar_interval
+        integrator_step = min(integrator_step, ar_interval)      # :265-267
+        print("Set up %d reactions in %d groups, interval %d" % (len(reactions), len(chem_fpls), ar_interval))
+    sim_step = args.run // integrator_step                       # :103,:268 (Python-2 integer division)
+    dynamic_types = sc.dynamic_types if sc else set()
+
+    # ---- force field (:298-310)
+    cr_observs = dict(sc.cr_observs) if sc else {}
+    cr_observs, _ = gromacs_topology.set_nonbonded_interactions(system, gt, verletlist, lj_cutoff, getattr(args, "coulomb_cutoff", None),
+                                                                cg_cutoff, tables=getattr(args, "table_groups", None), cr_observs=cr_observs)
+    dyn_fpl, static_fpl, _ = gromacs_topology.set_bonded_interactions(system, gt, dynamic_types)
+    dyn_ftl, static_ftl = gromacs_topology.set_angle_interactions(system, gt, dynamic_types)
+    dyn_fql, static_fql = gromacs_topology.set_dihedral_interactions(system, gt, dynamic_types)
+    gromacs_topology.set_pair_interactions(system, gt, args, dynamic_types)
+    print("Interactions: %s" % ", ".join(system.getNameOfInteraction(k) for k in range(system.getNumberOfInteractions())))
+
+    # ---- thermostat (:326-376)
+    if args.thermostat != "lv":
+        raise NotImplementedError("thermostat %r: only the Langevin thermostat (lv) is inside the engine's scope (SURVEY E20)" % args.thermostat)
+    thermostat = espressopp.integrator.LangevinThermostat(system)
+    thermostat.temperature = temperature
+    thermostat.gamma = args.thermostat_gamma
+    integrator.addExtension(thermostat)
+    if getattr(args, "barostat", None) and getattr(args, "pressure", None):
+        raise NotImplementedError("barostats are outside the engine's scope (SURVEY E20)")
+
+    # ---- dynamic exclusions and topology bookkeeping (:378-444)
+    for f in chem_fpls:
+        dynamic_exclude.observe_tuple(f.fpl)
+        topology_manager.observe_tuple(f.fpl)
+    for lst in list(dyn_fpl.values()) + list(static_fpl):
+        topology_manager.observe_tuple(lst)
+    for lst in dyn_ftl.values():
+        dynamic_exclude.observe_triple(lst)
+    for lst in dyn_fql.values():
+        dynamic_exclude.observe_quadruple(lst)
+    # registered type tuples: every dynamic angle/dihedral parameter set becomes a template for generated tuples
+    for arity, dyn, params in ((3, dyn_ftl, gt.angleparams), (4, dyn_fql, gt.dihedralparams)):
+        for key, lst in dyn.items():
+            for pt, p in params.items():
+                if int(p["func"]) != key.func or not (set(pt) & set(dynamic_types)):
+                    continue
+                if arity == 3:
+                    topology_manager.register_triplet(lst, *pt)
+                else:
+                    topology_manager.register_quadruplet(lst, *pt)
+    topology_manager.initialize_topology()
+    integrator.addExtension(topology_manager)
+
+    # ---- observables (:446-569)
+    energy_file = "%s_energy_%s.csv" % (args.output_prefix, rng_seed)
+    monitor = espressopp.analysis.SystemMonitor(system, integrator, espressopp.analysis.SystemMonitorOutputCSV(energy_file))
+    temp_obs = espressopp.analysis.Temperature(system)
+    monitor.add_observable("T", temp_obs)
+    monitor.add_observable("Ekin", espressopp.analysis.KineticEnergy(system, temp_obs))
+    for k in range(system.getNumberOfInteractions()):
+        label = system.getNameOfInteraction(k)
+        monitor.add_observable(label, espressopp.analysis.PotentialEnergy(system, system.getInteraction(k)), visible=label.startswith("lj"))
+    for (cr_type, cr_total, cr_state), obs in cr_observs.items():
+        monitor.add_observable("cr_%s_%s" % (cr_type, cr_state if cr_state is not None else "x"), obs)
+    for i, f in enumerate(chem_fpls):
+        monitor.add_observable("count_%d" % i, espressopp.analysis.NFixedPairListEntries(system, f.fpl))
+    energy_collect = max(1, args.energy_collect)
+    integrator.addExtension(espressopp.integrator.ExtAnalyze(monitor, energy_collect))
+
+    maximum_conversion = []
+    if args.maximum_conversion:
+        maximum_conversion = tools.get_maximum_conversion(args, system, chem_fpls, gt, cr_observs)
+
+    # ---- start/stop of the reactions in units of outer iterations (:700-721)
+    k_enable_reactions = (args.start_ar // integrator_step) if ar is not None else -1
+    k_stop_reactions = (args.stop_ar // integrator_step) if (ar is not None and getattr(args, "stop_ar", None)) else -1
+    print("Running %d steps as %d x integrator.run(%d); reactions start at outer step %d" % (args.run, sim_step, integrator_step, k_enable_reactions))
+    espressopp.analysis.CMVelocity(system).reset()
+
+    # ---- main loop (:728-797)
+    total_time0 = time.time()
+    integrator_loop = 0.0
+    reactions_enabled = False
+    stop_simulation = False
+    for k in range(sim_step):
+        monitor.info()
+        if k == k_enable_reactions and ar is not None:
+            print("Enabling chemical reactions at step %d" % integrator.step)
+            integrator.addExtension(ar)
+            for ext in ext_to_integrator:
+                integrator.addExtension(ext)
+            reactions_enabled = True
+            if "hook_init_reaction" in hooks:
+                hooks["hook_init_reaction"](system, integrator, ar, gt, args)
+        if reactions_enabled and maximum_conversion:
+            reached = [obs.compute() >= stop for obs, stop in maximum_conversion]
+            if all(reached):
+                print("Maximum conversion reached at step %d" % integrator.step)
+                stop_simulation = True
+        if reactions_enabled and (k == k_stop_reactions or stop_simulation):
+            ar.disconnect()
+            reactions_enabled = False
+            if stop_simulation and not getattr(args, "eq_steps", 0):
+                break
+        t0 = time.time()
+        integrator.run(integrator_step)                           # :780 -- 100 % of the compute
+        integrator_loop += time.time() - t0
+        if "hook_at_step" in hooks:
+            hooks["hook_at_step"](system, integrator, ar, gt, args, k)
+    total_time = time.time() - total_time0
+    monitor.dump()
+    monitor.info()
+
+    # ---- outputs (:800-1081)
+    e = system._ctx.require_engine()
+    g = e.get_particles(fields=("pos", "image", "type", "state", "res_id"))
+    ids = sorted(system._ctx.pid)
+    id2type = {v: k for k, v in gt.atomsym_atomtype.items()}
+    out_conf = files_io.GROFile("%s_confout.gro" % prefix)
+    out_conf.box = box
+    out_conf.title = "chemlab_b200 final configuration, step %d" % integrator.step
+    for k, pid in enumerate(ids):
+        a = conf.atoms[pid]
+        out_conf.atoms[pid] = a._replace(name=id2type.get(int(g["type"][k]), a.name), position=tuple(g["pos"][k]), velocity=None)
+    out_conf.write()
+    np.savetxt("%s_state.dat" % prefix, np.column_stack([ids, g["type"], g["state"], g["res_id"]]), fmt="%d", header="id type state res_id")
+    for i, f in enumerate(chem_fpls):
+        np.savetxt("%s_bonds_chem_%d.dat" % (prefix, i), np.asarray(f.fpl.getAllBonds(), np.int64).reshape(-1, 2), fmt="%d")
+    for label, lists, getter in (("bonds", list(dyn_fpl.values()) + list(static_fpl), "getAllBonds"),
+                                 ("angles", list(dyn_ftl.values()) + list(static_ftl), "getAllTriples"),
+                                 ("dihedrals", list(dyn_fql.values()) + list(static_fql), "getAllQuadruples")):
+        rows = [t for lst in lists for t in getattr(lst, getter)()]
+        if rows:
+            np.savetxt("%s_%s.dat" % (prefix, label), np.asarray(rows, np.int64), fmt="%d")
+    if ar is not None:
+        ar.save_reaction_counters("%s_reaction_counters.dat" % prefix)
+    with open("%s_benchmark.csv" % prefix, "a") as f:          # record format of the reference (:997-998)
+        f.write("1 %d %.6f %.6f\n" % (npart, total_time, integrator_loop))
+    timers = tools.get_integrator_timers(system, integrator)
+    print("final: steps=%d total=%.3fs integratorLoop=%.3fs (%.1f steps/s) setup=%.3fs" %
+          (integrator.step, total_time, integrator_loop, integrator.step / max(integrator_loop, 1e-9), total_time0 - time0))
+    print("engine timers/counters: %s" % {k: (round(v, 4) if isinstance(v, float) else v) for k, v in timers.items()})
+    if "hook_end" in hooks:
+        hooks["hook_end"](system, integrator, ar, gt, args)
+    return dict(system=system, integrator=integrator, ar=ar, topology=gt, chem_fpls=chem_fpls, reactions=reactions, prefix=prefix,
+                steps=integrator.step, integrator_loop=integrator_loop, monitor=monitor)
+
+
+if __name__ == "__main__":
+    main(sys.argv[1:])

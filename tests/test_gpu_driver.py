@@ -1,0 +1,63 @@
+"""Config 1 end to end (BASELINE.json configs[0]): examples/atrp_lj as shipped, through the chemlab driver
+(`python -m chemlab_b200.start_simulation @params`) on the GPU engine, and the SAME driver run on the oracle
+(tests/oracle_engine.py) -- topology, reaction bonds, types and states must agree bit-exactly, positions closely."""
+import os
+import shutil
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _run(tmp, backend, steps):
+    d = os.path.join(tmp, backend)
+    shutil.copytree(os.path.join(HERE, "golden", "atrp_lj"), d)
+    cwd = os.getcwd()
+    os.chdir(d)
+    try:
+        import chemlab_b200.espressopp._context as C
+        from chemlab_b200 import start_simulation as S
+        real = C.Engine
+        if backend == "oracle":
+            from oracle_engine import OracleEngine
+            C.Engine = OracleEngine
+        try:
+            # start_ar=200 -> reactions on after one outer iteration; nearest partner + p = rate*dt*interval
+            r = S.main(["@params", "--rng_seed", "42", "--run", str(steps), "--start_ar", "200", "--energy_collect", "200"])
+        finally:
+            C.Engine = real
+        e = r["system"]._ctx.engine
+        g = e.get_particles(fields=("pos", "type", "state", "mass"))
+        bonds = np.asarray(r["chem_fpls"][0].fpl.getAllBonds(), np.int64).reshape(-1, 2)
+        files = sorted(os.listdir(os.path.join(d, "data")))
+        return dict(g=g, bonds=bonds, files=files, steps=r["steps"], T=r["monitor"]._last[1][0], dir=d)
+    finally:
+        os.chdir(cwd)
+
+
+def _srt(a):
+    a = np.sort(np.asarray(a, np.int64).reshape(-1, 2), axis=1)
+    return a[np.lexsort((a[:, 1], a[:, 0]))] if len(a) else a
+
+
+def test_atrp_lj_driver_gpu_matches_oracle(tmp_path):
+    steps = 1200
+    a = _run(str(tmp_path), "gpu", steps)
+    assert a["steps"] == steps
+    # products of the reference driver (src/start_simulation.py:800-1081): final .gro, energy CSV, counters, benchmark record
+    for suffix in ("_confout.gro", "_energy_42.csv", "_reaction_counters.dat", "_benchmark.csv", "params.out"):
+        assert any(f.endswith(suffix) for f in a["files"]), (suffix, a["files"])
+    assert 0.8 < a["T"] < 1.25
+    t = a["g"]["type"]
+    assert len(a["bonds"]) > 0, "no ATRP growth step happened"
+    assert (t >= 2).sum() >= 60          # activated trimers + reaction products carry the dynamic types
+    b = _run(str(tmp_path), "oracle", steps)
+    assert (a["g"]["type"] == b["g"]["type"]).all() and (a["g"]["state"] == b["g"]["state"]).all()
+    assert np.allclose(a["g"]["mass"], b["g"]["mass"])
+    assert (_srt(a["bonds"]) == _srt(b["bonds"])).all()
+    d = a["g"]["pos"] - b["g"]["pos"]
+    box = 28.11442
+    d -= box * np.rint(d / box)
+    assert np.abs(d).max() < 2e-3, np.abs(d).max()
