@@ -264,7 +264,7 @@ def main():
                 "rebuilds": cn["rebuilds"], "reaction_passes": cn["reaction_passes"], "reaction_events": cn["reaction_events"],
                 "new_bonds_total": nbonds_new, "temperature": float(kin[1]), "wall_s": t_wall, "equil_steps": a.equil,
                 "ghost_beads_total": cn["ghosts"], "pair_threads": e.get_option("pair_threads"), "pair_grid": e.get_option("pair_grid"),
-                "home_max": e.get_option("home_max"), "tile_max": e.get_option("tile_max"),
+                "pair_nv": e.get_option("pair_nv"), "pair_smem": e.get_option("pair_smem"), "home_max": e.get_option("home_max"), "tile_max": e.get_option("tile_max"),
                 "buckets_s": {k: v for k, v in tm.items() if v > 0} if e.get_option("timers") else None}
 
     # e2e: public API with HOST buffers -- a fresh engine (one per rank when N > 1) restarted from the host snapshot:

@@ -23,6 +23,14 @@ struct ClbCand { int a, b, r, accepted; double d2; unsigned long long rnd; };
 struct ClbChange { int reaction, side, nb_level, old_type, new_type, state_mode, state_value, pad; double new_mass, new_q; };
 struct ClbTmReg { int list, arity; int t[4]; };
 struct ClbListDev { int* tuples; int arity, tm_observed, excl_observed, pad; };
+template <int N> struct ClbTup { int v[N]; };
+template <int N> struct ClbTupLess {
+    __host__ __device__ bool operator()(const ClbTup<N>& a, const ClbTup<N>& b) const {
+#pragma unroll
+        for (int k = 0; k < N; ++k) { if (a.v[k] != b.v[k]) return a.v[k] < b.v[k]; }
+        return false;
+    }
+};
 
 __device__ __forceinline__ bool side_ok(const ClbReactSpec& r, int wa, int wb) {
     int sa = pw_state(wa), sb = pw_state(wb);
@@ -54,39 +62,54 @@ __global__ void __launch_bounds__(512) k_react_scan(ClbGrid g, ClbGeom geo, cons
         for (int p = threadIdx.x; p < t.nh; p += blockDim.x) {
             const int gi = t.hs + p;
             const int4 pi = __ldg(pos + gi);
+            // a home particle that fits neither side of any active reaction has no candidate pair: skip its row
+            bool may = false;
+            for (int ri = 0; ri < nspec; ++ri) {
+                const ClbReactSpec& r = s_spec[ri];
+                if (!r.active) continue;
+                const int ty = pw_type(pi.w), st = pw_state(pi.w);
+                may |= (ty == r.type_1 && st >= r.min1 && st < r.max1) || (ty == r.type_2 && st >= r.min2 && st < r.max2);
+            }
+            if (!may) continue;
             const int si = __ldg(slot + gi);
             const int cnt = __ldg(nl_count + gi);
-            const unsigned short* ent = entries + (size_t)gi * cap;
-            for (int k = 0; k < cnt; ++k) {
-                const unsigned e = ent[k];
-                const int sj = s_slot[e];
-                if (si >= sj) continue;           // every unordered pair once, lower slot first
-                const int4 pj = s_pos[e];
-                double dx = lat2d(wsub(pi.x, pj.x)) * geo.q[0], dy = lat2d(wsub(pi.y, pj.y)) * geo.q[1], dz = lat2d(wsub(pi.z, pj.z)) * geo.q[2];
-                double d2 = dx * dx + dy * dy + dz * dz;
-                for (int ri = 0; ri < nspec; ++ri) {
-                    const ClbReactSpec& r = s_spec[ri];
-                    if (!r.active) continue;
-                    int A, B;
-                    if (side_ok(r, pi.w, pj.w)) { A = si; B = sj; }
-                    else if (side_ok(r, pj.w, pi.w)) { A = sj; B = si; }
-                    else continue;
-                    if (!(d2 >= r.min_cutoff2 && d2 < r.cutoff2)) continue;               // U3
-                    if (!r.intraresidual && __ldg(resid + A) == __ldg(resid + B)) continue; // U10
-                    if (!r.intramolecular && __ldg(mol + A) == __ldg(mol + B)) continue;
-                    uint32_t w[4], h[4];
-                    clb_draw_pair(seed, CLB_STREAM_REACT, step, (uint32_t)si, (uint32_t)sj, (uint32_t)ri, w);
-                    clb_draw_pair(seed, CLB_STREAM_PARTNER, step, (uint32_t)si, (uint32_t)sj, (uint32_t)ri, h);
-                    ClbCand c;
-                    c.a = A; c.b = B; c.r = ri; c.d2 = d2;
-                    c.accepted = ((double)w[0] * (1.0 / 4294967296.0) < r.p) ? 1 : 0;        // U5
-                    c.rnd = ((unsigned long long)h[0] << 32) | h[1];
-                    cg::coalesced_group grp = cg::coalesced_threads();
-                    unsigned long long base = 0;
-                    if (grp.thread_rank() == 0) base = atomicAdd(&ctl->ncand, (unsigned long long)grp.size());
-                    base = grp.shfl(base, 0);
-                    unsigned long long o = base + grp.thread_rank();
-                    if (o < candcap) cands[o] = c;
+            const uint4* row = reinterpret_cast<const uint4*>(entries + (size_t)gi * cap);   // cap % 8 == 0: 8 entries per load
+            for (int k0 = 0; k0 < cnt; k0 += 8) {
+                const uint4 q = __ldg(row + (k0 >> 3));
+                const unsigned wds[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    if (k0 + u >= cnt) break;
+                    const unsigned e = (u & 1) ? (wds[u >> 1] >> 16) : (wds[u >> 1] & 0xffffu);
+                    const int sj = s_slot[e];
+                    if (si >= sj) continue;           // every unordered pair once, lower slot first
+                    const int4 pj = s_pos[e];
+                    double dx = lat2d(wsub(pi.x, pj.x)) * geo.q[0], dy = lat2d(wsub(pi.y, pj.y)) * geo.q[1], dz = lat2d(wsub(pi.z, pj.z)) * geo.q[2];
+                    double d2 = dx * dx + dy * dy + dz * dz;
+                    for (int ri = 0; ri < nspec; ++ri) {
+                        const ClbReactSpec& r = s_spec[ri];
+                        if (!r.active) continue;
+                        int A, B;
+                        if (side_ok(r, pi.w, pj.w)) { A = si; B = sj; }
+                        else if (side_ok(r, pj.w, pi.w)) { A = sj; B = si; }
+                        else continue;
+                        if (!(d2 >= r.min_cutoff2 && d2 < r.cutoff2)) continue;               // U3
+                        if (!r.intraresidual && __ldg(resid + A) == __ldg(resid + B)) continue; // U10
+                        if (!r.intramolecular && __ldg(mol + A) == __ldg(mol + B)) continue;
+                        uint32_t w[4], h[4];
+                        clb_draw_pair(seed, CLB_STREAM_REACT, step, (uint32_t)si, (uint32_t)sj, (uint32_t)ri, w);
+                        clb_draw_pair(seed, CLB_STREAM_PARTNER, step, (uint32_t)si, (uint32_t)sj, (uint32_t)ri, h);
+                        ClbCand c;
+                        c.a = A; c.b = B; c.r = ri; c.d2 = d2;
+                        c.accepted = ((double)w[0] * (1.0 / 4294967296.0) < r.p) ? 1 : 0;        // U5
+                        c.rnd = ((unsigned long long)h[0] << 32) | h[1];
+                        cg::coalesced_group grp = cg::coalesced_threads();
+                        unsigned long long base = 0;
+                        if (grp.thread_rank() == 0) base = atomicAdd(&ctl->ncand, (unsigned long long)grp.size());
+                        base = grp.shfl(base, 0);
+                        unsigned long long o = base + grp.thread_rank();
+                        if (o < candcap) cands[o] = c;
+                    }
                 }
             }
         }

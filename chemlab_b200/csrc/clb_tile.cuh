@@ -42,6 +42,11 @@ __device__ __forceinline__ int tile_cell(const ClbGrid& g, const TileCtx& t, int
     int cx = t.whole ? m : wrapi(t.cx0 - 1 + m, g.ncx);
     return (lz * g.ncy + cy) * g.ncx + cx;
 }
+// A CTA may host several independent "virtual CTAs" (groups of whole warps with their own tile and their own named
+// barrier) that share read-only shared-memory data such as the force table: vc_sync is their private barrier.
+__device__ __forceinline__ void vc_sync(int bar_id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" :: "r"(bar_id), "r"(nthreads) : "memory");
+}
 // Builds s_off[0..9W] (exclusive prefix of cell counts in tile order) and s_src[tc] (global start of
 // each tile cell).  Needs blockDim.x >= 32.  Ends with __syncthreads().
 __device__ __forceinline__ void tile_offsets(const ClbGrid& g, TileCtx& t, const int* __restrict__ cell_start,
@@ -88,6 +93,46 @@ __device__ __forceinline__ void tile_stage(const TileCtx& t, const int* s_off, c
             if (s_slot) s_slot[o + i] = __ldg(slot + s + i);
             if (s_gidx) s_gidx[o + i] = s + i;
         }
+    }
+}
+// tile_offsets / tile_stage for a group of `nth` threads (tid in [0,nth), nth % 32 == 0) synchronised by named barrier `bar`
+__device__ __forceinline__ void tile_offsets_vc(const ClbGrid& g, TileCtx& t, const int* __restrict__ cell_start,
+                                                int* s_off, int* s_src, int tid, int nth, int bar) {
+    const int nct = CLB_TILE_ROWS * t.W;
+    for (int tc = tid; tc < nct; tc += nth) {
+        int k = tc / t.W, m = tc - k * t.W;
+        int gc = tile_cell(g, t, k, m);
+        int s = __ldg(cell_start + gc), e = __ldg(cell_start + gc + 1);
+        s_src[tc] = s;
+        s_off[tc + 1] = e - s;
+    }
+    vc_sync(bar, nth);
+    if (tid < 32) {
+        int lane = tid;
+        int per = (nct + 31) >> 5;
+        int lo = lane * per, hi = min(lo + per, nct);
+        int sum = 0;
+        for (int i = lo; i < hi; ++i) sum += s_off[i + 1];
+        int incl = sum;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { int v = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += v; }
+        int run = incl - sum;
+        for (int i = lo; i < hi; ++i) { int c = s_off[i + 1]; s_off[i + 1] = run + c; run += c; }
+        if (lane == 0) s_off[0] = 0;
+    }
+    vc_sync(bar, nth);
+    t.T = s_off[nct];
+    int mh0 = t.whole ? t.cx0 : 1;
+    t.hs = s_src[4 * t.W + mh0];
+    t.nh = s_off[4 * t.W + mh0 + t.bxe] - s_off[4 * t.W + mh0];
+}
+__device__ __forceinline__ void tile_stage_vc(const TileCtx& t, const int* s_off, const int* s_src,
+                                              const int4* __restrict__ pos, int4* s_pos, int tid, int nth) {
+    const int nct = CLB_TILE_ROWS * t.W;
+    const int warp = tid >> 5, lane = tid & 31, nw = nth >> 5;
+    for (int tc = warp; tc < nct; tc += nw) {
+        int o = s_off[tc], c = s_off[tc + 1] - o, s = s_src[tc];
+        for (int i = lane; i < c; i += 32) s_pos[o + i] = __ldg(pos + s + i);
     }
 }
 // tile column of the home cell that holds home particle p (local index in [0,nh))
@@ -252,6 +297,7 @@ struct ClbPairArgs {
     double* force; ClbCtl* ctl;
     int cap, ntypes, ntabs, nrows_total, fstride, npw;   // npw = warps per split group
     ClbTabMeta ugrid;                                      // common grid when UGRID
+    int b0, seg0, b1, nidx;   // row blocks of this launch: idx < seg0 -> b0 + idx, else b1 + (idx - seg0); idx in [0, nidx)
 };
 // CUBIC boxes work in lattice units end to end: r2 and the cutoffs are lattice^2, the table index uses
 // invdx*q, and F(r)*(1/r_lat)*d_lat is already the real force vector -- no per-pair unit conversion.
@@ -280,7 +326,8 @@ __global__ void __launch_bounds__(512) k_pair_forces(ClbGrid g, ClbGeom geo, Clb
     const double u_invdx = A.ugrid.invdx, u_ct = A.ugrid.c_t;
     const unsigned u_n = (unsigned)A.ugrid.n;
     unsigned err = 0;
-    for (int b = blockIdx.x; b < g.nblocks; b += gridDim.x) {
+    for (int idx = blockIdx.x; idx < A.nidx; idx += gridDim.x) {
+        const int b = idx < A.seg0 ? A.b0 + idx : A.b1 + (idx - A.seg0);
         TileCtx t;
         tile_geometry(g, b, t);
         __syncthreads();
@@ -392,7 +439,8 @@ __global__ void __launch_bounds__(512) k_pair_forces_tab(ClbGrid g, ClbGeom geo,
     const double u_invdx = A.ugrid.invdx, u_ct = A.ugrid.c_t;
     const unsigned u_nm1 = (unsigned)A.ugrid.n - 1u;
     unsigned err = 0;
-    for (int b = blockIdx.x; b < g.nblocks; b += gridDim.x) {
+    for (int idx = blockIdx.x; idx < A.nidx; idx += gridDim.x) {
+        const int b = idx < A.seg0 ? A.b0 + idx : A.b1 + (idx - A.seg0);
         TileCtx t;
         tile_geometry(g, b, t);
         __syncthreads();
@@ -516,6 +564,8 @@ struct ClbPairArgs2 {
     double invdx, cmagic;    // 1/dx (lattice units) and 1.5*2^52 - x0/dx (x0/dx integral: checked by the host)
     unsigned nm1;            // rows - 1 of every table
     double one_rc2; int one_off;   // ONEPD descriptor
+    int b0, seg0, b1, nidx;        // row blocks of this launch (see ClbPairArgs)
+    int nv, vc_bytes;              // virtual CTAs per CTA and their shared-memory stride (offset tables + tile)
 };
 __device__ __forceinline__ void rsqrt_seed2(double x, double& y0, double& yh) {
     int hi = __double2hiint(x), lo = __double2loint(x);
@@ -528,30 +578,37 @@ __device__ __forceinline__ void rsqrt_seed2(double x, double& y0, double& yh) {
     yh = __hiloint2double(h - 0x00100000, l);      // y0 / 2
 }
 template <bool TABS_SMEM, bool ONEPD, int NI>
-__global__ void __launch_bounds__(512) k_pair_forces_tab2(ClbGrid g, ClbPairArgs2 A) {
+__global__ void __launch_bounds__(1024) k_pair_forces_tab2(ClbGrid g, ClbPairArgs2 A) {
     if (*(volatile int*)&A.ctl->stall) return;
     extern __shared__ __align__(16) unsigned char smem[];
-    __shared__ int s_off[CLB_TILE_CELLS + 1];
-    __shared__ int s_src[CLB_TILE_CELLS];
     const int ntp = A.ntypes * A.ntypes;
+    // shared by the whole CTA: descriptors + table rows; per virtual CTA: offset tables + tile positions
     double2* s_pd = reinterpret_cast<double2*>(smem);
     double2* s_rows = s_pd + (ONEPD ? 0 : ntp);
-    int4* s_pos = reinterpret_cast<int4*>(s_rows + (TABS_SMEM ? A.nrows_total : 0));
+    unsigned char* vc_base = reinterpret_cast<unsigned char*>(s_rows + (TABS_SMEM ? A.nrows_total : 0));
+    const int nth = A.npw * 32;                               // threads of one virtual CTA
+    const int vc = threadIdx.x / nth, tid = threadIdx.x - vc * nth;
+    const int bar = 1 + vc;
+    int* s_off = reinterpret_cast<int*>(vc_base + (size_t)vc * A.vc_bytes);
+    int* s_src = s_off + (CLB_TILE_CELLS + 4);
+    int4* s_pos = reinterpret_cast<int4*>(s_src + CLB_TILE_CELLS);
     if (!ONEPD) for (int i = threadIdx.x; i < ntp; i += blockDim.x) s_pd[i] = A.pd2[i];
     if (TABS_SMEM) for (int i = threadIdx.x; i < A.nrows_total; i += blockDim.x) s_rows[i] = __ldg(A.trows + i);
+    __syncthreads();
     const double2* rows = TABS_SMEM ? s_rows : A.trows;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int nhpass = A.npw * 32;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int nhpass = nth;
     const double invdx = A.invdx, cmagic = A.cmagic;
     const unsigned nm1 = A.nm1;
     unsigned err = 0;
-    for (int b = blockIdx.x; b < g.nblocks; b += gridDim.x) {
+    for (int idx = blockIdx.x * A.nv + vc; idx < A.nidx; idx += gridDim.x * A.nv) {
+        const int b = idx < A.seg0 ? A.b0 + idx : A.b1 + (idx - A.seg0);
         TileCtx t;
         tile_geometry(g, b, t);
-        __syncthreads();
-        tile_offsets(g, t, A.cell_start, s_off, s_src);
-        tile_stage(t, s_off, s_src, A.pos, s_pos, nullptr, nullptr, nullptr);
-        __syncthreads();
+        vc_sync(bar, nth);
+        tile_offsets_vc(g, t, A.cell_start, s_off, s_src, tid, nth, bar);
+        tile_stage_vc(t, s_off, s_src, A.pos, s_pos, tid, nth);
+        vc_sync(bar, nth);
         for (int p0 = 0; p0 < t.nh; p0 += nhpass) {
             const int p = p0 + warp * 32 + lane;
             const bool act = p < t.nh;

@@ -192,10 +192,12 @@ extern "C" int clb_set_option(clb_engine* e, const char* name, double v) {
     else if (s == "timers") e->timers_on = (int)v;
     else if (s == "tables_in_smem") { e->tabs_smem_user = (int)v; if (e->lists_valid) return e->configure_pair_launch(); }
     else if (s == "pair_event_timing") e->pair_event_timing = (int)v;
+    else if (s == "overlap_halo") e->overlap_user = (int)v;
     else if (s == "pair_split") { e->pair_split_user = (int)v; if (e->lists_valid) return e->configure_pair_launch(); }
     else if (s == "build_threads") e->build_threads = (int)v;
     else if (s == "pair_warps") { e->pair_warps_user = (int)v; if (e->lists_valid) return e->configure_pair_launch(); }
     else if (s == "pair_kernel") { e->pair_kernel_user = (int)v; if (e->lists_valid) return e->configure_pair_launch(); }
+    else if (s == "pair_nv") { e->pair_nv_user = (int)v; if (e->lists_valid) return e->configure_pair_launch(); }
     else if (s == "pair_ni") { e->pair_ni = (int)v >= 4 ? 4 : 2; if (e->lists_valid) return e->configure_pair_launch(); }
     else if (s == "pair_branchfree") { e->branchfree_user = (int)v; if (e->lists_valid) return e->configure_pair_launch(); }
     else return e->fail(CLB_ERR_ARG, "unknown option %s", name);
@@ -220,6 +222,7 @@ extern "C" int clb_get_option(clb_engine* e, const char* name, double* v) {
     else if (s == "pair_split") *v = e->pair_split;
     else if (s == "pair_kernel") *v = e->pair_kernel_active;
     else if (s == "pair_onepd") *v = e->tab2_onepd;
+    else if (s == "pair_nv") *v = e->pair_nv;
     else if (s == "uniform_grid") *v = e->ugrid_on;
     else if (s == "pair_smem") *v = e->pair_smem;
     else if (s == "tables_in_smem") *v = e->tabs_smem;
@@ -1029,18 +1032,31 @@ int clb_engine::configure_pair_launch() {
         int npw = std::max(1, std::min((home_max + 31) / 32, (int)ceil((mean_home + 3.0 * sqrt(mean_home)) / 32.0)));
         if (pair_warps_user > 0) npw = pair_warps_user;
         npw = std::min(npw, 16);
-        size_t fixed = tab2_onepd ? 0 : (size_t)nt_dev * nt_dev * sizeof(double2);
-        size_t rows = (size_t)nrows_dev * sizeof(double2);
-        size_t tile = (size_t)tile_max * sizeof(int4) + 16;
-        bool in_smem = tabs_smem_user != 0 && fixed + rows + tile <= (size_t)std::min(smem_optin, 110 * 1024);
-        if (tabs_smem_user == 2 && fixed + rows + tile <= (size_t)smem_optin) in_smem = true;
-        tabs_smem = in_smem ? 1 : 0;
-        pair_split = 1; pair_npw = npw; pair_threads = npw * 32;
-        pair_smem = (int)(fixed + (in_smem ? rows : 0) + tile);
+        // one CTA hosts `nv` virtual CTAs (npw warps, one tile each) that share the table rows: pick the nv that keeps
+        // the most warps resident per SM (the kernel is latency-bound: DESIGN.md 3.1)
+        const size_t fixed = tab2_onepd ? 0 : (size_t)nt_dev * nt_dev * sizeof(double2);
+        const size_t rows = (size_t)nrows_dev * sizeof(double2);
+        const int tile_cap = (tile_max + 3) & ~3;
+        const size_t vcb = (size_t)(CLB_TILE_CELLS + 4 + CLB_TILE_CELLS) * sizeof(int) + (size_t)tile_cap * sizeof(int4);
+        tabs_smem = 1;
+        if (fixed + rows + vcb > (size_t)smem_optin || tabs_smem_user == 0) tabs_smem = 0;
+        const size_t shared_part = fixed + (tabs_smem ? rows : 0);
+        int best_nv = 1, best_nb = 1; double best_w = -1;
+        const int nv_max = pair_nv_user > 0 ? pair_nv_user : 15;
+        for (int nv = (pair_nv_user > 0 ? pair_nv_user : 1); nv <= nv_max; ++nv) {
+            if (nv * npw * 32 > 1024) break;
+            size_t smem = shared_part + nv * vcb;
+            if ((int)smem > smem_optin) break;
+            int nb = 0;
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, pair_kernel_tab2(tabs_smem, tab2_onepd, pair_ni), nv * npw * 32, smem);
+            double w = (double)nb * nv * npw;
+            if (w > best_w * 1.001) { best_w = w; best_nv = nv; best_nb = std::max(nb, 1); }
+        }
+        pair_nv = best_nv; pair_vc_bytes = (int)vcb;
+        pair_split = 1; pair_npw = npw; pair_threads = best_nv * npw * 32;
+        pair_smem = (int)(shared_part + best_nv * vcb);
         if (pair_smem > smem_optin) return fail(CLB_ERR_UNSUPPORTED, "pair kernel needs %d B of shared memory: lower block_cells", pair_smem);
-        int nb = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, pair_kernel_tab2(tabs_smem, tab2_onepd, pair_ni), pair_threads, pair_smem);
-        pair_grid = std::min(grid.nblocks, std::max(1, nb) * nsm);
+        pair_grid = std::min(ceil_div(grid.nblocks, best_nv), best_nb * nsm);
         return CLB_OK;
     }
     // warps that cover the home particles of a block: mean + 3 sigma (Poisson); rarer, fuller blocks take a second pass
@@ -1169,27 +1185,60 @@ extern "C" int clb_decompose(clb_engine* e) {
 }
 
 // ------------------------------------------------------------------------------------------ forces
-void clb_engine::enqueue_forces() {
-    bucket_begin(CLB_B_PAIR);
-    if (pair_event_timing) { pair_event_valid.resize(pair_event_used / 2 + 1, 1); pair_event_valid[pair_event_used / 2] = 1; cudaEventRecord(next_pair_event(), stream); }
+void clb_engine::launch_pair(int b0, int seg0, int b1, int nidx) {
+    const int gridsz = std::max(1, std::min(pair_grid, nidx));
     if (pair_kernel_active == 2) {
         ClbPairArgs2 A;
         A.cell_start = cell_start.p; A.pos = pos.p; A.entries = nl_entries.p; A.nl_count = nl_count.p;
         A.pd2 = d_pd2.p; A.trows = d_rows2.p; A.force = force.p; A.ctl = d_ctl;
         A.cap = nl_cap; A.ntypes = nt_dev; A.nrows_total = nrows_dev; A.fstride = ncap; A.npw = pair_npw;
         A.invdx = tab2_invdx; A.cmagic = tab2_cmagic; A.nm1 = tab2_nm1; A.one_rc2 = tab2_one_rc2; A.one_off = tab2_one_off;
-        pair_kernel_tab2(tabs_smem, tab2_onepd, pair_ni)<<<pair_grid, pair_threads, pair_smem, stream>>>(grid, A);
+        A.b0 = b0; A.seg0 = seg0; A.b1 = b1; A.nidx = nidx; A.nv = pair_nv; A.vc_bytes = pair_vc_bytes;
+        pair_kernel_tab2(tabs_smem, tab2_onepd, pair_ni)<<<std::max(1, std::min(pair_grid, ceil_div(nidx, pair_nv))), pair_threads, pair_smem, stream>>>(grid, A);
     } else {
         ClbPairArgs A;
         A.cell_start = cell_start.p; A.pos = pos.p; A.entries = nl_entries.p; A.nl_count = nl_count.p;
         A.pdesc = d_pd.p; A.plj = d_plj.p; A.tmeta = d_tm.p; A.trows = d_frows.p; A.force = force.p; A.ctl = d_ctl;
         A.cap = nl_cap; A.ntypes = nt_dev; A.ntabs = ntabs_dev; A.nrows_total = nrows_dev; A.fstride = ncap; A.npw = pair_npw;
         A.ugrid = ugrid_meta;
-        clb_engine_pair_fn(this, tabs_smem, pair_split)<<<pair_grid, pair_threads, pair_smem, stream>>>(grid, geo, A);
+        A.b0 = b0; A.seg0 = seg0; A.b1 = b1; A.nidx = nidx;
+        clb_engine_pair_fn(this, tabs_smem, pair_split)<<<gridsz, pair_threads, pair_smem, stream>>>(grid, geo, A);
     }
+    ++launches;
+}
+
+// Pair + bonded forces of the owned particles.  overlap_halo (multi-GPU steps): the row blocks of the interior planes
+// need no ghost, so they are launched first while the halo of this step is still in flight on the comm stream; the
+// caller then makes the main stream wait for the halo (k_check_resort in between) and the two boundary planes follow.
+void clb_engine::enqueue_forces(bool overlap_halo) {
+    bucket_begin(CLB_B_PAIR);
+    const int nb = grid.nblocks;
+    const int R = grid.nbx * grid.ncy;                   // row blocks per cell plane
+    const bool split = overlap_halo && nranks > 1 && grid.nczl >= 3;
+    const size_t slot_i = pair_event_used / 2;
+    if (pair_event_timing) {
+        pair_event_valid.resize(slot_i + 1, 1); pair_event_valid[slot_i] = 1;
+        pair_event_has2.resize(slot_i + 1, 0); pair_event_has2[slot_i] = 0;
+        cudaEventRecord(next_pair_event(), stream);
+    }
+    if (split) launch_pair(R, nb - 2 * R, 0, nb - 2 * R);            // interior planes
+    else if (!overlap_halo || nranks == 1) launch_pair(0, nb, 0, nb);
     if (pair_event_timing) cudaEventRecord(next_pair_event(), stream);
+    if (overlap_halo && nranks > 1) {
+        cudaStreamWaitEvent(stream, ev_comm, 0);                      // halo + global max displacement have arrived
+        k_check_resort<<<1, 1, 0, stream>>>(d_ctl, criterion, 0.5 * skin, pending_step_index);
+        ++launches;
+        if (pair_event_timing) {
+            while (pair_events2.size() < 2 * (slot_i + 1)) { cudaEvent_t ev; cudaEventCreate(&ev); pair_events2.push_back(ev); }
+            pair_event_has2[slot_i] = 1;
+            cudaEventRecord(pair_events2[2 * slot_i], stream);
+        }
+        if (split) launch_pair(0, R, nb - R, 2 * R);                  // bottom and top owned planes
+        else launch_pair(0, nb, 0, nb);
+        if (pair_event_timing) cudaEventRecord(pair_events2[2 * slot_i + 1], stream);
+    }
     bucket_end(CLB_B_PAIR);
-    ++launches; ++pair_launches_total;
+    ++pair_launches_total;
     if (nterms > 0) {
         bucket_begin(CLB_B_BONDED);
         int no = own1 - own0;
@@ -1353,11 +1402,22 @@ extern "C" int clb_run(clb_engine* e, int64_t nsteps) {
                 if (pend) e->enqueue_integrate(CLB_INT_SECOND, (uint64_t)(e->step + s - 1));
                 e->enqueue_integrate(CLB_INT_FIRST, 0);
             }
-            if (e->nranks > 1) TRY(e->comm_max_displacement());
-            k_check_resort<<<1, 1, 0, e->stream>>>(e->d_ctl, e->criterion, half_skin, (int)(s - i));
-            ++e->launches;
-            if (e->nranks > 1) TRY(e->comm_halo_positions());
-            e->enqueue_forces();
+            if (e->nranks > 1 && e->overlap_user) {
+                // global max displacement + position halo travel on the comm stream while the interior planes compute
+                cudaEventRecord(e->ev_int, e->stream);
+                cudaStreamWaitEvent(e->comm_stream, e->ev_int, 0);
+                TRY(e->comm_max_displacement(e->comm_stream));
+                TRY(e->comm_halo_positions(e->comm_stream));
+                cudaEventRecord(e->ev_comm, e->comm_stream);
+                e->pending_step_index = (int)(s - i);
+                e->enqueue_forces(true);            // interior blocks, wait, k_check_resort, boundary blocks, bonded
+            } else {
+                if (e->nranks > 1) TRY(e->comm_max_displacement(e->stream));
+                k_check_resort<<<1, 1, 0, e->stream>>>(e->d_ctl, e->criterion, half_skin, (int)(s - i));
+                ++e->launches;
+                if (e->nranks > 1) TRY(e->comm_halo_positions(e->stream));
+                e->enqueue_forces();
+            }
             pend = true;
             if (boundary_after(s)) { j = s + 1; break; }
         }
@@ -1451,10 +1511,15 @@ void clb_engine::collect_timers() {
     for (size_t k = 0; k + 1 < pair_event_used; k += 2) {
         float t = 0;
         if (k / 2 < pair_event_valid.size() && !pair_event_valid[k / 2]) continue;
-        if (cudaEventElapsedTime(&t, pair_events[k], pair_events[k + 1]) == cudaSuccess) { pair_ms += t; ++pair_launches; }
+        if (cudaEventElapsedTime(&t, pair_events[k], pair_events[k + 1]) == cudaSuccess) {
+            pair_ms += t; ++pair_launches;
+            float t2 = 0;   // boundary-plane launch of an overlapped multi-GPU step
+            if (k / 2 < pair_event_has2.size() && pair_event_has2[k / 2] && cudaEventElapsedTime(&t2, pair_events2[k], pair_events2[k + 1]) == cudaSuccess) pair_ms += t2;
+        }
     }
     pair_event_used = 0;
     pair_event_valid.clear();
+    pair_event_has2.clear();
 }
 extern "C" int clb_timers(clb_engine* e, double out[8], int64_t counters[8]) {
     if (!e) return CLB_ERR_ARG;
@@ -1487,6 +1552,7 @@ extern "C" int clb_stream(clb_engine* e, void** s) { if (!e || !s) return CLB_ER
 void clb_engine::free_all() {
     for (auto& l : lists) l.d.release();
     for (auto ev : pair_events) cudaEventDestroy(ev);
+    for (auto ev : pair_events2) cudaEventDestroy(ev);
     for (int i = 0; i < CLB_NBUCKET; ++i) { cudaEventDestroy(ev_a[i]); cudaEventDestroy(ev_b[i]); }
     if (d_ctl) cudaFree(d_ctl);
     if (h_ctl) cudaFreeHost(h_ctl);

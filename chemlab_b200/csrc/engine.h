@@ -113,6 +113,7 @@ struct clb_engine {
     DevBuf<double2> d_frows, d_erows, d_rows2, d_pd2;
     int tab2_ok = 0, tab2_onepd = 0, tab2_one_off = 0, pair_kernel_user = 0, pair_kernel_active = 1, pair_ni = 4;
     unsigned tab2_nm1 = 0;
+    int pair_nv = 1, pair_nv_user = 0, pair_vc_bytes = 0;
     double tab2_invdx = 0, tab2_cmagic = 0, tab2_one_rc2 = 0;
 
     // tuple lists and bonded interactions
@@ -154,7 +155,11 @@ struct clb_engine {
     double bucket_s[CLB_NBUCKET] = {0};
     int64_t nsteps_total = 0, nrebuild = 0, launches = 0, nreact_pass = 0, nreact_events = 0, pair_launches_total = 0;
     int pair_event_timing = 0;
-    std::vector<cudaEvent_t> pair_events;
+    std::vector<cudaEvent_t> pair_events, pair_events2;   // second pair: boundary-block launch of an overlapped step
+    std::vector<char> pair_event_has2;
+    cudaStream_t comm_stream = nullptr;
+    cudaEvent_t ev_int = nullptr, ev_comm = nullptr;
+    int overlap_user = 1;
     std::vector<char> pair_event_valid;
     size_t pair_event_used = 0;
     double pair_ms = 0;
@@ -170,8 +175,9 @@ struct clb_engine {
     CommDev* cd = nullptr;
     int comm_migrate();
     int comm_exchange_ghosts();
-    int comm_halo_positions();
-    int comm_max_displacement();
+    int comm_halo_positions(cudaStream_t st);
+    int comm_max_displacement(cudaStream_t st);
+    int pending_step_index = 0;
     int comm_allreduce_sum(double* v, int n);
     int comm_allreduce_sum_dev(double* d, size_t n);
     int comm_allgatherv(const void* dsend, size_t bytes, void** dout, size_t* total);
@@ -194,7 +200,8 @@ struct clb_engine {
     int setup_sync();
     int rebuild();
     int configure_pair_launch();
-    void enqueue_forces();
+    void enqueue_forces(bool overlap_halo = false);
+    void launch_pair(int b0, int seg0, int b1, int nidx);
     void enqueue_integrate(int mode, uint64_t key_step);
     ClbIntegParams integ_params(uint64_t key_step) const;
     int check_device_errors(const char* where);

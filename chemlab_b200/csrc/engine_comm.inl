@@ -125,6 +125,10 @@ extern "C" int clb_comm_init(clb_engine* e, int rank, int nranks, const void* nc
     e->set_block_cells(g.bx);
     CK(cd->cnt.ensure(64));
     CK(cudaMallocHost(&cd->h_cnt, 64 * sizeof(int)));
+    // per-step communication (global max displacement + position halo) runs beside the interior-plane force kernel
+    CK(cudaStreamCreateWithFlags(&e->comm_stream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&e->ev_int, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&e->ev_comm, cudaEventDisableTiming));
     return CLB_OK;
 }
 
@@ -132,6 +136,9 @@ void clb_engine::comm_destroy() {
     if (!cd) return;
     if (cd->comm) g_nccl.CommDestroy(cd->comm);
     if (cd->h_cnt) cudaFreeHost(cd->h_cnt);
+    if (comm_stream) { cudaStreamSynchronize(comm_stream); cudaStreamDestroy(comm_stream); comm_stream = nullptr; }
+    if (ev_int) cudaEventDestroy(ev_int);
+    if (ev_comm) cudaEventDestroy(ev_comm);
     delete cd; cd = nullptr;
 }
 
@@ -273,22 +280,22 @@ int clb_engine::comm_exchange_ghosts() {
 }
 
 // per-step forward halo: boundary-plane positions (with their type|state word) -> the neighbours' ghost planes
-int clb_engine::comm_halo_positions() {
+int clb_engine::comm_halo_positions(cudaStream_t st) {
     clb_engine* e = this;
     CommDev& c = *cd;
     NC(g_nccl.GroupStart());
-    NC(g_nccl.Send(pos.p + c.send_lo0, (size_t)(c.send_lo1 - c.send_lo0) * sizeof(int4), ncclChar, c.dn, c.comm, stream));
-    NC(g_nccl.Send(pos.p + c.send_hi0, (size_t)(c.send_hi1 - c.send_hi0) * sizeof(int4), ncclChar, c.up, c.comm, stream));
-    NC(g_nccl.Recv(pos.p + own1, (size_t)c.n_hi * sizeof(int4), ncclChar, c.up, c.comm, stream));
-    NC(g_nccl.Recv(pos.p + own1 + c.n_hi, (size_t)c.n_lo * sizeof(int4), ncclChar, c.dn, c.comm, stream));
+    NC(g_nccl.Send(pos.p + c.send_lo0, (size_t)(c.send_lo1 - c.send_lo0) * sizeof(int4), ncclChar, c.dn, c.comm, st));
+    NC(g_nccl.Send(pos.p + c.send_hi0, (size_t)(c.send_hi1 - c.send_hi0) * sizeof(int4), ncclChar, c.up, c.comm, st));
+    NC(g_nccl.Recv(pos.p + own1, (size_t)c.n_hi * sizeof(int4), ncclChar, c.up, c.comm, st));
+    NC(g_nccl.Recv(pos.p + own1 + c.n_hi, (size_t)c.n_lo * sizeof(int4), ncclChar, c.dn, c.comm, st));
     NC(g_nccl.GroupEnd());
     ++launches;
     return CLB_OK;
 }
 // global maximum displacement of this step (float bits of a non-negative number order like unsigned integers)
-int clb_engine::comm_max_displacement() {
+int clb_engine::comm_max_displacement(cudaStream_t st) {
     clb_engine* e = this;
-    NC(g_nccl.AllReduce(&d_ctl->maxdisp2_bits, &d_ctl->maxdisp2_bits, 1, ncclUint32, ncclMax, cd->comm, stream));
+    NC(g_nccl.AllReduce(&d_ctl->maxdisp2_bits, &d_ctl->maxdisp2_bits, 1, ncclUint32, ncclMax, cd->comm, st));
     ++launches;
     return CLB_OK;
 }

@@ -184,7 +184,8 @@ int clb_engine::react_pass(int64_t* events_out) {
     ReactDev& R = *rd;
     ++nreact_pass;
     // 1. candidate scan (retry on buffer overflow)
-    if (R.candcap == 0) { R.candcap = std::max<size_t>(4096, (size_t)n * 2); CK(R.cands.ensure(R.candcap)); }
+    // candidates are a small fraction of the Verlet pairs (reactive types, reaction cutoff < rc): start at n/4, regrow on overflow
+    if (R.candcap == 0) { R.candcap = std::max<size_t>(65536, (size_t)n / 4); CK(R.cands.ensure(R.candcap)); }
     size_t smem = (size_t)tile_max * (sizeof(int4) + sizeof(int)) + 16;
     int nb = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_react_scan, 256, smem);
@@ -324,17 +325,19 @@ int clb_engine::react_pass(int64_t* events_out) {
                 k_topo_tuples<1><<<ge, 128, 0, stream>>>(nev, R.ev.p, R.cands_sorted.p, R.specs.p, R.lists.p, R.regs.p, (int)tmregs.size(), R.adj.p, R.deg.p, R.ev_of_slot.p,
                                                          wslot.p, R.list_n.p, R.list_cnt.p, excl_pairs.p, R.scalars.p + 2, R.scalars.p + 6);
                 CK(cudaStreamSynchronize(stream));
-                // deterministic order of the appended tuples: sort each new segment on the host
+                // deterministic order of the appended tuples: sort each new segment (device merge sort, lexicographic)
                 for (size_t l = 0; l < lists.size(); ++l) if (hc[l]) {
-                    int ar = lists[l].arity;
-                    std::vector<int> seg((size_t)hc[l] * ar);
-                    CK(cudaMemcpy(seg.data(), lists[l].d.p + (size_t)lists[l].n * ar, seg.size() * 4, cudaMemcpyDeviceToHost));
-                    std::vector<int> idx(hc[l]);
-                    for (int k = 0; k < hc[l]; ++k) idx[k] = k;
-                    std::sort(idx.begin(), idx.end(), [&](int x, int y) { return std::lexicographical_compare(seg.begin() + (size_t)x * ar, seg.begin() + (size_t)(x + 1) * ar, seg.begin() + (size_t)y * ar, seg.begin() + (size_t)(y + 1) * ar); });
-                    std::vector<int> out(seg.size());
-                    for (int k = 0; k < hc[l]; ++k) memcpy(&out[(size_t)k * ar], &seg[(size_t)idx[k] * ar], ar * 4);
-                    CK(cudaMemcpy(lists[l].d.p + (size_t)lists[l].n * ar, out.data(), out.size() * 4, cudaMemcpyHostToDevice));
+                    int* seg = lists[l].d.p + (size_t)lists[l].n * lists[l].arity;
+                    size_t tb2 = 0;
+                    if (lists[l].arity == 3) {
+                        cub::DeviceMergeSort::SortKeys(nullptr, tb2, (ClbTup<3>*)seg, hc[l], ClbTupLess<3>(), stream);
+                        CK(cubtmp2.ensure(tb2 + 256));
+                        cub::DeviceMergeSort::SortKeys(cubtmp2.p, tb2, (ClbTup<3>*)seg, hc[l], ClbTupLess<3>(), stream);
+                    } else if (lists[l].arity == 4) {
+                        cub::DeviceMergeSort::SortKeys(nullptr, tb2, (ClbTup<4>*)seg, hc[l], ClbTupLess<4>(), stream);
+                        CK(cubtmp2.ensure(tb2 + 256));
+                        cub::DeviceMergeSort::SortKeys(cubtmp2.p, tb2, (ClbTup<4>*)seg, hc[l], ClbTupLess<4>(), stream);
+                    }
                     lists[l].n += hc[l];
                 }
                 nexcl += (long long)nx;
