@@ -190,6 +190,20 @@ __device__ __forceinline__ const ClbBPot* bpot_lookup(const ClbBondedDesc& d, co
     }
     return nullptr;
 }
+// 1/sqrt(x) in fp64 without the slow-path library call: MUFU.RSQ seed (24 bits) + two Newton steps (the second is
+// nearly free and leaves ~1 ulp); x > 0 and finite.  Divisions and square roots of the bonded terms are built from it.
+__device__ __forceinline__ double clb_rsqrt(double x) {
+    int hi = __double2hiint(x), lo = __double2loint(x);
+    unsigned fb = ((unsigned)(hi - 0x38000000) << 3) | ((unsigned)lo >> 29);
+    float yf;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(yf) : "f"(__uint_as_float(fb)));
+    unsigned yb = __float_as_uint(yf);
+    double y = __hiloint2double((int)((yb >> 3) + 0x38000000u), (int)(yb << 29));
+    double e = fma(-x * y, y, 1.0);
+    y = fma(0.5 * y, e, y);
+    e = fma(-x * y, y, 1.0);
+    return fma(0.5 * y, e, y);
+}
 // returns F = -dU/dx and U for the scalar coordinate x (r, theta or phi)
 __device__ __forceinline__ void bpot_eval(const ClbBPot* p, double x, const ClbBTabMeta* tm, const double4* cf, const double4* ce,
                                           double& F, double& E, bool want_e, unsigned& err) {
@@ -248,24 +262,27 @@ __global__ void __launch_bounds__(256) k_bonded(int i0, int i1, const int4* __re
             if (d.arity == 2) {
                 int o = 1 - role;
                 double dx = lat2d(wsub(P[role].x, P[o].x)) * geo.q[0], dy = lat2d(wsub(P[role].y, P[o].y)) * geo.q[1], dz = lat2d(wsub(P[role].z, P[o].z)) * geo.q[2];
-                double r = sqrt(dx * dx + dy * dy + dz * dz);
+                const double r2 = dx * dx + dy * dy + dz * dz, ir = clb_rsqrt(r2), r = r2 * ir;
                 bpot_eval(pp, r, btm, cf, ce, F, E, ENERGY, err);
-                double fr = F / r;
+                double fr = F * ir;
                 ax += fr * dx; ay += fr * dy; az += fr * dz;
             } else if (d.arity == 3) {
                 double d1[3] = {lat2d(wsub(P[0].x, P[1].x)) * geo.q[0], lat2d(wsub(P[0].y, P[1].y)) * geo.q[1], lat2d(wsub(P[0].z, P[1].z)) * geo.q[2]};
                 double d2[3] = {lat2d(wsub(P[2].x, P[1].x)) * geo.q[0], lat2d(wsub(P[2].y, P[1].y)) * geo.q[1], lat2d(wsub(P[2].z, P[1].z)) * geo.q[2]};
-                double r1 = sqrt(d1[0] * d1[0] + d1[1] * d1[1] + d1[2] * d1[2]);
-                double r2 = sqrt(d2[0] * d2[0] + d2[1] * d2[1] + d2[2] * d2[2]);
-                double c = (d1[0] * d2[0] + d1[1] * d2[1] + d1[2] * d2[2]) / (r1 * r2);
+                const double i1 = clb_rsqrt(d1[0] * d1[0] + d1[1] * d1[1] + d1[2] * d1[2]);      // 1/r1
+                const double i2 = clb_rsqrt(d2[0] * d2[0] + d2[1] * d2[1] + d2[2] * d2[2]);      // 1/r2
+                const double i12 = i1 * i2;
+                double c = (d1[0] * d2[0] + d1[1] * d2[1] + d1[2] * d2[2]) * i12;
                 c = fmin(1.0, fmax(-1.0, c));
-                double th = acos(c), sn = sqrt(1.0 - c * c);
-                if (sn < 1e-9) sn = 1e-9;
+                double th = acos(c);
+                const double s2 = fmax(1.0 - c * c, 1e-18);                                          // sin^2, floor = (1e-9)^2
+                const double isn = clb_rsqrt(s2);                                                    // 1/sin(theta)
                 bpot_eval(pp, th, btm, cf, ce, F, E, ENERGY, err);
                 double g[3];
+                const double c11 = c * i1 * i1, c22 = c * i2 * i2;
                 for (int k = 0; k < 3; ++k) {
-                    double g1 = -(d2[k] / (r1 * r2) - c * d1[k] / (r1 * r1)) / sn;
-                    double g3 = -(d1[k] / (r1 * r2) - c * d2[k] / (r2 * r2)) / sn;
+                    double g1 = -(d2[k] * i12 - c11 * d1[k]) * isn;
+                    double g3 = -(d1[k] * i12 - c22 * d2[k]) * isn;
                     g[k] = role == 0 ? F * g1 : (role == 2 ? F * g3 : -F * (g1 + g3));
                 }
                 ax += g[0]; ay += g[1]; az += g[2];

@@ -234,6 +234,7 @@ extern "C" int clb_get_option(clb_engine* e, const char* name, double* v) {
 
 // ------------------------------------------------------------------------------------------ particles
 int clb_engine::slot_of(int64_t id) const {
+    if (ids_dense) { int64_t s = id - id_base; return (s >= 0 && s < (int64_t)n) ? (int)s : -1; }
     auto it = id2slot.find(id);
     return it == id2slot.end() ? -1 : it->second;
 }
@@ -244,17 +245,21 @@ extern "C" int clb_set_particles(clb_engine* e, int64_t n, const int64_t* id, co
     if (!e || n <= 0 || !id || !type || !pos || !mass) return e ? e->fail(CLB_ERR_ARG, "clb_set_particles: bad argument") : CLB_ERR_ARG;
     if (n >= (1ll << 28)) return e->fail(CLB_ERR_UNSUPPORTED, "more than 2^28 particles");
     cudaSetDevice(e->device);
-    // slots = rank in ascending id order
+    // slots = rank in ascending id order.  Ids given as a dense ascending run (the usual .gro numbering) need neither a
+    // sort nor a hash map: slot = id - first id.
     std::vector<int64_t> order(n);
     for (int64_t i = 0; i < n; ++i) order[i] = i;
-    std::sort(order.begin(), order.end(), [&](int64_t a, int64_t b) { return id[a] < id[b]; });
+    bool dense = true;
+    for (int64_t i = 1; i < n && dense; ++i) dense = id[i] == id[0] + i;
+    if (!dense) std::sort(order.begin(), order.end(), [&](int64_t a, int64_t b) { return id[a] < id[b]; });
     e->ids.resize(n);
     e->id2slot.clear();
-    e->id2slot.reserve(n * 2);
+    e->ids_dense = dense; e->id_base = id[0];
+    if (!dense) e->id2slot.reserve(n * 2);
     for (int64_t s = 0; s < n; ++s) {
         e->ids[s] = id[order[s]];
         if (s && e->ids[s] == e->ids[s - 1]) return e->fail(CLB_ERR_ARG, "duplicate particle id %lld", (long long)e->ids[s]);
-        e->id2slot[e->ids[s]] = (int)s;
+        if (!dense) e->id2slot[e->ids[s]] = (int)s;
     }
     e->n = (int)n;
     std::vector<int4> hp(n); std::vector<float4> hv(n); std::vector<int> himg(3 * n), hres(n), hslot(n); std::vector<double> hq(n);
@@ -513,14 +518,17 @@ extern "C" int clb_set_positions(clb_engine* e, int64_t n, const double* pos) {
 extern "C" int clb_set_exclusions(clb_engine* e, int64_t n, const int64_t* pairs) {
     if (!e || n < 0 || (n && !pairs)) return CLB_ERR_ARG;
     cudaSetDevice(e->device);
-    std::vector<int2> h; h.reserve(n);
+    // canonical (min slot, max slot) pairs packed into 64-bit keys: one integer sort, skipped when the caller's list is sorted
+    std::vector<uint64_t> keys; keys.reserve(n);
     for (int64_t k = 0; k < n; ++k) {
         int a = e->slot_of(pairs[2 * k]), b = e->slot_of(pairs[2 * k + 1]);
         if (a < 0 || b < 0) return e->fail(CLB_ERR_ARG, "exclusion %lld names an unknown particle", (long long)k);
-        if (a != b) h.push_back(make_int2(std::min(a, b), std::max(a, b)));
+        if (a != b) keys.push_back(((uint64_t)(uint32_t)std::min(a, b) << 32) | (uint32_t)std::max(a, b));
     }
-    std::sort(h.begin(), h.end(), [](const int2& x, const int2& y) { return x.x != y.x ? x.x < y.x : x.y < y.y; });
-    h.erase(std::unique(h.begin(), h.end(), [](const int2& x, const int2& y) { return x.x == y.x && x.y == y.y; }), h.end());
+    if (!std::is_sorted(keys.begin(), keys.end())) std::sort(keys.begin(), keys.end());
+    keys.erase(std::unique(keys.begin(), keys.end()), keys.end());
+    std::vector<int2> h(keys.size());
+    for (size_t k = 0; k < keys.size(); ++k) h[k] = make_int2((int)(keys[k] >> 32), (int)(keys[k] & 0xffffffffu));
     e->nexcl = (long long)h.size();
     CK(e->excl_pairs.ensure(h.size() * 2 + (size_t)e->n + 1024));
     if (!h.empty()) CK(cudaMemcpy(e->excl_pairs.p, h.data(), h.size() * sizeof(int2), cudaMemcpyHostToDevice));

@@ -72,6 +72,7 @@ struct clb_engine {
     std::vector<int64_t> ids;                 // slot -> caller id (ascending)
     std::unordered_map<int64_t, int> id2slot;
     int slot_of(int64_t id) const;
+    bool ids_dense = false; int64_t id_base = 0;
     DevBuf<int4> pos, pos2, xref;
     DevBuf<float4> vel, vel2;
     DevBuf<int> slot, slot2, id2idx, image, resid, mol;
