@@ -279,10 +279,14 @@ def main():
         barrier()
         t0 = time.perf_counter()
         e2.set_particles(snap["ids"], snap["type"], snap["pos"], snap["mass"], vel=snap["vel"], state=snap["state"], res_id=snap["resid"])
+        t_a = time.perf_counter() - t0
         h2 = synthetic.setup_reactive_melt(e2, snap, rc=RC, dt=DT, kT=KT, gamma=GAMMA, interval=INTERVAL, p_accept=P_ACCEPT)
+        t_b = time.perf_counter() - t0
         restore_into(e2, snap, h2)
         e2.reaction_general(1, INTERVAL, 1, 0)
         t_up = time.perf_counter() - t0
+        if os.environ.get("CLB_BENCH_VERBOSE"):
+            print("e2e upload: set_particles %.3fs, force field + lists %.3fs, restore %.3fs" % (t_a, t_b - t_a, t_up - t_b), file=sys.stderr)
         done = 0
         obs = []
         while done < a.steps:

@@ -193,6 +193,7 @@ extern "C" int clb_set_option(clb_engine* e, const char* name, double v) {
     else if (s == "tables_in_smem") { e->tabs_smem_user = (int)v; if (e->lists_valid) return e->configure_pair_launch(); }
     else if (s == "pair_event_timing") e->pair_event_timing = (int)v;
     else if (s == "overlap_halo") e->overlap_user = (int)v;
+    else if (s == "comm_group") e->comm_group_user = (int)v;
     else if (s == "pair_split") { e->pair_split_user = (int)v; if (e->lists_valid) return e->configure_pair_launch(); }
     else if (s == "build_threads") e->build_threads = (int)v;
     else if (s == "pair_warps") { e->pair_warps_user = (int)v; if (e->lists_valid) return e->configure_pair_launch(); }
@@ -1410,20 +1411,23 @@ extern "C" int clb_run(clb_engine* e, int64_t nsteps) {
                 if (pend) e->enqueue_integrate(CLB_INT_SECOND, (uint64_t)(e->step + s - 1));
                 e->enqueue_integrate(CLB_INT_FIRST, 0);
             }
-            if (e->nranks > 1 && e->overlap_user) {
+            if (e->nranks > 1 && (e->overlap_user > 0 || (e->overlap_user < 0 && e->nranks >= 4))) {
                 // global max displacement + position halo travel on the comm stream while the interior planes compute
                 cudaEventRecord(e->ev_int, e->stream);
                 cudaStreamWaitEvent(e->comm_stream, e->ev_int, 0);
-                TRY(e->comm_max_displacement(e->comm_stream));
-                TRY(e->comm_halo_positions(e->comm_stream));
+                if (e->comm_group_user) TRY(e->comm_step(e->comm_stream));
+                else { TRY(e->comm_max_displacement(e->comm_stream)); TRY(e->comm_halo_positions(e->comm_stream)); }
                 cudaEventRecord(e->ev_comm, e->comm_stream);
                 e->pending_step_index = (int)(s - i);
                 e->enqueue_forces(true);            // interior blocks, wait, k_check_resort, boundary blocks, bonded
             } else {
-                if (e->nranks > 1) TRY(e->comm_max_displacement(e->stream));
+                // single stream: the halo may travel before the resort check (a stalled step re-sends it after the rebuild)
+                if (e->nranks > 1) {
+                    if (e->comm_group_user) TRY(e->comm_step(e->stream));
+                    else { TRY(e->comm_max_displacement(e->stream)); TRY(e->comm_halo_positions(e->stream)); }
+                }
                 k_check_resort<<<1, 1, 0, e->stream>>>(e->d_ctl, e->criterion, half_skin, (int)(s - i));
                 ++e->launches;
-                if (e->nranks > 1) TRY(e->comm_halo_positions(e->stream));
                 e->enqueue_forces();
             }
             pend = true;

@@ -292,6 +292,20 @@ int clb_engine::comm_halo_positions(cudaStream_t st) {
     ++launches;
     return CLB_OK;
 }
+// both per-step operations in ONE NCCL group (one host-side launch sequence, no gap between the two kernels)
+int clb_engine::comm_step(cudaStream_t st) {
+    clb_engine* e = this;
+    CommDev& c = *cd;
+    NC(g_nccl.GroupStart());
+    NC(g_nccl.AllReduce(&d_ctl->maxdisp2_bits, &d_ctl->maxdisp2_bits, 1, ncclUint32, ncclMax, c.comm, st));
+    NC(g_nccl.Send(pos.p + c.send_lo0, (size_t)(c.send_lo1 - c.send_lo0) * sizeof(int4), ncclChar, c.dn, c.comm, st));
+    NC(g_nccl.Send(pos.p + c.send_hi0, (size_t)(c.send_hi1 - c.send_hi0) * sizeof(int4), ncclChar, c.up, c.comm, st));
+    NC(g_nccl.Recv(pos.p + own1, (size_t)c.n_hi * sizeof(int4), ncclChar, c.up, c.comm, st));
+    NC(g_nccl.Recv(pos.p + own1 + c.n_hi, (size_t)c.n_lo * sizeof(int4), ncclChar, c.dn, c.comm, st));
+    NC(g_nccl.GroupEnd());
+    launches += 2;
+    return CLB_OK;
+}
 // global maximum displacement of this step (float bits of a non-negative number order like unsigned integers)
 int clb_engine::comm_max_displacement(cudaStream_t st) {
     clb_engine* e = this;
