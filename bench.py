@@ -251,7 +251,12 @@ def main():
         step_bytes = (128.0 + 4.0 * lh) * n_per_gpu
         t_pair = (pair_ms * 1e-3 / pair_launches) if pair_launches else None
         roof = {"bound": "hbm", "kernel": "k_pair_forces", "achieved": (pair_bytes / t_pair / 1e9) if t_pair else None, "peak": peak,
-                "unit": "GB/s", "frac": (pair_bytes / t_pair / 1e9 / peak) if t_pair else None, "traffic": None, "peak_source": peak_src,
+                "unit": "GB/s", "frac": (pair_bytes / t_pair / 1e9 / peak) if t_pair else None,
+                # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel on this workload, from the committed
+                # `ncu --set full` capture (profiles/r1g_ncu_full_raw.csv: 293.9 MB + 20.8 MB); only quoted for the profiled case
+                "traffic": 314.7e6 if (world == 1 and a.n_side == 100) else None, "traffic_source": "profiles/r1g_ncu_full_raw.csv",
+                "binding_roof": "shared-memory wavefronts (56.5 M per launch, 52 % bank conflicts of the two random 16-byte gathers per pair); not HBM",
+                "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": pair_bytes, "kernel_ms": (t_pair * 1e3) if t_pair else None, "launches_timed": pair_launches,
                 "kernel_share_of_step": (pair_ms * 1e-3 / t_dev) if t_dev else None,
                 "step_achieved": step_bytes * steps_per_s / 1e9, "step_frac": step_bytes * steps_per_s / 1e9 / peak,
