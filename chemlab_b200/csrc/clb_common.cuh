@@ -17,6 +17,7 @@
 #define CLB_EF_CAND_OVERFLOW 8u // reaction candidate buffer overflow -> host regrows and rescans
 #define CLB_EF_TUPLE_OVERFLOW 16u
 #define CLB_EF_PARTNER_LOST 32u // bonded partner not resolvable (outside ghost layer)
+#define CLB_EF_TILE_OVERFLOW 64u // a tile holds more particles than the shared-memory carve-up assumed -> host retries
 
 // pos.w packing: type in bits 0..7, chemical state in bits 8..23 (signed 16 bit)
 __host__ __device__ inline int pw_type(int w) { return w & 0xff; }

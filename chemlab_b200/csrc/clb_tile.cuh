@@ -177,6 +177,8 @@ __global__ void __launch_bounds__(512) k_build_lists(ClbGrid g, ClbGeom geo, uns
         tile_geometry(g, b, t);
         __syncthreads();
         tile_offsets(g, t, cell_start, s_off, s_src);
+        // the host sizes the tile from the previous rebuild (no extra host check per rebuild); a fuller tile is reported
+        if (t.T > tile_cap) { if (threadIdx.x == 0) atomicOr(&ctl->err, CLB_EF_TILE_OVERFLOW); continue; }
         tile_stage(t, s_off, s_src, pos, s_pos, slot, s_slot, nullptr);
         const int mh0 = t.whole ? t.cx0 : 1;
         if (threadIdx.x == 0) {
@@ -601,7 +603,9 @@ __global__ void __launch_bounds__(1024) k_pair_forces_tab2(ClbGrid g, ClbPairArg
     const double invdx = A.invdx, cmagic = A.cmagic;
     const unsigned nm1 = A.nm1;
     unsigned err = 0;
-    for (int idx = blockIdx.x * A.nv + vc; idx < A.nidx; idx += gridDim.x * A.nv) {
+    // virtual CTA v of CTA c takes tiles v*gridDim + c, + nv*gridDim, ...: the tiles of the last, partial round land on
+    // DIFFERENT SMs (one each) instead of filling a few SMs completely
+    for (int idx = vc * gridDim.x + blockIdx.x; idx < A.nidx; idx += gridDim.x * A.nv) {
         const int b = idx < A.seg0 ? A.b0 + idx : A.b1 + (idx - A.seg0);
         TileCtx t;
         tile_geometry(g, b, t);

@@ -1014,7 +1014,8 @@ int clb_engine::read_ctl() {
     CK(cudaStreamSynchronize(stream));
     return CLB_OK;
 }
-__global__ void k_ctl_reset_stats(ClbCtl* c) { c->tile_max = 0; c->home_max = 0; c->cell_max = 0; c->nl_max = 0; c->nl_total = 0; c->err &= ~CLB_EF_LIST_OVERFLOW; }
+__global__ void k_ctl_reset_stats(ClbCtl* c) { c->tile_max = 0; c->home_max = 0; c->cell_max = 0; c->nl_max = 0; c->nl_total = 0; c->err &= ~(CLB_EF_LIST_OVERFLOW | CLB_EF_TILE_OVERFLOW); }
+__global__ void k_ctl_reset_after_overflow(ClbCtl* c) { c->nl_max = 0; c->nl_total = 0; c->err &= ~(CLB_EF_LIST_OVERFLOW | CLB_EF_TILE_OVERFLOW); }
 __global__ void k_ctl_after_rebuild(ClbCtl* c) { c->stall = 0; c->accum_maxdist = 0.0; c->maxdisp2_bits = 0u; c->force_rebuild = 0; }
 
 int clb_engine::setup_sync() {
@@ -1133,12 +1134,14 @@ int clb_engine::rebuild() {
     }
     k_cell_start<<<ceil_div(ns + 1, 256), 256, 0, stream>>>(ns, key2.p, grid.ncell, cell_start.p);
     tr.mark("sort");
-    // 2. tile statistics
+    // 2. tile statistics (read back together with the build result: one host check per rebuild instead of two)
     k_ctl_reset_stats<<<1, 1, 0, stream>>>(d_ctl);
     k_block_stats<<<ceil_div(grid.nblocks, 128), 128, 0, stream>>>(grid, cell_start.p, d_ctl);
-    TRY(read_ctl());
-    tile_max = h_ctl->tile_max; home_max = h_ctl->home_max;
-    if (tile_max > 65535) return fail(CLB_ERR_UNSUPPORTED, "tile of %d particles exceeds 16-bit list entries: lower block_cells", tile_max);
+    int tile_guess = tile_max > 0 ? (int)(tile_max * 1.08) + 32 : 0;
+    if (tile_guess == 0) {                       // first rebuild: nothing to extrapolate from
+        TRY(read_ctl());
+        tile_guess = h_ctl->tile_max;
+    }
     tr.mark("stats");
     // 3. neighbour lists (retry with a larger capacity on overflow)
     if (nl_cap == 0 || nl_cap_user != nl_cap_user_seen) {
@@ -1152,7 +1155,7 @@ int clb_engine::rebuild() {
     const unsigned long long rl2_lat = (unsigned long long)floor(geo.rl2 / geo.q2);
     for (int attempt = 0;; ++attempt) {
         CK(nl_entries.ensure((size_t)ncap * nl_cap));
-        const int tile_cap = (tile_max + 3) & ~3;     // keeps the per-warp staging rows 16-byte aligned
+        const int tile_cap = (tile_guess + 3) & ~3;     // keeps the per-warp staging rows 16-byte aligned
         size_t smem = (size_t)tile_cap * (sizeof(int4) + sizeof(int)) + (size_t)(threads / 32) * CLB_BUILD_G * nl_cap * sizeof(unsigned short) + 16;
         if ((int)smem > smem_optin) return fail(CLB_ERR_UNSUPPORTED, "tile needs %zu B of shared memory: lower block_cells", smem);
         int nb = 0;
@@ -1163,10 +1166,15 @@ int clb_engine::rebuild() {
         else k_build_lists<false><<<gridsz, threads, smem, stream>>>(grid, geo, rl2_lat, cell_start.p, pos.p, slot.p, excl_off.p, excl_ids.p, nl_entries.p, nl_count.p, nl_cap, tile_cap, d_ctl);
         ++launches;
         TRY(read_ctl());
-        if (!(h_ctl->err & CLB_EF_LIST_OVERFLOW)) break;
-        if (attempt > 6) return fail(CLB_ERR_RANGE, "neighbour list keeps overflowing (max %d entries)", h_ctl->nl_max);
-        nl_cap = ((h_ctl->nl_max * 5 / 4 + 8 + 7) / 8) * 8;   // multiple of 8: rows are read as uint4
-        k_ctl_reset_stats<<<1, 1, 0, stream>>>(d_ctl);
+        tile_max = h_ctl->tile_max; home_max = h_ctl->home_max;
+        if (tile_max > 65535) return fail(CLB_ERR_UNSUPPORTED, "tile of %d particles exceeds 16-bit list entries: lower block_cells", tile_max);
+        const bool tile_over = (h_ctl->err & CLB_EF_TILE_OVERFLOW) || tile_max > tile_cap;
+        const bool list_over = (h_ctl->err & CLB_EF_LIST_OVERFLOW) != 0;
+        if (!tile_over && !list_over) break;
+        if (attempt > 6) return fail(CLB_ERR_RANGE, "neighbour list keeps overflowing (max %d entries, tile %d)", h_ctl->nl_max, tile_max);
+        if (tile_over) tile_guess = tile_max;
+        if (list_over) nl_cap = ((h_ctl->nl_max * 5 / 4 + 8 + 7) / 8) * 8;   // multiple of 8: rows are read as uint4
+        k_ctl_reset_after_overflow<<<1, 1, 0, stream>>>(d_ctl);
     }
     nl_max = h_ctl->nl_max; nl_total = h_ctl->nl_total;
     tr.mark("build");
@@ -1447,7 +1455,7 @@ extern "C" int clb_run(clb_engine* e, int64_t nsteps) {
             e->enqueue_forces();
             done = s;
         } else done = j - 1;
-        if (e->h_ctl->err & ~CLB_EF_LIST_OVERFLOW) { TRY(e->check_device_errors("clb_run")); }
+        if (e->h_ctl->err & ~(CLB_EF_LIST_OVERFLOW | CLB_EF_TILE_OVERFLOW)) { TRY(e->check_device_errors("clb_run")); }
         pend = true;
         if (boundary_after(done)) {
             e->enqueue_integrate(CLB_INT_SECOND, (uint64_t)(e->step + done));
