@@ -389,34 +389,32 @@ extern "C" int clb_get_particles(clb_engine* e, int64_t n, const int64_t* ids, d
 
 // multi-rank read-back: every rank fills the rows of the particles it owns, the rows are summed over the ranks
 // (exact: one non-zero contribution per row), so all ranks return the full, identical state
+__global__ void k_pack_state(int no, int K, const int4* __restrict__ pos, const float4* __restrict__ vel, const double* __restrict__ force,
+                             int fstride, const int* __restrict__ slot, const int* __restrict__ image, double* __restrict__ M) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= no) return;
+    const int s = slot[i];
+    const int4 p = pos[i]; const float4 v = vel[i];
+    double* r = M + (size_t)s * K;
+    r[0] = (double)(unsigned)p.x; r[1] = (double)(unsigned)p.y; r[2] = (double)(unsigned)p.z;
+    r[3] = v.x; r[4] = v.y; r[5] = v.z;
+    r[6] = force[i]; r[7] = force[i + fstride]; r[8] = force[i + 2 * (size_t)fstride];
+    r[9] = image[3 * s]; r[10] = image[3 * s + 1]; r[11] = image[3 * s + 2];
+    r[12] = pw_type(p.w); r[13] = pw_state(p.w); r[14] = v.w;
+}
 int clb_engine::get_particles_gathered(int64_t nq, const int64_t* ids, double* pos_o, int32_t* image_o, double* vel_o, double* force_o,
                                        int32_t* type_o, int32_t* state_o, double* mass_o, double* q_o, int32_t* res_o) {
     clb_engine* e = this;
     const int K = 15;
     const int no = own1;
-    std::vector<int4> hp(no); std::vector<float4> hv(no); std::vector<int> hs(no), himg(3 * (size_t)n); std::vector<double> hf(3 * (size_t)ncap);
-    if (no) {
-        CK(cudaMemcpyAsync(hp.data(), this->pos.p, no * sizeof(int4), cudaMemcpyDeviceToHost, stream));
-        CK(cudaMemcpyAsync(hv.data(), this->vel.p, no * sizeof(float4), cudaMemcpyDeviceToHost, stream));
-        CK(cudaMemcpyAsync(hs.data(), slot.p, no * sizeof(int), cudaMemcpyDeviceToHost, stream));
-    }
-    CK(cudaMemcpyAsync(himg.data(), image.p, himg.size() * 4, cudaMemcpyDeviceToHost, stream));
-    CK(cudaMemcpyAsync(hf.data(), this->force.p, hf.size() * 8, cudaMemcpyDeviceToHost, stream));
-    CK(cudaStreamSynchronize(stream));
-    std::vector<double> M((size_t)n * K, 0.0);
-    for (int i = 0; i < no; ++i) {
-        double* r = &M[(size_t)hs[i] * K];
-        r[0] = (double)(uint32_t)hp[i].x; r[1] = (double)(uint32_t)hp[i].y; r[2] = (double)(uint32_t)hp[i].z;
-        r[3] = hv[i].x; r[4] = hv[i].y; r[5] = hv[i].z;
-        r[6] = hf[i]; r[7] = hf[i + ncap]; r[8] = hf[i + 2 * (size_t)ncap];
-        r[9] = himg[3 * hs[i]]; r[10] = himg[3 * hs[i] + 1]; r[11] = himg[3 * hs[i] + 2];
-        r[12] = pw_type(hp[i].w); r[13] = pw_state(hp[i].w); r[14] = hv[i].w;
-    }
+    // owned rows are packed on the device into a zeroed [n x K] matrix, summed over the ranks, downloaded once
     DevBuf<double> d;
-    CK(d.ensure(M.size()));
-    CK(cudaMemcpyAsync(d.p, M.data(), M.size() * 8, cudaMemcpyHostToDevice, stream));
-    int rr = comm_allreduce_sum_dev(d.p, M.size());
+    CK(d.ensure((size_t)n * K));
+    CK(cudaMemsetAsync(d.p, 0, (size_t)n * K * sizeof(double), stream));
+    if (no) k_pack_state<<<ceil_div(no, 256), 256, 0, stream>>>(no, K, this->pos.p, this->vel.p, this->force.p, ncap, slot.p, image.p, d.p);
+    int rr = comm_allreduce_sum_dev(d.p, (size_t)n * K);
     if (rr != CLB_OK) { d.release(); return rr; }
+    std::vector<double> M((size_t)n * K);
     CK(cudaMemcpyAsync(M.data(), d.p, M.size() * 8, cudaMemcpyDeviceToHost, stream));
     CK(cudaStreamSynchronize(stream));
     d.release();

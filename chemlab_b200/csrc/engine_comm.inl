@@ -129,6 +129,27 @@ extern "C" int clb_comm_init(clb_engine* e, int rank, int nranks, const void* nc
     CK(cudaStreamCreateWithFlags(&e->comm_stream, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&e->ev_int, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&e->ev_comm, cudaEventDisableTiming));
+    // NCCL builds its peer connections lazily at the first use of each pattern (100s of ms each): do that here, once, so
+    // that the first rebuild / reaction pass of a run does not pay for it
+    CK(cudaMemsetAsync(cd->cnt.p, 0, 64 * sizeof(int), e->stream));
+    CK(cd->sizes.ensure(2 * (size_t)nranks));
+    for (int pass = 0; pass < 2; ++pass) {
+        cudaStream_t st = pass == 0 ? e->stream : e->comm_stream;
+        NC(g_nccl.AllReduce(cd->cnt.p, cd->cnt.p, 1, ncclUint32, ncclMax, cd->comm, st));
+        NC(g_nccl.GroupStart());
+        NC(g_nccl.Send(cd->cnt.p + 1, 1, ncclInt32, cd->up, cd->comm, st));
+        NC(g_nccl.Send(cd->cnt.p + 2, 1, ncclInt32, cd->dn, cd->comm, st));
+        NC(g_nccl.Recv(cd->cnt.p + 4, 1, ncclInt32, cd->dn, cd->comm, st));
+        NC(g_nccl.Recv(cd->cnt.p + 5, 1, ncclInt32, cd->up, cd->comm, st));
+        NC(g_nccl.GroupEnd());
+        CK(cudaStreamSynchronize(st));
+    }
+    NC(g_nccl.AllGather(cd->sizes.p + nranks + rank, cd->sizes.p, 1, ncclInt64, cd->comm, e->stream));
+    NC(g_nccl.GroupStart());
+    for (int r2 = 0; r2 < nranks; ++r2) NC(g_nccl.Broadcast(cd->cnt.p + 16 + (r2 == rank ? 0 : 1), cd->cnt.p + 18, 4, ncclChar, r2, cd->comm, e->stream));
+    NC(g_nccl.GroupEnd());
+    NC(g_nccl.AllReduce(cd->cnt.p + 24, cd->cnt.p + 24, 2, ncclDouble, ncclSum, cd->comm, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
     return CLB_OK;
 }
 
