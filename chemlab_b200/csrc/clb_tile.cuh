@@ -225,7 +225,13 @@ __global__ void __launch_bounds__(512) k_build_lists(ClbGrid g, ClbGeom geo, uns
                             pass = valid && (fx * fx + fy * fy + fz * fz) <= geo.rl2;
                         }
                         const unsigned bal = __ballot_sync(0xffffffffu, pass);
-                        if (pass) { int o = cnt[q] + __popc(bal & lt_mask); if (o < cap) s_rows[q * cap + o] = (unsigned short)j; }
+                        // ballot compaction with a PREDICATED store: some lane passes in ~95 % of the chunks, so a branch
+                        // around the store is almost always taken and only adds BSSY/BRA/BSYNC overhead
+                        const int o = cnt[q] + __popc(bal & lt_mask);
+                        const unsigned st = (pass && o < cap) ? 1u : 0u;
+                        const unsigned addr = (unsigned)__cvta_generic_to_shared(s_rows + q * cap + o);
+                        asm volatile("{ .reg .pred p; setp.ne.u32 p, %2, 0; @p st.shared.u16 [%0], %1; }"
+                                     :: "r"(addr), "h"((unsigned short)j), "r"(st) : "memory");
                         cnt[q] += __popc(bal);
                     }
                 }
