@@ -52,7 +52,18 @@ class Context:
             raise RuntimeError("System needs system.bc (box) and a VerletList (cutoff) before it can run")
         if not self.pid:
             raise RuntimeError("no particles: call storage.addParticles first")
-        e = Engine(self.box, self.rc, self.skin, seed=self.seed)
+        # under torchrun (the mpirun of this engine) every rank builds the same system and joins the slab decomposition
+        device, join = 0, False
+        try:
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+                import os
+                device, join = int(os.environ.get("LOCAL_RANK", "0")), True
+        except ImportError:
+            pass
+        e = Engine(self.box, self.rc, self.skin, seed=self.seed, device=device)
+        if join:
+            e.join()
         P = self.props
         e.set_particles(np.asarray(self.pid, np.int64), np.asarray(P["type"], np.int32), np.asarray(P["pos"], float),
                         np.asarray(P["mass"], float), vel=np.asarray(P["v"], float), q=np.asarray(P["q"], float),

@@ -110,6 +110,9 @@ class SystemMonitorOutputCSV:
         self._fh = None
 
     def write(self, header, row):
+        import os
+        if int(os.environ.get("RANK", "0")) != 0:      # multi-GPU: every rank computes (collectives), rank 0 writes
+            return
         if self._fh is None:
             self._fh = open(self.filename, "w")
             self._fh.write(self.delimiter.join(header) + "\n")

@@ -40,12 +40,40 @@ def _load_hooks(path="hooks.py"):
     return hooks
 
 
+def _init_ranks():
+    """`torchrun --nproc-per-node N -m chemlab_b200.start_simulation @params` replaces `mpirun -n N start_simulation.py @params`
+    (examples/*/run_simulation.pbs): one process per GPU, every rank runs the same driver, rank 0 prints and writes files."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world <= 1:
+        return 0, 1
+    import torch
+    import torch.distributed as dist
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if not dist.is_initialized():
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return dist.get_rank(), world
+
+
 def main(argv=None):
+    rank, world = _init_ranks()
+    if rank == 0:
+        return _main(argv, rank, world)
+    out, sys.stdout = sys.stdout, open(os.devnull, "w")      # only rank 0 talks
+    try:
+        return _main(argv, rank, world)
+    finally:
+        sys.stdout.close()
+        sys.stdout = out
+
+
+def _main(argv, rank, world):
     args = app_args._args().parse_args(argv)
     prefix_dir = os.path.dirname(args.output_prefix)
     if prefix_dir:
         os.makedirs(prefix_dir, exist_ok=True)
-    app_args._args().save_to_file("%sparams.out" % args.output_prefix, args)
+    if rank == 0:
+        app_args._args().save_to_file("%sparams.out" % args.output_prefix, args)
 
     kb = args.kb if args.kb else 0.0083144621                   # :53-61 (GROMACS units unless overridden)
     mass_factor = args.mass_factor if args.mass_factor else 1.6605402
@@ -67,6 +95,11 @@ def main(argv=None):
     rng_seed = args.rng_seed
     if not rng_seed or rng_seed == -1:
         rng_seed = random.randint(10, 1000000)
+        if world > 1:                          # every rank must use the same seed
+            import torch.distributed as dist
+            box_ = [rng_seed]
+            dist.broadcast_object_list(box_, src=0)
+            rng_seed = box_[0]
         args.rng_seed = rng_seed
     prefix = "%s_%s" % (args.output_prefix, rng_seed)
     print("Skin: %s\nRNG Seed: %s\nBoltzmann constant: %s" % (skin, rng_seed, kb))
@@ -112,8 +145,9 @@ def main(argv=None):
         print("Read exclusion list from %s (%d pairs)" % (args.exclusion_list, len(exclusions)))
     else:
         exclusions = sorted(gt.exclusions)
-        with open("exclusion_%s.list" % os.path.basename(args.top).split(".")[0], "w") as f:
-            f.writelines("%d %d\n" % p for p in exclusions)
+        if rank == 0:
+            with open("exclusion_%s.list" % os.path.basename(args.top).split(".")[0], "w") as f:
+                f.writelines("%d %d\n" % p for p in exclusions)
     print("Excluded pairs from LJ interaction: %d" % len(exclusions))
     dynamic_exclude = espressopp.DynamicExcludeList(integrator, exclusions)
     verletlist = espressopp.VerletList(system, cutoff=max_cutoff, exclusionlist=dynamic_exclude)
@@ -246,26 +280,30 @@ def main(argv=None):
     g = e.get_particles(fields=("pos", "image", "type", "state", "res_id"))
     ids = sorted(system._ctx.pid)
     id2type = {v: k for k, v in gt.atomsym_atomtype.items()}
-    out_conf = files_io.GROFile("%s_confout.gro" % prefix)
-    out_conf.box = box
-    out_conf.title = "chemlab_b200 final configuration, step %d" % integrator.step
-    for k, pid in enumerate(ids):
-        a = conf.atoms[pid]
-        out_conf.atoms[pid] = a._replace(name=id2type.get(int(g["type"][k]), a.name), position=tuple(g["pos"][k]), velocity=None)
-    out_conf.write()
-    np.savetxt("%s_state.dat" % prefix, np.column_stack([ids, g["type"], g["state"], g["res_id"]]), fmt="%d", header="id type state res_id")
-    for i, f in enumerate(chem_fpls):
-        np.savetxt("%s_bonds_chem_%d.dat" % (prefix, i), np.asarray(f.fpl.getAllBonds(), np.int64).reshape(-1, 2), fmt="%d")
+    chem_bonds = [np.asarray(f.fpl.getAllBonds(), np.int64).reshape(-1, 2) for f in chem_fpls]
+    tuple_rows = []
     for label, lists, getter in (("bonds", list(dyn_fpl.values()) + list(static_fpl), "getAllBonds"),
                                  ("angles", list(dyn_ftl.values()) + list(static_ftl), "getAllTriples"),
                                  ("dihedrals", list(dyn_fql.values()) + list(static_fql), "getAllQuadruples")):
-        rows = [t for lst in lists for t in getattr(lst, getter)()]
-        if rows:
-            np.savetxt("%s_%s.dat" % (prefix, label), np.asarray(rows, np.int64), fmt="%d")
-    if ar is not None:
-        ar.save_reaction_counters("%s_reaction_counters.dat" % prefix)
-    with open("%s_benchmark.csv" % prefix, "a") as f:          # record format of the reference (:997-998)
-        f.write("1 %d %.6f %.6f\n" % (npart, total_time, integrator_loop))
+        tuple_rows.append((label, [t for lst in lists for t in getattr(lst, getter)()]))
+    if rank == 0:
+        out_conf = files_io.GROFile("%s_confout.gro" % prefix)
+        out_conf.box = box
+        out_conf.title = "chemlab_b200 final configuration, step %d" % integrator.step
+        for k, pid in enumerate(ids):
+            a = conf.atoms[pid]
+            out_conf.atoms[pid] = a._replace(name=id2type.get(int(g["type"][k]), a.name), position=tuple(g["pos"][k]), velocity=None)
+        out_conf.write()
+        np.savetxt("%s_state.dat" % prefix, np.column_stack([ids, g["type"], g["state"], g["res_id"]]), fmt="%d", header="id type state res_id")
+        for i, bonds_i in enumerate(chem_bonds):
+            np.savetxt("%s_bonds_chem_%d.dat" % (prefix, i), bonds_i, fmt="%d")
+        for label, rows in tuple_rows:
+            if rows:
+                np.savetxt("%s_%s.dat" % (prefix, label), np.asarray(rows, np.int64), fmt="%d")
+        if ar is not None:
+            ar.save_reaction_counters("%s_reaction_counters.dat" % prefix)
+        with open("%s_benchmark.csv" % prefix, "a") as f:          # record format of the reference (:997-998): nranks NPart total loop
+            f.write("%d %d %.6f %.6f\n" % (world, npart, total_time, integrator_loop))
     timers = tools.get_integrator_timers(system, integrator)
     print("final: steps=%d total=%.3fs integratorLoop=%.3fs (%.1f steps/s) setup=%.3fs" %
           (integrator.step, total_time, integrator_loop, integrator.step / max(integrator_loop, 1e-9), total_time0 - time0))
