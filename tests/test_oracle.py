@@ -118,3 +118,20 @@ def test_akima_and_linear_tables():
         assert abs(e2 - np.sin(3 * xv)) < 2e-5       # Akima interpolates a smooth function to O(h^3..4)
         assert abs(f2 + 3 * np.cos(3 * xv)) < 2e-4
     assert o.table_eval(t1, 2.5)[2] == 1 and o.table_eval(t1, 0.05)[2] == 1  # out of range flagged
+
+
+def test_akima_and_cubic_match_scipy_on_a_shipped_table():
+    """U13 (itype 2 / 3): the oracle's Akima and natural cubic spline agree with scipy's public implementations on a table
+    shipped by the reference (examples/hyperbranched/table_b0.pot) -- energy and force columns splined independently."""
+    import os
+    from scipy.interpolate import Akima1DInterpolator, CubicSpline
+    d = np.loadtxt(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "table_b0.pot"))
+    x, e, f = d[:, 0], d[:, 1], d[:, 2]
+    o = pyoracle.Oracle(8, [10, 10, 10], 2.5, 0.3)
+    ta, tc = o.add_table(x, e, f, 2), o.add_table(x, e, f, 3)
+    xs = np.random.default_rng(0).uniform(x[3], x[-4], 500)       # interior: the end treatment of Akima differs between codes
+    oa = np.array([o.table_eval(ta, v)[:2] for v in xs])
+    oc = np.array([o.table_eval(tc, v)[:2] for v in xs])
+    for got, ref in ((oa[:, 0], Akima1DInterpolator(x, e)(xs)), (oa[:, 1], Akima1DInterpolator(x, f)(xs)),
+                     (oc[:, 0], CubicSpline(x, e, bc_type="natural")(xs)), (oc[:, 1], CubicSpline(x, f, bc_type="natural")(xs))):
+        assert np.abs(got - ref).max() <= 1e-12 * np.abs(ref).max()
