@@ -135,3 +135,38 @@ def test_akima_and_cubic_match_scipy_on_a_shipped_table():
     for got, ref in ((oa[:, 0], Akima1DInterpolator(x, e)(xs)), (oa[:, 1], Akima1DInterpolator(x, f)(xs)),
                      (oc[:, 0], CubicSpline(x, e, bc_type="natural")(xs)), (oc[:, 1], CubicSpline(x, f, bc_type="natural")(xs))):
         assert np.abs(got - ref).max() <= 1e-12 * np.abs(ref).max()
+
+
+def test_tabulated_pair_forces_match_independent_numpy_brute_force():
+    """SURVEY 3.4 restated a second time, in numpy, O(N^2), minimum image: idx = floor((r-r0)/dr), F = (1-b) f[idx] + b f[idx+1],
+    f_i += F/r * d for r <= rc, pairs in the exclusion set skipped.  The C oracle (cell list + Verlet list) must agree."""
+    import clb_testutil as util
+    m = util.melt(7, seed=11)
+    n = len(m["pos"]); box = m["box"]; rc = 2.5
+    o = pyoracle.Oracle(n, box, rc, 0.3, seed=1)
+    o.set_particles(m["pos"], np.zeros((n, 3)), np.ones(n), None, m["type"], None, m["resid"])
+    ex = util.exclusions_from(m["bonds"], m["angles"])
+    o.set_exclusions(ex)
+    r, e, f = util.lj_table()
+    tab = o.add_table(r, e, f, 1)
+    nb = o.add_nonbonded(1)
+    for a, b in util.type_pairs(2):
+        o.nb_set_tab(nb, a, b, tab, rc)
+    o.compute_forces()
+    got = o.get()["force"]
+    d = m["pos"][:, None, :] - m["pos"][None, :, :]
+    d -= box * np.rint(d / box)
+    rr = np.sqrt((d * d).sum(-1))
+    mask = (rr <= rc) & ~np.eye(n, dtype=bool)
+    mask[ex[:, 0], ex[:, 1]] = False; mask[ex[:, 1], ex[:, 0]] = False
+    dr = r[1] - r[0]
+    s = (rr - r[0]) / dr
+    idx = np.clip(np.floor(s).astype(int), 0, len(r) - 2)
+    bfr = s - idx
+    F = (1 - bfr) * f[idx] + bfr * f[idx + 1]
+    E = (1 - bfr) * e[idx] + bfr * e[idx + 1]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        w = np.where(mask, F / rr, 0.0)
+    ref = (w[:, :, None] * d).sum(1)
+    assert util.rel_force_err(got, ref) < 1e-12
+    assert abs(o.energy(nb) - 0.5 * E[mask].sum()) <= 1e-12 * abs(0.5 * E[mask].sum())
