@@ -120,7 +120,8 @@ def process_group(items):
 
 
 def parse_config(path):
-    cp = configparser.ConfigParser(interpolation=None)
+    # strict=False: Python 2's ConfigParser (the reference) let a repeated option overwrite the earlier one
+    cp = configparser.ConfigParser(interpolation=None, strict=False)
     cp.optionxform = str.lower
     if not cp.read(path):
         raise RuntimeError("cannot read reaction config %s" % path)
