@@ -11,9 +11,9 @@ pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-def _run(tmp, backend, steps):
-    d = os.path.join(tmp, backend)
-    shutil.copytree(os.path.join(HERE, "golden", "atrp_lj"), d)
+def _run(tmp, backend, steps, example="atrp_lj", extra=("--rng_seed", "42", "--start_ar", "200", "--energy_collect", "200")):
+    d = os.path.join(tmp, example + "_" + backend)
+    shutil.copytree(os.path.join(HERE, "golden", example), d)
     cwd = os.getcwd()
     os.chdir(d)
     try:
@@ -25,13 +25,14 @@ def _run(tmp, backend, steps):
             C.Engine = OracleEngine
         try:
             # start_ar=200 -> reactions on after one outer iteration; nearest partner + p = rate*dt*interval
-            r = S.main(["@params", "--rng_seed", "42", "--run", str(steps), "--start_ar", "200", "--energy_collect", "200"])
+            r = S.main(["@params", "--run", str(steps)] + list(extra))
         finally:
             C.Engine = real
         e = r["system"]._ctx.engine
         g = e.get_particles(fields=("pos", "type", "state", "mass"))
         bonds = np.asarray(r["chem_fpls"][0].fpl.getAllBonds(), np.int64).reshape(-1, 2)
-        files = sorted(os.listdir(os.path.join(d, "data")))
+        out_dir = os.path.join(d, "data") if os.path.isdir(os.path.join(d, "data")) else d
+        files = sorted(os.listdir(out_dir))
         return dict(g=g, bonds=bonds, files=files, steps=r["steps"], T=r["monitor"]._last[1][0], dir=d)
     finally:
         os.chdir(cwd)
@@ -61,3 +62,16 @@ def test_atrp_lj_driver_gpu_matches_oracle(tmp_path):
     box = 28.11442
     d -= box * np.rint(d / box)
     assert np.abs(d).max() < 2e-3, np.abs(d).max()
+
+
+def test_chain_growth_catalytic_driver_gpu_matches_oracle(tmp_path):
+    """examples/chain_growth_catalytic as shipped: the reference's RNG-free reaction config (p = 2.5 >= 1, nearest partner,
+    two VIRTUAL reactions that only move states/types, two bond-forming ones) -- SURVEY 8c names it the first reaction parity
+    case.  1500 steps with reactions from step 500: passes at 1000 and 1500."""
+    steps = 1500
+    a = _run(str(tmp_path), "gpu", steps, example="chain_growth_catalytic", extra=("--start_ar", "500"))
+    b = _run(str(tmp_path), "oracle", steps, example="chain_growth_catalytic", extra=("--start_ar", "500"))
+    assert a["steps"] == b["steps"] == steps
+    assert (a["g"]["type"] == b["g"]["type"]).all() and (a["g"]["state"] == b["g"]["state"]).all()
+    assert len(a["bonds"]) > 0 and (_srt(a["bonds"]) == _srt(b["bonds"])).all()
+    assert (a["g"]["type"] != 0).sum() > 0
