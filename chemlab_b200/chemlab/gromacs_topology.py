@@ -310,6 +310,8 @@ def _bond_pot(func, raw):
         return I.Tabulated(itype=1, filename=pot_table("table_b%d.xvg" % int(float(raw[0]))))
     if func == 7:
         return I.FENE(K=float(raw[1]), r0=0.0, rMax=float(raw[0]))
+    if func == 9:                                                                # FENE + LJ: rMax K sigma epsilon (:935-944)
+        return I.FENELennardJones(K=float(raw[1]), r0=0.0, rMax=float(raw[0]), sigma=float(raw[2]), epsilon=float(raw[3]))
     raise RuntimeError("Unknown bond func type %s" % func)
 
 
@@ -335,8 +337,8 @@ def _dihedral_pot(func, raw):
 
 _KINDS = {
     2: dict(params="bondparams", tuples="bonds", make=_bond_pot, List=lambda: espressopp.FixedPairList, add="addBonds", label="bonds",
-            static={1: "FixedPairListHarmonic", 7: "FixedPairListFENE", 8: "FixedPairListTabulated"},
-            typed={1: "FixedPairListTypesHarmonic", 7: "FixedPairListTypesFENE", 8: "FixedPairListTypesTabulated"}),
+            static={1: "FixedPairListHarmonic", 7: "FixedPairListFENE", 8: "FixedPairListTabulated", 9: "FixedPairListFENELennardJones"},
+            typed={1: "FixedPairListTypesHarmonic", 7: "FixedPairListTypesFENE", 8: "FixedPairListTypesTabulated", 9: "FixedPairListTypesFENELennardJones"}),
     3: dict(params="angleparams", tuples="angles", make=_angle_pot, List=lambda: espressopp.FixedTripleList, add="addTriples", label="angles",
             static={1: "FixedTripleListAngularHarmonic", 8: "FixedTripleListTabulatedAngular", 11: "FixedTripleListCosine"},
             typed={1: "FixedTripleListTypesAngularHarmonic", 8: "FixedTripleListTypesTabulatedAngular", 11: "FixedTripleListTypesCosine"}),

@@ -177,7 +177,7 @@ __global__ void k_check_resort(ClbCtl* ctl, int criterion, double half_skin, int
 
 // ---------------------------------------------------------------- bonded --------------------
 struct ClbBondedDesc { int arity, typed, inter, npot, pot_off, active; };
-struct ClbBPot { int t[4]; int kind, table; double p[4]; };
+struct ClbBPot { int t[4]; int kind, table; double p[6]; };
 struct ClbBTabMeta { double x0, invdx, dx; int n, off; };
 
 __device__ __forceinline__ const ClbBPot* bpot_lookup(const ClbBondedDesc& d, const ClbBPot* pots, const int* ty) {
@@ -213,6 +213,9 @@ __device__ __forceinline__ void bpot_eval(const ClbBPot* p, double x, const ClbB
         case 6: { F = p->p[0] * sin(x - p->p[1]); E = p->p[0] * (1.0 + cos(x - p->p[1])); break; }         // Cosine
         case 7: { double d = x - p->p[1], xx = d / p->p[2]; F = -p->p[0] * d / (1.0 - xx * xx);
                   E = -0.5 * p->p[0] * p->p[2] * p->p[2] * log(1.0 - xx * xx); break; }                      // FENE
+        case 9: { double d = x - p->p[1], xx = d / p->p[2], sr2 = p->p[3] * p->p[3] / (x * x), sr6 = sr2 * sr2 * sr2;          // FENE + LJ (func 9)
+                  F = -p->p[0] * d / (1.0 - xx * xx) + 24.0 * p->p[4] * (2.0 * sr6 * sr6 - sr6) / x;
+                  E = -0.5 * p->p[0] * p->p[2] * p->p[2] * log(1.0 - xx * xx) + 4.0 * p->p[4] * (sr6 * sr6 - sr6); break; }
         case 8: { double d = x - p->p[1]; d -= 6.283185307179586 * rint(d / 6.283185307179586);
                   F = -2.0 * p->p[0] * d; E = p->p[0] * d * d; break; }                                      // DihedralHarmonic
         case 2: case 4: case 5: {                                                                            // tables

@@ -916,13 +916,13 @@ extern "C" int clb_bonded_set_potential(clb_engine* e, int inter, int t1, int t2
     if (!e || inter < 0 || inter >= (int)e->inters.size() || e->inters[inter].bonded < 0) return e ? e->fail(CLB_ERR_ARG, "bad bonded interaction handle") : CLB_ERR_ARG;
     HostBonded& b = e->bondeds[e->inters[inter].bonded];
     int ar = e->lists[b.list].arity;
-    bool ok = (ar == 2 && (kind == CLB_POT_HARMONIC || kind == CLB_POT_TABULATED || kind == CLB_POT_FENE)) ||
+    bool ok = (ar == 2 && (kind == CLB_POT_HARMONIC || kind == CLB_POT_TABULATED || kind == CLB_POT_FENE || kind == CLB_POT_FENE_LJ)) ||
               (ar == 3 && (kind == CLB_POT_ANGULAR_HARMONIC || kind == CLB_POT_TABULATED_ANGULAR || kind == CLB_POT_COSINE)) ||
               (ar == 4 && (kind == CLB_POT_TABULATED_DIHEDRAL || kind == CLB_POT_DIHEDRAL_HARMONIC));
     if (!ok) return e->fail(CLB_ERR_ARG, "potential kind %d does not fit a list of arity %d", kind, ar);
     ClbBPot p; memset(&p, 0, sizeof(p));
     p.kind = kind; p.table = table; p.t[0] = t1; p.t[1] = t2; p.t[2] = t3; p.t[3] = t4;
-    for (int i = 0; i < np && i < 4; ++i) p.p[i] = params[i];
+    for (int i = 0; i < np && i < 6; ++i) p.p[i] = params[i];
     if (kind == 2 || kind == 4 || kind == 5) { if (table < 0 || table >= (int)e->tables.size()) return e->fail(CLB_ERR_ARG, "bad table handle"); }
     if (!b.typed) { b.pots.clear(); b.pots.push_back(p); }
     else {

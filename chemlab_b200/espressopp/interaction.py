@@ -77,6 +77,17 @@ class FENE(_Pot):
         return (self.K, self.r0, self.rMax)
 
 
+class FENELennardJones(_Pot):
+    """FENELennardJones(K, r0, rMax, sigma, epsilon): [ bondtypes ] func 9 (gromacs_topology.py:935-961; doc/topology.rst:72-79)."""
+    kind = "FENELennardJones"
+
+    def __init__(self, K=1.0, r0=0.0, rMax=1.0, sigma=1.0, epsilon=1.0, **kw):
+        self.K, self.r0, self.rMax, self.sigma, self.epsilon = float(K), float(r0), float(rMax), float(sigma), float(epsilon)
+
+    def params(self):
+        return (self.K, self.r0, self.rMax, self.sigma, self.epsilon)
+
+
 class AngularHarmonic(_Pot):
     """AngularHarmonic(K, theta0): gromacs_topology.py:1073."""
     kind = "AngularHarmonic"
@@ -215,8 +226,8 @@ class _TypedFixedListInteraction(_FixedListInteraction):
     _typed = 1
 
 
-FixedPairListHarmonic = FixedPairListTabulated = FixedPairListFENE = _FixedListInteraction
-FixedPairListTypesHarmonic = FixedPairListTypesTabulated = FixedPairListTypesFENE = _TypedFixedListInteraction
+FixedPairListHarmonic = FixedPairListTabulated = FixedPairListFENE = FixedPairListFENELennardJones = _FixedListInteraction
+FixedPairListTypesHarmonic = FixedPairListTypesTabulated = FixedPairListTypesFENE = FixedPairListTypesFENELennardJones = _TypedFixedListInteraction
 FixedTripleListAngularHarmonic = FixedTripleListTabulatedAngular = FixedTripleListCosine = _FixedListInteraction
 FixedTripleListTypesAngularHarmonic = FixedTripleListTypesTabulatedAngular = FixedTripleListTypesCosine = _TypedFixedListInteraction
 FixedQuadrupleListTabulatedDihedral = FixedQuadrupleListDihedralHarmonic = _FixedListInteraction
@@ -226,8 +237,7 @@ FixedQuadrupleListTypesTabulatedDihedral = FixedQuadrupleListTypesDihedralHarmon
 for _n in ("VerletListTabulatedCapped", "VerletListLennardJonesEnergyCapped", "VerletListMultiTabulated", "VerletListMultiMixedTabulated",
            "VerletListScaleTabulated", "VerletListCoulombTruncated", "VerletListDynamicResolutionTabulated",
            "VerletListDynamicResolutionLennardJones", "TabulatedCapped", "LennardJonesEnergyCapped", "MultiTabulated",
-           "MultiMixedTabulated", "ScaleTabulated", "CoulombTruncated", "FENELennardJones", "FixedPairListFENELennardJones",
-           "FixedPairListTypesFENELennardJones", "FixedPairListLambdaHarmonic", "FixedPairListLambdaTabulated",
+           "MultiMixedTabulated", "ScaleTabulated", "CoulombTruncated", "FixedPairListLambdaHarmonic", "FixedPairListLambdaTabulated",
            "FixedTripleListLambdaAngularHarmonic", "FixedTripleListLambdaTabulatedAngular", "FixedQuadrupleListLambdaTabulatedDihedral",
            "DihedralRB", "DihedralHarmonicNCos", "FixedQuadrupleListDihedralRB", "FixedQuadrupleListDihedralHarmonicNCos",
            "FixedQuadrupleListTypesDihedralRB", "FixedQuadrupleListTypesDihedralHarmonicNCos", "ParticlePairScaling"):

@@ -32,7 +32,12 @@ def _load_hooks(path="hooks.py"):
     if os.path.exists(path):
         ns = {"espressopp": espressopp, "__name__": "hooks"}
         with open(path) as f:
-            exec(compile(f.read(), path, "exec"), ns)
+            try:
+                code = compile(f.read(), path, "exec")
+            except SyntaxError as e:      # the hooks shipped with the reference's examples are Python-2 user code
+                raise RuntimeError("%s is not valid Python 3 (%s, line %s): port the hook file (print statements, "
+                                   "random.sample on sets, ...)" % (path, e.msg, e.lineno)) from e
+            exec(code, ns)
         for name in ("hook_init_reaction", "hook_at_step", "hook_postsetup_interaction", "hook_setup_interactions", "hook_end"):
             if callable(ns.get(name)):
                 hooks[name] = ns[name]

@@ -152,8 +152,8 @@ typedef struct {
 } orc_pairpot;
 
 enum { POT_HARMONIC = 1, POT_TAB = 2, POT_ANG_HARM = 3, POT_TAB_ANG = 4, POT_TAB_DIH = 5,
-       POT_COSINE = 6, POT_FENE = 7, POT_DIH_HARM = 8 };
-typedef struct { int kind, table; double p[4]; } orc_bpot;
+       POT_COSINE = 6, POT_FENE = 7, POT_DIH_HARM = 8, POT_FENE_LJ = 9 };
+typedef struct { int kind, table; double p[6]; } orc_bpot;
 typedef struct { int t[4]; orc_bpot pot; } orc_typed_pot;
 
 typedef struct { int arity; int64_t n, cap; int *ids; } orc_list;
@@ -439,7 +439,7 @@ void orc_bonded_set_potential(orc_sim *s, int inter, int t1, int t2, int t3, int
                               int np, int table) {
     orc_bonded *b = bonded_by_inter(s, inter);
     orc_bpot p; memset(&p, 0, sizeof(p)); p.kind = kind; p.table = table;
-    for (int i = 0; i < np && i < 4; ++i) p.p[i] = params[i];
+    for (int i = 0; i < np && i < 6; ++i) p.p[i] = params[i];
     if (!b->typed) { b->pot = p; }
     else {
         b->tp = realloc(b->tp, sizeof(orc_typed_pot) * (b->ntp + 1));
@@ -630,6 +630,11 @@ static int bond_eval(orc_sim *s, const orc_bpot *p, double r, double *F, double 
         case POT_HARMONIC: *E = p->p[0] * (r - p->p[1]) * (r - p->p[1]); *F = -2 * p->p[0] * (r - p->p[1]); return 0;
         case POT_FENE: { double x = (r - p->p[1]) / p->p[2]; *E = -0.5 * p->p[0] * p->p[2] * p->p[2] * log(1 - x * x);
                          *F = -p->p[0] * (r - p->p[1]) / (1 - x * x); return 0; }
+        /* FENE + LJ bond, [ bondtypes ] func 9 (doc/topology.rst:72-79, gromacs_topology.py:935-944): p = {K, r0, rMax, sigma, epsilon};
+         * U = -K rMax^2/2 ln(1 - ((r-r0)/rMax)^2) + 4 eps [(sigma/r)^12 - (sigma/r)^6], no cutoff on the LJ part (formula as documented) */
+        case POT_FENE_LJ: { double x = (r - p->p[1]) / p->p[2], sr2 = p->p[3] * p->p[3] / (r * r), sr6 = sr2 * sr2 * sr2;
+                            *E = -0.5 * p->p[0] * p->p[2] * p->p[2] * log(1 - x * x) + 4 * p->p[4] * (sr6 * sr6 - sr6);
+                            *F = -p->p[0] * (r - p->p[1]) / (1 - x * x) + 24 * p->p[4] * (2 * sr6 * sr6 - sr6) / r; return 0; }
         case POT_TAB: return table_eval(&s->tables[p->table], r, E, F);
     }
     *E = *F = 0; return 0;

@@ -164,7 +164,10 @@ def test_bonded_forces_all_kinds():
     l4 = P.add_list(4, quads); i4 = P.add_bonded(l4); P.bonded_pot(i4, (), "TabulatedDihedral", (), td)
     # type-dispatched bonds: (0,1) harmonic, (1,1) not registered -> skipped on both sides
     l5 = P.add_list(2, m["bonds"]); i5 = P.add_bonded(l5, typed=1); P.bonded_pot(i5, (1, 0), "Harmonic", (10.0, 1.1))
-    _compare_forces(P, [ib, ia, iq, i1, i2, i3, i4, i5])
+    # Kremer-Grest bonds of examples/pccg_lj: FENE (func 7) and FENE + LJ (func 9, gromacs_topology.py:935-961)
+    l6 = P.add_list(2, m["bonds"][:250]); i6 = P.add_bonded(l6); P.bonded_pot(i6, (), "FENE", (30.0, 0.0, 1.5))
+    l7 = P.add_list(2, m["bonds"][250:]); i7 = P.add_bonded(l7); P.bonded_pot(i7, (), "FENELennardJones", (30.0, 0.0, 1.5, 1.0, 1.0))
+    _compare_forces(P, [ib, ia, iq, i1, i2, i3, i4, i5, i6, i7])
     P.close()
 
 
