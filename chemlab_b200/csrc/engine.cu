@@ -627,7 +627,9 @@ extern "C" int clb_add_table(clb_engine* e, int64_t n, const double* x, const do
     t.n = (int)n; t.x0 = x[0]; t.dx = (x[n - 1] - x[0]) / (double)(n - 1); t.interp = interp;
     if (!(t.dx > 0)) return e->fail(CLB_ERR_ARG, "table abscissa must increase");
     for (int64_t i = 0; i < n; ++i)
-        if (fabs(x[i] - (t.x0 + i * t.dx)) > 1e-6 * t.dx + 1e-9 * fabs(x[i]) + 5e-9)
+        // `.pot` files carry 8 significant digits ("%15.8g", tools/convert_gromacs2espp.py:84): angle/dihedral abscissae in radians
+        // are off the exact grid by up to 1e-7; the knots used are x0 + i*dx (U12), as in the oracle
+        if (fabs(x[i] - (t.x0 + i * t.dx)) > 1e-3 * t.dx + 1e-7 * fabs(x[i]) + 5e-9)
             return e->fail(CLB_ERR_ARG, "table abscissa is not uniform at row %lld", (long long)i);
     t.e.assign(energy, energy + n); t.f.assign(force, force + n);
     e->tables.push_back(std::move(t));

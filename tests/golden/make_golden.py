@@ -26,3 +26,37 @@ for f in FILES:
     os.makedirs(dst_dir, exist_ok=True)
     shutil.copy(src, os.path.join(dst_dir, os.path.basename(f)))
     print("copied", f, os.path.getsize(src))
+
+
+# rim135 (config 5 base system): topology, coordinates, arg-file, reaction config as shipped; the 28 non-bonded, 5 bond and 3 angle
+# tables are converted .xvg -> .pot with the reference's converter logic (chemlab_b200.espressopp.tools.convert.gromacs ==
+# tools/convert_gromacs2espp.py, byte-exact on the shipped pairs) and packed into one compressed npz (710 KB instead of 2.8 MB of
+# text; "%15.8g" text round-trips exactly through float64).  table_a1 / table_a2 are missing from the reference
+# (.MISSING_LARGE_BLOBS) and are copies of the shipped table_a3.
+def pack_rim135():
+    import glob
+    import sys
+    import tempfile
+    import numpy as np
+    sys.path.insert(0, os.path.join(HERE, "..", ".."))
+    from chemlab_b200.espressopp.tools.convert.gromacs import convertTable
+    src = os.path.join(REF, "examples", "rim135")
+    dst = os.path.join(HERE, "rim135")
+    os.makedirs(dst, exist_ok=True)
+    for f in ("cg_conf.gro", "cg_topol.top", "params", "reaction.cfg"):
+        shutil.copy(os.path.join(src, f), os.path.join(dst, f))
+    arrays = {}
+    with tempfile.TemporaryDirectory() as tmp:
+        for xvg in sorted(glob.glob(os.path.join(src, "table_*.xvg"))):
+            name = os.path.basename(xvg)[:-4]
+            pot = os.path.join(tmp, name + ".pot")
+            convertTable(xvg, pot)
+            arrays[name] = np.loadtxt(pot)
+    for k in (1, 2):
+        arrays["table_a%d" % k] = arrays["table_a3"]
+    np.savez_compressed(os.path.join(dst, "tables.npz"), **arrays)
+    print("rim135: %d tables packed" % len(arrays))
+
+
+if __name__ == "__main__":
+    pack_rim135()
