@@ -58,5 +58,21 @@ def pack_rim135():
     print("rim135: %d tables packed" % len(arrays))
 
 
+# hyperbranched (config 3 base system): inputs as shipped + the shipped .pot tables packed like rim135's.  The angle and dihedral
+# tables are missing from the reference (.MISSING_LARGE_BLOBS); the test synthesises smooth ones (tests/test_gpu_driver.py).
+def pack_hyperbranched():
+    import glob
+    import numpy as np
+    src = os.path.join(REF, "examples", "hyperbranched")
+    dst = os.path.join(HERE, "hyperbranched")
+    os.makedirs(dst, exist_ok=True)
+    for f in ("conf.gro", "topol.top", "ffnb.itp", "params", "reaction.cfg"):
+        shutil.copy(os.path.join(src, f), os.path.join(dst, f))
+    arrays = {os.path.basename(p)[:-4]: np.loadtxt(p) for p in sorted(glob.glob(os.path.join(src, "table_*.pot")))}
+    np.savez_compressed(os.path.join(dst, "tables.npz"), **arrays)
+    print("hyperbranched: %d tables packed" % len(arrays))
+
+
 if __name__ == "__main__":
     pack_rim135()
+    pack_hyperbranched()

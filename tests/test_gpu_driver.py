@@ -14,6 +14,17 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 def _run(tmp, backend, steps, example="atrp_lj", extra=("--rng_seed", "42", "--start_ar", "200", "--energy_collect", "200")):
     d = os.path.join(tmp, example + "_" + backend)
     shutil.copytree(os.path.join(HERE, "golden", example), d)
+    if example == "hyperbranched":
+        # the reference ships no angle / dihedral tables for this example (.MISSING_LARGE_BLOBS): smooth stand-ins on the usual grids
+        th = np.radians(np.arange(0.5, 180.01, 0.5))
+        for k in range(11):
+            t0, K = np.radians(100 + 6 * k), 40.0 + 3 * k
+            with open(os.path.join(d, "table_a%d.pot" % k), "w") as f:
+                f.writelines("%15.8g %15.8g %15.8g\n" % (x, 0.5 * K * (x - t0) ** 2, -K * (x - t0)) for x in th)
+        ph = np.radians(np.arange(-180.0, 180.01, 1.0))
+        for k in range(8):
+            with open(os.path.join(d, "table_d%d.pot" % k), "w") as f:
+                f.writelines("%15.8g %15.8g %15.8g\n" % (x, 2.0 * (1 + np.cos(2 * x - 0.3 * k)), 4.0 * np.sin(2 * x - 0.3 * k)) for x in ph)
     if os.path.exists(os.path.join(d, "tables.npz")):          # packed `.pot` tables (tests/golden/make_golden.py)
         with np.load(os.path.join(d, "tables.npz")) as z:
             for name in z.files:
@@ -100,3 +111,16 @@ def test_rim135_driver_gpu_matches_oracle(tmp_path):
     # 2 ps at 700 K with stiff tabulated bonds: the fp32-stored velocities of the engine let the trajectories drift apart by
     # ~0.01 nm (measured 0.012) while every discrete decision (types, states, bonds) still agrees
     assert np.abs(d).max() < 0.05, np.abs(d).max()
+
+
+def test_hyperbranched_driver_gpu_matches_oracle(tmp_path):
+    """examples/hyperbranched as shipped (config 3's base system): 8 types, 21 plain + 15 MIXED tabulated pair potentials whose
+    mixing follows the chemical conversion N(RA)/1000 (nonbond_params func 10), tabulated bonds, angles and dihedrals, step-growth
+    reactions with neighbour-type changes from step 0.  1000 steps = two reaction passes and two re-mixes of the tables."""
+    steps = 1000
+    extra = ("--rng_seed", "5")
+    a = _run(str(tmp_path), "gpu", steps, example="hyperbranched", extra=extra)
+    b = _run(str(tmp_path), "oracle", steps, example="hyperbranched", extra=extra)
+    assert a["steps"] == b["steps"] == steps
+    assert (a["g"]["type"] == b["g"]["type"]).all() and (a["g"]["state"] == b["g"]["state"]).all()
+    assert len(b["bonds"]) > 10 and a["bonds"].shape == b["bonds"].shape and (_srt(a["bonds"]) == _srt(b["bonds"])).all()
