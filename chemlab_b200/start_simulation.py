@@ -15,6 +15,7 @@ top of `chemlab_b200.espressopp`.  Stages follow the reference one to one (SURVE
   main loop :728-797  integrator.run(integrator_step) with reaction start/stop and the conversion stop criterion
   outputs   :800-1081 final .gro, bond/angle/dihedral lists, reaction counters, benchmark record
 """
+import math
 import os
 import random
 import sys
@@ -259,6 +260,12 @@ def _main(argv, rank, world):
             for ext in ext_to_integrator:
                 integrator.addExtension(ext)
             reactions_enabled = True
+            if getattr(args, "save_before_reaction", False):       # :743-746
+                before = files_io.GROFile("%s_before_reaction_confout.gro" % prefix)
+                before.box, before.title, before.atoms = box, "before reaction, step %d" % integrator.step, dict(conf.atoms)
+                before.update_position(system, unfolded=False)
+                if rank == 0:
+                    before.write(with_velocity=True)
             if "hook_init_reaction" in hooks:
                 hooks["hook_init_reaction"](system, integrator, ar, gt, args)
         if reactions_enabled and maximum_conversion:
@@ -271,11 +278,24 @@ def _main(argv, rank, world):
             reactions_enabled = False
             if stop_simulation and not getattr(args, "eq_steps", 0):
                 break
+        if getattr(args, "rate_arrhenius", False) and reactions_enabled:
+            bonds0 = sum(f.fpl.totalSize() for f in chem_fpls)
+            monitor.perform_action()
+            energy0 = monitor.potential_energy
         t0 = time.time()
         integrator.run(integrator_step)                           # :780 -- 100 % of the compute
         integrator_loop += time.time() - t0
+        if getattr(args, "rate_arrhenius", False) and reactions_enabled:      # :785-796: k = exp(-dE/kT) per new bond
+            delta_bonds = sum(f.fpl.totalSize() for f in chem_fpls) - bonds0
+            if delta_bonds > 0:
+                monitor.perform_action()
+                energy_delta = (monitor.potential_energy - energy0) / float(delta_bonds)
+                new_rate = math.exp(-energy_delta / temperature)
+                print("%d\tChange reaction rate, delta_E=%s, new_k=%s, delta_bonds=%d" % (k * integrator_step, energy_delta, new_rate, delta_bonds))
+                for r_ in reactions:
+                    r_.rate = new_rate
         if "hook_at_step" in hooks:
-            hooks["hook_at_step"](system, integrator, ar, gt, args, k)
+            hooks["hook_at_step"](system, integrator, ar, gt, args, k * integrator_step)     # :783
     total_time = time.time() - total_time0
     monitor.dump()
     monitor.info()
@@ -305,6 +325,11 @@ def _main(argv, rank, world):
         for label, rows in tuple_rows:
             if rows:
                 np.savetxt("%s_%s.dat" % (prefix, label), np.asarray(rows, np.int64), fmt="%d")
+        # final topology (:834-994): current types, the static lists and everything the reactions added
+        top_atoms = {pid: dict(gt.atoms[pid], type_id=int(g["type"][k])) for k, pid in enumerate(ids) if pid in gt.atoms}
+        rows = dict(tuple_rows)
+        gt.gt.write_system("%s_output_topol.top" % prefix, top_atoms, list(rows["bonds"]) + [tuple(b_) for bb in chem_bonds for b_ in bb.tolist()],
+                           rows["angles"], rows["dihedrals"], {v: k_ for k_, v in gt.atomsym_atomtype.items()})
         if ar is not None:
             ar.save_reaction_counters("%s_reaction_counters.dat" % prefix)
         with open("%s_benchmark.csv" % prefix, "a") as f:          # record format of the reference (:997-998): nranks NPart total loop

@@ -91,3 +91,35 @@ def test_molecule_exclusions_nrexcl():
     assert G.molecule_exclusions(chain, 1) == {(1, 2), (2, 3), (3, 4), (4, 5)}
     assert G.molecule_exclusions(chain, 2) == {(1, 2), (2, 3), (3, 4), (4, 5), (1, 3), (2, 4), (3, 5)}
     assert (1, 4) in G.molecule_exclusions(chain, 3) and (1, 5) not in G.molecule_exclusions(chain, 3)
+
+
+def test_driver_host_logic_on_the_oracle_backend(tmp_path, monkeypatch):
+    """The whole driver (arg-file, topology, exclusions, reactions, ATRP activator, hooks, observers, outputs) with the engine
+    swapped for the CPU checker (tests/oracle_engine.py): host logic only, no GPU.  The products of the reference driver must
+    appear (src/start_simulation.py:800-1081) and must be readable by our own readers."""
+    import shutil
+    import sys
+    sys.path.insert(0, HERE)
+    import chemlab_b200.espressopp._context as C
+    from oracle_engine import OracleEngine
+    from chemlab_b200 import start_simulation as S
+    from chemlab_b200.chemlab.files_io import GROFile
+    from chemlab_b200.chemlab.gromacs_topology import GromacsTopology
+    d = str(tmp_path / "atrp")
+    shutil.copytree(os.path.join(GOLD, "atrp_lj"), d)
+    monkeypatch.chdir(d)
+    monkeypatch.setattr(C, "Engine", OracleEngine)
+    r = S.main(["@params", "--rng_seed", "42", "--run", "600", "--start_ar", "200", "--energy_collect", "200", "--save_before_reaction", "True"])
+    assert r["steps"] == 600
+    out = set(os.listdir("data"))
+    for name in ("cpc01_42_confout.gro", "cpc01_42_before_reaction_confout.gro", "cpc01_42_output_topol.top", "cpc01_42_state.dat",
+                 "cpc01_42_bonds.dat", "cpc01_42_angles.dat", "cpc01_42_reaction_counters.dat", "cpc01_42_benchmark.csv",
+                 "cpc01_energy_42.csv", "cpc01params.out", "cpc01_42_atrp_stats.dat"):
+        assert name in out, name
+    g = GROFile(os.path.join("data", "cpc01_42_confout.gro")); g.read()
+    assert len(g.atoms) == 6000 and {a.name for a in g.atoms.values()} >= {"MA", "ML", "FA", "PL"}      # activated trimers renamed
+    csv = open(os.path.join("data", "cpc01_energy_42.csv")).read().splitlines()
+    assert csv[0].split("\t")[:4] == ["step", "time", "T", "Ekin"] and len(csv) == 1 + 3 + 1                  # 3 collections + final dump
+    assert open(os.path.join("data", "cpc01_42_benchmark.csv")).read().split()[:2] == ["1", "6000"]
+    gt = GromacsTopology(os.path.join("data", "cpc01_42_output_topol.top")).read()
+    assert len(gt.atoms) == 6000 and len(gt.bonds) >= 4000 and len(gt.angles) >= 2000
