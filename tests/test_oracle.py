@@ -171,3 +171,71 @@ def test_tabulated_pair_forces_match_independent_numpy_brute_force():
     ref = (w[:, :, None] * d).sum(1)
     assert util.rel_force_err(got, ref) < 1e-12
     assert abs(o.energy(nb) - 0.5 * E[mask].sum()) <= 1e-12 * abs(0.5 * E[mask].sum())
+
+
+def test_react_matches_an_independent_python_restatement():
+    """ChemicalReaction::React (SURVEY 3.3, U3-U8, U20, U21) restated a second time in plain Python on the oracle's own pair
+    list and Philox draws: candidate rows, acceptance, UniqueA -> UniqueB (nearest and random), one reaction per particle,
+    max_per_interval, state deltas and the bond list must equal what the C oracle does."""
+    STREAM_REACT, STREAM_PARTNER = 0x52454143, 0x50415254
+    for nearest, cap in ((1, 0), (0, 0), (1, 25)):
+        m = util.melt(10, seed=21)
+        n = len(m["pos"]); box = m["box"]; seed = 77; dt = 0.004; interval = 10
+        state = np.where(m["type"] == 0, 1, 0).astype(np.int32)
+        o = pyoracle.Oracle(n, box, 2.5, 0.3, seed=seed)
+        o.set_particles(m["pos"], np.zeros((n, 3)), np.ones(n), None, m["type"], state, m["resid"])
+        o.set_exclusions(util.exclusions_from(m["bonds"], m["angles"]))
+        rl = o.add_list(2)
+        o.set_dt(dt); o.reaction_general(1, interval, nearest, cap)
+        # two reactions: A(1,2)+A(1,2)->A(1):A(1) with p = 0.6, and A(1,2)+L(0,1)->A(1):L(1) with p >= 1
+        specs = [dict(t1=0, t2=0, d1=1, d2=1, w1=(1, 2), w2=(1, 2), rate=0.6 / (dt * interval), rc=1.25),
+                 dict(t1=0, t2=1, d1=1, d2=1, w1=(1, 2), w2=(0, 1), rate=1e6, rc=1.1)]
+        for s in specs:
+            o.add_reaction(s["t1"], s["t2"], s["d1"], s["d2"], s["w1"][0], s["w1"][1], s["w2"][0], s["w2"][1], s["rate"], s["rc"], rl,
+                           intramolecular=1, intraresidual=0)
+        pairs = o.pairs()
+        typ, st, resid, pos = m["type"].copy(), state.copy(), m["resid"], m["pos"]
+        step = o.step()
+
+        def draw(stream, i, j, r):
+            return pyoracle.philox([i, j, step & 0xffffffff, (((step >> 32) & 0xffffffff) << 8) ^ r], [seed & 0xffffffff, ((seed >> 32) & 0xffffffff) ^ stream])
+
+        def side_ok(s, a, b):
+            return typ[a] == s["t1"] and typ[b] == s["t2"] and s["w1"][0] <= st[a] < s["w1"][1] and s["w2"][0] <= st[b] < s["w2"][1]
+        cands = []
+        for i, j in pairs:
+            d = pos[i] - pos[j]; d -= box * np.rint(d / box); d2 = float(d @ d)
+            for r, s in enumerate(specs):
+                if side_ok(s, i, j): a, b = i, j
+                elif side_ok(s, j, i): a, b = j, i
+                else: continue
+                if resid[a] == resid[b] or not (d2 < s["rc"] ** 2): continue
+                w = draw(STREAM_REACT, int(i), int(j), r); h = draw(STREAM_PARTNER, int(i), int(j), r)
+                cands.append(dict(a=int(a), b=int(b), r=r, d2=d2, acc=(w[0] / 4294967296.0) < s["rate"] * dt * interval, rnd=(h[0] << 32) | h[1]))
+        cands.sort(key=lambda c: (c["a"], c["b"], c["r"]))
+        key = (lambda c, partner: ((c["d2"] if nearest else c["rnd"]), c[partner], c["r"]))
+        alive = [c for c in cands if c["acc"]]
+        best = {}
+        for c in alive:
+            if c["a"] not in best or key(c, "b") < key(best[c["a"]], "b"): best[c["a"]] = c
+        alive = [c for c in alive if best[c["a"]] is c]
+        best = {}
+        for c in alive:
+            if c["b"] not in best or key(c, "a") < key(best[c["b"]], "a"): best[c["b"]] = c
+        alive = [c for c in alive if best[c["b"]] is c]
+        used, events = set(), []
+        for c in alive:
+            if c["a"] in used or c["b"] in used or (cap and len(events) >= cap): continue
+            used.update((c["a"], c["b"])); events.append(c)
+        for c in events:
+            st[c["a"]] += specs[c["r"]]["d1"]; st[c["b"]] += specs[c["r"]]["d2"]
+        nev = o.react()
+        rows, d2o = o.candidates()
+        assert len(rows) == len(cands) > 100
+        assert (rows == np.array([[c["a"], c["b"], c["r"], int(c["acc"])] for c in cands])).all()
+        assert np.allclose(d2o, [c["d2"] for c in cands], rtol=1e-13)
+        assert nev == len(events) > (10 if not cap else 0) and (not cap or nev == cap)
+        got = o.list_get(rl, 2)
+        want = np.array([[c["a"], c["b"]] for c in events])
+        assert (got[np.lexsort((got[:, 1], got[:, 0]))] == want[np.lexsort((want[:, 1], want[:, 0]))]).all()
+        assert (o.get()["state"] == st).all()
