@@ -206,6 +206,7 @@ typedef struct orc_sim {
     int64_t last_events;
     int range_error;
     int nthreads;
+    double *fbuf; size_t fbuf_cap;   /* per-thread force buffers (force_buffers) */
 } orc_sim;
 
 static inline double minimg(double d, double L) { return d - L * nearbyint(d / L); }
@@ -227,7 +228,7 @@ void orc_destroy(orc_sim *s) {
     if (!s) return;
     free(s->x); free(s->v); free(s->f); free(s->xref); free(s->mass); free(s->q); free(s->image);
     free(s->type); free(s->state); free(s->resid); free(s->mol); free(s->deg); free(s->adj);
-    free(s->excl); free(s->pairs); free(s->cands);
+    free(s->excl); free(s->pairs); free(s->cands); free(s->fbuf);
     for (int i = 0; i < s->ntables; ++i) { free(s->tables[i].e); free(s->tables[i].f); free(s->tables[i].ce); free(s->tables[i].cf); }
     free(s->tables);
     for (int i = 0; i < s->nlists; ++i) free(s->lists[i].ids);
@@ -586,10 +587,34 @@ static inline int pair_eval(orc_sim *s, const orc_pairpot *p, double r2, double 
     }
     return bad;
 }
-static void nonbonded_forces(orc_sim *s) {
+/* Threading of the force evaluation (the reference parallelises by MPI domains; this restatement by OpenMP threads):
+ * every thread accumulates into its own force buffer, the buffers are summed in thread order afterwards, so the result is
+ * reproducible for a given thread count.  One thread writes straight into s->f (the order of the serial code). */
+static double *force_buffers(orc_sim *s) {
+    int nth = s->nthreads;
+    if (nth <= 1) return NULL;
+    size_t n3 = 3 * (size_t)s->n, need = n3 * (size_t)nth;
+    if (s->fbuf_cap < need) { free(s->fbuf); s->fbuf = malloc(need * 8); s->fbuf_cap = need; }
+#pragma omp parallel num_threads(nth)
+    {
+        int tid = 0;
+#ifdef _OPENMP
+        tid = omp_get_thread_num();
+#endif
+        memset(s->fbuf + n3 * tid, 0, n3 * 8);          /* first touch by the owning thread */
+    }
+    return s->fbuf;
+}
+static void reduce_force_buffers(orc_sim *s, const double *fbuf) {
+    int nth = s->nthreads;
+    if (nth <= 1 || !fbuf) return;
+    size_t n3 = 3 * (size_t)s->n;
+#pragma omp parallel for num_threads(nth) schedule(static)
+    for (int64_t i = 0; i < (int64_t)n3; ++i) { double a = 0; for (int t = 0; t < nth; ++t) a += fbuf[n3 * t + i]; s->f[i] += a; }
+}
+static void nonbonded_forces(orc_sim *s, double *fbuf) {
     int nth = s->nthreads;
     size_t n3 = 3 * (size_t)s->n;
-    double *fbuf = nth > 1 ? calloc(n3 * nth, 8) : NULL;
     double *ebuf = calloc((size_t)nth * 256, 8);
     int bad = 0;
 #pragma omp parallel num_threads(nth) reduction(| : bad)
@@ -612,11 +637,6 @@ static void nonbonded_forces(orc_sim *s) {
             for (int c = 0; c < 3; ++c) { f[3 * i + c] += fr * d[c]; f[3 * j + c] -= fr * d[c]; }
             en[p->inter] += e;
         }
-    }
-    if (nth > 1) {
-#pragma omp parallel for num_threads(nth) schedule(static)
-        for (int64_t i = 0; i < (int64_t)n3; ++i) { double a = 0; for (int t = 0; t < nth; ++t) a += fbuf[n3 * t + i]; s->f[i] += a; }
-        free(fbuf);
     }
     for (int t = 0; t < nth; ++t) for (int k = 0; k < s->ninter; ++k) s->inter_energy[k] += ebuf[256 * t + k];
     free(ebuf);
@@ -658,11 +678,24 @@ static void cross(const double a[3], const double b[3], double c[3]) {
     c[0] = a[1] * b[2] - a[2] * b[1]; c[1] = a[2] * b[0] - a[0] * b[2]; c[2] = a[0] * b[1] - a[1] * b[0];
 }
 static double dot(const double a[3], const double b[3]) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
-static void bonded_forces(orc_sim *s) {
+static void bonded_forces(orc_sim *s, double *fbuf) {
+    const int nth = s->nthreads;
+    const size_t n3 = 3 * (size_t)s->n;
     for (int bi = 0; bi < s->nbonded; ++bi) {
         orc_bonded *b = &s->bonded[bi];
         orc_list *l = &s->lists[b->list];
         double etot = 0;
+        int bad = 0;
+        double *et = calloc((size_t)nth, 8);
+#pragma omp parallel num_threads(nth) reduction(| : bad)
+        {
+        int tid = 0;
+#ifdef _OPENMP
+        tid = omp_get_thread_num();
+#endif
+        double *f = nth > 1 ? fbuf + n3 * tid : s->f;
+        double esum = 0;
+#pragma omp for schedule(static)
         for (int64_t k = 0; k < l->n; ++k) {
             const int *id = l->ids + k * l->arity;
             const orc_bpot *p = &b->pot;
@@ -674,19 +707,19 @@ static void bonded_forces(orc_sim *s) {
             double F, E;
             if (l->arity == 2) {
                 double d[3], r2 = dist2(s, id[0], id[1], d), r = sqrt(r2);
-                if (bond_eval(s, p, r, &F, &E)) s->range_error = 1;
-                for (int c = 0; c < 3; ++c) { s->f[3 * id[0] + c] += F / r * d[c]; s->f[3 * id[1] + c] -= F / r * d[c]; }
+                if (bond_eval(s, p, r, &F, &E)) bad = 1;
+                for (int c = 0; c < 3; ++c) { f[3 * id[0] + c] += F / r * d[c]; f[3 * id[1] + c] -= F / r * d[c]; }
             } else if (l->arity == 3) {
                 double d1[3], d2[3];
                 double r1 = sqrt(dist2(s, id[0], id[1], d1)), r2 = sqrt(dist2(s, id[2], id[1], d2));
                 double c = dot(d1, d2) / (r1 * r2); if (c > 1) c = 1; if (c < -1) c = -1;
                 double th = acos(c), sn = sqrt(1 - c * c); if (sn < 1e-9) sn = 1e-9;
-                if (angle_eval(s, p, th, &F, &E)) s->range_error = 1;
+                if (angle_eval(s, p, th, &F, &E)) bad = 1;
                 /* F = -dU/dtheta ; dtheta/dx_i = -(1/sin) * (d2/(r1 r2) - c d1/r1^2) */
                 for (int k3 = 0; k3 < 3; ++k3) {
                     double g1 = -(d2[k3] / (r1 * r2) - c * d1[k3] / (r1 * r1)) / sn;
                     double g3 = -(d1[k3] / (r1 * r2) - c * d2[k3] / (r2 * r2)) / sn;
-                    s->f[3 * id[0] + k3] += F * g1; s->f[3 * id[2] + k3] += F * g3; s->f[3 * id[1] + k3] -= F * (g1 + g3);
+                    f[3 * id[0] + k3] += F * g1; f[3 * id[2] + k3] += F * g3; f[3 * id[1] + k3] -= F * (g1 + g3);
                 }
             } else {
                 /* GROMACS/IUPAC convention (U15): r_ij = xi-xj, r_kj = xk-xj, r_kl = xk-xl */
@@ -696,7 +729,7 @@ static void bonded_forces(orc_sim *s) {
                 double m2 = dot(m, m), n2 = dot(nn, nn), rkj2 = dot(rkj, rkj), nrkj = sqrt(rkj2);
                 double cphi = dot(m, nn) / sqrt(m2 * n2); if (cphi > 1) cphi = 1; if (cphi < -1) cphi = -1;
                 double phi = acos(cphi); if (dot(rij, nn) < 0) phi = -phi;
-                if (dih_eval(s, p, phi, &F, &E)) s->range_error = 1;
+                if (dih_eval(s, p, phi, &F, &E)) bad = 1;
                 /* GROMACS do_dih_fup with ddphi = dU/dphi = -F (Bekker et al. 1995):
                  * f_i = -ddphi nrkj/|m|^2 m ; f_l = +ddphi nrkj/|n|^2 n */
                 double fi[3], fl[3], pp = dot(rij, rkj) / rkj2, qq = dot(rkl, rkj) / rkj2;
@@ -704,11 +737,16 @@ static void bonded_forces(orc_sim *s) {
                 for (int c = 0; c < 3; ++c) {
                     double sv = pp * fi[c] - qq * fl[c];
                     double fj = -fi[c] + sv, fk = -fl[c] - sv;
-                    s->f[3 * id[0] + c] += fi[c]; s->f[3 * id[1] + c] += fj; s->f[3 * id[2] + c] += fk; s->f[3 * id[3] + c] += fl[c];
+                    f[3 * id[0] + c] += fi[c]; f[3 * id[1] + c] += fj; f[3 * id[2] + c] += fk; f[3 * id[3] + c] += fl[c];
                 }
             }
-            etot += E;
+            esum += E;
         }
+        et[tid] = esum;
+        }
+        for (int t = 0; t < nth; ++t) etot += et[t];
+        free(et);
+        if (bad) s->range_error = 1;
         s->inter_energy[b->inter] += etot;
     }
 }
@@ -717,8 +755,10 @@ void orc_compute_forces(orc_sim *s) {
     if (!s->lists_valid) orc_rebuild(s);
     memset(s->f, 0, 24 * (size_t)s->n);
     for (int k = 0; k < s->ninter; ++k) s->inter_energy[k] = 0;
-    nonbonded_forces(s);
-    bonded_forces(s);
+    double *fbuf = force_buffers(s);
+    nonbonded_forces(s, fbuf);
+    bonded_forces(s, fbuf);
+    reduce_force_buffers(s, fbuf);
     s->forces_valid = 1;
 }
 double orc_energy(orc_sim *s, int inter) {
@@ -743,6 +783,7 @@ void orc_set_langevin(orc_sim *s, int on, double kT, double gamma, int ntypes, c
 static void thermalize(orc_sim *s, uint32_t stream, uint64_t step, double scale) {
     if (!s->lang_on) return;
     double pref1 = -s->gamma, pref2 = sqrt(24.0 * s->kT * s->gamma / s->dt) * scale;
+#pragma omp parallel for num_threads(s->nthreads) schedule(static)
     for (int i = 0; i < s->n; ++i) {
         if (!s->lang_all && !s->lang_type[s->type[i]]) continue;
         double u[3]; draw3(s->seed, stream, step, (uint32_t)i, u);
@@ -751,6 +792,7 @@ static void thermalize(orc_sim *s, uint32_t stream, uint64_t step, double scale)
     }
 }
 static void fold(orc_sim *s) {
+#pragma omp parallel for num_threads(s->nthreads) schedule(static)
     for (int i = 0; i < s->n; ++i) for (int d = 0; d < 3; ++d) {
         double L = s->box[d], xx = s->x[3 * i + d];
         if (xx < 0 || xx >= L) { double im = floor(xx / L); s->image[3 * i + d] += (int)im; xx -= im * L; if (xx >= L) { xx -= L; s->image[3 * i + d]++; } s->x[3 * i + d] = xx; }
@@ -765,6 +807,7 @@ void orc_run(orc_sim *s, int64_t nsteps) {
     double dt = s->dt;
     for (int64_t it = 0; it < nsteps; ++it) {
         double maxsq = 0;
+#pragma omp parallel for num_threads(s->nthreads) schedule(static) reduction(max : maxsq)
         for (int i = 0; i < s->n; ++i) {
             double dtfm = 0.5 * dt / s->mass[i], sq = 0;
             for (int c = 0; c < 3; ++c) {
@@ -778,12 +821,14 @@ void orc_run(orc_sim *s, int64_t nsteps) {
         if (s->criterion == 0) { s->maxdist += sqrt(maxsq); resort = s->maxdist > 0.5 * s->skin; }
         else {
             double m2 = 0;
+#pragma omp parallel for num_threads(s->nthreads) schedule(static) reduction(max : m2)
             for (int i = 0; i < s->n; ++i) { double q = 0; for (int c = 0; c < 3; ++c) { double d = minimg(s->x[3 * i + c] - s->xref[3 * i + c], s->box[c]); q += d * d; } if (q > m2) m2 = q; }
             resort = sqrt(m2) > 0.5 * s->skin;
         }
         if (resort || !s->lists_valid) { fold(s); orc_rebuild(s); }
         orc_compute_forces(s);
         thermalize(s, STREAM_LANGEVIN, (uint64_t)(s->step + it), 1.0);
+#pragma omp parallel for num_threads(s->nthreads) schedule(static)
         for (int i = 0; i < s->n; ++i) {
             double dtfm = 0.5 * dt / s->mass[i];
             for (int c = 0; c < 3; ++c) s->v[3 * i + c] += dtfm * s->f[3 * i + c];
