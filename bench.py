@@ -1,21 +1,28 @@
 #!/usr/bin/env python
 """bench.py -- MD steps/s and pair-interactions/s of chemlab's reactive-MD hot path on B200.
 
-Workload (BASELINE.json configs[1], SURVEY 8d "config 2"): synthetic 1,000,000-bead LJ reactive melt of
+Default workload (BASELINE.json configs[1], SURVEY 8d "config 2"): synthetic 1,000,000-bead LJ reactive melt of
 A-L-A trimers, rho=0.8442, rc=2.5, skin=0.3, dt=0.005, kT=1, gamma=1, pair potential = LJ tabulated on
 1500 rows (dr=0.002, linear interpolation), harmonic bonds K=30 r0=0.97, harmonic angle 180 deg,
 step-growth reaction A(1,2)+A(1,2)->A(1):A(1), cutoff 1.2, interval 200, p=0.05, nearest partner.
+The start state is the periodic replication of an EQUILIBRATED 8000-bead tile (chemlab_b200/data/melt_tile_20.npz),
+identical for the GPU arm, its cpu_baseline leg and the `--impl reference` arm.  `--workload c3|c4|c5` selects the
+multi-table configurations (replicated hyperbranched / dacron / rim135 systems, chemlab_b200/synthetic.py).
 
-A "step" is one Velocity-Verlet step of the whole system (neighbour rebuilds and reaction passes included
-at their natural frequency).  One JSON line is printed by rank 0:
-  value   : steps/s, device-timed (CUDA events on the engine's stream), state resident in HBM
-  e2e     : steps/s through the public C-ABI with HOST buffers: upload of the full particle state,
-            run in chunks of 200 steps with the observables read back per chunk, final state download
-  roofline: pair-force kernel, algorithmic bytes (40 + 4*L_half per particle per launch) over
-            its CUDA-event duration, against MEASURED_PEAKS.json hbm_gbs
-  cpu_baseline: the fp64 CPU restatement (oracle/) of the same path timed on the host cores
-`--impl reference` times that CPU restatement alone (the reference's own ESPResSo++ cannot be built
-here: SURVEY 8c) and prints the same line with "impl": "reference".
+A "step" is one Velocity-Verlet step of the whole system (neighbour rebuilds and reaction passes included at their
+natural frequency).  One JSON line is printed by rank 0:
+  value   : steps/s over EXACTLY --steps steps, device-timed (CUDA events on the engine's stream), state resident in HBM
+  e2e     : steps/s through the public C-ABI with (pinned) HOST buffers: upload of the full particle state, the same
+            number of steps with the observables read back per chunk, final state download -- all inside the timed region
+  e2e_steady : the same engine, a further chunk of steps + observables with no state round trip
+  roofline: pair-force kernel, algorithmic bytes (40 + 4*L_half per particle per launch) over its CUDA-event
+            duration, against MEASURED_PEAKS.json hbm_gbs
+  reaction_pass_ms / steps_per_s_amortised : one reaction pass timed on its own; steps/s with one pass per `interval` steps
+  parity  : GPU engine vs the fp64 CPU oracle ON THE BENCHMARKED STATE: Verlet pair set, forces, per-interaction energies,
+            then one reaction pass on both (events, bond lists, types, states)
+  cpu_baseline: the fp64 CPU restatement (oracle/) of the same path timed on the host cores (all of them)
+`--impl reference` times that CPU restatement alone for --warmup + --steps steps (the reference's own ESPResSo++ cannot
+be built here: SURVEY 8c) and prints the same line with "impl": "reference".
 """
 import argparse
 import json
@@ -35,8 +42,8 @@ INTERVAL, P_ACCEPT = 200, 0.05
 SEED = 12347
 
 
-def l_half():
-    return (2.0 * np.pi / 3.0) * (RC + SKIN) ** 3 * RHO
+def l_half(rc=RC, skin=SKIN, rho=RHO):
+    return (2.0 * np.pi / 3.0) * (rc + skin) ** 3 * rho
 
 
 def measured_peaks():
@@ -47,6 +54,14 @@ def measured_peaks():
         except Exception:
             pass
     return 6650.0, "fallback"
+
+
+def host_threads():
+    """Cores this process may use.  torch.distributed.run exports OMP_NUM_THREADS=1: the CPU arms ignore it on purpose."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
 
 
 class ClockSampler(threading.Thread):
@@ -61,19 +76,20 @@ class ClockSampler(threading.Thread):
     def run(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             for line in self.proc.stdout:
-                self.rows.append([c.strip() for c in line.split(",")])
+                self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
         except Exception:
             pass
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
         if self.proc:
             self.proc.terminate()
         self.join(timeout=2)
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        rows = [r for (t, r) in self.rows if t0 is None or (t0 <= t <= t1)] or [r for (_, r) in self.rows]
+        for r in rows:
             try:
                 sm.append(float(r[0])); mx.append(float(r[1]))
                 for k, nme in enumerate(names):
@@ -85,91 +101,222 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def build_engine(sysd, seed=SEED, device=0):
-    from chemlab_b200 import Engine
+# ------------------------------------------------------------------------------------------------ workload C2
+class WorkloadC2:
+    name = "c2"
+    rc, skin, dt, kT, gamma, rho, interval, p_accept, nearest = RC, SKIN, DT, KT, GAMMA, RHO, INTERVAL, P_ACCEPT, True
+
+    def __init__(self, n_side):
+        self.n_side = n_side
+        self.replicated = (n_side % 20 == 0)
+        self.description = ("C2 synthetic %d-bead LJ reactive trimer melt (tabulated LJ 1500 rows + harmonic bonds/angles + step-growth reaction; %s)"
+                            % (n_side ** 3, "replicated equilibrated 8000-bead tile" if self.replicated else "jittered lattice start"))
+
+    def system(self):
+        from chemlab_b200 import synthetic
+        if self.replicated:
+            return synthetic.replicated_melt(self.n_side)
+        return synthetic.trimer_melt(self.n_side, rho=RHO, seed=12345, kT=KT)
+
+    def setup(self, api, sysd):
+        from chemlab_b200 import synthetic
+        return synthetic.setup_reactive_melt(api, sysd, rc=RC, dt=DT, kT=KT, gamma=GAMMA, interval=INTERVAL, p_accept=P_ACCEPT)
+
+    def l_half(self):
+        return l_half()
+
+    def config(self, gpus):
+        return {"workload": self.description, "n_beads": self.n_side ** 3, "rho": RHO, "rc": RC, "skin": SKIN, "dt": DT, "kT": KT, "gamma": GAMMA,
+                "reaction_interval": INTERVAL, "p_accept": P_ACCEPT, "nearest": True,
+                "l2": "per-step working set (pos+vel+force+lists ~0.4 GB at 1M beads) exceeds the 126 MB L2; no explicit flush",
+                "parallelism": "slab%d" % gpus if gpus > 1 else "single"}
+
+
+def make_workload(a):
+    if a.workload == "c2":
+        return WorkloadC2(a.n_side)
     from chemlab_b200 import synthetic
-    e = Engine(sysd["box"], RC, SKIN, seed=seed, device=device)
-    e.set_particles(sysd["ids"], sysd["type"], sysd["pos"], sysd["mass"], vel=sysd["vel"], state=sysd["state"], res_id=sysd["resid"])
-    h = synthetic.setup_reactive_melt(e, sysd, rc=RC, dt=DT, kT=KT, gamma=GAMMA, interval=INTERVAL, p_accept=P_ACCEPT)
-    return e, h
+    return synthetic.make_workload(a.workload, a.scale)
 
 
-def snapshot(e, sysd, h):
-    """Host copy of the full dynamic state of an engine (the e2e leg and the CPU baseline restart from it)."""
+# ------------------------------------------------------------------------------------------------ state hand-over
+def snapshot(e, sysd, h, pinned=False):
+    """Host copy of the full dynamic state of an engine (the e2e leg, the parity oracle and the CPU baseline restart from it)."""
     st = e.get_particles(fields=("pos", "vel", "type", "state", "mass", "image"))
     s = dict(sysd)
     s["pos"] = st["pos"] + st["image"] * sysd["box"]
     s["vel"] = st["vel"]; s["type"] = st["type"]; s["state"] = st["state"]; s["mass"] = st["mass"]
-    s["react_bonds"] = e.list_get(h["react_list"], 2)
-    s["angles_now"] = e.list_get(h["angle_list"], 3)
+    s["lists_now"] = {k: e.list_get(v, a) for k, (v, a) in h["lists"].items()}
     s["excl_now"] = e.get_exclusions()
+    s["step"] = e.step()
+    if pinned:
+        import torch
+        for k in ("pos", "vel", "mass", "type", "state", "resid", "ids"):
+            t = torch.from_numpy(np.ascontiguousarray(s[k])).pin_memory()
+            s[k] = t.numpy(); s.setdefault("_keep", []).append(t)
     return s
 
 
 def restore_into(api, s, h):
-    if len(s["react_bonds"]):
-        api.list_add(h["react_list"], s["react_bonds"])
-    extra = s["angles_now"][len(s["angles"]):]
-    if len(extra):
-        api.list_add(h["angle_list"], extra)
+    """Tuples created by reactions since the start (appended behind the initial ones) and the current exclusions."""
+    for k, (lst, ar) in h["lists"].items():
+        now, init = s["lists_now"].get(k), h["initial"].get(k, 0)
+        if now is not None and len(now) > init:
+            api.list_add(lst, now[init:])
     api.set_exclusions(s["excl_now"])
 
 
-def cpu_baseline(s, target_seconds=15.0, threads=None):
-    """Time the CPU restatement (oracle/) on the same state: all host threads, bounded sample."""
+def oracle_from(wl, s, threads):
     from oracle import pyoracle
-    from chemlab_b200 import synthetic
-    n = s["n"]
-    o = pyoracle.Oracle(n, s["box"], RC, SKIN, seed=SEED)
-    nt = threads or o.max_threads()
-    o.set_threads(nt)
+    o = pyoracle.Oracle(s["n"], s["box"], wl.rc, wl.skin, seed=SEED)
+    o.set_threads(threads)
     o.set_particles(s["pos"], s["vel"], s["mass"], None, s["type"], s["state"], s["resid"])
-    h = synthetic.setup_reactive_melt(o, s, rc=RC, dt=DT, kT=KT, gamma=GAMMA, interval=INTERVAL, p_accept=P_ACCEPT)
+    h = wl.setup(o, s)
     restore_into(o, s, h)
-    o.reaction_general(1, INTERVAL, 1, 0)
-    t0 = time.perf_counter(); o.run(1); t1 = time.perf_counter() - t0   # includes the first list build
-    t0 = time.perf_counter(); o.run(2); t2 = (time.perf_counter() - t0) / 2
-    nsteps = int(max(3, min(200, target_seconds / max(t2, 1e-6))))
-    t0 = time.perf_counter(); o.run(nsteps); dt = time.perf_counter() - t0
-    return {"value": nsteps / dt, "unit": "steps/s", "cores": nt, "kind": "port",
-            "sample": "%d MD steps of the same %d-bead workload (fp64 C restatement, OpenMP x%d; first step incl. list build %.2fs)" % (nsteps, n, nt, t1),
-            "seconds": dt, "steps": nsteps}
+    o.set_option("step", s.get("step", 0))
+    return o, h
 
 
+def cpu_run(wl, s, steps, warmup, threads, reactions=True):
+    """CPU restatement (oracle/) on state s: `warmup` untimed steps (the first includes the list build), then EXACTLY `steps`
+    timed steps in up to 3 segments (median and spread of the segment rates are reported)."""
+    o, h = oracle_from(wl, s, threads)
+    if reactions:
+        o.reaction_general(1, wl.interval, 1 if wl.nearest else 0, 0)
+    t0 = time.perf_counter(); o.run(max(1, warmup)); t_warm = time.perf_counter() - t0
+    nseg = 3 if steps >= 6 else 1
+    seg = [steps // nseg + (1 if k < steps % nseg else 0) for k in range(nseg)]
+    rates, total = [], 0.0
+    for m in seg:
+        t0 = time.perf_counter(); o.run(m); dt = time.perf_counter() - t0
+        total += dt; rates.append(m / dt)
+    return {"value": steps / total, "unit": "steps/s", "cores": threads, "kind": "port",
+            "sample": "%d MD steps (after %d warm-up steps, %.2fs incl. the list build) of the same %d-bead workload from the same state (fp64 C restatement, OpenMP x%d, pinned threads)"
+                      % (steps, max(1, warmup), t_warm, s["n"], threads),
+            "seconds": total, "steps": steps, "segment_rates": rates, "median_rate": float(np.median(rates)),
+            "spread": (max(rates) - min(rates)) / float(np.median(rates)) if len(rates) > 1 else 0.0}
+
+
+def bounded_cpu_steps(wl, n, threads, seconds):
+    """Steps that fit the CPU time budget (about 1.5 us per bead-step per core for C2 on the round-1 boxes)."""
+    est = 1.6e-6 * n * (wl.l_half() / 38.8) / max(1, min(threads, 32)) + 1e-4
+    return int(max(3, min(200, seconds / est)))
+
+
+# ------------------------------------------------------------------------------------------------ parity
+def sorted_pair_keys(p):
+    p = np.asarray(p)
+    k = (p[:, 0].astype(np.uint64) << np.uint64(32)) | p[:, 1].astype(np.uint64)
+    k.sort()
+    return k
+
+
+def rel_force_err(f, fref):
+    d = np.linalg.norm(f - fref, axis=1)
+    nr = np.linalg.norm(fref, axis=1)
+    rms = np.sqrt((nr ** 2).mean())
+    return float((d / np.maximum(nr, rms)).max())
+
+
+def parity_block(e, wl, sysd, h, rank, threads, do_reaction=True):
+    """GPU engine vs CPU oracle on the engine's CURRENT (benchmarked) state.  Collective on a multi-rank engine: every rank
+    makes the engine calls, rank 0 runs the oracle and compares.  Returns (dict on rank 0 | None, reaction_pass_seconds)."""
+    t_start = time.perf_counter()
+    snap = snapshot(e, sysd, h)
+    pe = e.pairs()                                   # canonical sorted (id_a < id_b) rows
+    e.compute_forces()
+    fe = e.get_particles(fields=("force",))["force"]
+    en_e = {k: e.energy(v) for k, v in h["energies"].items()}
+    out = None
+    o = None
+    if rank == 0:
+        o, ho = oracle_from(wl, snap, threads)
+        ko = sorted_pair_keys(o.pairs_raw())
+        ke = (pe[:, 0].astype(np.uint64) << np.uint64(32)) | pe[:, 1].astype(np.uint64)
+        pairs_equal = bool(len(ko) == len(ke) and np.array_equal(ko, ke))
+        o.compute_forces()
+        fo = o.get()["force"]
+        en_o = {k: o.energy(v) for k, v in ho["energies"].items()}
+        e_err = max(abs(en_e[k] - en_o[k]) / max(abs(en_o[k]), 1e-300) for k in en_o if en_o[k] != 0.0 or en_e[k] != 0.0) if en_o else 0.0
+        out = {"state": "benchmarked state after the timed steps (%d beads, step %d)" % (snap["n"], snap["step"]),
+               "pairs": int(len(ke)), "pairs_equal": pairs_equal, "force_rel_err": rel_force_err(fe, fo), "force_bar": 1e-6,
+               "energy_rel_err": float(e_err), "energy_bar": 1e-8, "energies": {k: en_e[k] for k in en_e}}
+    t_react = None
+    if do_reaction:
+        e.reaction_general(1, wl.interval, 1 if wl.nearest else 0, 0)
+        t0 = time.perf_counter()
+        nev = e.react_now()
+        t_react = time.perf_counter() - t0
+        st = e.get_particles(fields=("type", "state", "mass"))
+        lists_e = {k: e.list_get(v, a) for k, (v, a) in h["lists"].items()}
+        ex_e = e.get_exclusions()
+        if rank == 0:
+            o.reaction_general(1, wl.interval, 1 if wl.nearest else 0, 0)
+            nev_o = o.react()
+            so = o.get()
+
+            def canon(a):
+                a = np.asarray(a, np.int64)
+                return a[np.lexsort(a.T[::-1])] if len(a) else a
+            lists_equal = all(np.array_equal(canon(lists_e[k]), canon(o.list_get(ho["lists"][k][0], ho["lists"][k][1]))) for k in lists_e)
+            out["reaction"] = {"events": int(nev), "events_oracle": int(nev_o), "bond_lists_equal": bool(lists_equal),
+                               "types_equal": bool(np.array_equal(st["type"], so["type"])), "states_equal": bool(np.array_equal(st["state"], so["state"])),
+                               "masses_equal": bool(np.array_equal(st["mass"], so["mass"])),
+                               "exclusions_equal": bool(np.array_equal(canon(ex_e), canon(o.get_exclusions())))}
+    if rank == 0:
+        r = out.get("reaction", {})
+        out["green"] = bool(out["pairs_equal"] and out["force_rel_err"] < 1e-6 and out["energy_rel_err"] < 1e-8 and
+                            all(v for k, v in r.items() if k.endswith("_equal")) and r.get("events", 0) == r.get("events_oracle", 0))
+        out["oracle"] = "oracle/chemlab_oracle.c (fp64 CPU restatement; PARITY UNPINNED against ESPResSo++ itself: SURVEY 8c, REFERENCE_UNVERIFIED.md)"
+        out["seconds"] = time.perf_counter() - t_start
+    return out, t_react
+
+
+# ------------------------------------------------------------------------------------------------ main
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=200)
-    ap.add_argument("--equil", type=int, default=1000, help="untimed equilibration steps before warm-up (reactions off)")
-    ap.add_argument("--n_side", type=int, default=100, help="beads per box edge (100 -> 1,000,000 beads)")
+    ap.add_argument("--equil", type=int, default=0, help="untimed extra steps before warm-up (reactions off); the replicated tile needs none")
+    ap.add_argument("--n_side", type=int, default=100, help="C2: beads per box edge (100 -> 1,000,000 beads; multiples of 20 use the equilibrated tile)")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c5"])
+    ap.add_argument("--scale", type=int, default=0, help="c3/c4/c5: replications per box edge (0 = the BASELINE size)")
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--no_cpu_baseline", action="store_true")
     ap.add_argument("--no_e2e", action="store_true")
+    ap.add_argument("--no_parity", action="store_true")
     ap.add_argument("--cpu_seconds", type=float, default=15.0)
     ap.add_argument("--option", action="append", default=[], help="engine option name=value")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    from chemlab_b200 import synthetic
-    workload = "C2 synthetic %d-bead LJ reactive trimer melt (tabulated LJ 1500 rows + harmonic bonds/angles + step-growth reaction)" % (a.n_side ** 3)
-    config = {"workload": workload, "n_beads": a.n_side ** 3, "rho": RHO, "rc": RC, "skin": SKIN, "dt": DT, "kT": KT, "gamma": GAMMA,
-              "reaction_interval": INTERVAL, "p_accept": P_ACCEPT, "nearest": True,
-              "l2": "per-step working set (pos+vel+force+lists ~0.36 GB at 1M beads) exceeds the 126 MB L2; no explicit flush",
-              "parallelism": "slab%d" % a.gpus if a.gpus > 1 else "single"}
+    threads = host_threads()
+    # the CPU arms use every core this process may run on, pinned (set before libgomp loads)
+    os.environ["OMP_NUM_THREADS"] = str(threads)
+    os.environ.setdefault("OMP_PROC_BIND", "close")
+    os.environ.setdefault("OMP_PLACES", "cores")
+    wl = make_workload(a)
+    config = wl.config(a.gpus)
 
     if a.impl == "reference":
         if rank != 0:
             return 0
-        sysd = synthetic.trimer_melt(a.n_side, rho=RHO, seed=12345, kT=KT)
-        s = dict(sysd); s["react_bonds"] = np.zeros((0, 2), np.int64); s["angles_now"] = sysd["angles"]; s["excl_now"] = sysd["exclusions"]
-        cb = cpu_baseline(s, target_seconds=min(60.0, max(5.0, a.cpu_seconds * 2)))
-        line = {"impl": "reference", "metric": "md_steps_per_s", "value": cb["value"], "unit": "steps/s", "n_gpus": a.gpus, "steps": cb["steps"],
-                "warmup": 3, "ms_per_step": 1e3 / cb["value"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        sysd = wl.system()
+        s = dict(sysd); s["lists_now"] = {}; s["excl_now"] = sysd["exclusions"]; s["step"] = 0
+        steps = a.steps
+        cap = bounded_cpu_steps(wl, sysd["n"], threads, 120.0)
+        note_cap = ""
+        if steps > cap:
+            note_cap = "; --steps %d capped to %d so that the CPU run ends within a few minutes" % (steps, cap)
+            steps = cap
+        cb = cpu_run(wl, s, steps, a.warmup, threads)
+        line = {"impl": "reference", "metric": "md_steps_per_s", "value": cb["value"], "unit": "steps/s", "n_gpus": a.gpus, "steps": steps,
+                "warmup": max(1, a.warmup), "ms_per_step": 1e3 / cb["value"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic", "config": config, "cpu_baseline": cb,
                 "e2e": {"value": cb["value"], "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                "note": "CPU restatement of the reference algorithm (oracle/), NOT ESPResSo++ itself: cgchemlab/espressopp is not vendored and cannot be built here (SURVEY 8c); bounded sample, rate is per MD step of the full workload"}
+                "note": "CPU restatement of the reference algorithm (oracle/), NOT ESPResSo++ itself: cgchemlab/espressopp is not vendored and cannot be built here (SURVEY 8c); every step is a full MD step of the whole workload" + note_cap}
         print(json.dumps(line))
         return 0
 
@@ -184,17 +331,21 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     device = local
 
-    sysd = synthetic.trimer_melt(a.n_side, rho=RHO, seed=12345, kT=KT)
+    sysd = wl.system()
     n = sysd["n"]
     from chemlab_b200 import Engine as _E
-    e = _E(sysd["box"], RC, SKIN, seed=SEED, device=device)
-    for kv in a.option:
-        k, v = kv.split("=")
-        e.set_option(k, float(v))
-    if world > 1:
-        e.join()          # one engine per rank = one z-slab; torch.distributed only carries the NCCL id
+
+    def new_engine():
+        e_ = _E(sysd["box"], wl.rc, wl.skin, seed=SEED, device=device)
+        for kv in a.option:
+            k, v = kv.split("=")
+            e_.set_option(k, float(v))
+        if world > 1:
+            e_.join()          # one engine per rank = one slab; torch.distributed only carries the NCCL id
+        return e_
+    e = new_engine()
     e.set_particles(sysd["ids"], sysd["type"], sysd["pos"], sysd["mass"], vel=sysd["vel"], state=sysd["state"], res_id=sysd["resid"])
-    h = synthetic.setup_reactive_melt(e, sysd, rc=RC, dt=DT, kT=KT, gamma=GAMMA, interval=INTERVAL, p_accept=P_ACCEPT)
+    h = wl.setup(e, sysd)
 
     def barrier():
         torch.cuda.synchronize()
@@ -202,26 +353,30 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
-    # untimed equilibration (lattice start -> melt), then enable reactions, then warm-up
     if a.equil > 0:
+        e.reaction_general(0, wl.interval, 1 if wl.nearest else 0, 0)
         e.run(a.equil)
-    e.reaction_general(1, INTERVAL, 1, 0)
+    e.reaction_general(1, wl.interval, 1 if wl.nearest else 0, 0)
     if a.warmup > 0:
         e.run(a.warmup)
-    # the read-back is collective on a multi-rank engine: every rank takes the snapshot
-    snap = snapshot(e, sysd, h) if not (a.no_e2e and (a.no_cpu_baseline or world > 1)) else None
+    # host snapshot of the warmed-up state: the e2e leg and the CPU baseline restart from it (collective read-back)
+    snap = snapshot(e, sysd, h, pinned=True) if not (a.no_e2e and (a.no_cpu_baseline or world > 1)) else None
 
     e.reset_timers()
     e.set_option("pair_event_timing", 1)
     sampler = ClockSampler(device)
     if rank == 0:
         sampler.start()
+        time.sleep(0.15)
     barrier()
     t_wall0 = time.perf_counter()
     e.run(a.steps)
     barrier()
-    t_wall = time.perf_counter() - t_wall0
-    clocks = sampler.stop() if rank == 0 else None
+    t_wall1 = time.perf_counter()
+    t_wall = t_wall1 - t_wall0
+    if rank == 0 and t_wall < 0.3:
+        time.sleep(0.1)
+    clocks = sampler.stop(t_wall0 - 0.02, t_wall1 + 0.05) if rank == 0 else None
     tm, cn = e.timers()
     t_dev = tm["total"]
     pair_ms = e.get_option("pair_kernel_ms")
@@ -239,91 +394,145 @@ def main():
     _, cn2 = e.timers()
     interacting = cn2["interacting_pairs"]
     kin = e.kinetics()
-    nbonds_new = e.list_size(h["react_list"])
+    nbonds_new = e.list_size(h["react_list"]) - h["initial"].get("react", 0) if "react_list" in h else 0
+
+    # parity on the benchmarked state (+ one reaction pass on both sides, which is also the timed reaction pass)
+    parity, t_react = (None, None)
+    if not a.no_parity:
+        parity, t_react = parity_block(e, wl, sysd, h, rank, threads)
+    else:
+        e.reaction_general(1, wl.interval, 1 if wl.nearest else 0, 0)
+        t0 = time.perf_counter(); e.react_now(); t_react = time.perf_counter() - t0
+    if dist is not None and t_react is not None:
+        tt = torch.tensor([t_react], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_react = float(tt[0])
 
     line = None
     if rank == 0:
         steps_per_s = a.steps / t_dev
         peak, peak_src = measured_peaks()
-        lh = l_half()
+        lh = wl.l_half()
         n_per_gpu = n / world
         pair_bytes = (40.0 + 4.0 * lh) * n_per_gpu            # pos 16 + list 4*L_half + force 24 per particle
         step_bytes = (128.0 + 4.0 * lh) * n_per_gpu
         t_pair = (pair_ms * 1e-3 / pair_launches) if pair_launches else None
+        traffic, traffic_src = profiled_traffic(wl, world)
         roof = {"bound": "hbm", "kernel": "k_pair_forces", "achieved": (pair_bytes / t_pair / 1e9) if t_pair else None, "peak": peak,
                 "unit": "GB/s", "frac": (pair_bytes / t_pair / 1e9 / peak) if t_pair else None,
-                # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel on this workload, from the committed
-                # `ncu --set full` capture (profiles/r1g_ncu_full_raw.csv: 293.9 MB + 20.8 MB); only quoted for the profiled case
-                "traffic": 314.7e6 if (world == 1 and a.n_side == 100) else None, "traffic_source": "profiles/r1g_ncu_full_raw.csv",
-                "binding_roof": "shared-memory wavefronts (56.5 M per launch, 52 % bank conflicts of the two random 16-byte gathers per pair); not HBM",
+                "traffic": traffic, "traffic_source": traffic_src,
+                "binding_roof": "shared-memory gather wavefronts (two random 16-byte gathers per listed pair) and fp64 issue; not HBM (DESIGN.md 3.1)",
                 "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": pair_bytes, "kernel_ms": (t_pair * 1e3) if t_pair else None, "launches_timed": pair_launches,
                 "kernel_share_of_step": (pair_ms * 1e-3 / t_dev) if t_dev else None,
                 "step_achieved": step_bytes * steps_per_s / 1e9, "step_frac": step_bytes * steps_per_s / 1e9 / peak,
                 "step_algorithmic_bytes": step_bytes}
+        npass_win = cn["reaction_passes"]
+        amort = None
+        if t_react is not None:
+            t_md = max(t_dev - npass_win * t_react, 1e-9)
+            amort = a.steps / (t_md + (a.steps / wl.interval) * t_react)
         line = {"metric": "md_steps_per_s", "value": steps_per_s, "unit": "steps/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
                 "ms_per_step": 1e3 * t_dev / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic", "config": config, "roofline": roof, "clocks": clocks, "gpu_launches": cn["launches"],
                 "pair_interactions_per_s": interacting * steps_per_s, "interacting_pairs_per_step": interacting,
-                "list_pairs_per_particle": cn["list_entries"] / 2.0 / n, "ns_per_day_at_dt_ps": steps_per_s * DT * 86.4,
-                "rebuilds": cn["rebuilds"], "reaction_passes": cn["reaction_passes"], "reaction_events": cn["reaction_events"],
+                "list_pairs_per_particle": cn["list_entries"] / 2.0 / n, "ns_per_day_at_dt_ps": steps_per_s * wl.dt * 86.4,
+                "rebuilds": cn["rebuilds"], "reaction_passes": npass_win, "reaction_events": cn["reaction_events"],
+                "reaction_pass_ms": (1e3 * t_react) if t_react is not None else None,
+                "steps_per_s_amortised": amort,
+                "amortised_note": "steps/s with exactly one reaction pass per %d steps (the timed window held %d); reaction_pass_ms is one pass timed on its own (host wall clock, synchronous call)" % (wl.interval, npass_win),
                 "new_bonds_total": nbonds_new, "temperature": float(kin[1]), "wall_s": t_wall, "equil_steps": a.equil,
                 "ghost_beads_total": cn["ghosts"], "pair_threads": e.get_option("pair_threads"), "pair_grid": e.get_option("pair_grid"),
                 "pair_nv": e.get_option("pair_nv"), "pair_smem": e.get_option("pair_smem"), "home_max": e.get_option("home_max"), "tile_max": e.get_option("tile_max"),
-                "buckets_s": {k: v for k, v in tm.items() if v > 0} if e.get_option("timers") else None}
+                "buckets_s": {k: v for k, v in tm.items() if v > 0} if e.get_option("timers") else None, "parity": parity}
 
-    # e2e: public API with HOST buffers -- a fresh engine (one per rank when N > 1) restarted from the host snapshot:
-    # upload of the particle state, run in chunks with observables read back, final state download
+    # e2e: public API with HOST buffers -- a fresh engine (one per rank when N > 1) restarted from the pinned host snapshot:
+    # upload of the particle state, the same number of steps with observables read back per chunk, final state download
     if not a.no_e2e:
-        chunk = INTERVAL
+        chunk = wl.interval
         barrier()
         # engine creation and the NCCL rendezvous are one-off setup, not data movement: outside the timed region
-        e2 = _E(snap["box"], RC, SKIN, seed=SEED, device=device)
-        if world > 1:
-            e2.join()
+        e2 = new_engine()
+        outbuf = {k: torch.empty(sh, dtype=dt_, pin_memory=True).numpy() for k, sh, dt_ in
+                  (("pos", (n, 3), torch.float64), ("vel", (n, 3), torch.float64), ("image", (n, 3), torch.int32), ("type", (n,), torch.int32), ("state", (n,), torch.int32))}
         barrier()
         t0 = time.perf_counter()
         e2.set_particles(snap["ids"], snap["type"], snap["pos"], snap["mass"], vel=snap["vel"], state=snap["state"], res_id=snap["resid"])
         t_a = time.perf_counter() - t0
-        h2 = synthetic.setup_reactive_melt(e2, snap, rc=RC, dt=DT, kT=KT, gamma=GAMMA, interval=INTERVAL, p_accept=P_ACCEPT)
+        h2 = wl.setup(e2, snap)
         t_b = time.perf_counter() - t0
         restore_into(e2, snap, h2)
-        e2.reaction_general(1, INTERVAL, 1, 0)
+        e2.set_option("step", snap["step"])
+        e2.reaction_general(1, wl.interval, 1 if wl.nearest else 0, 0)
         t_up = time.perf_counter() - t0
-        if os.environ.get("CLB_BENCH_VERBOSE"):
-            print("e2e upload: set_particles %.3fs, force field + lists %.3fs, restore %.3fs" % (t_a, t_b - t_a, t_up - t_b), file=sys.stderr)
         done = 0
         obs = []
+
+        def observe():
+            obs.append((e2.kinetics()[1],) + tuple(e2.energy(v) for v in h2["energies"].values()))
         while done < a.steps:
             m = min(chunk, a.steps - done)
             e2.run(m); done += m
-            obs.append((e2.kinetics()[1], e2.energy(h2["nb"]), e2.energy(h2["bonds"]), e2.energy(h2["angles"]), e2.energy(h2["react_bonds"])))
+            observe()
         t_run = time.perf_counter() - t0 - t_up
-        out = e2.get_particles(fields=("pos", "vel", "type", "state", "image"))
+        nobs = len(obs)
+        e2.get_particles(fields=("pos", "vel", "type", "state", "image"), out=outbuf)
         barrier()
         t_e2e = time.perf_counter() - t0
+        # steady state: a further chunk of steps + observables, no state round trip
+        barrier()
+        t1 = time.perf_counter()
+        done = 0
+        while done < a.steps:
+            m = min(chunk, a.steps - done)
+            e2.run(m); done += m
+            observe()
+        barrier()
+        t_steady = time.perf_counter() - t1
+        if os.environ.get("CLB_BENCH_VERBOSE"):
+            print("e2e upload: set_particles %.4fs, force field + lists %.4fs, restore %.4fs; run %.4fs; download %.4fs; steady %.4fs"
+                  % (t_a, t_b - t_a, t_up - t_b, t_run, t_e2e - t_up - t_run, t_steady), file=sys.stderr)
         if dist is not None:
-            tt = torch.tensor([t_e2e], dtype=torch.float64, device="cuda")
+            tt = torch.tensor([t_e2e, t_steady], dtype=torch.float64, device="cuda")
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            t_e2e = float(tt[0])
-        h2d = n * (8 + 4 + 24 + 24 + 8 + 4 + 4) + snap["bonds"].size * 8 + snap["angles_now"].size * 8 + snap["excl_now"].size * 8 + 3 * 1500 * 8
-        d2h = n * (24 + 24 + 4 + 4 + 12) + len(obs) * 5 * 8
+            t_e2e, t_steady = float(tt[0]), float(tt[1])
+        nlist = sum(v.size for v in snap["lists_now"].values()) + sum(np.asarray(sysd[k]).size for k in ("bonds", "angles") if k in sysd)
+        h2d = n * (8 + 4 + 24 + 24 + 8 + 4 + 4) + nlist * 8 + snap["excl_now"].size * 8 + h2.get("table_bytes", 3 * 1500 * 8)
+        d2h = n * (24 + 24 + 4 + 4 + 12) + nobs * (1 + len(h2["energies"])) * 8
         if rank == 0:
             line["e2e"] = {"value": a.steps / t_e2e, "unit": "steps/s", "h2d_bytes_per_step": h2d / a.steps, "d2h_bytes_per_step": d2h / a.steps,
                            "seconds": t_e2e, "upload_s": t_up, "run_s": t_run, "download_s": t_e2e - t_up - t_run,
-                           "what": "(engine create%s outside) full state upload + run in %d-step chunks with T/Epot read back per chunk + final state download (N > 1: every rank uploads and downloads the full state)" % (" + NCCL join" if world > 1 else "", chunk)}
+                           "what": "(engine create%s outside) full state upload from pinned host memory + force field, lists, exclusions + %d steps in %d-step chunks with T/Epot read back per chunk + final state download (N > 1: every rank uploads and downloads the full state)"
+                                   % (" + NCCL join" if world > 1 else "", a.steps, chunk)}
+            line["e2e_steady"] = {"value": a.steps / t_steady, "unit": "steps/s", "seconds": t_steady,
+                                  "what": "the same engine, a further %d steps in %d-step chunks with T/Epot read back per chunk, no state round trip" % (a.steps, chunk)}
         e2.close()
     elif rank == 0:
         line["e2e"] = None
 
     if world == 1 and rank == 0 and not a.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline(snap, target_seconds=a.cpu_seconds)
+        ksteps = bounded_cpu_steps(wl, n, threads, a.cpu_seconds)
+        line["cpu_baseline"] = cpu_run(wl, snap, ksteps, 3, threads)
     if rank == 0:
         print(json.dumps(line))
     e.close()
     if dist is not None:
         dist.destroy_process_group()
     return 0
+
+
+def profiled_traffic(wl, world):
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the pair kernel on this workload, from the committed
+    `ncu --set full` capture named in profiles/traffic.json (a profile cannot be taken inside a timed run)."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        t = json.load(open(p))
+        ent = t.get("%s_n%d" % (wl.name, world))
+        if ent:
+            return float(ent["bytes_per_launch"]), "from profile: " + ent["source"]
+    except Exception:
+        pass
+    return None, "no ncu capture committed for this workload / rank count"
 
 
 if __name__ == "__main__":

@@ -17,7 +17,12 @@
 #define CLB_EF_CAND_OVERFLOW 8u // reaction candidate buffer overflow -> host regrows and rescans
 #define CLB_EF_TUPLE_OVERFLOW 16u
 #define CLB_EF_PARTNER_LOST 32u // bonded partner not resolvable (outside ghost layer)
+#define CLB_EF_BFS_OVERFLOW 128u // neighbour-property BFS frontier exceeded its fixed buffers, or molecule-id hooking did not converge
 #define CLB_EF_TILE_OVERFLOW 64u // a tile holds more particles than the shared-memory carve-up assumed -> host retries
+
+// velocity + mass per sorted particle: fp64 throughout ({vx, vy, vz, mass}); the reference's `real` is double
+typedef double4 ClbVel;
+__host__ __device__ inline ClbVel clb_make_vel(double x, double y, double z, double m) { ClbVel v; v.x = x; v.y = y; v.z = z; v.w = m; return v; }
 
 // pos.w packing: type in bits 0..7, chemical state in bits 8..23 (signed 16 bit)
 __host__ __device__ inline int pw_type(int w) { return w & 0xff; }

@@ -18,8 +18,8 @@ __global__ void k_cell_keys(int n, const int4* __restrict__ pos, ClbGrid g, int*
     key[i] = lz < 0 ? g.ncell - 1 : (lz * g.ncy + cy) * g.ncx + cx;
     val[i] = i;
 }
-__global__ void k_gather(int n, const int* __restrict__ perm, const int4* __restrict__ pos_in, const float4* __restrict__ vel_in,
-                         const int* __restrict__ slot_in, int4* __restrict__ pos, float4* __restrict__ vel,
+__global__ void k_gather(int n, const int* __restrict__ perm, const int4* __restrict__ pos_in, const ClbVel* __restrict__ vel_in,
+                         const int* __restrict__ slot_in, int4* __restrict__ pos, ClbVel* __restrict__ vel,
                          int* __restrict__ slot, int4* __restrict__ xref, int* __restrict__ id2idx) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -87,7 +87,7 @@ struct ClbIntegParams {
 // MODE = SECOND|FIRST fuses the closing half-kick of step i-1 with the opening half-kick and drift
 // of step i (one pass over pos/vel/force instead of two).
 template <int MODE>
-__global__ void __launch_bounds__(256) k_integrate(ClbIntegParams P, int4* __restrict__ pos, float4* __restrict__ vel,
+__global__ void __launch_bounds__(256) k_integrate(ClbIntegParams P, int4* __restrict__ pos, ClbVel* __restrict__ vel,
                                                    double* __restrict__ force, int fstride,
                                                    const int4* __restrict__ xref, const int* __restrict__ slot,
                                                    int* __restrict__ image, ClbCtl* ctl) {
@@ -95,8 +95,8 @@ __global__ void __launch_bounds__(256) k_integrate(ClbIntegParams P, int4* __res
     int i = P.i0 + blockIdx.x * blockDim.x + threadIdx.x;
     float d2 = 0.f;
     if (i < P.i1) {
-        float4 v4 = vel[i];
-        double m = (double)v4.w;
+        const ClbVel v4 = vel[i];
+        const double m = v4.w;
         double vx = v4.x, vy = v4.y, vz = v4.z;
         double fx = force[i], fy = force[i + fstride], fz = force[i + 2 * fstride];
         int4 p = pos[i];
@@ -113,12 +113,9 @@ __global__ void __launch_bounds__(256) k_integrate(ClbIntegParams P, int4* __res
         }
         double k = ((MODE & CLB_INT_SECOND) && (MODE & CLB_INT_FIRST)) ? P.dt / m : 0.5 * P.dt / m;
         vx += k * fx; vy += k * fy; vz += k * fz;
-        // stored velocity is fp32: round once, then drift with the STORED value so that a split and a
-        // fused sequence see the same positions up to that rounding
-        float vxf = (float)vx, vyf = (float)vy, vzf = (float)vz;
-        vel[i] = make_float4(vxf, vyf, vzf, v4.w);
+        vel[i] = clb_make_vel(vx, vy, vz, m);
         if (MODE & CLB_INT_FIRST) {
-            double dpx = P.dt * (double)vxf, dpy = P.dt * (double)vyf, dpz = P.dt * (double)vzf;
+            double dpx = P.dt * vx, dpy = P.dt * vy, dpz = P.dt * vz;
             int dx = __double2int_rn(dpx * P.invq[0]), dy = __double2int_rn(dpy * P.invq[1]), dz = __double2int_rn(dpz * P.invq[2]);
             int nx = wadd(p.x, dx), ny = wadd(p.y, dy), nz = wadd(p.z, dz);
             int wx = (dx > 0 && (unsigned)nx < (unsigned)p.x) ? 1 : ((dx < 0 && (unsigned)nx > (unsigned)p.x) ? -1 : 0);
@@ -149,13 +146,13 @@ __global__ void __launch_bounds__(256) k_integrate(ClbIntegParams P, int4* __res
 }
 // LangevinThermostat at run entry (recalc1/updateForces/recalc2 with heatUp: pref2 *= sqrt(3))
 __global__ void k_thermalize(ClbIntegParams P, double scale, uint32_t stream, const int4* __restrict__ pos,
-                             const float4* __restrict__ vel, const int* __restrict__ slot, double* __restrict__ force,
+                             const ClbVel* __restrict__ vel, const int* __restrict__ slot, double* __restrict__ force,
                              int fstride) {
     int i = P.i0 + blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.i1) return;
     int4 p = pos[i];
     if (!((P.type_mask_lo >> pw_type(p.w)) & 1ull)) return;
-    float4 v4 = vel[i];
+    const ClbVel v4 = vel[i];
     double m = v4.w, sm = sqrt(m), u[3];
     clb_draw3(P.seed, stream, P.step, (uint32_t)slot[i], u);
     force[i] += P.pref1 * m * v4.x + P.pref2 * scale * sm * (u[0] - 0.5);
@@ -378,10 +375,10 @@ __global__ void k_lower_bounds(int nkeys, const int* __restrict__ keys, int nslo
 }
 
 // ---------------------------------------------------------------- observables ---------------
-__global__ void __launch_bounds__(256) k_kinetic(int i0, int i1, const float4* __restrict__ vel, double* __restrict__ partial) {
+__global__ void __launch_bounds__(256) k_kinetic(int i0, int i1, const ClbVel* __restrict__ vel, double* __restrict__ partial) {
     int i = i0 + blockIdx.x * blockDim.x + threadIdx.x;
     double e = 0;
-    if (i < i1) { float4 v = vel[i]; e = 0.5 * (double)v.w * ((double)v.x * v.x + (double)v.y * v.y + (double)v.z * v.z); }
+    if (i < i1) { const ClbVel v = vel[i]; e = 0.5 * v.w * (v.x * v.x + v.y * v.y + v.z * v.z); }
     __shared__ double s_red[8];
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) e += __shfl_down_sync(0xffffffffu, e, d);

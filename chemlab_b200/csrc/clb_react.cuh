@@ -224,19 +224,19 @@ __global__ void __launch_bounds__(1024) k_resolve(int ns, const int* __restrict_
 // Particle properties during a reaction pass: the type|state word of EVERY particle lives in the replicated
 // per-slot array `wslot` (identical on all ranks, so every rank takes identical decisions); the copy inside
 // pos[].w, the mass (vel[].w) and the charge are updated when the particle is stored locally (idx >= 0).
-__device__ __forceinline__ void apply_props(const ClbChange& g, int idx, int s, int* wslot, int4* pos, float4* vel, double* charge) {
+__device__ __forceinline__ void apply_props(const ClbChange& g, int idx, int s, int* wslot, int4* pos, ClbVel* vel, double* charge) {
     int w = wslot[s];
     if (pw_type(w) != g.old_type) return;
     int st = pw_state(w);
     if (g.state_mode == 1) st = g.state_value; else if (g.state_mode == 2) st += g.state_value;
     w = pw_pack(g.new_type, st);
     wslot[s] = w;
-    if (idx >= 0) { pos[idx].w = w; if (g.new_mass > 0) vel[idx].w = (float)g.new_mass; }
+    if (idx >= 0) { pos[idx].w = w; if (g.new_mass > 0) vel[idx].w = g.new_mass; }
     if (g.new_q == g.new_q) charge[s] = g.new_q;
 }
 // phase 5: reactant changes (nb_level 0) in rule order, then state deltas; per-list bond ranks
 __global__ void k_apply_reactants(int nev, const int* __restrict__ ev, const ClbCand* __restrict__ c, const ClbReactSpec* __restrict__ specs,
-                                  const ClbChange* __restrict__ chg, int nchg, const int* __restrict__ id2idx, int* wslot, int4* pos, float4* vel,
+                                  const ClbChange* __restrict__ chg, int nchg, const int* __restrict__ id2idx, int* wslot, int4* pos, ClbVel* vel,
                                   double* charge, unsigned long long* __restrict__ counters) {
     int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= nev) return;
@@ -320,7 +320,7 @@ __global__ void k_apply_bonds(int nev, const int* __restrict__ ev, const ClbCand
 __global__ void k_nb_claims(int nev, const int* __restrict__ ev, const ClbCand* __restrict__ c, const ClbChange* __restrict__ chg, int nchg,
                             const int* __restrict__ adj, const int* __restrict__ deg, const int* __restrict__ wslot,
                             unsigned long long* __restrict__ claim, int* __restrict__ touched,
-                            unsigned long long* __restrict__ ntouched, unsigned long long touchcap) {
+                            unsigned long long* __restrict__ ntouched, unsigned long long touchcap, ClbCtl* ctl) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= 2 * nev) return;
     int e = t >> 1, side = (t & 1) + 1;
@@ -337,7 +337,10 @@ __global__ void k_nb_claims(int nev, const int* __restrict__ ev, const ClbCand* 
             int y = adj[front[a] * CLB_MAXDEG + k];
             bool dup = false;
             for (int z = 0; z < ns; ++z) dup |= (seen[z] == y);
-            if (!dup && nn < 64 && ns < 192) { nxt[nn++] = y; seen[ns++] = y; }
+            if (!dup) {
+                if (nn < 64 && ns < 192) { nxt[nn++] = y; seen[ns++] = y; }
+                else atomicOr(&ctl->err, CLB_EF_BFS_OVERFLOW);   // a silently dropped neighbour would miss its type change
+            }
         }
         for (int a = 0; a < nn; ++a) {
             int ty = pw_type(wslot[nxt[a]]);
@@ -356,7 +359,7 @@ __global__ void k_nb_claims(int nev, const int* __restrict__ ev, const ClbCand* 
     }
 }
 __global__ void k_nb_apply(int ntouched, const int* __restrict__ touched, unsigned long long* __restrict__ claim, const ClbChange* __restrict__ chg,
-                           const int* __restrict__ id2idx, int* wslot, int4* pos, float4* vel, double* charge) {
+                           const int* __restrict__ id2idx, int* wslot, int4* pos, ClbVel* vel, double* charge) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= ntouched) return;
     int s = touched[t];

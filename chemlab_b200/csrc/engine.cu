@@ -185,6 +185,7 @@ extern "C" int clb_set_option(clb_engine* e, const char* name, double v) {
     if (!e || !name) return CLB_ERR_ARG;
     std::string s(name);
     if (s == "resort_criterion") e->criterion = (int)v;
+    else if (s == "step") e->step = (int64_t)v;               // integrator.step (restart): keys the thermostat and reaction draws
     else if (s == "block_cells") { e->set_block_cells((int)v); e->lists_valid = false; }
     else if (s == "list_capacity") { e->nl_cap_user = (int)v; e->lists_valid = false; }
     else if (s == "fuse_integrator") e->fuse = (int)v;
@@ -240,6 +241,66 @@ int clb_engine::slot_of(int64_t id) const {
     return it == id2slot.end() ? -1 : it->second;
 }
 
+// ---- host arrays <-> device state.  The conversion (fold into the box, 2^32 lattice, image counters, packing) runs on
+// the device: the host only moves the caller's arrays (pinned buffers are copied by DMA, pageable ones through the driver)
+struct ClbIngestArgs {
+    const double *pos, *vel, *mass, *q; const int *type, *state, *resid, *order;
+    double box[3];
+};
+__global__ void k_ingest(int n, ClbIngestArgs A, int4* __restrict__ P, ClbVel* __restrict__ V, int* __restrict__ image, int* __restrict__ res_o,
+                         double* __restrict__ charge, int* __restrict__ wslot, int* __restrict__ flags) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    const int i = A.order ? A.order[s] : s;
+    int xi[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        // same arithmetic as the host formula of round 1 (IEEE division, floor, rint): bit-identical lattice values
+        double fr = A.pos[3 * (size_t)i + d] / A.box[d];
+        double fl = floor(fr);
+        double u = rint((fr - fl) * 4294967296.0);
+        int im = (int)fl;
+        if (u >= 4294967296.0) { u -= 4294967296.0; im += 1; }
+        xi[d] = (int)(unsigned)(unsigned long long)u;
+        image[3 * (size_t)s + d] = im;
+    }
+    const int t = A.type[i];
+    if (t < 0 || t >= CLB_MAX_TYPES) { atomicMin(flags + 1, i); }
+    atomicMax(flags, t);
+    const int w = pw_pack(t, A.state ? A.state[i] : 0);
+    P[s] = make_int4(xi[0], xi[1], xi[2], w);
+    V[s] = clb_make_vel(A.vel ? A.vel[3 * (size_t)i] : 0.0, A.vel ? A.vel[3 * (size_t)i + 1] : 0.0, A.vel ? A.vel[3 * (size_t)i + 2] : 0.0, A.mass[i]);
+    wslot[s] = w;
+    res_o[s] = A.resid ? A.resid[i] : 0;
+    charge[s] = A.q ? A.q[i] : 0.0;
+}
+__global__ void k_identity_slots(int n, int* __restrict__ slot, int* __restrict__ id2idx) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < n) { slot[s] = s; id2idx[s] = s; }
+}
+// multi-GPU: flag the particles whose cell plane this rank owns
+__global__ void k_owned_flags(int n, const int4* __restrict__ P, ClbGrid g, unsigned char* __restrict__ flag) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    int cz = __umulhi((unsigned)P[s].z, (unsigned)g.ncz);
+    int l = cz - g.cz0; if (l < 0) l += g.ncz;
+    flag[s] = l < g.nczl ? 1 : 0;
+}
+__global__ void k_take_owned(int nloc, const int* __restrict__ sel, const int4* __restrict__ P, const ClbVel* __restrict__ V,
+                             int4* __restrict__ pos, ClbVel* __restrict__ vel, int* __restrict__ slot, int* __restrict__ id2idx) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nloc) return;
+    const int s = sel[k];
+    pos[k] = P[s]; vel[k] = V[s]; slot[k] = s; id2idx[s] = k;
+}
+
+// staging area on the device for whole-array transfers (grow-only, reused by set/get)
+static cudaError_t stage_reserve(clb_engine* e, size_t bytes) { return e->stage.ensure(bytes + 256); }
+struct StageCursor {
+    unsigned char* base; size_t off = 0;
+    template <typename T> T* take(size_t count) { off = (off + 255) & ~(size_t)255; T* p = reinterpret_cast<T*>(base + off); off += count * sizeof(T); return p; }
+};
+
 extern "C" int clb_set_particles(clb_engine* e, int64_t n, const int64_t* id, const int32_t* type, const double* pos,
                                  const double* vel, const double* mass, const double* q, const int32_t* state,
                                  const int32_t* res_id) {
@@ -248,81 +309,81 @@ extern "C" int clb_set_particles(clb_engine* e, int64_t n, const int64_t* id, co
     cudaSetDevice(e->device);
     // slots = rank in ascending id order.  Ids given as a dense ascending run (the usual .gro numbering) need neither a
     // sort nor a hash map: slot = id - first id.
-    std::vector<int64_t> order(n);
-    for (int64_t i = 0; i < n; ++i) order[i] = i;
     bool dense = true;
     for (int64_t i = 1; i < n && dense; ++i) dense = id[i] == id[0] + i;
-    if (!dense) std::sort(order.begin(), order.end(), [&](int64_t a, int64_t b) { return id[a] < id[b]; });
-    e->ids.resize(n);
+    std::vector<int> order;
+    e->ids.assign(id, id + n);
     e->id2slot.clear();
     e->ids_dense = dense; e->id_base = id[0];
-    if (!dense) e->id2slot.reserve(n * 2);
-    for (int64_t s = 0; s < n; ++s) {
-        e->ids[s] = id[order[s]];
-        if (s && e->ids[s] == e->ids[s - 1]) return e->fail(CLB_ERR_ARG, "duplicate particle id %lld", (long long)e->ids[s]);
-        if (!dense) e->id2slot[e->ids[s]] = (int)s;
+    if (!dense) {
+        order.resize(n);
+        for (int64_t i = 0; i < n; ++i) order[i] = (int)i;
+        std::sort(order.begin(), order.end(), [&](int a, int b) { return id[a] < id[b]; });
+        e->id2slot.reserve(n * 2);
+        for (int64_t s = 0; s < n; ++s) {
+            e->ids[s] = id[order[s]];
+            if (s && e->ids[s] == e->ids[s - 1]) return e->fail(CLB_ERR_ARG, "duplicate particle id %lld", (long long)e->ids[s]);
+            e->id2slot[e->ids[s]] = (int)s;
+        }
     }
     e->n = (int)n;
-    std::vector<int4> hp(n); std::vector<float4> hv(n); std::vector<int> himg(3 * n), hres(n), hslot(n); std::vector<double> hq(n);
-    int maxtype = 0;
-    for (int64_t s = 0; s < n; ++s) {
-        int64_t i = order[s];
-        int xi[3];
-        for (int d = 0; d < 3; ++d) {
-            double fr = pos[3 * i + d] / e->box[d];
-            double fl = floor(fr);
-            double u = rint((fr - fl) * 4294967296.0);
-            int im = (int)fl;
-            if (u >= 4294967296.0) { u -= 4294967296.0; im += 1; }
-            xi[d] = (int)(uint32_t)(uint64_t)u;
-            himg[3 * s + d] = im;
-        }
-        if (type[i] < 0 || type[i] >= CLB_MAX_TYPES) return e->fail(CLB_ERR_ARG, "particle type %d out of range [0,%d)", type[i], CLB_MAX_TYPES);
-        maxtype = std::max(maxtype, (int)type[i]);
-        hp[s] = make_int4(xi[0], xi[1], xi[2], pw_pack(type[i], state ? state[i] : 0));
-        hv[s] = make_float4(vel ? (float)vel[3 * i] : 0.f, vel ? (float)vel[3 * i + 1] : 0.f, vel ? (float)vel[3 * i + 2] : 0.f, (float)mass[i]);
-        hres[s] = res_id ? res_id[i] : 0;
-        hq[s] = q ? q[i] : 0.0;
-        hslot[s] = (int)s;
-    }
-    e->ntypes = std::max(e->ntypes, maxtype + 1);
-    std::vector<int> hw(n);
-    for (int64_t s = 0; s < n; ++s) hw[s] = hp[s].w;
-    // multi-GPU: every rank receives the full set and keeps the particles of its own cell planes; the per-slot
-    // arrays (image, res_id, charge, type|state word, id2idx) stay full size
-    std::vector<int> hid2idx(n, -1);
+    // per-slot arrays are full size on every rank
+    CK(e->id2idx.ensure(n)); CK(e->image.ensure(3 * (size_t)n)); CK(e->resid.ensure(n)); CK(e->charge.ensure(n)); CK(e->mol.ensure(n)); CK(e->wslot.ensure(n));
+    const size_t N = (size_t)n;
+    CK(stage_reserve(e, N * (24 + 24 + 8 + 8 + 4 + 4 + 4 + 4 + 16 + 32 + 4 + 1) + 16 * 256));
+    StageCursor sc{e->stage.p};
+    double* d_pos = sc.take<double>(3 * N); double* d_vel = vel ? sc.take<double>(3 * N) : nullptr; double* d_mass = sc.take<double>(N);
+    double* d_q = q ? sc.take<double>(N) : nullptr; int* d_type = sc.take<int>(N); int* d_state = state ? sc.take<int>(N) : nullptr;
+    int* d_res = res_id ? sc.take<int>(N) : nullptr; int* d_order = dense ? nullptr : sc.take<int>(N);
+    int4* d_P = sc.take<int4>(N); ClbVel* d_V = sc.take<ClbVel>(N); int* d_sel = sc.take<int>(N); unsigned char* d_flag = sc.take<unsigned char>(N);
+    int* d_flags = sc.take<int>(4);
+    cudaStream_t st = e->stream;
+    CK(cudaMemcpyAsync(d_pos, pos, 24 * N, cudaMemcpyHostToDevice, st));
+    if (vel) CK(cudaMemcpyAsync(d_vel, vel, 24 * N, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_mass, mass, 8 * N, cudaMemcpyHostToDevice, st));
+    if (q) CK(cudaMemcpyAsync(d_q, q, 8 * N, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_type, type, 4 * N, cudaMemcpyHostToDevice, st));
+    if (state) CK(cudaMemcpyAsync(d_state, state, 4 * N, cudaMemcpyHostToDevice, st));
+    if (res_id) CK(cudaMemcpyAsync(d_res, res_id, 4 * N, cudaMemcpyHostToDevice, st));
+    if (!dense) CK(cudaMemcpyAsync(d_order, order.data(), 4 * N, cudaMemcpyHostToDevice, st));
+    const int hflags0[4] = {0, 0x7fffffff, 0, 0};
+    CK(cudaMemcpyAsync(d_flags, hflags0, 16, cudaMemcpyHostToDevice, st));
+    ClbIngestArgs A; A.pos = d_pos; A.vel = d_vel; A.mass = d_mass; A.q = d_q; A.type = d_type; A.state = d_state; A.resid = d_res; A.order = d_order;
+    for (int d = 0; d < 3; ++d) A.box[d] = e->box[d];
+    const bool multi = e->nranks > 1;
+    if (!multi) TRY(e->alloc_particles(e->n));
+    // single rank: the ingest kernel writes the particle arrays directly (slot order = initial order)
+    k_ingest<<<ceil_div(n, 256), 256, 0, st>>>((int)n, A, multi ? d_P : e->pos.p, multi ? d_V : e->vel.p, e->image.p, e->resid.p, e->charge.p, e->wslot.p, d_flags);
     int64_t nloc = n;
-    if (e->nranks > 1) {
+    if (multi) {
+        // every rank receives the full set and keeps the particles of its own cell planes (stable compaction)
+        k_owned_flags<<<ceil_div(n, 256), 256, 0, st>>>((int)n, d_P, e->grid, d_flag);
+        size_t tb = 0;
+        cub::DeviceSelect::Flagged(nullptr, tb, cub::CountingInputIterator<int>(0), d_flag, d_sel, d_flags + 2, (int)n, st);
+        CK(e->cubtmp2.ensure(tb + 256));
+        cub::DeviceSelect::Flagged(e->cubtmp2.p, tb, cub::CountingInputIterator<int>(0), d_flag, d_sel, d_flags + 2, (int)n, st);
+    }
+    int hflags[4];
+    CK(cudaMemcpyAsync(hflags, d_flags, 16, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (hflags[1] != 0x7fffffff) return e->fail(CLB_ERR_ARG, "particle type %d out of range [0,%d)", type[hflags[1]], CLB_MAX_TYPES);
+    e->ntypes = std::max(e->ntypes, hflags[0] + 1);
+    if (multi) {
+        nloc = hflags[2];
         const ClbGrid& g = e->grid;
-        nloc = 0;
-        for (int64_t s = 0; s < n; ++s) {
-            int cz = (int)(((uint64_t)(uint32_t)hp[s].z * (uint64_t)g.ncz) >> 32);
-            int l = cz - g.cz0; if (l < 0) l += g.ncz;
-            if (l >= g.nczl) continue;
-            hp[nloc] = hp[s]; hv[nloc] = hv[s]; hslot[nloc] = (int)s; hid2idx[s] = (int)nloc;
-            ++nloc;
-        }
         double frac = (double)(g.nczl + 2) / g.ncz;
         int64_t cap = std::min<int64_t>(n, (int64_t)(n * frac * 1.5) + 16384);
         TRY(e->alloc_particles((int)std::max<int64_t>(cap, nloc)));
+        CK(cudaMemsetAsync(e->id2idx.p, 0xff, N * sizeof(int), st));
+        if (nloc) k_take_owned<<<ceil_div(nloc, 256), 256, 0, st>>>((int)nloc, d_sel, d_P, d_V, e->pos.p, e->vel.p, e->slot.p, e->id2idx.p);
     } else {
-        for (int64_t s = 0; s < n; ++s) hid2idx[s] = (int)s;
-        TRY(e->alloc_particles(e->n));
+        k_identity_slots<<<ceil_div(n, 256), 256, 0, st>>>((int)n, e->slot.p, e->id2idx.p);
     }
-    if (nloc) {
-        CK(cudaMemcpyAsync(e->pos.p, hp.data(), nloc * sizeof(int4), cudaMemcpyHostToDevice, e->stream));
-        CK(cudaMemcpyAsync(e->vel.p, hv.data(), nloc * sizeof(float4), cudaMemcpyHostToDevice, e->stream));
-        CK(cudaMemcpyAsync(e->slot.p, hslot.data(), nloc * sizeof(int), cudaMemcpyHostToDevice, e->stream));
-    }
-    CK(cudaMemcpyAsync(e->id2idx.p, hid2idx.data(), n * sizeof(int), cudaMemcpyHostToDevice, e->stream));
-    CK(cudaMemcpyAsync(e->wslot.p, hw.data(), n * sizeof(int), cudaMemcpyHostToDevice, e->stream));
-    CK(cudaMemcpyAsync(e->image.p, himg.data(), 3 * n * sizeof(int), cudaMemcpyHostToDevice, e->stream));
-    CK(cudaMemcpyAsync(e->resid.p, hres.data(), n * sizeof(int), cudaMemcpyHostToDevice, e->stream));
-    CK(cudaMemcpyAsync(e->charge.p, hq.data(), n * sizeof(double), cudaMemcpyHostToDevice, e->stream));
-    CK(cudaMemsetAsync(e->force.p, 0, 3 * (size_t)e->ncap * sizeof(double), e->stream));
-    CK(cudaStreamSynchronize(e->stream));
+    CK(cudaMemsetAsync(e->force.p, 0, 3 * (size_t)e->ncap * sizeof(double), st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
     e->nstored = (int)nloc; e->own0 = 0; e->own1 = (int)nloc;
-    e->lists_valid = false; e->forces_valid = false; e->excl_dirty = true; e->terms_dirty = true; e->topo_dirty = true;
+    e->lists_valid = false; e->forces_valid = false; e->cont_ok = false; e->excl_dirty = true; e->terms_dirty = true; e->topo_dirty = true;
     return CLB_OK;
 }
 extern "C" int64_t clb_num_particles(const clb_engine* e) { return e ? e->n : 0; }
@@ -346,15 +407,45 @@ int clb_engine::alloc_particles(int nlocal_cap) {
     return CLB_OK;
 }
 
-// fetch per-particle state in ascending-id order into host vectors (slot order)
-int clb_engine::download_state(std::vector<int4>& hp, std::vector<float4>& hv, std::vector<int>& hidx) {
-    clb_engine* e = this;
-    hp.resize(nstored); hv.resize(nstored); hidx.resize(n);
-    CK(cudaMemcpyAsync(hp.data(), pos.p, nstored * sizeof(int4), cudaMemcpyDeviceToHost, stream));
-    CK(cudaMemcpyAsync(hv.data(), vel.p, nstored * sizeof(float4), cudaMemcpyDeviceToHost, stream));
-    CK(cudaMemcpyAsync(hidx.data(), id2idx.p, n * sizeof(int), cudaMemcpyDeviceToHost, stream));
-    CK(cudaStreamSynchronize(stream));
+// query slots of a get/modify call: NULL ids -> all particles in ascending-id order
+static int query_slots(clb_engine* e, int64_t n, const int64_t* ids, std::vector<int>& qs) {
+    if (!ids) return CLB_OK;
+    qs.resize(n);
+    for (int64_t k = 0; k < n; ++k) {
+        int s = e->slot_of(ids[k]);
+        if (s < 0) return e->fail(CLB_ERR_ARG, "unknown particle id %lld", (long long)ids[k]);
+        qs[k] = s;
+    }
     return CLB_OK;
+}
+struct ClbExportArgs {
+    double *pos, *vel, *force, *mass, *q; int *image, *type, *state, *resid;
+    double qd[3];
+};
+__global__ void k_export(int cnt, const int* __restrict__ qslot, const int* __restrict__ id2idx, const int4* __restrict__ pos,
+                         const ClbVel* __restrict__ vel, const double* __restrict__ force, int fstride, const int* __restrict__ image,
+                         const double* __restrict__ charge, const int* __restrict__ resid, ClbExportArgs O, int* __restrict__ missing) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= cnt) return;
+    const int s = qslot ? qslot[k] : k;
+    const int i = id2idx[s];
+    if (i < 0) { atomicAdd(missing, 1); return; }
+    const size_t k3 = 3 * (size_t)k;
+    if (O.pos || O.type || O.state) {
+        const int4 p = pos[i];
+        if (O.pos) { O.pos[k3] = (double)(unsigned)p.x * O.qd[0]; O.pos[k3 + 1] = (double)(unsigned)p.y * O.qd[1]; O.pos[k3 + 2] = (double)(unsigned)p.z * O.qd[2]; }
+        if (O.type) O.type[k] = pw_type(p.w);
+        if (O.state) O.state[k] = pw_state(p.w);
+    }
+    if (O.vel || O.mass) {
+        const ClbVel v = vel[i];
+        if (O.vel) { O.vel[k3] = v.x; O.vel[k3 + 1] = v.y; O.vel[k3 + 2] = v.z; }
+        if (O.mass) O.mass[k] = v.w;
+    }
+    if (O.force) { O.force[k3] = force[i]; O.force[k3 + 1] = force[i + fstride]; O.force[k3 + 2] = force[i + 2 * (size_t)fstride]; }
+    if (O.image) { O.image[k3] = image[3 * (size_t)s]; O.image[k3 + 1] = image[3 * (size_t)s + 1]; O.image[k3 + 2] = image[3 * (size_t)s + 2]; }
+    if (O.q) O.q[k] = charge[s];
+    if (O.resid) O.resid[k] = resid[s];
 }
 
 extern "C" int clb_get_particles(clb_engine* e, int64_t n, const int64_t* ids, double* pos, int32_t* image, double* vel,
@@ -362,39 +453,45 @@ extern "C" int clb_get_particles(clb_engine* e, int64_t n, const int64_t* ids, d
     if (!e) return CLB_ERR_ARG;
     cudaSetDevice(e->device);
     if (e->nranks > 1) return e->get_particles_gathered(n, ids, pos, image, vel, force, type, state, mass, q, res_id);
-    std::vector<int4> hp; std::vector<float4> hv; std::vector<int> hidx;
-    TRY(e->download_state(hp, hv, hidx));
-    std::vector<double> hf; std::vector<int> himg, hres; std::vector<double> hq;
-    if (force) { hf.resize(3 * (size_t)e->ncap); CK(cudaMemcpy(hf.data(), e->force.p, hf.size() * 8, cudaMemcpyDeviceToHost)); }
-    if (image) { himg.resize(3 * (size_t)e->n); CK(cudaMemcpy(himg.data(), e->image.p, himg.size() * 4, cudaMemcpyDeviceToHost)); }
-    if (res_id) { hres.resize(e->n); CK(cudaMemcpy(hres.data(), e->resid.p, hres.size() * 4, cudaMemcpyDeviceToHost)); }
-    if (q) { hq.resize(e->n); CK(cudaMemcpy(hq.data(), e->charge.p, hq.size() * 8, cudaMemcpyDeviceToHost)); }
-    int64_t cnt = ids ? n : e->n;
-    for (int64_t k = 0; k < cnt; ++k) {
-        int s = ids ? e->slot_of(ids[k]) : (int)k;
-        if (s < 0) return e->fail(CLB_ERR_ARG, "unknown particle id %lld", (long long)ids[k]);
-        int i = hidx[s];
-        if (pos) { pos[3 * k] = (double)(uint32_t)hp[i].x * e->geo.q[0]; pos[3 * k + 1] = (double)(uint32_t)hp[i].y * e->geo.q[1]; pos[3 * k + 2] = (double)(uint32_t)hp[i].z * e->geo.q[2]; }
-        if (vel) { vel[3 * k] = hv[i].x; vel[3 * k + 1] = hv[i].y; vel[3 * k + 2] = hv[i].z; }
-        if (force) { force[3 * k] = hf[i]; force[3 * k + 1] = hf[i + e->ncap]; force[3 * k + 2] = hf[i + 2 * (size_t)e->ncap]; }
-        if (image) { image[3 * k] = himg[3 * s]; image[3 * k + 1] = himg[3 * s + 1]; image[3 * k + 2] = himg[3 * s + 2]; }
-        if (type) type[k] = pw_type(hp[i].w);
-        if (state) state[k] = pw_state(hp[i].w);
-        if (mass) mass[k] = hv[i].w;
-        if (q) q[k] = hq[s];
-        if (res_id) res_id[k] = hres[s];
-    }
+    const int64_t cnt = ids ? n : e->n;
+    if (cnt <= 0) return CLB_OK;
+    std::vector<int> qs;
+    TRY(query_slots(e, cnt, ids, qs));
+    const size_t N = (size_t)cnt;
+    CK(stage_reserve(e, N * (24 * 3 + 8 * 2 + 12 + 4 * 4) + 16 * 256));
+    StageCursor sc{e->stage.p};
+    ClbExportArgs O;
+    O.pos = pos ? sc.take<double>(3 * N) : nullptr; O.vel = vel ? sc.take<double>(3 * N) : nullptr; O.force = force ? sc.take<double>(3 * N) : nullptr;
+    O.mass = mass ? sc.take<double>(N) : nullptr; O.q = q ? sc.take<double>(N) : nullptr; O.image = image ? sc.take<int>(3 * N) : nullptr;
+    O.type = type ? sc.take<int>(N) : nullptr; O.state = state ? sc.take<int>(N) : nullptr; O.resid = res_id ? sc.take<int>(N) : nullptr;
+    int* d_qs = ids ? sc.take<int>(N) : nullptr; int* d_missing = sc.take<int>(1);
+    for (int d = 0; d < 3; ++d) O.qd[d] = e->geo.q[d];
+    cudaStream_t st = e->stream;
+    if (ids) CK(cudaMemcpyAsync(d_qs, qs.data(), 4 * N, cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(d_missing, 0, 4, st));
+    k_export<<<ceil_div(cnt, 256), 256, 0, st>>>((int)cnt, d_qs, e->id2idx.p, e->pos.p, e->vel.p, e->force.p, e->ncap, e->image.p, e->charge.p, e->resid.p, O, d_missing);
+    if (pos) CK(cudaMemcpyAsync(pos, O.pos, 24 * N, cudaMemcpyDeviceToHost, st));
+    if (vel) CK(cudaMemcpyAsync(vel, O.vel, 24 * N, cudaMemcpyDeviceToHost, st));
+    if (force) CK(cudaMemcpyAsync(force, O.force, 24 * N, cudaMemcpyDeviceToHost, st));
+    if (mass) CK(cudaMemcpyAsync(mass, O.mass, 8 * N, cudaMemcpyDeviceToHost, st));
+    if (q) CK(cudaMemcpyAsync(q, O.q, 8 * N, cudaMemcpyDeviceToHost, st));
+    if (image) CK(cudaMemcpyAsync(image, O.image, 12 * N, cudaMemcpyDeviceToHost, st));
+    if (type) CK(cudaMemcpyAsync(type, O.type, 4 * N, cudaMemcpyDeviceToHost, st));
+    if (state) CK(cudaMemcpyAsync(state, O.state, 4 * N, cudaMemcpyDeviceToHost, st));
+    if (res_id) CK(cudaMemcpyAsync(res_id, O.resid, 4 * N, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
     return CLB_OK;
 }
 
 // multi-rank read-back: every rank fills the rows of the particles it owns, the rows are summed over the ranks
 // (exact: one non-zero contribution per row), so all ranks return the full, identical state
-__global__ void k_pack_state(int no, int K, const int4* __restrict__ pos, const float4* __restrict__ vel, const double* __restrict__ force,
+__global__ void k_pack_state(int no, int K, const int4* __restrict__ pos, const ClbVel* __restrict__ vel, const double* __restrict__ force,
                              int fstride, const int* __restrict__ slot, const int* __restrict__ image, double* __restrict__ M) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= no) return;
     const int s = slot[i];
-    const int4 p = pos[i]; const float4 v = vel[i];
+    const int4 p = pos[i]; const ClbVel v = vel[i];
     double* r = M + (size_t)s * K;
     r[0] = (double)(unsigned)p.x; r[1] = (double)(unsigned)p.y; r[2] = (double)(unsigned)p.z;
     r[3] = v.x; r[4] = v.y; r[5] = v.z;
@@ -470,46 +567,67 @@ extern "C" int clb_modify_particle(clb_engine* e, int64_t id, int field, const d
     CK(cudaMemcpy(e->wslot.p + s, &w, 4, cudaMemcpyHostToDevice));
     e->forces_valid = false;
     if (i < 0) return CLB_OK;
-    int4 p; float4 v;
+    int4 p; ClbVel v;
     CK(cudaMemcpy(&p, e->pos.p + i, sizeof(p), cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(&v, e->vel.p + i, sizeof(v), cudaMemcpyDeviceToHost));
     p.w = w;
     switch (field) {
-        case 2: v.w = (float)value[0]; break;
+        case 2: v.w = value[0]; break;
         case 5: { int im[3]; p.x = lattice_of(value[0], e->box[0], &im[0]); p.y = lattice_of(value[1], e->box[1], &im[1]); p.z = lattice_of(value[2], e->box[2], &im[2]);
-                  CK(cudaMemcpy(e->image.p + 3 * s, im, 12, cudaMemcpyHostToDevice)); e->lists_valid = false; break; }
-        case 6: v.x = (float)value[0]; v.y = (float)value[1]; v.z = (float)value[2]; break;
+                  CK(cudaMemcpy(e->image.p + 3 * s, im, 12, cudaMemcpyHostToDevice)); e->lists_valid = false; e->cont_ok = false; break; }
+        case 6: v.x = value[0]; v.y = value[1]; v.z = value[2]; break;
         default: break;
     }
     CK(cudaMemcpy(e->pos.p + i, &p, sizeof(p), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(e->vel.p + i, &v, sizeof(v), cudaMemcpyHostToDevice));
     return CLB_OK;
 }
+__global__ void k_set_velocities(int n, const int* __restrict__ id2idx, const double* __restrict__ v, ClbVel* __restrict__ vel) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    const int i = id2idx[s];
+    if (i < 0) return;
+    ClbVel o = vel[i];
+    o.x = v[3 * (size_t)s]; o.y = v[3 * (size_t)s + 1]; o.z = v[3 * (size_t)s + 2];
+    vel[i] = o;
+}
+__global__ void k_set_positions(int n, const int* __restrict__ id2idx, const double* __restrict__ x, double bx, double by, double bz,
+                                int4* __restrict__ pos, int* __restrict__ image) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    const int i = id2idx[s];
+    if (i < 0) return;
+    const double box[3] = {bx, by, bz};
+    int xi[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        double fr = x[3 * (size_t)s + d] / box[d], fl = floor(fr), u = rint((fr - fl) * 4294967296.0);
+        int im = (int)fl;
+        if (u >= 4294967296.0) { u -= 4294967296.0; im += 1; }
+        xi[d] = (int)(unsigned)(unsigned long long)u;
+        image[3 * (size_t)s + d] = im;
+    }
+    int4 p = pos[i];
+    pos[i] = make_int4(xi[0], xi[1], xi[2], p.w);
+}
 extern "C" int clb_set_velocities(clb_engine* e, int64_t n, const double* vel) {
     if (!e || n != e->n || !vel) return e ? e->fail(CLB_ERR_ARG, "clb_set_velocities: n mismatch") : CLB_ERR_ARG;
     cudaSetDevice(e->device);
-    std::vector<int4> hp; std::vector<float4> hv; std::vector<int> hidx;
-    TRY(e->download_state(hp, hv, hidx));
-    for (int s = 0; s < e->n; ++s) { int i = hidx[s]; if (i < 0) continue; hv[i].x = (float)vel[3 * s]; hv[i].y = (float)vel[3 * s + 1]; hv[i].z = (float)vel[3 * s + 2]; }
-    CK(cudaMemcpy(e->vel.p, hv.data(), e->nstored * sizeof(float4), cudaMemcpyHostToDevice));
+    CK(stage_reserve(e, 24 * (size_t)n));
+    CK(cudaMemcpyAsync(e->stage.p, vel, 24 * (size_t)n, cudaMemcpyHostToDevice, e->stream));
+    k_set_velocities<<<ceil_div(n, 256), 256, 0, e->stream>>>((int)n, e->id2idx.p, (const double*)e->stage.p, e->vel.p);
+    CK(cudaStreamSynchronize(e->stream));
     return CLB_OK;
 }
 extern "C" int clb_set_positions(clb_engine* e, int64_t n, const double* pos) {
     if (!e || n != e->n || !pos) return e ? e->fail(CLB_ERR_ARG, "clb_set_positions: n mismatch") : CLB_ERR_ARG;
     if (e->nranks > 1) return e->fail(CLB_ERR_UNSUPPORTED, "clb_set_positions on a multi-rank engine: call clb_set_particles again");
     cudaSetDevice(e->device);
-    std::vector<int4> hp; std::vector<float4> hv; std::vector<int> hidx;
-    TRY(e->download_state(hp, hv, hidx));
-    std::vector<int> himg(3 * (size_t)e->n);
-    for (int s = 0; s < e->n; ++s) {
-        int i = hidx[s];
-        hp[i].x = lattice_of(pos[3 * s], e->box[0], &himg[3 * s]);
-        hp[i].y = lattice_of(pos[3 * s + 1], e->box[1], &himg[3 * s + 1]);
-        hp[i].z = lattice_of(pos[3 * s + 2], e->box[2], &himg[3 * s + 2]);
-    }
-    CK(cudaMemcpy(e->pos.p, hp.data(), e->nstored * sizeof(int4), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(e->image.p, himg.data(), himg.size() * 4, cudaMemcpyHostToDevice));
-    e->lists_valid = false; e->forces_valid = false;
+    CK(stage_reserve(e, 24 * (size_t)n));
+    CK(cudaMemcpyAsync(e->stage.p, pos, 24 * (size_t)n, cudaMemcpyHostToDevice, e->stream));
+    k_set_positions<<<ceil_div(n, 256), 256, 0, e->stream>>>((int)n, e->id2idx.p, (const double*)e->stage.p, e->box[0], e->box[1], e->box[2], e->pos.p, e->image.p);
+    CK(cudaStreamSynchronize(e->stream));
+    e->lists_valid = false; e->forces_valid = false; e->cont_ok = false;
     return CLB_OK;
 }
 
@@ -531,7 +649,7 @@ extern "C" int clb_set_exclusions(clb_engine* e, int64_t n, const int64_t* pairs
     e->nexcl = (long long)h.size();
     CK(e->excl_pairs.ensure(h.size() * 2 + (size_t)e->n + 1024));
     if (!h.empty()) CK(cudaMemcpy(e->excl_pairs.p, h.data(), h.size() * sizeof(int2), cudaMemcpyHostToDevice));
-    e->excl_dirty = true; e->lists_valid = false;
+    e->excl_dirty = true; e->lists_valid = false; e->cont_ok = false;
     return CLB_OK;
 }
 extern "C" int64_t clb_num_exclusions(const clb_engine* e) { return e ? e->nexcl : 0; }
@@ -662,7 +780,7 @@ extern "C" int clb_nb_set_tabulated(clb_engine* e, int inter, int t1, int t2, in
     if (e->tables[table].interp != 1) return e->fail(CLB_ERR_UNSUPPORTED, "non-bonded tables use linear interpolation (itype=1) as chemlab does (gromacs_topology.py:696-707)");
     HostPairPot p; p.kind = 1; p.inter = inter; p.tab1 = table; p.tab2 = -1; p.rc = cutoff;
     e->pp[t1][t2] = e->pp[t2][t1] = p;
-    e->pots_dirty = true; e->forces_valid = false;
+    e->pots_dirty = true; e->forces_valid = false; e->cont_ok = false;
     return CLB_OK;
 }
 extern "C" int clb_nb_set_lj(clb_engine* e, int inter, int t1, int t2, double eps, double sig, double cutoff, int shift_auto) {
@@ -672,7 +790,7 @@ extern "C" int clb_nb_set_lj(clb_engine* e, int inter, int t1, int t2, double ep
     double sr6 = pow(sig / cutoff, 6);
     p.shift = shift_auto ? 4 * eps * (sr6 * sr6 - sr6) : 0.0;
     e->pp[t1][t2] = e->pp[t2][t1] = p;
-    e->pots_dirty = true; e->forces_valid = false;
+    e->pots_dirty = true; e->forces_valid = false; e->cont_ok = false;
     return CLB_OK;
 }
 extern "C" int clb_nb_set_mixed(clb_engine* e, int inter, int t1, int t2, int table1, int table2, double mix, int conv_type,
@@ -685,7 +803,7 @@ extern "C" int clb_nb_set_mixed(clb_engine* e, int inter, int t1, int t2, int ta
         return e->fail(CLB_ERR_UNSUPPORTED, "mixed tables must share one grid and use linear interpolation");
     HostPairPot p; p.kind = 3; p.inter = inter; p.tab1 = table1; p.tab2 = table2; p.mix = mix; p.conv_type = conv_type; p.conv_total = conv_total; p.rc = cutoff;
     e->pp[t1][t2] = e->pp[t2][t1] = p;
-    e->pots_dirty = true; e->forces_valid = false; e->has_mixed = true;
+    e->pots_dirty = true; e->forces_valid = false; e->cont_ok = false; e->has_mixed = true;
     return CLB_OK;
 }
 
@@ -879,7 +997,7 @@ extern "C" int clb_list_add(clb_engine* e, int list, int64_t n, const int64_t* i
     TRY(e->list_reserve(list, l.n + n));
     if (n) CK(cudaMemcpy(l.d.p + (size_t)l.n * l.arity, h.data(), h.size() * 4, cudaMemcpyHostToDevice));
     l.n += n;
-    e->terms_dirty = true; e->forces_valid = false;
+    e->terms_dirty = true; e->forces_valid = false; e->cont_ok = false;
     if (l.arity == 2 && l.tm_observed) e->topo_dirty = true;
     return CLB_OK;
 }
@@ -936,7 +1054,7 @@ extern "C" int clb_bonded_set_potential(clb_engine* e, int inter, int t1, int t2
         }
         if (!replaced) b.pots.push_back(p);
     }
-    e->pots_dirty = true; e->forces_valid = false;
+    e->pots_dirty = true; e->forces_valid = false; e->cont_ok = false;
     return CLB_OK;
 }
 
@@ -1272,6 +1390,7 @@ int clb_engine::check_device_errors(const char* where) {
     if (er & CLB_EF_PARTNER_LOST) return fail(CLB_ERR_RANGE, "%s: a bonded partner is outside the ghost layer", where);
     if (er & CLB_EF_DEGREE) return fail(CLB_ERR_RANGE, "%s: more than %d bonds on one particle", where, CLB_MAXDEG);
     if (er & CLB_EF_TUPLE_OVERFLOW) return fail(CLB_ERR_RANGE, "%s: tuple list overflow", where);
+    if (er & CLB_EF_BFS_OVERFLOW) return fail(CLB_ERR_RANGE, "%s: neighbour-property search exceeded its buffers (more than 64 particles in one bond shell)", where);
     return CLB_OK;
 }
 
@@ -1358,7 +1477,12 @@ extern "C" int clb_count_type(clb_engine* e, int type, int state, int64_t* out) 
 }
 
 // ------------------------------------------------------------------------------------------ integrator
-extern "C" int clb_set_dt(clb_engine* e, double dt) { if (!e || dt <= 0) return CLB_ERR_ARG; e->dt = dt; return CLB_OK; }
+extern "C" int clb_set_dt(clb_engine* e, double dt) {
+    if (!e || dt <= 0) return CLB_ERR_ARG;
+    if (dt != e->dt) e->react_dirty = true;      // acceptance probability p = rate * dt * interval (U5)
+    e->dt = dt;
+    return CLB_OK;
+}
 extern "C" int clb_set_langevin(clb_engine* e, int enabled, double kT, double gamma, int ntypes, const int32_t* types) {
     if (!e) return CLB_ERR_ARG;
     e->lang_on = enabled; e->kT = kT; e->gamma = gamma;
@@ -1389,20 +1513,35 @@ void clb_engine::enqueue_integrate(int mode, uint64_t key_step) {
 
 // integrator.run(n) -- SURVEY 3.2.  Steps are enqueued in chunks without host synchronisation; the
 // skin/2 test runs on the device and stalls the rest of the chunk when a rebuild is due.
-extern "C" int clb_run(clb_engine* e, int64_t nsteps) {
+// cont: continuation of the previous clb_run inside ONE integrator.run of the reference (the Python surface splits a
+// run at ExtAnalyze / ATRPActivator intervals): the force array still holds the thermostatted forces of the last
+// step, so neither the run-entry recalculation nor the heat-up kick is repeated (VelocityVerlet::run does them once).
+static int run_impl(clb_engine* e, int64_t nsteps, bool cont) {
     if (!e || nsteps < 0) return CLB_ERR_ARG;
     cudaSetDevice(e->device);
-    TRY(e->setup_sync());
-    if (e->pending_rebuild) { e->lists_valid = false; e->pending_rebuild = false; }
-    if (!e->lists_valid) TRY(e->rebuild());
+    cont = cont && e->cont_ok && e->lists_valid;
+    if (cont) {
+        // list / term / exclusion updates left by a reaction pass are picked up at the forced rebuild of the first step
+        if (e->pots_dirty) TRY(e->upload_potentials());
+        if (e->topo_dirty) TRY(e->build_topology());
+        if (e->react_dirty) TRY(e->upload_reactions());
+        if (!e->pending_rebuild && (e->excl_dirty || e->terms_dirty)) cont = false;
+    }
+    if (!cont) {
+        TRY(e->setup_sync());
+        if (e->pending_rebuild) { e->lists_valid = false; e->pending_rebuild = false; }
+        if (!e->lists_valid) TRY(e->rebuild());
+    }
     cudaEventRecord(e->ev_a[CLB_B_TOTAL], e->stream);
-    // run entry: recalc forces (+ thermostat heat-up), SURVEY 3.2
-    e->enqueue_forces();
-    if (e->lang_on) {
-        ClbIntegParams P = e->integ_params((uint64_t)e->step);
-        int no = e->own1 - e->own0;
-        k_thermalize<<<ceil_div(no, 256), 256, 0, e->stream>>>(P, sqrt(3.0), CLB_STREAM_HEATUP, e->pos.p, e->vel.p, e->slot.p, e->force.p, e->ncap);
-        ++e->launches;
+    if (!cont) {
+        // run entry: recalc forces (+ thermostat heat-up), SURVEY 3.2
+        e->enqueue_forces();
+        if (e->lang_on) {
+            ClbIntegParams P = e->integ_params((uint64_t)e->step);
+            int no = e->own1 - e->own0;
+            k_thermalize<<<ceil_div(no, 256), 256, 0, e->stream>>>(P, sqrt(3.0), CLB_STREAM_HEATUP, e->pos.p, e->vel.p, e->slot.p, e->force.p, e->ncap);
+            ++e->launches;
+        }
     }
     const double half_skin = 0.5 * e->skin;
     int64_t i = 0;
@@ -1477,8 +1616,11 @@ extern "C" int clb_run(clb_engine* e, int64_t nsteps) {
     e->collect_timers();
     e->nsteps_total += nsteps;
     e->forces_valid = true; // force array holds the thermostatted force of the last step
+    e->cont_ok = true;
     return e->check_device_errors("clb_run");
 }
+extern "C" int clb_run(clb_engine* e, int64_t nsteps) { return run_impl(e, nsteps, false); }
+extern "C" int clb_run_continue(clb_engine* e, int64_t nsteps) { return run_impl(e, nsteps, true); }
 
 // ------------------------------------------------------------------------------------------ parity / timers
 extern "C" int clb_get_pairs(clb_engine* e, int64_t cap, int64_t* pairs, int64_t* n_out) {
@@ -1571,6 +1713,17 @@ extern "C" int clb_stream(clb_engine* e, void** s) { if (!e || !s) return CLB_ER
 
 void clb_engine::free_all() {
     for (auto& l : lists) l.d.release();
+    // device buffers are plain handles (DevBuf has no destructor): release them here so that a process creating many
+    // engines (tests, the e2e leg of bench.py) does not accumulate device memory
+    pos.release(); pos2.release(); xref.release(); vel.release(); vel2.release(); slot.release(); slot2.release(); id2idx.release();
+    image.release(); resid.release(); mol.release(); wslot.release(); force.release(); charge.release(); key.release(); key2.release();
+    val.release(); val2.release(); cell_start.release(); cubtmp.release(); cubtmp2.release(); stage.release(); partial.release();
+    partial_u64.release(); nl_entries.release(); nl_count.release(); excl_pairs.release(); excl_off.release(); excl_ids.release();
+    ekey.release(); ekey2.release(); eval.release(); d_pd.release(); d_pd_e.release(); d_plj.release(); d_pe.release(); d_tm.release();
+    d_tm_e.release(); d_frows.release(); d_erows.release(); d_rows2.release(); d_pd2.release(); d_bdesc.release(); d_bpots.release();
+    d_btm.release(); d_bcf.release(); d_bce.release(); d_list_ptrs.release(); term_off.release(); term_meta.release(); term_tuple.release();
+    tkey.release(); tkey2.release(); tval.release(); tval2.release(); rt_off.release(); rt_cnt.release(); rt_meta.release(); rt_mem.release();
+    react_free();
     for (auto ev : pair_events) cudaEventDestroy(ev);
     for (auto ev : pair_events2) cudaEventDestroy(ev);
     for (int i = 0; i < CLB_NBUCKET; ++i) { cudaEventDestroy(ev_a[i]); cudaEventDestroy(ev_b[i]); }

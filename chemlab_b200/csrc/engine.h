@@ -74,12 +74,12 @@ struct clb_engine {
     int slot_of(int64_t id) const;
     bool ids_dense = false; int64_t id_base = 0;
     DevBuf<int4> pos, pos2, xref;
-    DevBuf<float4> vel, vel2;
+    DevBuf<ClbVel> vel, vel2;
     DevBuf<int> slot, slot2, id2idx, image, resid, mol;
     DevBuf<int> wslot;                        // replicated per-slot type|state word (reaction decisions; clb_react.cuh)
     DevBuf<double> force, charge;
     DevBuf<int> key, key2, val, val2, cell_start;
-    DevBuf<unsigned char> cubtmp, cubtmp2;
+    DevBuf<unsigned char> cubtmp, cubtmp2, stage;
     DevBuf<double> partial;
     DevBuf<unsigned long long> partial_u64;
     ClbCtl *d_ctl = nullptr, *h_ctl = nullptr;
@@ -93,7 +93,7 @@ struct clb_engine {
     int pair_grid = 0, pair_threads = 128, pair_smem = 0, tabs_smem = 1, pair_split = 1, pair_split_user = 0, pair_npw = 1, build_threads = 256;
     int ugrid_on = 0, all_tab = 0, branchfree_user = 1, pair_warps_user = 0;
     ClbTabMeta ugrid_meta;
-    bool lists_valid = false, forces_valid = false;
+    bool lists_valid = false, forces_valid = false, cont_ok = false;
 
     // exclusions
     DevBuf<int2> excl_pairs;
@@ -192,7 +192,6 @@ struct clb_engine {
     int alloc_particles(int nlocal_cap);
     int get_particles_gathered(int64_t nq, const int64_t* ids, double* pos, int32_t* image, double* vel, double* force, int32_t* type,
                                int32_t* state, double* mass, double* q, int32_t* res_id);
-    int download_state(std::vector<int4>& hp, std::vector<float4>& hv, std::vector<int>& hidx);
     int build_excl_csr();
     int upload_potentials();
     int list_reserve(int li, long long need);
@@ -215,4 +214,5 @@ struct clb_engine {
     int react_pass(int64_t* events_out);
     int update_mixing();
     void free_all();
+    void react_free();
 };

@@ -60,7 +60,7 @@ static NcclApi g_nccl;
     } while (0)
 
 // migrating particle: everything that is stored per sorted index plus the owner-only per-slot image counters
-struct ClbMig { int4 p; float4 v; int slot, ix, iy, iz; };
+struct ClbMig { int4 p; ClbVel v; int slot, ix, iy, iz; };
 
 struct clb_engine::CommDev {
     ncclComm_t comm = nullptr;
@@ -174,7 +174,7 @@ __global__ void k_mig_classify(int n, const int4* __restrict__ pos, ClbGrid g, i
     key[i] = l < g.nczl ? 0 : (l == g.nczl ? 1 : 2);
     val[i] = i;
 }
-__global__ void k_mig_pack(int n, const int* __restrict__ perm, const int4* __restrict__ pos, const float4* __restrict__ vel,
+__global__ void k_mig_pack(int n, const int* __restrict__ perm, const int4* __restrict__ pos, const ClbVel* __restrict__ vel,
                            const int* __restrict__ slot, const int* __restrict__ image, int* __restrict__ id2idx, ClbMig* __restrict__ out) {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
@@ -184,14 +184,14 @@ __global__ void k_mig_pack(int n, const int* __restrict__ perm, const int4* __re
     out[k] = m;
 }
 // new owned set = stayers (in their previous order) followed by the immigrants
-__global__ void k_mig_compact(int nstay, const int* __restrict__ perm, const int4* __restrict__ pos_in, const float4* __restrict__ vel_in,
-                              const int* __restrict__ slot_in, int4* __restrict__ pos, float4* __restrict__ vel, int* __restrict__ slot) {
+__global__ void k_mig_compact(int nstay, const int* __restrict__ perm, const int4* __restrict__ pos_in, const ClbVel* __restrict__ vel_in,
+                              const int* __restrict__ slot_in, int4* __restrict__ pos, ClbVel* __restrict__ vel, int* __restrict__ slot) {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= nstay) return;
     int i = perm[k];
     pos[k] = pos_in[i]; vel[k] = vel_in[i]; slot[k] = slot_in[i];
 }
-__global__ void k_mig_unpack(int n, const ClbMig* __restrict__ in, int base, int4* __restrict__ pos, float4* __restrict__ vel,
+__global__ void k_mig_unpack(int n, const ClbMig* __restrict__ in, int base, int4* __restrict__ pos, ClbVel* __restrict__ vel,
                              int* __restrict__ slot, int* __restrict__ image) {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;

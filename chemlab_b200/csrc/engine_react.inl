@@ -13,8 +13,20 @@ struct clb_engine::ReactDev {
     bool slot_arrays_init = false;
 };
 
+void clb_engine::react_free() {
+    if (!rd) return;
+    ReactDev& R = *rd;
+    R.specs.release(); R.chg.release(); R.regs.release(); R.lists.release(); R.cands.release(); R.cands_sorted.release();
+    R.ckey.release(); R.ckey2.release(); R.best1.release(); R.best2.release(); R.claim.release(); R.counters.release(); R.scalars.release();
+    R.cval.release(); R.cval2.release(); R.alive.release(); R.surv.release(); R.status.release(); R.ev.release(); R.erank.release();
+    R.asA.release(); R.inB.release(); R.adj.release(); R.deg.release(); R.ev_of_slot.release(); R.list_n.release(); R.list_cnt.release();
+    R.touched.release(); R.evpairs.release(); R.flag.release(); R.iota.release();
+    delete rd; rd = nullptr;
+}
+
 extern "C" int clb_reaction_general(clb_engine* e, int enabled, int interval, int nearest, int max_per_interval) {
     if (!e || interval < 1) return e ? e->fail(CLB_ERR_ARG, "reaction interval must be >= 1") : CLB_ERR_ARG;
+    if (interval != e->react_interval) e->react_dirty = true;       // p = rate * dt * interval is cached in upload_reactions
     e->react_on = enabled; e->react_interval = interval; e->react_nearest = nearest; e->react_max_per_interval = max_per_interval;
     return CLB_OK;
 }
@@ -22,7 +34,9 @@ extern "C" int clb_add_reaction(clb_engine* e, const clb_reaction_spec* s, int* 
     if (!e || !s || !out) return CLB_ERR_ARG;
     if (e->reactions.size() >= CLB_MAX_REACTIONS) return e->fail(CLB_ERR_UNSUPPORTED, "too many reactions");
     if (s->list < 0 || s->list >= (int)e->lists.size() || e->lists[s->list].arity != 2) return e->fail(CLB_ERR_ARG, "reaction needs a pair list (fpl=)");
-    if (s->cutoff > e->rc + e->skin) return e->fail(CLB_ERR_ARG, "reaction cutoff %g exceeds the Verlet radius", s->cutoff);
+    // between rebuilds the Verlet rows are only complete up to rc: a larger reaction cutoff would make the candidate set depend
+    // on the rebuild schedule (and on the rank count)
+    if (s->cutoff > e->rc * (1 + 1e-12)) return e->fail(CLB_ERR_ARG, "reaction cutoff %g exceeds the Verlet cutoff %g", s->cutoff, e->rc);
     e->reactions.push_back(*s);
     e->react_counters.push_back(0);
     e->ntypes = std::max(e->ntypes, std::max(s->type_1, s->type_2) + 1);
@@ -147,6 +161,7 @@ int clb_engine::build_topology() {
             CK(cudaMemcpyAsync(&changed, rd->flag.p, 4, cudaMemcpyDeviceToHost, stream));
             CK(cudaStreamSynchronize(stream));
             if (!changed) break;
+            if (it == 63) return fail(CLB_ERR_RANGE, "molecule ids did not converge in 64 hooking rounds");
         }
         k_mol_compress<<<ceil_div(n, 256), 256, 0, stream>>>(n, mol.p);
     }
@@ -276,6 +291,7 @@ int clb_engine::react_pass(int64_t* events_out) {
                 CK(cudaMemcpyAsync(&changed, R.flag.p, 4, cudaMemcpyDeviceToHost, stream));
                 CK(cudaStreamSynchronize(stream));
                 if (!changed) break;
+                if (it == 63) return fail(CLB_ERR_RANGE, "molecule ids did not converge in 64 hooking rounds");
             }
             k_mol_compress<<<ceil_div(n, 256), 256, 0, stream>>>(n, mol.p);
         }
@@ -287,7 +303,7 @@ int clb_engine::react_pass(int64_t* events_out) {
             CK(R.touched.ensure(touchcap));
             CK(cudaMemsetAsync(R.scalars.p + 4, 0, 8, stream));
             k_nb_claims<<<ceil_div(2 * nev, 128), 128, 0, stream>>>(nev, R.ev.p, R.cands_sorted.p, R.chg.p, (int)changes.size(), R.adj.p, R.deg.p, wslot.p,
-                                                                   R.claim.p, R.touched.p, R.scalars.p + 4, (unsigned long long)touchcap);
+                                                                   R.claim.p, R.touched.p, R.scalars.p + 4, (unsigned long long)touchcap, d_ctl);
             unsigned long long nt = 0;
             CK(cudaMemcpyAsync(&nt, R.scalars.p + 4, 8, cudaMemcpyDeviceToHost, stream));
             CK(cudaStreamSynchronize(stream));

@@ -116,19 +116,26 @@ class Engine:
     def num_particles(self):
         return int(self.L.clb_num_particles(self.h))
 
-    def get_particles(self, ids=None, fields=("pos", "vel", "force", "type", "state", "mass", "image", "q", "res_id")):
+    _FIELD_SPEC = dict(pos=(3, np.float64), image=(3, np.int32), vel=(3, np.float64), force=(3, np.float64), type=(1, np.int32),
+                       state=(1, np.int32), mass=(1, np.float64), q=(1, np.float64), res_id=(1, np.int32))
+
+    def get_particles(self, ids=None, fields=("pos", "vel", "force", "type", "state", "mass", "image", "q", "res_id"), out=None):
+        """Per-particle state in ascending-id order (or for `ids`).  `out` may hold caller-owned C-contiguous arrays of the right
+        shape and dtype (e.g. pinned host memory): the engine then copies straight into them."""
         n = self.num_particles() if ids is None else len(ids)
         ids_a = _i64(ids)
-        out = {}
-        if "pos" in fields: out["pos"] = np.zeros((n, 3))
-        if "image" in fields: out["image"] = np.zeros((n, 3), np.int32)
-        if "vel" in fields: out["vel"] = np.zeros((n, 3))
-        if "force" in fields: out["force"] = np.zeros((n, 3))
-        if "type" in fields: out["type"] = np.zeros(n, np.int32)
-        if "state" in fields: out["state"] = np.zeros(n, np.int32)
-        if "mass" in fields: out["mass"] = np.zeros(n)
-        if "q" in fields: out["q"] = np.zeros(n)
-        if "res_id" in fields: out["res_id"] = np.zeros(n, np.int32)
+        res = {}
+        for f in fields:
+            w, dt = self._FIELD_SPEC[f]
+            shape = (n, 3) if w == 3 else (n,)
+            buf = out.get(f) if out is not None else None
+            if buf is not None:
+                if buf.shape != shape or buf.dtype != dt or not buf.flags["C_CONTIGUOUS"]:
+                    raise ValueError("out[%r] must be a C-contiguous %s array of shape %s" % (f, np.dtype(dt).name, shape))
+            else:
+                buf = np.empty(shape, dt)
+            res[f] = buf
+        out = res
         g = out.get
         self._ck(self.L.clb_get_particles(self.h, n, _p(ids_a, c_i64p), _p(g("pos"), c_f64p), _p(g("image"), c_i32p), _p(g("vel"), c_f64p),
                                           _p(g("force"), c_f64p), _p(g("type"), c_i32p), _p(g("state"), c_i32p), _p(g("mass"), c_f64p),
@@ -245,6 +252,10 @@ class Engine:
 
     def run(self, n):
         self._ck(self.L.clb_run(self.h, int(n)))
+
+    def run_continue(self, n):
+        """Next chunk of the same integrator.run(n): no run-entry force recalculation / heat-up (clb_run_continue)."""
+        self._ck(self.L.clb_run_continue(self.h, int(n)))
 
     def step(self):
         return int(self.L.clb_step(self.h))

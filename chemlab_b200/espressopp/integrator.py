@@ -72,7 +72,8 @@ class VelocityVerlet:
                 k = x._host_interval()
                 if k > 0:
                     chunk = min(chunk, k - (now % k))
-            e.run(chunk)
+            # one integrator.run of the reference = one run entry (force recalculation + heat-up), however many host actions
+            (e.run if done == 0 else e.run_continue)(chunk)
             done += chunk
             now += chunk
             for x in hosted:

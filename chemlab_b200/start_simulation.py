@@ -132,28 +132,33 @@ def _main(argv, rank, world):
     system.integrator = integrator
     part_prop = list(part_prop)
     mi = part_prop.index("mass")
-    masses = [p[mi] * mass_factor for p in particle_list]
-    has_vel = all(a.velocity is not None for a in conf.atoms.values())
-    if getattr(args, "gen_velocity", False) or not has_vel:    # :136-146
-        vx, vy, vz = espressopp.tools.velocities.gaussian(temperature, npart, masses, kb=1.0, seed=rng_seed)
+    # masses go to the engine UNSCALED, as in the reference (:168); mass_factor only enters the density print (:128) and the
+    # Maxwell-Boltzmann draw (:136-146).  The reaction post-processes later write the same unscaled topology masses.
+    density = sum(p[mi] for p in particle_list) * mass_factor / (box[0] * box[1] * box[2])
+    print("Density: %s kg/m^3\nBox: %s nm" % (density, list(box)))
+    if getattr(args, "gen_velocity", False):                    # :136-146
+        vx, vy, vz = espressopp.tools.velocities.gaussian(temperature, npart, [p[mi] * mass_factor for p in particle_list], kb=1.0, seed=rng_seed)
         vel = [espressopp.Real3D(a, b, c) for a, b, c in zip(vx, vy, vz)]
-        print("Generated Maxwell-Boltzmann velocities at T*kB = %s" % temperature)
-    else:
-        vel = [espressopp.Real3D(*conf.atoms[p[0]].velocity) for p in particle_list]
-    particle_list = [tuple(p[:mi]) + (m,) + tuple(p[mi + 1:]) + (v,) for p, m, v in zip(particle_list, masses, vel)]
-    part_prop.append("v")
+        print("Generating velocities from Maxwell-Boltzmann distribution T=%s (%s)" % (args.temperature, temperature))
+        particle_list = [tuple(p) + (v,) for p, v in zip(particle_list, vel)]
+        part_prop.append("v")
+    elif any(a.velocity is not None for a in conf.atoms.values()):
+        # gen_particle_list (gromacs_topology.py:1426) carries no 'v' property: the reference starts from zero velocities
+        print("Note: velocities in %s are not used (no gen_velocity): the run starts from zero velocities, as in the reference" % args.conf)
     system.storage.addParticles(particle_list, *part_prop)
     system.storage.decompose()
 
     # ---- exclusions + Verlet list (:174-197)
     if has_excl_file:
         exclusions = [tuple(int(x) for x in l.split()) for l in open(args.exclusion_list) if l.strip()]
-        print("Read exclusion list from %s (%d pairs)" % (args.exclusion_list, len(exclusions)))
-    else:
-        exclusions = sorted(gt.exclusions)
-        if rank == 0:
-            with open("exclusion_%s.list" % os.path.basename(args.top).split(".")[0], "w") as f:
-                f.writelines("%d %d\n" % p for p in exclusions)
+        print("Read exclusion list from %s (total: %d)" % (args.exclusion_list, len(exclusions)))
+        if len(exclusions) == 0 and gt.bonds and not getattr(args, "do_not_exclude_bonds", False):
+            raise RuntimeError("Exclusion list in %s is empty" % args.exclusion_list)
+        gt.exclusions = exclusions
+    exclusions = sorted(tuple(x) for x in gt.exclusions)
+    if exclusions and rank == 0:                                  # :182-187: rewritten whenever the list is non-empty
+        with open("exclusion_%s.list" % os.path.basename(args.top).split(".")[0], "w") as f:
+            f.write("\n".join("%d %d" % tuple(p) for p in exclusions))
     print("Excluded pairs from LJ interaction: %d" % len(exclusions))
     dynamic_exclude = espressopp.DynamicExcludeList(integrator, exclusions)
     verletlist = espressopp.VerletList(system, cutoff=max_cutoff, exclusionlist=dynamic_exclude)

@@ -1,5 +1,9 @@
 """Synthetic workloads of BASELINE.json `configs` (no dataset can be fetched here): seeded, vectorised."""
+import os
+
 import numpy as np
+
+DATA = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data")
 
 
 def lj_table(rmax=3.0, dr=0.002, eps=1.0, sig=1.0, rc=2.5):
@@ -47,6 +51,36 @@ def trimer_melt(n_side, rho=0.8442, seed=12345, jitter=0.08, kT=1.0, vel_seed=12
                 mass=np.ones(n), bonds=bonds, angles=angles, exclusions=excl)
 
 
+def replicated_melt(n_side, tile="melt_tile_20.npz"):
+    """The C2 melt as a periodic replication of an EQUILIBRATED 8000-bead tile ("a pre-equilibrated
+    replicated tile of a small box"; the tile was equilibrated for 30,000 steps by tests/golden/make_melt_tile.py).
+    n_side must be a multiple of the tile's 20 beads per edge: 100 -> 5x5x5 tiles = 1,000,000 beads
+    (320,000 A-L-A trimers + 40,000 free A monomers).  Same keys as trimer_melt()."""
+    d = np.load(os.path.join(DATA, tile))
+    ts = int(d["n_side"])
+    if n_side % ts:
+        raise ValueError("n_side must be a multiple of %d" % ts)
+    k = n_side // ts
+    nt = len(d["pos"])
+    tb = d["box"]
+    gz, gy, gx = np.meshgrid(np.arange(k), np.arange(k), np.arange(k), indexing="ij")
+    shift = np.stack([gx.ravel(), gy.ravel(), gz.ravel()], 1) * tb            # (k^3, 3)
+    nrep = len(shift)
+    pos = (d["pos"][None, :, :] + shift[:, None, :]).reshape(-1, 3)
+    vel = np.tile(d["vel"], (nrep, 1))
+    off = (np.arange(nrep, dtype=np.int64) * nt)
+
+    def rep(a):
+        a = np.asarray(a, np.int64)
+        return (a[None, :, :] + off[:, None, None]).reshape(-1, a.shape[1])
+    nres = int(d["resid"].max()) + 1
+    resid = (d["resid"][None, :].astype(np.int64) + (np.arange(nrep) * nres)[:, None]).reshape(-1).astype(np.int32)
+    n = nrep * nt
+    return dict(n=n, box=tb * k, pos=pos, vel=vel, type=np.tile(d["type"], nrep).astype(np.int32), state=np.tile(d["state"], nrep).astype(np.int32),
+                resid=resid, ids=np.arange(n, dtype=np.int64), mass=np.ones(n), bonds=rep(d["bonds"]), angles=rep(d["angles"]),
+                exclusions=rep(d["exclusions"]))
+
+
 def setup_reactive_melt(api, sysd, rc=2.5, dt=0.005, kT=1.0, gamma=1.0, interval=200, p_accept=0.05, reactions=True,
                         cutoff_react=1.2):
     """Wire config 2 onto any object with the Engine method names: tabulated LJ pairs, harmonic bonds K=30 r0=0.97, harmonic angle 180 deg K=1.25
@@ -67,7 +101,11 @@ def setup_reactive_melt(api, sysd, rc=2.5, dt=0.005, kT=1.0, gamma=1.0, interval
     api.set_exclusions(sysd["exclusions"])
     api.set_dt(dt)
     api.set_langevin(1, kT, gamma)
-    handles = dict(nb=nb, bonds=ib, angles=ia, react_bonds=irl, react_list=rl, bond_list=bl, angle_list=al)
+    handles = dict(nb=nb, bonds=ib, angles=ia, react_bonds=irl, react_list=rl, bond_list=bl, angle_list=al,
+                   # generic description used by bench.py (state hand-over, parity, observables)
+                   lists=dict(react=(rl, 2), bonds=(bl, 2), angles=(al, 3)),
+                   initial=dict(react=0, bonds=len(sysd["bonds"]), angles=len(sysd["angles"])),
+                   energies=dict(nb=nb, bonds=ib, angles=ia, react_bonds=irl), table_bytes=3 * len(r) * 8)
     if reactions:
         rate = p_accept / (dt * interval)
         api.reaction_general(0, interval, 1, 0)

@@ -165,6 +165,12 @@ int clb_set_langevin(clb_engine *e, int enabled, double kT, double gamma, int nt
                      const int32_t *types);
 /* integrator.run(n): src/start_simulation.py:780.  Synchronous. */
 int clb_run(clb_engine *e, int64_t nsteps);
+/* Continuation of the previous clb_run inside ONE integrator.run(n) of the reference: ExtAnalyze and
+ * ATRPActivator fire from signals inside VelocityVerlet::run (src/start_simulation.py:566-569, :780;
+ * src/chemlab/reaction_post_process.py:393-424), so the run-entry force recalculation and the thermostat
+ * heat-up happen once per integrator.run.  Falls back to clb_run when the last forces are not reusable
+ * (particles, lists, exclusions or potentials were changed by the caller in between). */
+int clb_run_continue(clb_engine *e, int64_t nsteps);
 int64_t clb_step(const clb_engine *e); /* integrator.step */
 /* force a decompose()+VerletList rebuild / a force evaluation now (storage.decompose(), :171,205,295) */
 int clb_decompose(clb_engine *e);

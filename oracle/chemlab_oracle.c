@@ -194,7 +194,7 @@ typedef struct orc_sim {
     orc_list *lists; int nlists;
     orc_bonded *bonded; int nbonded;
     /* integrator */
-    int64_t step; int forces_valid; int lists_valid;
+    int64_t step; int forces_valid; int lists_valid; int cont_ok;
     int lang_on; double kT, gamma; uint64_t seed; int lang_all; unsigned char lang_type[ORC_MAX_TYPES];
     /* reactions */
     int react_on, interval, nearest, max_per_interval;
@@ -252,6 +252,7 @@ int orc_max_threads(void) {
 }
 void orc_set_option(orc_sim *s, const char *name, double v) {
     if (!strcmp(name, "resort_criterion")) s->criterion = (int)v;
+    else if (!strcmp(name, "step")) s->step = (int64_t)v;   /* integrator.step: keys the thermostat and reaction draws */
 }
 /* storage.addParticles + decompose: fold into the box, keep image counters
  * (src/start_simulation.py:169-171) [EXT bc/OrthorhombicBC.cpp foldPosition] */
@@ -274,10 +275,10 @@ void orc_set_particles(orc_sim *s, const double *x, const double *v, const doubl
         if (type[i] + 1 > nt) nt = type[i] + 1;
     }
     if (nt > s->ntypes) s->ntypes = nt;
-    s->forces_valid = 0; s->lists_valid = 0;
+    s->forces_valid = 0; s->lists_valid = 0; s->cont_ok = 0;
 }
 void orc_set_positions(orc_sim *s, const double *x) {
-    memcpy(s->x, x, 3 * (size_t)s->n * 8); s->forces_valid = 0; s->lists_valid = 0;
+    memcpy(s->x, x, 3 * (size_t)s->n * 8); s->forces_valid = 0; s->lists_valid = 0; s->cont_ok = 0;
 }
 void orc_set_velocities(orc_sim *s, const double *v) { memcpy(s->v, v, 3 * (size_t)s->n * 8); }
 void orc_get(orc_sim *s, double *x, double *v, double *f, int *type, int *state, double *mass, int *image) {
@@ -297,7 +298,7 @@ void orc_modify(orc_sim *s, int i, int field, const double *val) {
         case 2: s->mass[i] = val[0]; break;
         case 3: s->q[i] = val[0]; break;
         case 4: s->resid[i] = (int)val[0]; break;
-        case 5: for (int d = 0; d < 3; ++d) s->x[3 * i + d] = val[d]; s->lists_valid = 0; break;
+        case 5: for (int d = 0; d < 3; ++d) s->x[3 * i + d] = val[d]; s->lists_valid = 0; s->cont_ok = 0; break;
         case 6: for (int d = 0; d < 3; ++d) s->v[3 * i + d] = val[d]; break;
     }
     s->forces_valid = 0;
@@ -329,7 +330,7 @@ static void excl_push(orc_sim *s, int a, int b) {
 void orc_set_exclusions(orc_sim *s, int64_t n, const int *pairs) {
     s->nexcl = 0;
     for (int64_t i = 0; i < n; ++i) if (pairs[2 * i] != pairs[2 * i + 1]) excl_push(s, pairs[2 * i], pairs[2 * i + 1]);
-    excl_finalize(s); s->lists_valid = 0;
+    excl_finalize(s); s->lists_valid = 0; s->cont_ok = 0;
 }
 int64_t orc_get_exclusions(orc_sim *s, int64_t cap, int *out) {
     for (int64_t i = 0; i < s->nexcl && i < cap; ++i) { out[2 * i] = (int)(s->excl[i] >> 32); out[2 * i + 1] = (int)(s->excl[i] & 0xffffffffu); }
@@ -363,11 +364,13 @@ int orc_table_eval(orc_sim *s, int tab, double x, double *e, double *f) { return
 int orc_add_interaction(orc_sim *s, int kind) { s->inter_kind[s->ninter] = kind; return s->ninter++; }
 static void grow_types(orc_sim *s, int t) { if (t + 1 > s->ntypes) s->ntypes = t + 1; }
 void orc_nb_set_tab(orc_sim *s, int inter, int t1, int t2, int tab, double rc) {
+    s->cont_ok = 0;
     orc_pairpot p; memset(&p, 0, sizeof(p)); p.kind = NB_TAB; p.inter = inter; p.tab1 = tab; p.rc2 = rc * rc;
     s->pp[t1][t2] = s->pp[t2][t1] = p; grow_types(s, t1); grow_types(s, t2); s->forces_valid = 0;
 }
 /* LennardJones(epsilon, sigma, cutoff, shift='auto'): gromacs_topology.py:715-721 [EXT LennardJones.hpp] */
 void orc_nb_set_lj(orc_sim *s, int inter, int t1, int t2, double eps, double sig, double rc, int shift_auto) {
+    s->cont_ok = 0;
     orc_pairpot p; memset(&p, 0, sizeof(p)); p.kind = NB_LJ; p.inter = inter; p.eps = eps; p.sig = sig; p.rc2 = rc * rc;
     double sr6 = pow(sig / rc, 6);
     p.shift = shift_auto ? 4 * eps * (sr6 * sr6 - sr6) : 0.0;
@@ -375,6 +378,7 @@ void orc_nb_set_lj(orc_sim *s, int inter, int t1, int t2, double eps, double sig
 }
 void orc_nb_set_mixed(orc_sim *s, int inter, int t1, int t2, int tab1, int tab2, double mix, int conv_type,
                       double conv_total, double rc) {
+    s->cont_ok = 0;
     orc_pairpot p; memset(&p, 0, sizeof(p)); p.kind = NB_MIX; p.inter = inter; p.tab1 = tab1; p.tab2 = tab2;
     p.mix = mix; p.conv_type = conv_type; p.conv_total = conv_total; p.rc2 = rc * rc;
     s->pp[t1][t2] = s->pp[t2][t1] = p; grow_types(s, t1); grow_types(s, t2); s->forces_valid = 0;
@@ -414,6 +418,7 @@ static void mol_union(orc_sim *s, int a, int b) {
     if (ra < rb) s->mol[rb] = ra; else s->mol[ra] = rb; /* representative = smallest index */
 }
 void orc_list_add(orc_sim *s, int list, int64_t n, const int *ids) {
+    s->cont_ok = 0;
     int ar = s->lists[list].arity;
     for (int64_t i = 0; i < n; ++i) {
         list_push(s, list, ids + i * ar);
@@ -438,6 +443,7 @@ int orc_add_bonded(orc_sim *s, int list, int typed) {
 static orc_bonded *bonded_by_inter(orc_sim *s, int inter) { for (int i = 0; i < s->nbonded; ++i) if (s->bonded[i].inter == inter) return &s->bonded[i]; return NULL; }
 void orc_bonded_set_potential(orc_sim *s, int inter, int t1, int t2, int t3, int t4, int kind, const double *params,
                               int np, int table) {
+    s->cont_ok = 0;
     orc_bonded *b = bonded_by_inter(s, inter);
     orc_bpot p; memset(&p, 0, sizeof(p)); p.kind = kind; p.table = table;
     for (int i = 0; i < np && i < 6; ++i) p.p[i] = params[i];
@@ -561,6 +567,14 @@ int64_t orc_get_pairs(orc_sim *s, int64_t cap, int *out) {
     int64_t m = s->npairs < cap ? s->npairs : cap;
     memcpy(out, s->pairs, m * 8);
     qsort(out, m, 8, cmp_pair);
+    return s->npairs;
+}
+
+/* the same pair set in list order (unsorted; rows are (min id, max id)): large systems are sorted by the caller (numpy) */
+int64_t orc_get_pairs_raw(orc_sim *s, int64_t cap, int *out) {
+    if (!s->lists_valid) orc_rebuild(s);
+    int64_t m = s->npairs < cap ? s->npairs : cap;
+    if (out) memcpy(out, s->pairs, m * 8);
     return s->npairs;
 }
 
@@ -799,11 +813,15 @@ static void fold(orc_sim *s) {
     }
 }
 void orc_react(orc_sim *s);
-void orc_run(orc_sim *s, int64_t nsteps) {
-    /* run entry: resort if flagged, recompute forces with the thermostat heat-up factor sqrt(3) */
-    if (!s->lists_valid) { fold(s); orc_rebuild(s); }
-    orc_compute_forces(s);
-    thermalize(s, STREAM_HEATUP, (uint64_t)s->step, sqrt(3.0));
+static void run_impl(orc_sim *s, int64_t nsteps, int cont) {
+    /* run entry: resort if flagged, recompute forces with the thermostat heat-up factor sqrt(3).
+     * cont: continuation inside one integrator.run of the reference (ExtAnalyze / ATRPActivator fire from signals inside
+     * VelocityVerlet::run [EXT]): the forces of the last step are still in place, runInit/recalc are not repeated. */
+    if (!cont) {
+        if (!s->lists_valid) { fold(s); orc_rebuild(s); }
+        orc_compute_forces(s);
+        thermalize(s, STREAM_HEATUP, (uint64_t)s->step, sqrt(3.0));
+    }
     double dt = s->dt;
     for (int64_t it = 0; it < nsteps; ++it) {
         double maxsq = 0;
@@ -839,7 +857,10 @@ void orc_run(orc_sim *s, int64_t nsteps) {
         }
     }
     s->step += nsteps;
+    s->cont_ok = 1;
 }
+void orc_run(orc_sim *s, int64_t nsteps) { run_impl(s, nsteps, 0); }
+void orc_run_continue(orc_sim *s, int64_t nsteps) { run_impl(s, nsteps, s->cont_ok); }
 int64_t orc_step(orc_sim *s) { return s->step; }
 int64_t orc_nrebuild(orc_sim *s) { return s->nrebuild; }
 int64_t orc_npairs(orc_sim *s) { return s->npairs; }

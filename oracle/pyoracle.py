@@ -37,7 +37,7 @@ def lib():
         L = C.CDLL(_SO)
         L.orc_create.restype = C.c_void_p
         L.orc_create.argtypes = [C.c_int, C.POINTER(C.c_double), C.c_double, C.c_double, C.c_uint64]
-        for name in ("orc_list_size", "orc_pairs_brute", "orc_get_pairs", "orc_list_get", "orc_step",
+        for name in ("orc_list_size", "orc_pairs_brute", "orc_get_pairs", "orc_get_pairs_raw", "orc_list_get", "orc_step",
                      "orc_nrebuild", "orc_npairs", "orc_count_interacting", "orc_reaction_counter",
                      "orc_last_events", "orc_get_candidates", "orc_count_type", "orc_get_exclusions"):
             getattr(L, name).restype = C.c_int64
@@ -188,6 +188,13 @@ class Oracle:
         self.L.orc_get_pairs(self.h, C.c_int64(n), _p(out, C.c_int))
         return out
 
+    def pairs_raw(self):
+        """Pair set in list order (rows (min, max), unsorted)."""
+        n = self.L.orc_get_pairs_raw(self.h, C.c_int64(0), None)
+        out = np.zeros((n, 2), np.int32)
+        self.L.orc_get_pairs_raw(self.h, C.c_int64(n), _p(out, C.c_int))
+        return out
+
     def pairs_brute(self):
         n = self.L.orc_pairs_brute(self.h, C.c_int64(0), None)
         out = np.zeros((n, 2), np.int32)
@@ -224,6 +231,9 @@ class Oracle:
 
     def run(self, n):
         self.L.orc_run(self.h, C.c_int64(n))
+
+    def run_continue(self, n):
+        self.L.orc_run_continue(self.h, C.c_int64(n))
 
     def step(self):
         return int(self.L.orc_step(self.h))
