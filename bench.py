@@ -118,6 +118,10 @@ class WorkloadC2:
             return synthetic.replicated_melt(self.n_side)
         return synthetic.trimer_melt(self.n_side, rho=RHO, seed=12345, kT=KT)
 
+    @property
+    def n(self):
+        return self.n_side ** 3
+
     def setup(self, api, sysd):
         from chemlab_b200 import synthetic
         return synthetic.setup_reactive_melt(api, sysd, rc=RC, dt=DT, kT=KT, gamma=GAMMA, interval=INTERVAL, p_accept=P_ACCEPT)
@@ -136,7 +140,7 @@ def make_workload(a):
     if a.workload == "c2":
         return WorkloadC2(a.n_side)
     from chemlab_b200 import synthetic
-    return synthetic.make_workload(a.workload, a.scale)
+    return synthetic.make_workload(a.workload, a.scale, example_root=os.path.join(ROOT, "tests", "golden"))
 
 
 # ------------------------------------------------------------------------------------------------ state hand-over
@@ -151,7 +155,7 @@ def snapshot(e, sysd, h, pinned=False):
     s["step"] = e.step()
     if pinned:
         import torch
-        for k in ("pos", "vel", "mass", "type", "state", "resid", "ids"):
+        for k in ("pos", "vel", "mass", "type", "state", "resid", "ids") + (("q",) if "q" in s else ()):
             t = torch.from_numpy(np.ascontiguousarray(s[k])).pin_memory()
             s[k] = t.numpy(); s.setdefault("_keep", []).append(t)
     return s
@@ -166,11 +170,16 @@ def restore_into(api, s, h):
     api.set_exclusions(s["excl_now"])
 
 
+def upload(api, s):
+    api.set_particles(s["ids"], s["type"], s["pos"], s["mass"], vel=s["vel"], q=s.get("q"), state=s["state"], res_id=s["resid"])
+
+
 def oracle_from(wl, s, threads):
-    from oracle import pyoracle
-    o = pyoracle.Oracle(s["n"], s["box"], wl.rc, wl.skin, seed=SEED)
+    """The CPU oracle (through its Engine-shaped adapter) holding state s with the workload's force field and lists."""
+    from oracle.engine_adapter import OracleEngine
+    o = OracleEngine(s["box"], wl.rc, wl.skin, seed=SEED)
+    upload(o, s)
     o.set_threads(threads)
-    o.set_particles(s["pos"], s["vel"], s["mass"], None, s["type"], s["state"], s["resid"])
     h = wl.setup(o, s)
     restore_into(o, s, h)
     o.set_option("step", s.get("step", 0))
@@ -235,7 +244,7 @@ def parity_block(e, wl, sysd, h, rank, threads, do_reaction=True):
         ke = (pe[:, 0].astype(np.uint64) << np.uint64(32)) | pe[:, 1].astype(np.uint64)
         pairs_equal = bool(len(ko) == len(ke) and np.array_equal(ko, ke))
         o.compute_forces()
-        fo = o.get()["force"]
+        fo = o.get_particles(fields=("force",))["force"]
         en_o = {k: o.energy(v) for k, v in ho["energies"].items()}
         e_err = max(abs(en_e[k] - en_o[k]) / max(abs(en_o[k]), 1e-300) for k in en_o if en_o[k] != 0.0 or en_e[k] != 0.0) if en_o else 0.0
         out = {"state": "benchmarked state after the timed steps (%d beads, step %d)" % (snap["n"], snap["step"]),
@@ -253,7 +262,7 @@ def parity_block(e, wl, sysd, h, rank, threads, do_reaction=True):
         if rank == 0:
             o.reaction_general(1, wl.interval, 1 if wl.nearest else 0, 0)
             nev_o = o.react()
-            so = o.get()
+            so = o.get_particles(fields=("type", "state", "mass"))
 
             def canon(a):
                 a = np.asarray(a, np.int64)
@@ -344,7 +353,7 @@ def main():
             e_.join()          # one engine per rank = one slab; torch.distributed only carries the NCCL id
         return e_
     e = new_engine()
-    e.set_particles(sysd["ids"], sysd["type"], sysd["pos"], sysd["mass"], vel=sysd["vel"], state=sysd["state"], res_id=sysd["resid"])
+    upload(e, sysd)
     h = wl.setup(e, sysd)
 
     def barrier():
@@ -394,7 +403,8 @@ def main():
     _, cn2 = e.timers()
     interacting = cn2["interacting_pairs"]
     kin = e.kinetics()
-    nbonds_new = e.list_size(h["react_list"]) - h["initial"].get("react", 0) if "react_list" in h else 0
+    rl_names = [k for k, (v, ar) in h["lists"].items() if v in h.get("react_lists", [h.get("react_list")])]
+    nbonds_new = sum(e.list_size(h["lists"][k][0]) - h["initial"].get(k, 0) for k in rl_names)
 
     # parity on the benchmarked state (+ one reaction pass on both sides, which is also the timed reaction pass)
     parity, t_react = (None, None)
@@ -457,7 +467,7 @@ def main():
                   (("pos", (n, 3), torch.float64), ("vel", (n, 3), torch.float64), ("image", (n, 3), torch.int32), ("type", (n,), torch.int32), ("state", (n,), torch.int32))}
         barrier()
         t0 = time.perf_counter()
-        e2.set_particles(snap["ids"], snap["type"], snap["pos"], snap["mass"], vel=snap["vel"], state=snap["state"], res_id=snap["resid"])
+        upload(e2, snap)
         t_a = time.perf_counter() - t0
         h2 = wl.setup(e2, snap)
         t_b = time.perf_counter() - t0
@@ -496,7 +506,7 @@ def main():
             tt = torch.tensor([t_e2e, t_steady], dtype=torch.float64, device="cuda")
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             t_e2e, t_steady = float(tt[0]), float(tt[1])
-        nlist = sum(v.size for v in snap["lists_now"].values()) + sum(np.asarray(sysd[k]).size for k in ("bonds", "angles") if k in sysd)
+        nlist = sum(v.size for v in snap["lists_now"].values())
         h2d = n * (8 + 4 + 24 + 24 + 8 + 4 + 4) + nlist * 8 + snap["excl_now"].size * 8 + h2.get("table_bytes", 3 * 1500 * 8)
         d2h = n * (24 + 24 + 4 + 4 + 12) + nobs * (1 + len(h2["energies"])) * 8
         if rank == 0:

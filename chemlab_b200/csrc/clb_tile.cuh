@@ -696,6 +696,179 @@ __global__ void __launch_bounds__(1024) k_pair_forces_tab2(ClbGrid g, ClbPairArg
 }
 
 // ------------------------------------------------------------------------------------------
+// Fourth generation (round 2): the all-tabulated kernel for MANY tables.  Same arithmetic as k_pair_forces_tab2 (bit-identical
+// forces), different table storage:
+//   * WINDOWS: a pair only ever reads the rows between the repulsive wall it cannot climb (U - U_min > 30 kT, chosen by the host
+//     from the energy column) and its cutoff -- about 600 of 1750 rows for the shipped chemlab tables.  Only that window of each
+//     type pair's table lives in shared memory, hottest pairs (by type population) first, until the budget is used; rows outside
+//     a window and tables without a window are read from global memory (L2) on a rare, divergent path.  28 tables x 1750 rows
+//     (784 KB) do not fit an SM; their hot windows (74 % of the pair work in 70 KB for rim135) do.
+//   * REPLICATION (RLOG = 3): 8 interleaved copies of the windows, lane l reads copy l & 7, so the 8 lanes of a quarter warp
+//     hit 8 different 16-byte bank groups: the random row gather becomes conflict-free (single-table systems, where it fits).
+//   * the row gather is PREDICATED on the cutoff test: lanes outside the cutoff do not take part in the gather (fewer bank
+//     conflicts), instead of gathering a clamped row and discarding the result.
+//   * tables may differ in length (common x0 and dx only): the range check uses the pair's own row count on the global path.
+struct ClbPairDesc3 {          // 16 bytes per type pair
+    double rc2;                // cutoff^2 in lattice^2; < 0: no potential
+    int soff;                  // shared-memory row of this pair's table row 0, (window start row - w0) << RLOG; unused when wn == 0
+    unsigned short w0, wn;     // first row and number of rows of the shared-memory window (wn == 0: global memory only)
+};
+struct ClbPairArgs3 {
+    const int* cell_start; const int4* pos; const unsigned short* entries; const int* nl_count;
+    const ClbPairDesc3* pd3;   // [ntypes^2]
+    const int2* gmeta;         // [ntypes^2] {first row of the pair's table in trows, rows - 1}
+    const double2* trows;      // {A_i, B_i} rows of all tables, lattice units (global memory)
+    const double2* swin;       // shared-memory image of the windows: nsrows << RLOG rows, copied in at kernel start
+    double* force; ClbCtl* ctl;
+    int cap, ntypes, nsrows, fstride, npw;
+    double invdx, cmagic;
+    ClbPairDesc3 one; int2 one_g;  // ONEPD: the only descriptor
+    int b0, seg0, b1, nidx;
+    int nv, vc_bytes;
+};
+// Rare path of k_pair_forces_tab3: the listed pairs of one 8-entry batch whose table row is NOT in a shared-memory window
+// (bit k of `defer`) are evaluated again from scratch with the row read from global memory.  Kept out of line so that its
+// registers do not burden the hot loop.
+__device__ __noinline__ void pair_tab3_slow(unsigned defer, uint4 cur, unsigned pix, unsigned piy, unsigned piz, const int4* s_pos,
+                                            const int2* __restrict__ gmeta_row, int2 one_g, bool onepd, const double2* __restrict__ trows,
+                                            double invdx, double cmagic, double* acc, unsigned* err) {
+    const unsigned wds[4] = {cur.x, cur.y, cur.z, cur.w};
+    while (defer) {
+        const int k = __ffs(defer) - 1;
+        defer &= defer - 1;
+        const unsigned w = wds[k >> 1];
+        const unsigned e = (k & 1) ? (w >> 16) : (w & 0xffffu);
+        const int4 pj = s_pos[e];
+        const double dx = __hiloint2double(0x43300000, (int)(pix - (unsigned)pj.x)) - 4503601774854144.0;
+        const double dy = __hiloint2double(0x43300000, (int)(piy - (unsigned)pj.y)) - 4503601774854144.0;
+        const double dz = __hiloint2double(0x43300000, (int)(piz - (unsigned)pj.z)) - 4503601774854144.0;
+        const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
+        double y0, yh;
+        rsqrt_seed2(r2, y0, yh);
+        const double h = r2 * y0, ee = fma(-h, yh, 0.5);
+        const double y = fma(y0, ee, y0), r = fma(h, ee, h);
+        const unsigned ix = (unsigned)__double2loint(__fma_rd(r, invdx, cmagic));
+        const int2 gm = onepd ? one_g : __ldg(gmeta_row + pw_type(pj.w));
+        if (ix > (unsigned)gm.y) *err |= CLB_EF_TABLE_RANGE;          // fatal in the reference (U12)
+        const double2 rw = __ldg(trows + gm.x + (int)min(ix, (unsigned)gm.y));
+        const double F = fma(r, rw.y, rw.x) * y;
+        acc[0] = fma(F, dx, acc[0]); acc[1] = fma(F, dy, acc[1]); acc[2] = fma(F, dz, acc[2]);
+    }
+}
+template <bool ONEPD, int RLOG, int NI>
+__global__ void __launch_bounds__(1024) k_pair_forces_tab3(ClbGrid g, ClbPairArgs3 A) {
+    if (*(volatile int*)&A.ctl->stall) return;
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int ntp = A.ntypes * A.ntypes;
+    ClbPairDesc3* s_pd = reinterpret_cast<ClbPairDesc3*>(smem);
+    double2* s_rows = reinterpret_cast<double2*>(s_pd + (ONEPD ? 0 : ntp));
+    unsigned char* vc_base = reinterpret_cast<unsigned char*>(s_rows + ((size_t)A.nsrows << RLOG));
+    const int nth = A.npw * 32;
+    const int vc = threadIdx.x / nth, tid = threadIdx.x - vc * nth;
+    const int bar = 1 + vc;
+    int* s_off = reinterpret_cast<int*>(vc_base + (size_t)vc * A.vc_bytes);
+    int* s_src = s_off + (CLB_TILE_CELLS + 4);
+    int4* s_pos = reinterpret_cast<int4*>(s_src + CLB_TILE_CELLS);
+    if (!ONEPD) for (int i = threadIdx.x; i < ntp; i += blockDim.x) s_pd[i] = A.pd3[i];
+    for (int i = threadIdx.x; i < (A.nsrows << RLOG); i += blockDim.x) s_rows[i] = __ldg(A.swin + i);
+    __syncthreads();
+    const int lane = tid & 31, warp = tid >> 5;
+    const double2* s_rows_rep = s_rows + (lane & ((1 << RLOG) - 1));     // this lane's copy of the replicated windows
+    const int nhpass = nth;
+    const double invdx = A.invdx, cmagic = A.cmagic;
+    unsigned err = 0;
+    for (int idx = vc * gridDim.x + blockIdx.x; idx < A.nidx; idx += gridDim.x * A.nv) {
+        const int b = idx < A.seg0 ? A.b0 + idx : A.b1 + (idx - A.seg0);
+        TileCtx t;
+        tile_geometry(g, b, t);
+        vc_sync(bar, nth);
+        tile_offsets_vc(g, t, A.cell_start, s_off, s_src, tid, nth, bar);
+        tile_stage_vc(t, s_off, s_src, A.pos, s_pos, tid, nth);
+        vc_sync(bar, nth);
+        for (int p0 = 0; p0 < t.nh; p0 += nhpass) {
+            const int p = p0 + warp * 32 + lane;
+            const bool act = p < t.nh;
+            const int gi = t.hs + (act ? p : 0);
+            const int4 pi = __ldg(A.pos + gi);
+            const unsigned pix = (unsigned)pi.x + 0x80000000u, piy = (unsigned)pi.y + 0x80000000u, piz = (unsigned)pi.z + 0x80000000u;
+            const int cnt = act ? __ldg(A.nl_count + gi) : 0;
+            const int trow = pw_type(pi.w) * A.ntypes;
+            const uint4* row = reinterpret_cast<const uint4*>(A.entries + (size_t)gi * A.cap);
+            const int nb = (cnt + 7) >> 3;
+            double ax = 0.0, ay = 0.0, az = 0.0;
+            uint4 ev = make_uint4(0, 0, 0, 0);
+            if (nb > 0) ev = __ldg(row);
+#pragma unroll 1
+            for (int bi = 0; bi < nb; ++bi) {
+                const uint4 cur = ev;
+                if (bi + 1 < nb) ev = __ldg(row + bi + 1);
+                const int ne = cnt - bi * 8;
+                const unsigned wds[4] = {cur.x, cur.y, cur.z, cur.w};
+                unsigned defer = 0;
+#pragma unroll
+                for (int s0 = 0; s0 < 8; s0 += NI) {
+                    bool in[NI];
+                    int4 pj[NI];
+                    double dx[NI], dy[NI], dz[NI], r2[NI], y0[NI], yh[NI], y[NI], r[NI], F[NI];
+                    ClbPairDesc3 d[NI];
+                    double2 rw[NI];
+#pragma unroll
+                    for (int q = 0; q < NI; ++q) {
+                        const int k = s0 + q;
+                        unsigned e = (k & 1) ? (wds[k >> 1] >> 16) : (wds[k >> 1] & 0xffffu);
+                        in[q] = k < ne;
+                        e = in[q] ? e : 0u;
+                        pj[q] = s_pos[e];
+                    }
+#pragma unroll
+                    for (int q = 0; q < NI; ++q) {
+                        dx[q] = __hiloint2double(0x43300000, (int)(pix - (unsigned)pj[q].x)) - 4503601774854144.0;
+                        dy[q] = __hiloint2double(0x43300000, (int)(piy - (unsigned)pj[q].y)) - 4503601774854144.0;
+                        dz[q] = __hiloint2double(0x43300000, (int)(piz - (unsigned)pj[q].z)) - 4503601774854144.0;
+                        if (ONEPD) d[q] = A.one;
+                        else d[q] = s_pd[trow + pw_type(pj[q].w)];
+                    }
+#pragma unroll
+                    for (int q = 0; q < NI; ++q) r2[q] = fma(dz[q], dz[q], fma(dy[q], dy[q], dx[q] * dx[q]));
+#pragma unroll
+                    for (int q = 0; q < NI; ++q) { in[q] = in[q] && (r2[q] <= d[q].rc2); rsqrt_seed2(r2[q], y0[q], yh[q]); }
+#pragma unroll
+                    for (int q = 0; q < NI; ++q) {
+                        const double h = r2[q] * y0[q];
+                        const double ee = fma(-h, yh[q], 0.5);
+                        y[q] = fma(y0[q], ee, y0[q]);             // 1/r
+                        r[q] = fma(h, ee, h);                     // r
+                    }
+#pragma unroll
+                    for (int q = 0; q < NI; ++q) {
+                        const double ti = __fma_rd(r[q], invdx, cmagic);    // low word = floor((r - x0)/dx) exactly
+                        const unsigned ix = (unsigned)__double2loint(ti);
+                        const bool inw = in[q] && (ix - (unsigned)d[q].w0) < (unsigned)d[q].wn;
+                        rw[q] = make_double2(0.0, 0.0);
+                        if (inw) rw[q] = s_rows_rep[d[q].soff + (int)(ix << RLOG)];     // predicated gather: lanes beyond the cutoff stay out
+                        else if (in[q]) defer |= 1u << (s0 + q);                              // row outside the window: out-of-line path below
+                    }
+#pragma unroll
+                    for (int q = 0; q < NI; ++q) {
+                        F[q] = fma(r[q], rw[q].y, rw[q].x) * y[q];
+                        F[q] = in[q] ? F[q] : 0.0;
+                    }
+#pragma unroll
+                    for (int q = 0; q < NI; ++q) { ax = fma(F[q], dx[q], ax); ay = fma(F[q], dy[q], ay); az = fma(F[q], dz[q], az); }
+                }
+                if (defer) {
+                    double acc[3] = {ax, ay, az};
+                    pair_tab3_slow(defer, cur, pix, piy, piz, s_pos, A.gmeta + trow, A.one_g, ONEPD, A.trows, invdx, cmagic, acc, &err);
+                    ax = acc[0]; ay = acc[1]; az = acc[2];
+                }
+            }
+            if (act) { A.force[gi] = ax; A.force[gi + A.fstride] = ay; A.force[gi + 2 * A.fstride] = az; }
+        }
+    }
+    if (err) atomicOr(&A.ctl->err, err);
+}
+
+// ------------------------------------------------------------------------------------------
 // Pair energy of one interaction handle (analysis.PotentialEnergy): fp64 throughout, each pair
 // visited twice (full list) -> factor 1/2.  Per-block partial sums are reduced in a fixed order
 // by k_sum_partials, so the result is bit-reproducible.

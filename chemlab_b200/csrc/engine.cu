@@ -77,6 +77,13 @@ static PairKernel2 pair_kernel_tab2(int smem, int onepd, int ni) {
     if (smem) return onepd ? k_pair_forces_tab2<true, true, 2> : k_pair_forces_tab2<true, false, 2>;
     return onepd ? k_pair_forces_tab2<false, true, 2> : k_pair_forces_tab2<false, false, 2>;
 }
+typedef void (*PairKernel3)(ClbGrid, ClbPairArgs3);
+static PairKernel3 pair_kernel_tab3(int onepd, int rlog, int ni) {
+    if (ni >= 4) { if (rlog) return onepd ? k_pair_forces_tab3<true, 3, 4> : k_pair_forces_tab3<false, 3, 4>;
+                   return onepd ? k_pair_forces_tab3<true, 0, 4> : k_pair_forces_tab3<false, 0, 4>; }
+    if (rlog) return onepd ? k_pair_forces_tab3<true, 3, 2> : k_pair_forces_tab3<false, 3, 2>;
+    return onepd ? k_pair_forces_tab3<true, 0, 2> : k_pair_forces_tab3<false, 0, 2>;
+}
 static PairKernel pair_kernel(int cubic, int smem, int ugrid, int split) {
     if (cubic) { if (smem) return ugrid ? pair_kernel_split<true, true, true>(split) : pair_kernel_split<true, true, false>(split);
                  return ugrid ? pair_kernel_split<true, false, true>(split) : pair_kernel_split<true, false, false>(split); }
@@ -154,6 +161,10 @@ extern "C" int clb_create(clb_engine** out, int device, const double box[3], dou
         cudaFuncSetAttribute(pair_kernel_tab2(sm, op, ni), cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
         cudaFuncSetAttribute(pair_kernel_tab2(sm, op, ni), cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     }
+    for (int op = 0; op < 2; ++op) for (int rl = 0; rl <= 3; rl += 3) for (int ni = 2; ni <= 4; ni += 2) {
+        cudaFuncSetAttribute(pair_kernel_tab3(op, rl, ni), cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+        cudaFuncSetAttribute(pair_kernel_tab3(op, rl, ni), cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    }
     cudaFuncSetAttribute(k_pair_energy<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
     cudaFuncSetAttribute(k_pair_energy<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
     cudaFuncSetAttribute(k_decode_pairs, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
@@ -186,7 +197,7 @@ extern "C" int clb_set_option(clb_engine* e, const char* name, double v) {
     std::string s(name);
     if (s == "resort_criterion") e->criterion = (int)v;
     else if (s == "step") e->step = (int64_t)v;               // integrator.step (restart): keys the thermostat and reaction draws
-    else if (s == "block_cells") { e->set_block_cells((int)v); e->lists_valid = false; }
+    else if (s == "block_cells") { e->set_block_cells((int)v); e->bx_user = (int)v > 0; e->lists_valid = false; }
     else if (s == "list_capacity") { e->nl_cap_user = (int)v; e->lists_valid = false; }
     else if (s == "fuse_integrator") e->fuse = (int)v;
     else if (s == "sync_chunk") e->chunk_user = (int)v;
@@ -201,6 +212,8 @@ extern "C" int clb_set_option(clb_engine* e, const char* name, double v) {
     else if (s == "pair_kernel") { e->pair_kernel_user = (int)v; if (e->lists_valid) return e->configure_pair_launch(); }
     else if (s == "pair_nv") { e->pair_nv_user = (int)v; if (e->lists_valid) return e->configure_pair_launch(); }
     else if (s == "pair_ni") { e->pair_ni = (int)v >= 4 ? 4 : 2; if (e->lists_valid) return e->configure_pair_launch(); }
+    else if (s == "pair_rep") { e->pair_rep_user = (int)v; e->t3_dirty = true; if (e->lists_valid) return e->configure_pair_launch(); }
+    else if (s == "pair_table_kb") { e->pair_table_kb_user = (int)v; e->t3_dirty = true; if (e->lists_valid) return e->configure_pair_launch(); }
     else if (s == "pair_branchfree") { e->branchfree_user = (int)v; if (e->lists_valid) return e->configure_pair_launch(); }
     else return e->fail(CLB_ERR_ARG, "unknown option %s", name);
     return CLB_OK;
@@ -229,6 +242,10 @@ extern "C" int clb_get_option(clb_engine* e, const char* name, double* v) {
     else if (s == "pair_smem") *v = e->pair_smem;
     else if (s == "tables_in_smem") *v = e->tabs_smem;
     else if (s == "pair_kernel_ms") *v = e->pair_ms;
+    else if (s == "pair_rep") *v = 1 << e->tab3_rlog;
+    else if (s == "pair_table_rows") *v = e->tab3_nsrows;
+    else if (s == "pair_tables_resident") *v = e->tab3_resident;
+    else if (s == "pair_tables_resident_weight") *v = e->tab3_resident_weight;
     else if (s == "pair_kernel_launches") *v = (double)e->pair_launches;
     else return e->fail(CLB_ERR_ARG, "unknown option %s", name);
     return CLB_OK;
@@ -327,6 +344,8 @@ extern "C" int clb_set_particles(clb_engine* e, int64_t n, const int64_t* id, co
         }
     }
     e->n = (int)n;
+    ClbTrace tr(e->stream, "set_particles");
+    tr.mark("ids");
     // per-slot arrays are full size on every rank
     CK(e->id2idx.ensure(n)); CK(e->image.ensure(3 * (size_t)n)); CK(e->resid.ensure(n)); CK(e->charge.ensure(n)); CK(e->mol.ensure(n)); CK(e->wslot.ensure(n));
     const size_t N = (size_t)n;
@@ -338,6 +357,7 @@ extern "C" int clb_set_particles(clb_engine* e, int64_t n, const int64_t* id, co
     int4* d_P = sc.take<int4>(N); ClbVel* d_V = sc.take<ClbVel>(N); int* d_sel = sc.take<int>(N); unsigned char* d_flag = sc.take<unsigned char>(N);
     int* d_flags = sc.take<int>(4);
     cudaStream_t st = e->stream;
+    tr.mark("alloc_stage");
     CK(cudaMemcpyAsync(d_pos, pos, 24 * N, cudaMemcpyHostToDevice, st));
     if (vel) CK(cudaMemcpyAsync(d_vel, vel, 24 * N, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(d_mass, mass, 8 * N, cudaMemcpyHostToDevice, st));
@@ -351,7 +371,9 @@ extern "C" int clb_set_particles(clb_engine* e, int64_t n, const int64_t* id, co
     ClbIngestArgs A; A.pos = d_pos; A.vel = d_vel; A.mass = d_mass; A.q = d_q; A.type = d_type; A.state = d_state; A.resid = d_res; A.order = d_order;
     for (int d = 0; d < 3; ++d) A.box[d] = e->box[d];
     const bool multi = e->nranks > 1;
+    tr.mark("h2d");
     if (!multi) TRY(e->alloc_particles(e->n));
+    tr.mark("alloc_particles");
     // single rank: the ingest kernel writes the particle arrays directly (slot order = initial order)
     k_ingest<<<ceil_div(n, 256), 256, 0, st>>>((int)n, A, multi ? d_P : e->pos.p, multi ? d_V : e->vel.p, e->image.p, e->resid.p, e->charge.p, e->wslot.p, d_flags);
     int64_t nloc = n;
@@ -382,6 +404,7 @@ extern "C" int clb_set_particles(clb_engine* e, int64_t n, const int64_t* id, co
     CK(cudaMemsetAsync(e->force.p, 0, 3 * (size_t)e->ncap * sizeof(double), st));
     CK(cudaStreamSynchronize(st));
     CK(cudaGetLastError());
+    tr.mark("ingest");
     e->nstored = (int)nloc; e->own0 = 0; e->own1 = (int)nloc;
     e->lists_valid = false; e->forces_valid = false; e->cont_ok = false; e->excl_dirty = true; e->terms_dirty = true; e->topo_dirty = true;
     return CLB_OK;
@@ -905,6 +928,58 @@ int clb_engine::upload_potentials() {
             tab2_one_rc2 = pd[0].rc2; tab2_one_off = pd[0].tab;
         }
     }
+    // fourth-generation kernel (k_pair_forces_tab3): cubic box, every pair tabulated, ONE (x0, dx) for all tables (lengths may
+    // differ); rows {A_i, B_i} as for tab2, windows chosen in configure_tables()
+    tab3_ok = 0;
+    {
+        bool same_grid = !tm.empty() && geo.cubic && all_tab;
+        for (size_t k = 1; k < tm.size() && same_grid; ++k) same_grid = tm[k].x0 == tm[0].x0 && tm[k].dx == tm[0].dx;
+        const double k0 = same_grid ? tm[0].x0 / tm[0].dx : 0.5;
+        if (same_grid && fabs(k0 - rint(k0)) < 1e-9 && rint(k0) < 1e6) {
+            const double q = geo.q[0];
+            t3_rows.assign(frows.size(), make_double2(0.0, 0.0));
+            t3_slots.clear();
+            for (size_t k = 0; k < tm.size(); ++k) {
+                const ClbTabMeta& m = tm[k];
+                if (m.n > 65000) { same_grid = false; break; }
+                double emin = 1e300;
+                for (int i = 0; i < m.n; ++i) {
+                    const double2 fr = frows[m.off + i];               // {f_i + df_i/2, df_i}
+                    const double fi = fr.x - 0.5 * fr.y, sl = fr.y / m.dx, xi = m.x0 + i * m.dx;
+                    t3_rows[m.off + i] = make_double2(fi - xi * sl, q * sl);
+                    emin = std::min(emin, erows[m.off + i].x);
+                }
+                // lower window edge: the first row a pair can reach thermally (U - U_min < 30 kT); without a thermostat: row 0
+                int w0 = 0;
+                if (lang_on && kT > 0) { while (w0 < m.n - 1 && erows[m.off + w0].x - emin > 30.0 * kT) ++w0; w0 = std::max(0, w0 - 2); }
+                clb_engine::T3Slot sl3 = {m.off, m.n, w0, m.n, 0.0, -1};
+                t3_slots.push_back(sl3);
+            }
+            if (same_grid) {
+                t3_pair_slot.assign(pd.size(), -1); t3_pair_rc2.assign(pd.size(), -1.0);
+                std::vector<double> rcmax(tm.size(), 0.0);
+                for (int a = 0; a < nt; ++a) for (int b = 0; b < nt; ++b) {
+                    const size_t k = (size_t)a * nt + b;
+                    if (!pd[k].kind) continue;
+                    // pd[k].tab: row offset when ugrid_on, slot index otherwise
+                    int slot_i = -1;
+                    if (ugrid_on) { for (size_t z = 0; z < tm.size(); ++z) if (tm[z].off == pd[k].tab) slot_i = (int)z; }
+                    else slot_i = pd[k].tab;
+                    t3_pair_slot[k] = slot_i; t3_pair_rc2[k] = pd[k].rc2;
+                    rcmax[slot_i] = std::max(rcmax[slot_i], pp[a][b].rc);
+                }
+                for (size_t z = 0; z < tm.size(); ++z) {
+                    int w1 = (int)floor((rcmax[z] - tm[z].x0) / tm[z].dx) + 2;
+                    t3_slots[z].w1 = std::max(t3_slots[z].w0 + 1, std::min(tm[z].n, w1));
+                }
+                CK(d_rows2.ensure(t3_rows.size()));
+                CK(cudaMemcpyAsync(d_rows2.p, t3_rows.data(), t3_rows.size() * sizeof(double2), cudaMemcpyHostToDevice, stream));
+                CK(cudaStreamSynchronize(stream));
+                tab2_invdx = q / tm[0].dx; tab2_cmagic = 6755399441055744.0 - rint(k0);
+                tab3_ok = 1; t3_dirty = true;
+            }
+        }
+    }
     CK(d_plj.ensure(plj.size()));
     CK(cudaMemcpyAsync(d_plj.p, plj.data(), plj.size() * sizeof(double2), cudaMemcpyHostToDevice, stream));
     nt_dev = nt; ntabs_dev = (int)tm.size(); nrows_dev = (int)frows.size();
@@ -1153,8 +1228,120 @@ PairKernel clb_engine_pair_fn(const clb_engine* e, int in_smem, int split) {
     return (e->all_tab && e->branchfree_user) ? pair_kernel_tab(e->geo.cubic, in_smem, e->ugrid_on, split) : pair_kernel(e->geo.cubic, in_smem, e->ugrid_on, split);
 }
 
+// type populations (replicated per-slot type|state words) -> residency weights of the table windows
+__global__ void k_type_hist(int n, const int* __restrict__ wslot, unsigned long long* __restrict__ hist) {
+    __shared__ unsigned int s_h[CLB_MAX_TYPES];
+    if (threadIdx.x < CLB_MAX_TYPES) s_h[threadIdx.x] = 0;
+    __syncthreads();
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) atomicAdd(&s_h[pw_type(wslot[i])], 1u);
+    __syncthreads();
+    if (threadIdx.x < CLB_MAX_TYPES && s_h[threadIdx.x]) atomicAdd(hist + threadIdx.x, (unsigned long long)s_h[threadIdx.x]);
+}
+// Choose which table windows live in shared memory (hottest type pairs first, by population product) and upload the
+// descriptors + the shared-memory image.  budget_bytes: shared memory available for the windows; rlog: log2 of the replication.
+int clb_engine::configure_tables(size_t budget_bytes, int rlog) {
+    clb_engine* e = this;
+    const int nt = nt_dev, ntp = nt * nt;
+    CK(d_hist.ensure(CLB_MAX_TYPES));
+    CK(cudaMemsetAsync(d_hist.p, 0, CLB_MAX_TYPES * 8, stream));
+    k_type_hist<<<std::min(ceil_div(n, 256), 4 * nsm), 256, 0, stream>>>(n, wslot.p, d_hist.p);
+    unsigned long long hist[CLB_MAX_TYPES];
+    CK(cudaMemcpyAsync(hist, d_hist.p, sizeof(hist), cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    for (auto& sl : t3_slots) { sl.weight = 0.0; sl.srow = -1; }
+    for (int a = 0; a < nt; ++a) for (int b = 0; b < nt; ++b) {
+        const int z = t3_pair_slot[(size_t)a * nt + b];
+        if (z >= 0) t3_slots[z].weight += (double)hist[a] * (double)hist[b];
+    }
+    std::vector<int> order(t3_slots.size());
+    for (size_t z = 0; z < order.size(); ++z) order[z] = (int)z;
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return t3_slots[x].weight > t3_slots[y].weight; });
+    const size_t budget_rows = budget_bytes / (sizeof(double2) << rlog);
+    size_t used = 0; double wsum = 0, wres = 0; int nres = 0;
+    for (int z : order) wsum += t3_slots[z].weight;
+    for (int z : order) {
+        T3Slot& sl = t3_slots[z];
+        const size_t rows = (size_t)(sl.w1 - sl.w0);
+        if (sl.weight <= 0 && nres > 0) continue;             // unpopulated type pairs stay in global memory
+        if (used + rows > budget_rows) continue;
+        sl.srow = (int)used; used += rows; wres += sl.weight; ++nres;
+    }
+    std::vector<double2> img(std::max<size_t>(used << rlog, 1));
+    const int R = 1 << rlog;
+    for (const T3Slot& sl : t3_slots) if (sl.srow >= 0)
+        for (int i = sl.w0; i < sl.w1; ++i) for (int c = 0; c < R; ++c) img[(((size_t)sl.srow + (i - sl.w0)) << rlog) + c] = t3_rows[sl.off + i];
+    std::vector<ClbPairDesc3> pd3(ntp); std::vector<int2> gm(ntp);
+    bool one = true;
+    for (int k = 0; k < ntp; ++k) {
+        ClbPairDesc3 d; d.rc2 = -1.0; d.soff = 0; d.w0 = 0; d.wn = 0;
+        gm[k] = make_int2(0, 0);
+        const int z = t3_pair_slot[k];
+        if (z >= 0) {
+            const T3Slot& sl = t3_slots[z];
+            d.rc2 = t3_pair_rc2[k];
+            gm[k] = make_int2(sl.off, sl.n - 1);
+            if (sl.srow >= 0) { d.soff = (sl.srow - sl.w0) * R; d.w0 = (unsigned short)sl.w0; d.wn = (unsigned short)(sl.w1 - sl.w0); }
+        }
+        pd3[k] = d;
+        one = one && z >= 0 && z == t3_pair_slot[0] && t3_pair_rc2[k] == t3_pair_rc2[0];
+    }
+    CK(d_pd3.ensure(ntp)); CK(d_gmeta.ensure(ntp)); CK(d_swin.ensure(img.size()));
+    CK(cudaMemcpyAsync(d_pd3.p, pd3.data(), ntp * sizeof(ClbPairDesc3), cudaMemcpyHostToDevice, stream));
+    CK(cudaMemcpyAsync(d_gmeta.p, gm.data(), ntp * sizeof(int2), cudaMemcpyHostToDevice, stream));
+    CK(cudaMemcpyAsync(d_swin.p, img.data(), img.size() * sizeof(double2), cudaMemcpyHostToDevice, stream));
+    CK(cudaStreamSynchronize(stream));
+    tab3_nsrows = (int)used; tab3_rlog = rlog; tab3_onepd = one ? 1 : 0; tab3_resident = nres;
+    tab3_resident_weight = wsum > 0 ? wres / wsum : 1.0;
+    tab3_one = pd3[0]; tab3_one_g = gm[0];
+    t3_dirty = false;
+    return CLB_OK;
+}
+
 int clb_engine::configure_pair_launch() {
     pair_kernel_active = (tab2_ok && branchfree_user && pair_kernel_user != 1) ? 2 : 1;
+    if (tab3_ok && branchfree_user && (pair_kernel_user == 0 || pair_kernel_user == 3)) pair_kernel_active = 3;
+    if (pair_kernel_active == 3) {
+        const double mean_home = (double)(own1 - own0) / std::max(1, grid.nblocks);
+        int npw = std::max(1, std::min((home_max + 31) / 32, (int)ceil((mean_home + 3.0 * sqrt(mean_home)) / 32.0)));
+        if (pair_warps_user > 0) npw = pair_warps_user;
+        npw = std::min(npw, 16);
+        const int tile_cap = (tile_max + 3) & ~3;
+        const size_t vcb = (size_t)(CLB_TILE_CELLS + 4 + CLB_TILE_CELLS) * sizeof(int) + (size_t)tile_cap * sizeof(int4);
+        size_t want_rows = 0;
+        bool single = true;
+        for (const T3Slot& sl : t3_slots) want_rows += (size_t)(sl.w1 - sl.w0);
+        for (size_t k = 0; k < t3_pair_slot.size(); ++k) single = single && t3_pair_slot[k] >= 0 && t3_pair_slot[k] == t3_pair_slot[0] && t3_pair_rc2[k] == t3_pair_rc2[0];
+        const size_t fixed = single ? 0 : (size_t)nt_dev * nt_dev * sizeof(ClbPairDesc3);
+        // replication: 8 conflict-free copies when ONE table serves every pair and the copies leave room for >= 3 tiles
+        int rlog = 0;
+        if (pair_rep_user >= 8) rlog = 3;
+        else if (pair_rep_user < 0 && single && fixed + (want_rows << 3) * sizeof(double2) + 3 * vcb <= (size_t)smem_optin) rlog = 3;
+        // table budget: everything that is wanted, but at least 3 tiles (virtual CTAs) must stay resident
+        const int nv_keep = 3;
+        size_t budget = (size_t)smem_optin > fixed + nv_keep * vcb ? (size_t)smem_optin - fixed - nv_keep * vcb : 0;
+        if (pair_table_kb_user >= 0) budget = std::min(budget, (size_t)pair_table_kb_user * 1024);
+        budget = std::min(budget, (want_rows << rlog) * sizeof(double2));
+        if (t3_dirty || rlog != tab3_rlog || ((size_t)tab3_nsrows << tab3_rlog) * sizeof(double2) > budget) { int r = configure_tables(budget, rlog); if (r != CLB_OK) return r; }
+        const size_t shared_part = fixed + ((size_t)tab3_nsrows << tab3_rlog) * sizeof(double2);
+        int best_nv = 1, best_nb = 1; double best_w = -1;
+        const int nv_max = pair_nv_user > 0 ? pair_nv_user : 15;
+        for (int nv = (pair_nv_user > 0 ? pair_nv_user : 1); nv <= nv_max; ++nv) {
+            if (nv * npw * 32 > 1024) break;
+            size_t smem = shared_part + nv * vcb;
+            if ((int)smem > smem_optin) break;
+            int nb = 0;
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, pair_kernel_tab3(tab3_onepd, tab3_rlog, pair_ni), nv * npw * 32, smem);
+            double w = (double)nb * nv * npw;
+            if (w > best_w * 1.001) { best_w = w; best_nv = nv; best_nb = std::max(nb, 1); }
+        }
+        pair_nv = best_nv; pair_vc_bytes = (int)vcb;
+        pair_split = 1; pair_npw = npw; pair_threads = best_nv * npw * 32;
+        pair_smem = (int)(shared_part + best_nv * vcb);
+        tabs_smem = tab3_nsrows > 0;
+        if (pair_smem > smem_optin) return fail(CLB_ERR_UNSUPPORTED, "pair kernel needs %d B of shared memory: lower block_cells", pair_smem);
+        pair_grid = std::min(ceil_div(grid.nblocks, best_nv), best_nb * nsm);
+        return CLB_OK;
+    }
     if (pair_kernel_active == 2) {
         const double mean_home = (double)(own1 - own0) / std::max(1, grid.nblocks);
         int npw = std::max(1, std::min((home_max + 31) / 32, (int)ceil((mean_home + 3.0 * sqrt(mean_home)) / 32.0)));
@@ -1235,6 +1422,14 @@ int clb_engine::rebuild() {
         // ghosts are dropped, owned particles that left the slab move to the neighbour ranks (engine_comm.inl)
         CK(cudaMemsetAsync(id2idx.p, 0xff, (size_t)n * sizeof(int), stream));
         TRY(comm_migrate());
+    }
+    if (!bx_user && !bx_auto_done) {
+        // row-block length from the mean cell occupancy: a tile (9 rows of bx+2 cells) of about 1800 beads keeps several
+        // virtual CTAs resident per SM; dense systems (hyperbranched: 38 beads per cell) get shorter blocks
+        const double ppc = (double)n / ((double)grid.ncx * grid.ncy * grid.ncz);
+        int bx = (int)floor(1800.0 / (9.0 * std::max(ppc, 1.0))) - 2;
+        set_block_cells(std::max(2, std::min(bx, 8)));
+        bx_auto_done = true;
     }
     int ns = own1;
     // 1. sort the owned particles by cell
@@ -1322,7 +1517,15 @@ extern "C" int clb_decompose(clb_engine* e) {
 // ------------------------------------------------------------------------------------------ forces
 void clb_engine::launch_pair(int b0, int seg0, int b1, int nidx) {
     const int gridsz = std::max(1, std::min(pair_grid, nidx));
-    if (pair_kernel_active == 2) {
+    if (pair_kernel_active == 3) {
+        ClbPairArgs3 A;
+        A.cell_start = cell_start.p; A.pos = pos.p; A.entries = nl_entries.p; A.nl_count = nl_count.p;
+        A.pd3 = d_pd3.p; A.gmeta = d_gmeta.p; A.trows = d_rows2.p; A.swin = d_swin.p; A.force = force.p; A.ctl = d_ctl;
+        A.cap = nl_cap; A.ntypes = nt_dev; A.nsrows = tab3_nsrows; A.fstride = ncap; A.npw = pair_npw;
+        A.invdx = tab2_invdx; A.cmagic = tab2_cmagic; A.one = tab3_one; A.one_g = tab3_one_g;
+        A.b0 = b0; A.seg0 = seg0; A.b1 = b1; A.nidx = nidx; A.nv = pair_nv; A.vc_bytes = pair_vc_bytes;
+        pair_kernel_tab3(tab3_onepd, tab3_rlog, pair_ni)<<<std::max(1, std::min(pair_grid, ceil_div(nidx, pair_nv))), pair_threads, pair_smem, stream>>>(grid, A);
+    } else if (pair_kernel_active == 2) {
         ClbPairArgs2 A;
         A.cell_start = cell_start.p; A.pos = pos.p; A.entries = nl_entries.p; A.nl_count = nl_count.p;
         A.pd2 = d_pd2.p; A.trows = d_rows2.p; A.force = force.p; A.ctl = d_ctl;
@@ -1485,6 +1688,7 @@ extern "C" int clb_set_dt(clb_engine* e, double dt) {
 }
 extern "C" int clb_set_langevin(clb_engine* e, int enabled, double kT, double gamma, int ntypes, const int32_t* types) {
     if (!e) return CLB_ERR_ARG;
+    if (enabled != e->lang_on || kT != e->kT) e->pots_dirty = true;     // the table windows of the pair kernel are thermal (30 kT)
     e->lang_on = enabled; e->kT = kT; e->gamma = gamma;
     if (ntypes <= 0) e->lang_mask = ~0ull;
     else { e->lang_mask = 0; for (int i = 0; i < ntypes; ++i) if (types[i] >= 0 && types[i] < 64) e->lang_mask |= 1ull << types[i]; }
@@ -1520,6 +1724,7 @@ static int run_impl(clb_engine* e, int64_t nsteps, bool cont) {
     if (!e || nsteps < 0) return CLB_ERR_ARG;
     cudaSetDevice(e->device);
     cont = cont && e->cont_ok && e->lists_valid;
+    ClbTrace trr(e->stream, "run");
     if (cont) {
         // list / term / exclusion updates left by a reaction pass are picked up at the forced rebuild of the first step
         if (e->pots_dirty) TRY(e->upload_potentials());
@@ -1530,7 +1735,9 @@ static int run_impl(clb_engine* e, int64_t nsteps, bool cont) {
     if (!cont) {
         TRY(e->setup_sync());
         if (e->pending_rebuild) { e->lists_valid = false; e->pending_rebuild = false; }
+        trr.mark("setup_sync");
         if (!e->lists_valid) TRY(e->rebuild());
+        trr.mark("rebuild");
     }
     cudaEventRecord(e->ev_a[CLB_B_TOTAL], e->stream);
     if (!cont) {
@@ -1610,6 +1817,7 @@ static int run_impl(clb_engine* e, int64_t nsteps, bool cont) {
     }
     if (pend) e->enqueue_integrate(CLB_INT_SECOND, (uint64_t)(e->step + nsteps - 1));
     e->step += nsteps;
+    trr.mark("steps");
     cudaEventRecord(e->ev_b[CLB_B_TOTAL], e->stream);
     TRY(e->read_ctl());
     CK(cudaGetLastError());

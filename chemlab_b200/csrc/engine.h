@@ -93,7 +93,7 @@ struct clb_engine {
     int pair_grid = 0, pair_threads = 128, pair_smem = 0, tabs_smem = 1, pair_split = 1, pair_split_user = 0, pair_npw = 1, build_threads = 256;
     int ugrid_on = 0, all_tab = 0, branchfree_user = 1, pair_warps_user = 0;
     ClbTabMeta ugrid_meta;
-    bool lists_valid = false, forces_valid = false, cont_ok = false;
+    bool lists_valid = false, forces_valid = false, cont_ok = false, bx_user = false, bx_auto_done = false;
 
     // exclusions
     DevBuf<int2> excl_pairs;
@@ -115,6 +115,18 @@ struct clb_engine {
     int tab2_ok = 0, tab2_onepd = 0, tab2_one_off = 0, pair_kernel_user = 0, pair_kernel_active = 1, pair_ni = 4;
     unsigned tab2_nm1 = 0;
     int pair_nv = 1, pair_nv_user = 0, pair_vc_bytes = 0;
+    // windowed multi-table kernel (k_pair_forces_tab3)
+    struct T3Slot { int off, n, w0, w1; double weight; int srow; };
+    std::vector<T3Slot> t3_slots;               // one per uploaded table slot (premixed rows)
+    std::vector<int> t3_pair_slot;              // [nt*nt] slot of the type pair, -1: no potential
+    std::vector<double> t3_pair_rc2;            // [nt*nt] cutoff^2 in lattice^2
+    std::vector<double2> t3_rows;               // host copy of all {A_i, B_i} rows
+    DevBuf<ClbPairDesc3> d_pd3; DevBuf<int2> d_gmeta; DevBuf<double2> d_swin; DevBuf<unsigned long long> d_hist;
+    int tab3_ok = 0, tab3_onepd = 0, tab3_nsrows = 0, tab3_rlog = 0, tab3_resident = 0, pair_rep_user = -1, pair_table_kb_user = -1;
+    double tab3_resident_weight = 0;
+    bool t3_dirty = true;
+    ClbPairDesc3 tab3_one; int2 tab3_one_g;
+    int configure_tables(size_t budget_bytes, int rlog);
     double tab2_invdx = 0, tab2_cmagic = 0, tab2_one_rc2 = 0;
 
     // tuple lists and bonded interactions

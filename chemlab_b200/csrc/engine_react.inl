@@ -370,6 +370,7 @@ int clb_engine::react_pass(int64_t* events_out) {
         nreact_events += nev;
         terms_dirty = true; excl_dirty = true; lists_ptr_dirty = true;
         if (has_mixed) TRY(update_mixing());
+        t3_dirty = true;      // type populations moved: the set of table windows kept in shared memory is re-ranked at the next rebuild
         tr.mark("tail");
         // U9: new exclusions / bonds take effect through a forced rebuild at the next resort check
         k_set_force_rebuild<<<1, 1, 0, stream>>>(d_ctl);

@@ -1,6 +1,7 @@
-"""Engine-shaped adapter over the fp64 CPU oracle (TEST INFRASTRUCTURE): lets the espressopp surface and the
-start_simulation driver run unchanged on the oracle, so that a whole chemlab run on the GPU engine can be compared
-with the same run on the checker.  Maps caller ids <-> the oracle's dense indices (ascending id order)."""
+"""Engine-shaped adapter over the fp64 CPU oracle (TEST INFRASTRUCTURE: tests/, smoke() and bench.py's CPU legs only):
+lets the espressopp surface, the start_simulation driver and the recorded workloads of bench.py run unchanged on the
+oracle, so that a whole chemlab run on the GPU engine can be compared with the same run on the checker.  Maps caller
+ids <-> the oracle's dense indices (ascending id order)."""
 import numpy as np
 
 from oracle import pyoracle
@@ -20,8 +21,10 @@ class OracleEngine:
         ids = np.asarray(ids, np.int64)
         order = np.argsort(ids, kind="stable")
         self.ids = ids[order]
-        self.idx = {int(p): k for k, p in enumerate(self.ids)}
         self.n = len(ids)
+        # dense ascending ids (the usual .gro numbering): index = id - first id, no dictionary
+        self.base = int(self.ids[0]) if self.n and np.array_equal(self.ids, self.ids[0] + np.arange(self.n, dtype=np.int64)) else None
+        self.idx = None if self.base is not None else {int(p): k for k, p in enumerate(self.ids)}
         rc, skin, seed = self._args
         self.o = pyoracle.Oracle(self.n, self.box, rc, skin, seed=seed)
         z = np.zeros((self.n, 3))
@@ -34,12 +37,16 @@ class OracleEngine:
 
     def _ix(self, a):
         a = np.asarray(a, np.int64)
+        if self.base is not None:
+            if a.size and (a.min() < self.base or a.max() >= self.base + self.n):
+                raise KeyError("unknown particle id")
+            return a - self.base
         return np.vectorize(self.idx.__getitem__, otypes=[np.int64])(a) if a.size else a
 
     def num_particles(self):
         return self.n
 
-    def get_particles(self, ids=None, fields=("pos", "vel", "force", "type", "state", "mass", "image", "q", "res_id")):
+    def get_particles(self, ids=None, fields=("pos", "vel", "force", "type", "state", "mass", "image", "q", "res_id"), out=None):
         g = self.o.get()
         sel = slice(None) if ids is None else self._ix(ids)
         out = {}
@@ -56,7 +63,7 @@ class OracleEngine:
 
     def modify_particle(self, pid, field, value):
         f = self.FIELDS[field] if isinstance(field, str) else int(field)
-        k = self.idx[int(pid)]
+        k = int(self._ix(np.array([pid]))[0])
         if f == 3:
             self._q[k] = float(np.atleast_1d(value)[0])
         if f == 4:
@@ -87,6 +94,18 @@ class OracleEngine:
     def pairs(self):
         return self.ids[self.o.pairs()]
 
+    def pairs_raw(self):
+        return self.ids[self.o.pairs_raw()]
+
+    def get(self):
+        return self.o.get()
+
+    def step(self):
+        return self.o.step()
+
+    def set_threads(self, nt):
+        self.o.set_threads(nt)
+
     def last_candidates(self):
         rows, d2 = self.o.candidates()
         rows = rows.astype(np.int64)
@@ -108,8 +127,8 @@ class OracleEngine:
     def decompose(self):
         self.o.rebuild()
 
-    def set_option(self, *a):
-        pass
+    def set_option(self, name, value):
+        self.o.set_option(name, value)       # the oracle knows "resort_criterion" and "step"; everything else is ignored there
 
     def close(self):
         pass

@@ -73,6 +73,40 @@ def pack_hyperbranched():
     print("hyperbranched: %d tables packed" % len(arrays))
 
 
+# dacron (config 4 base system): examples/dacron/no_water/test_1 as shipped (topology with its two .itp includes, coordinates,
+# arg-file, reaction config, exclusion list).  Pair tables: the 14 shipped .xvg of test_1 converted with the reference's converter
+# logic; the 7 type pairs test_1 lacks (C_D, D_E and the water pairs *_W) are the shipped .pot files of
+# examples/dacron/rev_with_water/test_3 (same force field).  Angle tables a0..a3 (45,000 rows each) and bond table b2 as shipped;
+# the dihedral tables d0/d1 are missing from the reference (.MISSING_LARGE_BLOBS) and are synthesised by the users of this fixture.
+def pack_dacron():
+    import glob
+    import sys
+    import tempfile
+    import numpy as np
+    sys.path.insert(0, os.path.join(HERE, "..", ".."))
+    from chemlab_b200.espressopp.tools.convert.gromacs import convertTable
+    src = os.path.join(REF, "examples", "dacron", "no_water", "test_1")
+    alt = os.path.join(REF, "examples", "dacron", "rev_with_water", "test_3")
+    dst = os.path.join(HERE, "dacron")
+    os.makedirs(dst, exist_ok=True)
+    for f in ("conf.gro", "topol.top", "diol_cg.itp", "ter_cg.itp", "params", "reaction.cfg", "exclusion_topol.list"):
+        shutil.copy(os.path.join(src, f), os.path.join(dst, f))
+    arrays = {}
+    with tempfile.TemporaryDirectory() as tmp:
+        for xvg in sorted(glob.glob(os.path.join(src, "table_*.xvg"))):
+            name = os.path.basename(xvg)[:-4]
+            pot = os.path.join(tmp, name + ".pot")
+            convertTable(xvg, pot)
+            arrays[name] = np.loadtxt(pot)
+    for pot in sorted(glob.glob(os.path.join(alt, "table_?_?.pot"))):
+        name = os.path.basename(pot)[:-4]
+        if name not in arrays:
+            arrays[name] = np.loadtxt(pot)
+    np.savez_compressed(os.path.join(dst, "tables.npz"), **arrays)
+    print("dacron: %d tables packed: %s" % (len(arrays), " ".join(sorted(arrays))))
+
+
 if __name__ == "__main__":
     pack_rim135()
     pack_hyperbranched()
+    pack_dacron()

@@ -95,13 +95,13 @@ def test_molecule_exclusions_nrexcl():
 
 def test_driver_host_logic_on_the_oracle_backend(tmp_path, monkeypatch):
     """The whole driver (arg-file, topology, exclusions, reactions, ATRP activator, hooks, observers, outputs) with the engine
-    swapped for the CPU checker (tests/oracle_engine.py): host logic only, no GPU.  The products of the reference driver must
+    swapped for the CPU checker (oracle/engine_adapter.py): host logic only, no GPU.  The products of the reference driver must
     appear (src/start_simulation.py:800-1081) and must be readable by our own readers."""
     import shutil
     import sys
     sys.path.insert(0, HERE)
     import chemlab_b200.espressopp._context as C
-    from oracle_engine import OracleEngine
+    from oracle.engine_adapter import OracleEngine
     from chemlab_b200 import start_simulation as S
     from chemlab_b200.chemlab.files_io import GROFile
     from chemlab_b200.chemlab.gromacs_topology import GromacsTopology

@@ -1,6 +1,6 @@
 """Config 1 end to end (BASELINE.json configs[0]): examples/atrp_lj as shipped, through the chemlab driver
 (`python -m chemlab_b200.start_simulation @params`) on the GPU engine, and the SAME driver run on the oracle
-(tests/oracle_engine.py) -- topology, reaction bonds, types and states must agree bit-exactly, positions closely."""
+(oracle/engine_adapter.py) -- topology, reaction bonds, types and states must agree bit-exactly, positions closely."""
 import os
 import shutil
 
@@ -12,24 +12,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 
 
 def _run(tmp, backend, steps, example="atrp_lj", extra=("--rng_seed", "42", "--start_ar", "200", "--energy_collect", "200")):
-    d = os.path.join(tmp, example + "_" + backend)
-    shutil.copytree(os.path.join(HERE, "golden", example), d)
-    if example == "hyperbranched":
-        # the reference ships no angle / dihedral tables for this example (.MISSING_LARGE_BLOBS): smooth stand-ins on the usual grids
-        th = np.radians(np.arange(0.5, 180.01, 0.5))
-        for k in range(11):
-            t0, K = np.radians(100 + 6 * k), 40.0 + 3 * k
-            with open(os.path.join(d, "table_a%d.pot" % k), "w") as f:
-                f.writelines("%15.8g %15.8g %15.8g\n" % (x, 0.5 * K * (x - t0) ** 2, -K * (x - t0)) for x in th)
-        ph = np.radians(np.arange(-180.0, 180.01, 1.0))
-        for k in range(8):
-            with open(os.path.join(d, "table_d%d.pot" % k), "w") as f:
-                f.writelines("%15.8g %15.8g %15.8g\n" % (x, 2.0 * (1 + np.cos(2 * x - 0.3 * k)), 4.0 * np.sin(2 * x - 0.3 * k)) for x in ph)
-    if os.path.exists(os.path.join(d, "tables.npz")):          # packed `.pot` tables (tests/golden/make_golden.py)
-        with np.load(os.path.join(d, "tables.npz")) as z:
-            for name in z.files:
-                with open(os.path.join(d, name + ".pot"), "w") as f:
-                    f.writelines("%15.8g %15.8g %15.8g\n" % tuple(r) for r in z[name])
+    from chemlab_b200 import synthetic
+    # copy of the shipped example + unpacked `.pot` tables + smooth stand-ins for the angle / dihedral tables the reference does not ship
+    d = synthetic.prepare_example(os.path.join(HERE, "golden", example), os.path.join(tmp, example + "_" + backend), example)
     cwd = os.getcwd()
     os.chdir(d)
     try:
@@ -37,7 +22,7 @@ def _run(tmp, backend, steps, example="atrp_lj", extra=("--rng_seed", "42", "--s
         from chemlab_b200 import start_simulation as S
         real = C.Engine
         if backend == "oracle":
-            from oracle_engine import OracleEngine
+            from oracle.engine_adapter import OracleEngine
             C.Engine = OracleEngine
         try:
             # start_ar=200 -> reactions on after one outer iteration; nearest partner + p = rate*dt*interval
@@ -108,9 +93,10 @@ def test_rim135_driver_gpu_matches_oracle(tmp_path):
     d = a["g"]["pos"] - b["g"]["pos"]
     box = 5.378
     d -= box * np.rint(d / box)
-    # 2 ps at 700 K with stiff tabulated bonds: the fp32-stored velocities of the engine let the trajectories drift apart by
-    # ~0.01 nm (measured 0.012) while every discrete decision (types, states, bonds) still agrees
+    # 2 ps at 700 K with stiff tabulated bonds.  Velocities and masses are fp64 on both sides (round 2); what remains is the
+    # 2^-32 L position lattice of the engine against the oracle's doubles, amplified by the chaotic dynamics
     assert np.abs(d).max() < 0.05, np.abs(d).max()
+    print("rim135 max position difference after %d steps: %.3e nm" % (steps, np.abs(d).max()))
 
 
 def test_hyperbranched_driver_gpu_matches_oracle(tmp_path):
@@ -124,3 +110,24 @@ def test_hyperbranched_driver_gpu_matches_oracle(tmp_path):
     assert a["steps"] == b["steps"] == steps
     assert (a["g"]["type"] == b["g"]["type"]).all() and (a["g"]["state"] == b["g"]["state"]).all()
     assert len(b["bonds"]) > 10 and a["bonds"].shape == b["bonds"].shape and (_srt(a["bonds"]) == _srt(b["bonds"])).all()
+
+
+def test_dacron_driver_gpu_matches_oracle(tmp_path):
+    """examples/dacron/no_water/test_1 as shipped (config 4's base system): 1000 DIO + 1000 TER molecules, 21 tabulated pair
+    potentials of 1000/1001 rows (tables of DIFFERENT length on one grid), harmonic bonds, tabulated angles of 45,000 rows, tabulated
+    dihedrals generated by the reactions (tables d0/d1 are missing upstream: smooth stand-ins), the condensation reactions
+    A(1,2)+D(1,3)->C(-1):E(-1) and A(1,2)+E(1,2)->C(-1):E(-1) with cutoff 0.48 (reaction.cfg:25-43), exclusions read from the shipped
+    exclusion_topol.list.  Dropped as out of scope: hybrid bonds (t_hybrid_bond) and the unused ReleaseMolecule
+    extension.  2000 steps = 4 reaction passes."""
+    steps = 2000
+    extra = ("--rng_seed", "7", "--t_hybrid_bond", "0", "--gen_velocity", "True", "--energy_collect", "500")
+    a = _run(str(tmp_path), "gpu", steps, example="dacron", extra=extra)
+    b = _run(str(tmp_path), "oracle", steps, example="dacron", extra=extra)
+    assert a["steps"] == b["steps"] == steps
+    assert (a["g"]["type"] == b["g"]["type"]).all() and (a["g"]["state"] == b["g"]["state"]).all()
+    assert np.array_equal(a["g"]["mass"], b["g"]["mass"])
+    assert len(b["bonds"]) > 5 and a["bonds"].shape == b["bonds"].shape and (_srt(a["bonds"]) == _srt(b["bonds"])).all()
+    # products C and E carry the topology masses (44.009, 28.053), NOT masses scaled by mass_factor (ADVICE round 1)
+    t, m = a["g"]["type"], a["g"]["mass"]
+    assert set(np.round(np.unique(m), 3)) <= {44.999, 76.098, 44.009, 62.05, 28.053}
+    assert (t >= 3).sum() > 0 or len(a["bonds"]) > 0

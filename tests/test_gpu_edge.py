@@ -60,15 +60,31 @@ def test_all_pair_kernel_variants_agree():
     tab = P.add_table(r, e, f, 1)
     P.nb_tab(util.type_pairs(2), tab, 2.5)
     fe, fo = _forces(P)
-    assert P.e.get_option("pair_kernel") == 2 and P.e.get_option("pair_onepd") == 1
+    assert P.e.get_option("pair_kernel") == 3      # windowed-table kernel (round 2) is the default for all-tabulated cubic systems
     assert util.rel_force_err(fe, fo) < 1e-6
-    for opts in (dict(pair_nv=1), dict(pair_nv=3), dict(pair_nv=0, pair_ni=2), dict(pair_ni=4, tables_in_smem=0), dict(tables_in_smem=1)):
+    # no thermostat -> the table window starts at row 0 and every listed pair inside the cutoff finds its row in shared memory:
+    # the same arithmetic in the same order as the round-1 kernel (pair_kernel=2) -> bit-identical forces for every layout
+    for opts in (dict(pair_nv=1), dict(pair_nv=3), dict(pair_nv=0, pair_ni=2), dict(pair_ni=4, pair_rep=8), dict(pair_rep=1),
+                 dict(pair_kernel=2), dict(pair_kernel=2, pair_ni=2), dict(pair_kernel=2, pair_ni=4, tables_in_smem=0), dict(tables_in_smem=1)):
         for k, v in opts.items():
             P.e.set_option(k, v)
         P.e.compute_forces()
         f2 = P.e.get_particles(fields=("force",))["force"]
-        assert (f2 == fe).all(), opts          # same arithmetic in the same order: bit-identical
-    P.e.set_option("pair_kernel", 1)           # previous-generation kernels: different arithmetic, same tolerance
+        assert (f2 == fe).all(), opts
+    # rows read through the global-memory path (no shared-memory budget at all; a thermal window): same rows, the out-of-window
+    # pairs are summed after the others -> equal within rounding, and still within the force bar
+    P.e.set_option("pair_kernel", 3)
+    for opts in (dict(pair_table_kb=0), dict(pair_table_kb=4), dict(pair_table_kb=-1)):
+        for k, v in opts.items():
+            P.e.set_option(k, v)
+        P.e.compute_forces()
+        f2 = P.e.get_particles(fields=("force",))["force"]
+        assert util.rel_force_err(f2, fo) < 1e-6 and np.abs(f2 - fe).max() <= 1e-9 * np.abs(fe).max(), opts
+    P.both("set_langevin", 1, 1.0, 1.0)        # thermostat on -> thermal window (U - Umin < 30 kT): the wall rows come from global memory
+    P.e.compute_forces()
+    f2 = P.e.get_particles(fields=("force",))["force"]
+    assert util.rel_force_err(f2, fo) < 1e-6 and P.e.get_option("pair_table_rows") < 1500
+    P.e.set_option("pair_kernel", 1)           # first-generation kernels: different arithmetic, same tolerance
     for bf in (1, 0):
         P.e.set_option("pair_branchfree", bf)
         P.e.compute_forces()
@@ -95,9 +111,16 @@ def test_several_tables_and_a_type_pair_without_potential():
         P.e.nb_set_tabulated(a, x, y, t, rc); P.o.nb_set_tab(b, x, y, t, rc)
     # pairs (1,2), (0,3), (2,3), (3,3) carry no potential at all
     fe, fo = _forces(P)
-    assert P.e.get_option("pair_kernel") == 2 and P.e.get_option("pair_onepd") == 0
+    assert P.e.get_option("pair_kernel") == 3 and P.e.get_option("pair_tables_resident") == 3
     assert util.rel_force_err(fe, fo) < 1e-6
     assert abs(P.e.energy(a) - P.o.energy(b)) <= 1e-8 * abs(P.o.energy(b))
+    # only the hottest table fits (24 KB budget), nothing fits, round-1 kernel: same forces
+    for opts in (dict(pair_table_kb=30), dict(pair_table_kb=0), dict(pair_kernel=2)):
+        for k, v in opts.items():
+            P.e.set_option(k, v)
+        P.e.compute_forces()
+        f2 = P.e.get_particles(fields=("force",))["force"]
+        assert util.rel_force_err(f2, fo) < 1e-6 and np.abs(f2 - fe).max() <= 1e-9 * np.abs(fe).max(), opts
     P.close()
 
 

@@ -16,7 +16,7 @@ def _build(backend):
     import chemlab_b200.espressopp._context as C
     real = C.Engine
     if backend == "oracle":
-        from oracle_engine import OracleEngine
+        from oracle.engine_adapter import OracleEngine
         C.Engine = OracleEngine
     try:
         rng = np.random.default_rng(3)
