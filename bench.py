@@ -452,10 +452,15 @@ def main():
                 "steps_per_s_amortised": amort,
                 "amortised_note": "steps/s with exactly one reaction pass per %d steps (the timed window held %d); reaction_pass_ms is one pass timed on its own (host wall clock, synchronous call)" % (wl.interval, npass_win),
                 "new_bonds_total": nbonds_new, "temperature": float(kin[1]), "wall_s": t_wall, "equil_steps": a.equil,
-                "ghost_beads_total": cn["ghosts"], "pair_threads": e.get_option("pair_threads"), "pair_grid": e.get_option("pair_grid"),
-                "pair_nv": e.get_option("pair_nv"), "pair_smem": e.get_option("pair_smem"), "home_max": e.get_option("home_max"), "tile_max": e.get_option("tile_max"),
-                "buckets_s": {k: v for k, v in tm.items() if v > 0} if e.get_option("timers") else None, "parity": parity}
+                "ghost_beads_total": cn["ghosts"], "parity": parity}
 
+    # the first engine is done (timed run, parity): its device blocks go to the engine's block cache and are reused below
+    pair_opts = {k: e.get_option(k) for k in ("pair_threads", "pair_grid", "pair_nv", "pair_smem", "home_max", "tile_max", "pair_kernel", "pair_rep",
+                                               "pair_table_rows", "pair_tables_resident", "pair_tables_resident_weight", "block_cells", "timers")}
+    if rank == 0:
+        line.update({k: pair_opts[k] for k in pair_opts if k != "timers"})
+        line["buckets_s"] = {k: v for k, v in tm.items() if v > 0} if pair_opts["timers"] else None
+    e.close()
     # e2e: public API with HOST buffers -- a fresh engine (one per rank when N > 1) restarted from the pinned host snapshot:
     # upload of the particle state, the same number of steps with observables read back per chunk, final state download
     if not a.no_e2e:
@@ -525,7 +530,6 @@ def main():
         line["cpu_baseline"] = cpu_run(wl, snap, ksteps, 3, threads)
     if rank == 0:
         print(json.dumps(line))
-    e.close()
     if dist is not None:
         dist.destroy_process_group()
     return 0

@@ -24,6 +24,7 @@ SIGNATURES = {
     "clb_destroy": (None, [C.c_void_p]),
     "clb_last_error": (C.c_char_p, [C.c_void_p]),
     "clb_abi_version": (C.c_int, []),
+    "clb_trim_cache": (C.c_int, []),
     "clb_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_double]),
     "clb_get_option": (C.c_int, [C.c_void_p, C.c_char_p, c_f64p]),
     "clb_set_particles": (C.c_int, [C.c_void_p, C.c_int64, c_i64p, c_i32p, c_f64p, c_f64p, c_f64p, c_f64p, c_i32p, c_i32p]),

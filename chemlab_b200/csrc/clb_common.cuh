@@ -18,6 +18,8 @@
 #define CLB_EF_TUPLE_OVERFLOW 16u
 #define CLB_EF_PARTNER_LOST 32u // bonded partner not resolvable (outside ghost layer)
 #define CLB_EF_BFS_OVERFLOW 128u // neighbour-property BFS frontier exceeded its fixed buffers, or molecule-id hooking did not converge
+#define CLB_EF_COMM_TIMEOUT 256u // a peer flag did not arrive within the time limit (a neighbour rank died or fell out of step)
+#define CLB_EF_COMM_OVERFLOW 512u // more boundary-plane particles / migrants than the peer mailbox holds
 #define CLB_EF_TILE_OVERFLOW 64u // a tile holds more particles than the shared-memory carve-up assumed -> host retries
 
 // velocity + mass per sorted particle: fp64 throughout ({vx, vy, vz, mass}); the reference's `real` is double
@@ -47,6 +49,9 @@ struct ClbCtl {
     int cell_max;
     int nl_max;             // max neighbour count
     unsigned long long nl_total;
+    unsigned long long halo_epoch;  // multi-GPU peer path: number of completed per-step halo exchanges (identical on every rank)
+    unsigned comm_done;             // block-completion counter of the push kernels
+    unsigned comm_pad;
 };
 
 struct ClbGrid {

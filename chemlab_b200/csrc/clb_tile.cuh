@@ -695,6 +695,71 @@ __global__ void __launch_bounds__(1024) k_pair_forces_tab2(ClbGrid g, ClbPairArg
     if (err) atomicOr(&A.ctl->err, err);
 }
 
+
+// ---- TMA bulk staging of a tile (round 2) -------------------------------------------------------------------------
+// With x-fastest cells a tile ROW (the W cells of one (dy,dz)) is ONE contiguous range of the sorted particle arrays
+// (two when the row wraps around the periodic x boundary), so a whole tile is the concatenation of at most 18 contiguous
+// global ranges.  The pair kernel needs no per-cell offsets: warp 0 reads the 18 range bounds from cell_start, a warp scan
+// gives the tile offsets, and lanes 0..17 each issue ONE cp.async.bulk (global -> shared, completion on an mbarrier).  The
+// other warps never touch the staging: they wait on the mbarrier.  (Round 1 staged cell by cell through registers: 15
+// dependent global-load latencies per warp and a serial prefix over 90 cells, 20 % of the kernel in barrier stalls.)
+#define CLB_TILE_RANGES 18
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* mbar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(mbar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* mbar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(mbar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* mbar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "CLB_MBAR_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra CLB_MBAR_DONE;\n"
+        "bra CLB_MBAR_WAIT;\n"
+        "CLB_MBAR_DONE:\n"
+        "}\n" :: "r"(smem_u32(mbar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, unsigned bytes, unsigned long long* mbar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(mbar)) : "memory");
+}
+struct TileMeta { int hs, nh, T, pad; };   // per virtual CTA, in shared memory behind the mbarrier
+// Warp 0 of a virtual CTA (all 32 lanes) computes the ranges of tile `b` and launches the bulk copies; returns nothing: the
+// caller synchronises the group, reads *meta and waits on the mbarrier.  tile order = rows k = 0..8, cells m = 0..W-1 (tile_cell).
+__device__ __forceinline__ void tile_stage_bulk(const ClbGrid& g, const TileCtx& t, const int* __restrict__ cell_start,
+                                                const int4* __restrict__ pos, int4* s_pos, TileMeta* meta,
+                                                unsigned long long* mbar, int lane) {
+    int cnt = 0, gs = 0;
+    if (lane < CLB_TILE_RANGES) {
+        const int k = lane >> 1, half = lane & 1;
+        const int dy = k % 3 - 1, dz = k / 3 - 1;
+        const int rowbase = (wrapi(t.lz + dz, g.nplanes) * g.ncy + wrapi(t.cy + dy, g.ncy)) * g.ncx;
+        int c0, c1;
+        if (t.whole) { c0 = 0; c1 = half ? 0 : g.ncx; }
+        else {
+            const int a0 = wrapi(t.cx0 - 1, g.ncx), lenA = min(t.W, g.ncx - a0);
+            if (!half) { c0 = a0; c1 = a0 + lenA; } else { c0 = 0; c1 = t.W - lenA; }
+        }
+        if (c1 > c0) { gs = __ldg(cell_start + rowbase + c0); cnt = __ldg(cell_start + rowbase + c1) - gs; }
+    } else if (lane == CLB_TILE_RANGES) {
+        const int c = (t.lz * g.ncy + t.cy) * g.ncx + t.cx0;
+        gs = __ldg(cell_start + c); cnt = __ldg(cell_start + c + t.bxe) - gs;     // home range (not part of the scan)
+    }
+    int incl = lane < CLB_TILE_RANGES ? cnt : 0;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { int v = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += v; }
+    const int T = __shfl_sync(0xffffffffu, incl, CLB_TILE_RANGES - 1);
+    const int ts = incl - cnt;
+    if (lane == CLB_TILE_RANGES) { meta->hs = gs; meta->nh = cnt; meta->T = T; }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // earlier generic reads of the tile are ordered before the async writes
+    if (lane == 0) mbar_expect_tx(mbar, (unsigned)T * 16u);
+    __syncwarp();
+    if (lane < CLB_TILE_RANGES && cnt > 0) bulk_g2s(s_pos + ts, pos + gs, (unsigned)cnt * 16u, mbar);
+}
+
 // ------------------------------------------------------------------------------------------
 // Fourth generation (round 2): the all-tabulated kernel for MANY tables.  Same arithmetic as k_pair_forces_tab2 (bit-identical
 // forces), different table storage:
@@ -716,7 +781,8 @@ struct ClbPairDesc3 {          // 16 bytes per type pair
 struct ClbPairArgs3 {
     const int* cell_start; const int4* pos; const unsigned short* entries; const int* nl_count;
     const ClbPairDesc3* pd3;   // [ntypes^2]
-    const int2* gmeta;         // [ntypes^2] {first row of the pair's table in trows, rows - 1}
+    const int2* gmeta;         // [ntypes^2] {first row of the pair's table in trows - shift, (shift << 20) | (rows - 1)}; shift = rows between
+                               // the common grid origin and the table's first abscissa (tables may start at different r)
     const double2* trows;      // {A_i, B_i} rows of all tables, lattice units (global memory)
     const double2* swin;       // shared-memory image of the windows: nsrows << RLOG rows, copied in at kernel start
     double* force; ClbCtl* ctl;
@@ -749,13 +815,17 @@ __device__ __noinline__ void pair_tab3_slow(unsigned defer, uint4 cur, unsigned 
         const double y = fma(y0, ee, y0), r = fma(h, ee, h);
         const unsigned ix = (unsigned)__double2loint(__fma_rd(r, invdx, cmagic));
         const int2 gm = onepd ? one_g : __ldg(gmeta_row + pw_type(pj.w));
-        if (ix > (unsigned)gm.y) *err |= CLB_EF_TABLE_RANGE;          // fatal in the reference (U12)
-        const double2 rw = __ldg(trows + gm.x + (int)min(ix, (unsigned)gm.y));
+        const unsigned sh = (unsigned)gm.y >> 20, nm1 = (unsigned)gm.y & 0xfffffu;      // this table covers common rows [sh, sh + nm1]
+        if (ix - sh > nm1) *err |= CLB_EF_TABLE_RANGE;                // fatal in the reference (U12)
+        const double2 rw = __ldg(trows + gm.x + (int)min(max(ix, sh), sh + nm1));
         const double F = fma(r, rw.y, rw.x) * y;
         acc[0] = fma(F, dx, acc[0]); acc[1] = fma(F, dy, acc[1]); acc[2] = fma(F, dz, acc[2]);
     }
 }
-template <bool ONEPD, int RLOG, int NI>
+// INLINE_FB: type pairs whose table has no shared-memory window are common (many-table systems: rim135 keeps 13 of 28 windows
+// resident = 90 % of the pair work) -> their rows are gathered from global memory by a predicated load inside the hot loop
+// instead of the out-of-line rare path (which re-evaluates the pair and serialises a warp whenever ANY lane needs it).
+template <bool ONEPD, int RLOG, int NI, bool INLINE_FB>
 __global__ void __launch_bounds__(1024) k_pair_forces_tab3(ClbGrid g, ClbPairArgs3 A) {
     if (*(volatile int*)&A.ctl->stall) return;
     extern __shared__ __align__(16) unsigned char smem[];
@@ -766,13 +836,23 @@ __global__ void __launch_bounds__(1024) k_pair_forces_tab3(ClbGrid g, ClbPairArg
     const int nth = A.npw * 32;
     const int vc = threadIdx.x / nth, tid = threadIdx.x - vc * nth;
     const int bar = 1 + vc;
-    int* s_off = reinterpret_cast<int*>(vc_base + (size_t)vc * A.vc_bytes);
-    int* s_src = s_off + (CLB_TILE_CELLS + 4);
-    int4* s_pos = reinterpret_cast<int4*>(s_src + CLB_TILE_CELLS);
+    // per virtual CTA: [mbarrier 16 B][TileMeta 16 B][tile positions]
+    unsigned long long* mbar = reinterpret_cast<unsigned long long*>(vc_base + (size_t)vc * A.vc_bytes);
+    TileMeta* meta = reinterpret_cast<TileMeta*>(mbar + 2);
+    int4* s_pos = reinterpret_cast<int4*>(meta + 1);
     if (!ONEPD) for (int i = threadIdx.x; i < ntp; i += blockDim.x) s_pd[i] = A.pd3[i];
     for (int i = threadIdx.x; i < (A.nsrows << RLOG); i += blockDim.x) s_rows[i] = __ldg(A.swin + i);
+    if (tid == 0) { mbar_init(mbar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
     __syncthreads();
+    unsigned phase = 0;
     const int lane = tid & 31, warp = tid >> 5;
+    // neighbour-row batches (8 entries = 16 B per lane) are prefetched ONE BATCH AHEAD with cp.async into two private 16-byte
+    // slots per thread.  (Round 1 / first round-2 version prefetched into registers: ptxas sank the load to the end of the loop
+    // body, right in front of its use, and the warps spent 20 % of the kernel waiting for DRAM at that one instruction --
+    // profiles/r2c_ncu_pair_sass.csv.)
+    uint4* s_ev = reinterpret_cast<uint4*>(vc_base + (size_t)A.nv * A.vc_bytes) + threadIdx.x;
+    const unsigned s_ev_u32 = smem_u32(s_ev);
+    const unsigned ev_stride = blockDim.x * 16u;
     const double2* s_rows_rep = s_rows + (lane & ((1 << RLOG) - 1));     // this lane's copy of the replicated windows
     const int nhpass = nth;
     const double invdx = A.invdx, cmagic = A.cmagic;
@@ -781,10 +861,11 @@ __global__ void __launch_bounds__(1024) k_pair_forces_tab3(ClbGrid g, ClbPairArg
         const int b = idx < A.seg0 ? A.b0 + idx : A.b1 + (idx - A.seg0);
         TileCtx t;
         tile_geometry(g, b, t);
-        vc_sync(bar, nth);
-        tile_offsets_vc(g, t, A.cell_start, s_off, s_src, tid, nth, bar);
-        tile_stage_vc(t, s_off, s_src, A.pos, s_pos, tid, nth);
-        vc_sync(bar, nth);
+        vc_sync(bar, nth);                                     // every warp is done with the previous tile
+        if (warp == 0) tile_stage_bulk(g, t, A.cell_start, A.pos, s_pos, meta, mbar, lane);
+        vc_sync(bar, nth);                                     // meta visible
+        t.hs = meta->hs; t.nh = meta->nh;
+        mbar_wait(mbar, phase); phase ^= 1u;                   // tile landed
         for (int p0 = 0; p0 < t.nh; p0 += nhpass) {
             const int p = p0 + warp * 32 + lane;
             const bool act = p < t.nh;
@@ -796,12 +877,15 @@ __global__ void __launch_bounds__(1024) k_pair_forces_tab3(ClbGrid g, ClbPairArg
             const uint4* row = reinterpret_cast<const uint4*>(A.entries + (size_t)gi * A.cap);
             const int nb = (cnt + 7) >> 3;
             double ax = 0.0, ay = 0.0, az = 0.0;
-            uint4 ev = make_uint4(0, 0, 0, 0);
-            if (nb > 0) ev = __ldg(row);
+            if (nb > 0) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(s_ev_u32), "l"(row) : "memory");
+            asm volatile("cp.async.commit_group;" ::: "memory");
 #pragma unroll 1
             for (int bi = 0; bi < nb; ++bi) {
-                const uint4 cur = ev;
-                if (bi + 1 < nb) ev = __ldg(row + bi + 1);
+                if (bi + 1 < nb) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(s_ev_u32 + ((bi + 1) & 1) * ev_stride), "l"(row + bi + 1) : "memory");
+                asm volatile("cp.async.commit_group;" ::: "memory");
+                asm volatile("cp.async.wait_group 1;" ::: "memory");          // batch bi has landed (only the newest group may be pending)
+                uint4 cur;
+                asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(cur.x), "=r"(cur.y), "=r"(cur.z), "=r"(cur.w) : "r"(s_ev_u32 + (bi & 1) * ev_stride) : "memory");
                 const int ne = cnt - bi * 8;
                 const unsigned wds[4] = {cur.x, cur.y, cur.z, cur.w};
                 unsigned defer = 0;
@@ -811,6 +895,7 @@ __global__ void __launch_bounds__(1024) k_pair_forces_tab3(ClbGrid g, ClbPairArg
                     int4 pj[NI];
                     double dx[NI], dy[NI], dz[NI], r2[NI], y0[NI], yh[NI], y[NI], r[NI], F[NI];
                     ClbPairDesc3 d[NI];
+                    int tpj[NI];
                     double2 rw[NI];
 #pragma unroll
                     for (int q = 0; q < NI; ++q) {
@@ -826,7 +911,7 @@ __global__ void __launch_bounds__(1024) k_pair_forces_tab3(ClbGrid g, ClbPairArg
                         dy[q] = __hiloint2double(0x43300000, (int)(piy - (unsigned)pj[q].y)) - 4503601774854144.0;
                         dz[q] = __hiloint2double(0x43300000, (int)(piz - (unsigned)pj[q].z)) - 4503601774854144.0;
                         if (ONEPD) d[q] = A.one;
-                        else d[q] = s_pd[trow + pw_type(pj[q].w)];
+                        else { d[q] = s_pd[trow + pw_type(pj[q].w)]; if (INLINE_FB) tpj[q] = pw_type(pj[q].w); }
                     }
 #pragma unroll
                     for (int q = 0; q < NI; ++q) r2[q] = fma(dz[q], dz[q], fma(dy[q], dy[q], dx[q] * dx[q]));
@@ -846,7 +931,14 @@ __global__ void __launch_bounds__(1024) k_pair_forces_tab3(ClbGrid g, ClbPairArg
                         const bool inw = in[q] && (ix - (unsigned)d[q].w0) < (unsigned)d[q].wn;
                         rw[q] = make_double2(0.0, 0.0);
                         if (inw) rw[q] = s_rows_rep[d[q].soff + (int)(ix << RLOG)];     // predicated gather: lanes beyond the cutoff stay out
-                        else if (in[q]) defer |= 1u << (s0 + q);                              // row outside the window: out-of-line path below
+                        else if (in[q]) {
+                            if (INLINE_FB) {                                                  // cold type pair / wall row: global memory (L2), same arithmetic
+                                const int2 gm = ONEPD ? A.one_g : __ldg(A.gmeta + trow + tpj[q]);
+                                const unsigned sh = (unsigned)gm.y >> 20, nm1 = (unsigned)gm.y & 0xfffffu;
+                                if (ix - sh > nm1) err |= CLB_EF_TABLE_RANGE;
+                                rw[q] = __ldg(A.trows + gm.x + (int)min(max(ix, sh), sh + nm1));
+                            } else defer |= 1u << (s0 + q);                                   // rare: out-of-line path below
+                        }
                     }
 #pragma unroll
                     for (int q = 0; q < NI; ++q) {
@@ -856,7 +948,7 @@ __global__ void __launch_bounds__(1024) k_pair_forces_tab3(ClbGrid g, ClbPairArg
 #pragma unroll
                     for (int q = 0; q < NI; ++q) { ax = fma(F[q], dx[q], ax); ay = fma(F[q], dy[q], ay); az = fma(F[q], dz[q], az); }
                 }
-                if (defer) {
+                if (!INLINE_FB && defer) {
                     double acc[3] = {ax, ay, az};
                     pair_tab3_slow(defer, cur, pix, piy, piz, s_pos, A.gmeta + trow, A.one_g, ONEPD, A.trows, invdx, cmagic, acc, &err);
                     ax = acc[0]; ay = acc[1]; az = acc[2];

@@ -21,6 +21,56 @@
 
 static std::string g_create_error;
 
+// ---- device block cache (engine.h) ----
+#include <map>
+#include <mutex>
+static std::mutex g_cache_mu;
+static std::multimap<size_t, void*> g_cache[16];        // per device: block size -> pointer
+static size_t g_cache_bytes[16] = {0};
+cudaError_t clb_cache_alloc(void** p, size_t bytes, size_t* got) {
+    int dev = 0; cudaGetDevice(&dev);
+    bytes = (bytes + 511) & ~(size_t)511;
+    if (dev >= 0 && dev < 16) {
+        std::lock_guard<std::mutex> lk(g_cache_mu);
+        auto it = g_cache[dev].lower_bound(bytes);
+        // reuse a cached block of at most twice the size (bounded internal fragmentation)
+        if (it != g_cache[dev].end() && it->first <= 2 * bytes + (1 << 20)) {
+            *p = it->second; *got = it->first; g_cache_bytes[dev] -= it->first; g_cache[dev].erase(it);
+            return cudaSuccess;
+        }
+    }
+    cudaError_t e = cudaMalloc(p, bytes);
+    if (e != cudaSuccess && dev >= 0 && dev < 16) {
+        // out of memory: give the cache back to the driver and retry once
+        { std::lock_guard<std::mutex> lk(g_cache_mu);
+          for (auto& kv : g_cache[dev]) cudaFree(kv.second);
+          g_cache[dev].clear(); g_cache_bytes[dev] = 0; }
+        (void)cudaGetLastError();
+        e = cudaMalloc(p, bytes);
+    }
+    *got = bytes;
+    return e;
+}
+void clb_cache_free(void* p, size_t bytes) {
+    if (!p) return;
+    int dev = 0; cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 16 || bytes == 0) { cudaFree(p); return; }
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    g_cache[dev].insert({bytes, p}); g_cache_bytes[dev] += bytes;
+}
+extern "C" int clb_trim_cache(void) {
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    int dev0 = 0; cudaGetDevice(&dev0);
+    for (int d = 0; d < 16; ++d) {
+        if (g_cache[d].empty()) continue;
+        cudaSetDevice(d);
+        for (auto& kv : g_cache[d]) cudaFree(kv.second);
+        g_cache[d].clear(); g_cache_bytes[d] = 0;
+    }
+    cudaSetDevice(dev0);
+    return CLB_OK;
+}
+
 #define CK(call)                                                                                 \
     do {                                                                                         \
         cudaError_t _e = (call);                                                                 \
@@ -78,11 +128,13 @@ static PairKernel2 pair_kernel_tab2(int smem, int onepd, int ni) {
     return onepd ? k_pair_forces_tab2<false, true, 2> : k_pair_forces_tab2<false, false, 2>;
 }
 typedef void (*PairKernel3)(ClbGrid, ClbPairArgs3);
-static PairKernel3 pair_kernel_tab3(int onepd, int rlog, int ni) {
-    if (ni >= 4) { if (rlog) return onepd ? k_pair_forces_tab3<true, 3, 4> : k_pair_forces_tab3<false, 3, 4>;
-                   return onepd ? k_pair_forces_tab3<true, 0, 4> : k_pair_forces_tab3<false, 0, 4>; }
-    if (rlog) return onepd ? k_pair_forces_tab3<true, 3, 2> : k_pair_forces_tab3<false, 3, 2>;
-    return onepd ? k_pair_forces_tab3<true, 0, 2> : k_pair_forces_tab3<false, 0, 2>;
+// variants: one descriptor in registers (ONEPD, optionally 8-way replicated rows) with the rare out-of-line global path;
+// many tables with the out-of-line path (all hot windows resident) or with the inline predicated global gather (fb = 1)
+static PairKernel3 pair_kernel_tab3(int onepd, int rlog, int ni, int fb) {
+    if (onepd) { if (rlog) return ni >= 4 ? k_pair_forces_tab3<true, 3, 4, false> : k_pair_forces_tab3<true, 3, 2, false>;
+                 return ni >= 4 ? k_pair_forces_tab3<true, 0, 4, false> : k_pair_forces_tab3<true, 0, 2, false>; }
+    if (fb) return ni >= 4 ? k_pair_forces_tab3<false, 0, 4, true> : k_pair_forces_tab3<false, 0, 2, true>;   // (4 spills at 64 registers: 2 is the default)
+    return ni >= 4 ? k_pair_forces_tab3<false, 0, 4, false> : k_pair_forces_tab3<false, 0, 2, false>;
 }
 static PairKernel pair_kernel(int cubic, int smem, int ugrid, int split) {
     if (cubic) { if (smem) return ugrid ? pair_kernel_split<true, true, true>(split) : pair_kernel_split<true, true, false>(split);
@@ -161,9 +213,9 @@ extern "C" int clb_create(clb_engine** out, int device, const double box[3], dou
         cudaFuncSetAttribute(pair_kernel_tab2(sm, op, ni), cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
         cudaFuncSetAttribute(pair_kernel_tab2(sm, op, ni), cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     }
-    for (int op = 0; op < 2; ++op) for (int rl = 0; rl <= 3; rl += 3) for (int ni = 2; ni <= 4; ni += 2) {
-        cudaFuncSetAttribute(pair_kernel_tab3(op, rl, ni), cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
-        cudaFuncSetAttribute(pair_kernel_tab3(op, rl, ni), cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    for (int op = 0; op < 2; ++op) for (int rl = 0; rl <= 3; rl += 3) for (int ni = 2; ni <= 4; ni += 2) for (int fb = 0; fb < 2; ++fb) {
+        cudaFuncSetAttribute(pair_kernel_tab3(op, rl, ni, fb), cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+        cudaFuncSetAttribute(pair_kernel_tab3(op, rl, ni, fb), cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     }
     cudaFuncSetAttribute(k_pair_energy<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
     cudaFuncSetAttribute(k_pair_energy<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
@@ -206,13 +258,15 @@ extern "C" int clb_set_option(clb_engine* e, const char* name, double v) {
     else if (s == "pair_event_timing") e->pair_event_timing = (int)v;
     else if (s == "overlap_halo") e->overlap_user = (int)v;
     else if (s == "comm_group") e->comm_group_user = (int)v;
+    else if (s == "comm_peer") e->peer_user = (int)v;
     else if (s == "pair_split") { e->pair_split_user = (int)v; if (e->lists_valid) return e->configure_pair_launch(); }
     else if (s == "build_threads") e->build_threads = (int)v;
     else if (s == "pair_warps") { e->pair_warps_user = (int)v; if (e->lists_valid) return e->configure_pair_launch(); }
     else if (s == "pair_kernel") { e->pair_kernel_user = (int)v; if (e->lists_valid) return e->configure_pair_launch(); }
     else if (s == "pair_nv") { e->pair_nv_user = (int)v; if (e->lists_valid) return e->configure_pair_launch(); }
-    else if (s == "pair_ni") { e->pair_ni = (int)v >= 4 ? 4 : 2; if (e->lists_valid) return e->configure_pair_launch(); }
+    else if (s == "pair_ni") { e->pair_ni = (int)v >= 4 ? 4 : 2; e->pair_ni_user = (int)v > 0; if (e->lists_valid) return e->configure_pair_launch(); }
     else if (s == "pair_rep") { e->pair_rep_user = (int)v; e->t3_dirty = true; if (e->lists_valid) return e->configure_pair_launch(); }
+    else if (s == "pair_inline_fallback") { e->pair_fb_user = (int)v; if (e->lists_valid) return e->configure_pair_launch(); }
     else if (s == "pair_table_kb") { e->pair_table_kb_user = (int)v; e->t3_dirty = true; if (e->lists_valid) return e->configure_pair_launch(); }
     else if (s == "pair_branchfree") { e->branchfree_user = (int)v; if (e->lists_valid) return e->configure_pair_launch(); }
     else return e->fail(CLB_ERR_ARG, "unknown option %s", name);
@@ -233,6 +287,7 @@ extern "C" int clb_get_option(clb_engine* e, const char* name, double* v) {
     else if (s == "nl_total") *v = (double)e->nl_total;
     else if (s == "ncx") *v = e->grid.ncx;
     else if (s == "pair_grid") *v = e->pair_grid;
+    else if (s == "comm_peer") *v = e->peer_active() ? 1 : 0;
     else if (s == "pair_threads") *v = e->pair_threads;
     else if (s == "pair_split") *v = e->pair_split;
     else if (s == "pair_kernel") *v = e->pair_kernel_active;
@@ -243,6 +298,7 @@ extern "C" int clb_get_option(clb_engine* e, const char* name, double* v) {
     else if (s == "tables_in_smem") *v = e->tabs_smem;
     else if (s == "pair_kernel_ms") *v = e->pair_ms;
     else if (s == "pair_rep") *v = 1 << e->tab3_rlog;
+    else if (s == "pair_inline_fallback") *v = e->tab3_fb;
     else if (s == "pair_table_rows") *v = e->tab3_nsrows;
     else if (s == "pair_tables_resident") *v = e->tab3_resident;
     else if (s == "pair_tables_resident_weight") *v = e->tab3_resident_weight;
@@ -396,6 +452,7 @@ extern "C" int clb_set_particles(clb_engine* e, int64_t n, const int64_t* id, co
         double frac = (double)(g.nczl + 2) / g.ncz;
         int64_t cap = std::min<int64_t>(n, (int64_t)(n * frac * 1.5) + 16384);
         TRY(e->alloc_particles((int)std::max<int64_t>(cap, nloc)));
+        TRY(e->comm_peer_setup());
         CK(cudaMemsetAsync(e->id2idx.p, 0xff, N * sizeof(int), st));
         if (nloc) k_take_owned<<<ceil_div(nloc, 256), 256, 0, st>>>((int)nloc, d_sel, d_P, d_V, e->pos.p, e->vel.p, e->slot.p, e->id2idx.p);
     } else {
@@ -522,40 +579,60 @@ __global__ void k_pack_state(int no, int K, const int4* __restrict__ pos, const 
     r[9] = image[3 * s]; r[10] = image[3 * s + 1]; r[11] = image[3 * s + 2];
     r[12] = pw_type(p.w); r[13] = pw_state(p.w); r[14] = v.w;
 }
+__global__ void k_export_matrix(int cnt, const int* __restrict__ qslot, int K, const double* __restrict__ M, const double* __restrict__ charge,
+                                const int* __restrict__ resid, ClbExportArgs O) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= cnt) return;
+    const int s = qslot ? qslot[k] : k;
+    const double* r = M + (size_t)s * K;
+    const size_t k3 = 3 * (size_t)k;
+    if (O.pos) { O.pos[k3] = r[0] * O.qd[0]; O.pos[k3 + 1] = r[1] * O.qd[1]; O.pos[k3 + 2] = r[2] * O.qd[2]; }
+    if (O.vel) { O.vel[k3] = r[3]; O.vel[k3 + 1] = r[4]; O.vel[k3 + 2] = r[5]; }
+    if (O.force) { O.force[k3] = r[6]; O.force[k3 + 1] = r[7]; O.force[k3 + 2] = r[8]; }
+    if (O.image) { O.image[k3] = (int)r[9]; O.image[k3 + 1] = (int)r[10]; O.image[k3 + 2] = (int)r[11]; }
+    if (O.type) O.type[k] = (int)r[12];
+    if (O.state) O.state[k] = (int)r[13];
+    if (O.mass) O.mass[k] = r[14];
+    if (O.q) O.q[k] = charge[s];
+    if (O.resid) O.resid[k] = resid[s];
+}
 int clb_engine::get_particles_gathered(int64_t nq, const int64_t* ids, double* pos_o, int32_t* image_o, double* vel_o, double* force_o,
                                        int32_t* type_o, int32_t* state_o, double* mass_o, double* q_o, int32_t* res_o) {
     clb_engine* e = this;
     const int K = 15;
     const int no = own1;
-    // owned rows are packed on the device into a zeroed [n x K] matrix, summed over the ranks, downloaded once
-    DevBuf<double> d;
-    CK(d.ensure((size_t)n * K));
-    CK(cudaMemsetAsync(d.p, 0, (size_t)n * K * sizeof(double), stream));
-    if (no) k_pack_state<<<ceil_div(no, 256), 256, 0, stream>>>(no, K, this->pos.p, this->vel.p, this->force.p, ncap, slot.p, image.p, d.p);
-    int rr = comm_allreduce_sum_dev(d.p, (size_t)n * K);
-    if (rr != CLB_OK) { d.release(); return rr; }
-    std::vector<double> M((size_t)n * K);
-    CK(cudaMemcpyAsync(M.data(), d.p, M.size() * 8, cudaMemcpyDeviceToHost, stream));
+    const int64_t cnt = ids ? nq : n;
+    if (cnt <= 0) return CLB_OK;
+    std::vector<int> qs;
+    TRY(query_slots(e, cnt, ids, qs));
+    // owned rows are packed on the device into a zeroed [n x K] matrix and summed over the ranks (exact: one non-zero
+    // contribution per row); the requested fields are then unpacked on the device and copied straight into the caller's arrays
+    const size_t N = (size_t)cnt;
+    CK(stage_reserve(e, (size_t)n * K * 8 + N * (24 * 3 + 8 * 2 + 12 + 4 * 4) + 16 * 256));
+    StageCursor sc{stage.p};
+    double* M = sc.take<double>((size_t)n * K);
+    ClbExportArgs O;
+    O.pos = pos_o ? sc.take<double>(3 * N) : nullptr; O.vel = vel_o ? sc.take<double>(3 * N) : nullptr; O.force = force_o ? sc.take<double>(3 * N) : nullptr;
+    O.mass = mass_o ? sc.take<double>(N) : nullptr; O.q = q_o ? sc.take<double>(N) : nullptr; O.image = image_o ? sc.take<int>(3 * N) : nullptr;
+    O.type = type_o ? sc.take<int>(N) : nullptr; O.state = state_o ? sc.take<int>(N) : nullptr; O.resid = res_o ? sc.take<int>(N) : nullptr;
+    int* d_qs = ids ? sc.take<int>(N) : nullptr;
+    for (int d = 0; d < 3; ++d) O.qd[d] = geo.q[d];
+    CK(cudaMemsetAsync(M, 0, (size_t)n * K * sizeof(double), stream));
+    if (no) k_pack_state<<<ceil_div(no, 256), 256, 0, stream>>>(no, K, this->pos.p, this->vel.p, this->force.p, ncap, slot.p, image.p, M);
+    TRY(comm_allreduce_sum_dev(M, (size_t)n * K));
+    if (ids) CK(cudaMemcpyAsync(d_qs, qs.data(), 4 * N, cudaMemcpyHostToDevice, stream));
+    k_export_matrix<<<ceil_div(cnt, 256), 256, 0, stream>>>((int)cnt, d_qs, K, M, charge.p, resid.p, O);
+    if (pos_o) CK(cudaMemcpyAsync(pos_o, O.pos, 24 * N, cudaMemcpyDeviceToHost, stream));
+    if (vel_o) CK(cudaMemcpyAsync(vel_o, O.vel, 24 * N, cudaMemcpyDeviceToHost, stream));
+    if (force_o) CK(cudaMemcpyAsync(force_o, O.force, 24 * N, cudaMemcpyDeviceToHost, stream));
+    if (mass_o) CK(cudaMemcpyAsync(mass_o, O.mass, 8 * N, cudaMemcpyDeviceToHost, stream));
+    if (q_o) CK(cudaMemcpyAsync(q_o, O.q, 8 * N, cudaMemcpyDeviceToHost, stream));
+    if (image_o) CK(cudaMemcpyAsync(image_o, O.image, 12 * N, cudaMemcpyDeviceToHost, stream));
+    if (type_o) CK(cudaMemcpyAsync(type_o, O.type, 4 * N, cudaMemcpyDeviceToHost, stream));
+    if (state_o) CK(cudaMemcpyAsync(state_o, O.state, 4 * N, cudaMemcpyDeviceToHost, stream));
+    if (res_o) CK(cudaMemcpyAsync(res_o, O.resid, 4 * N, cudaMemcpyDeviceToHost, stream));
     CK(cudaStreamSynchronize(stream));
-    d.release();
-    std::vector<int> hres; std::vector<double> hq;
-    if (res_o) { hres.resize(n); CK(cudaMemcpy(hres.data(), resid.p, (size_t)n * 4, cudaMemcpyDeviceToHost)); }
-    if (q_o) { hq.resize(n); CK(cudaMemcpy(hq.data(), charge.p, (size_t)n * 8, cudaMemcpyDeviceToHost)); }
-    int64_t cnt = ids ? nq : n;
-    for (int64_t k = 0; k < cnt; ++k) {
-        int s = ids ? slot_of(ids[k]) : (int)k;
-        if (s < 0) return fail(CLB_ERR_ARG, "unknown particle id %lld", (long long)ids[k]);
-        const double* r = &M[(size_t)s * K];
-        if (pos_o) for (int d3 = 0; d3 < 3; ++d3) pos_o[3 * k + d3] = r[d3] * geo.q[d3];
-        if (vel_o) for (int d3 = 0; d3 < 3; ++d3) vel_o[3 * k + d3] = r[3 + d3];
-        if (force_o) for (int d3 = 0; d3 < 3; ++d3) force_o[3 * k + d3] = r[6 + d3];
-        if (image_o) for (int d3 = 0; d3 < 3; ++d3) image_o[3 * k + d3] = (int)r[9 + d3];
-        if (type_o) type_o[k] = (int)r[12];
-        if (state_o) state_o[k] = (int)r[13];
-        if (mass_o) mass_o[k] = r[14];
-        if (q_o) q_o[k] = hq[s];
-        if (res_o) res_o[k] = hres[s];
-    }
+    CK(cudaGetLastError());
     return CLB_OK;
 }
 
@@ -655,23 +732,82 @@ extern "C" int clb_set_positions(clb_engine* e, int64_t n, const double* pos) {
 }
 
 // ------------------------------------------------------------------------------------------ exclusions
+// caller ids -> slots on the device for DENSE ids (slot = id - first id); flags[0] counts ids out of range
+__global__ void k_ids_to_slots(long long m, const long long* __restrict__ ids, long long base, int n, int* __restrict__ out, int* __restrict__ flags) {
+    long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (k >= m) return;
+    const long long s = ids[k] - base;
+    if (s < 0 || s >= n) { atomicAdd(flags, 1); out[k] = 0; return; }
+    out[k] = (int)s;
+}
+__global__ void k_excl_keys(long long m, const int* __restrict__ slots, unsigned long long* __restrict__ keys) {
+    long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (k >= m) return;
+    const int a = slots[2 * k], b = slots[2 * k + 1];
+    // self pairs sort to the end and are cut off
+    keys[k] = a == b ? ~0ull : (((unsigned long long)(unsigned)min(a, b) << 32) | (unsigned)max(a, b));
+}
+__global__ void k_excl_unpack(long long m, const unsigned long long* __restrict__ keys, int2* __restrict__ pairs, int* __restrict__ nvalid) {
+    long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (k >= m) return;
+    const unsigned long long v = keys[k];
+    if (v == ~0ull) return;
+    pairs[k] = make_int2((int)(v >> 32), (int)(v & 0xffffffffu));
+    if (k + 1 == m || keys[k + 1] == ~0ull) *nvalid = (int)(k + 1);
+}
+// slots of a host id array, on the device (dense ids) or through the host map (arbitrary ids); result in d_out[0..m)
+static int slots_to_device(clb_engine* e, long long m, const int64_t* ids, int* d_out, const char* what) {
+    if (m == 0) return CLB_OK;
+    if (e->ids_dense) {
+        CK(stage_reserve(e, (size_t)m * 8 + 512));
+        long long* d_ids = reinterpret_cast<long long*>(e->stage.p);
+        int* d_flag = reinterpret_cast<int*>(e->stage.p + (((size_t)m * 8 + 255) & ~(size_t)255));
+        CK(cudaMemcpyAsync(d_ids, ids, (size_t)m * 8, cudaMemcpyHostToDevice, e->stream));
+        CK(cudaMemsetAsync(d_flag, 0, 4, e->stream));
+        k_ids_to_slots<<<ceil_div(m, 256), 256, 0, e->stream>>>(m, d_ids, (long long)e->id_base, e->n, d_out, d_flag);
+        int bad = 0;
+        CK(cudaMemcpyAsync(&bad, d_flag, 4, cudaMemcpyDeviceToHost, e->stream));
+        CK(cudaStreamSynchronize(e->stream));
+        if (bad) return e->fail(CLB_ERR_ARG, "%s names %d unknown particle id(s)", what, bad);
+        return CLB_OK;
+    }
+    std::vector<int> h((size_t)m);
+    for (long long k = 0; k < m; ++k) { int s = e->slot_of(ids[k]); if (s < 0) return e->fail(CLB_ERR_ARG, "%s names unknown particle id %lld", what, (long long)ids[k]); h[k] = s; }
+    CK(cudaMemcpy(d_out, h.data(), (size_t)m * 4, cudaMemcpyHostToDevice));
+    return CLB_OK;
+}
+
 extern "C" int clb_set_exclusions(clb_engine* e, int64_t n, const int64_t* pairs) {
     if (!e || n < 0 || (n && !pairs)) return CLB_ERR_ARG;
     cudaSetDevice(e->device);
-    // canonical (min slot, max slot) pairs packed into 64-bit keys: one integer sort, skipped when the caller's list is sorted
-    std::vector<uint64_t> keys; keys.reserve(n);
-    for (int64_t k = 0; k < n; ++k) {
-        int a = e->slot_of(pairs[2 * k]), b = e->slot_of(pairs[2 * k + 1]);
-        if (a < 0 || b < 0) return e->fail(CLB_ERR_ARG, "exclusion %lld names an unknown particle", (long long)k);
-        if (a != b) keys.push_back(((uint64_t)(uint32_t)std::min(a, b) << 32) | (uint32_t)std::max(a, b));
+    // canonical (min slot, max slot) pairs as 64-bit keys, sorted and made unique on the device
+    CK(e->excl_pairs.ensure((size_t)n * 2 + (size_t)e->n + 1024));
+    e->nexcl = 0;
+    if (n > 0) {
+        DevBuf<int> dsl; DevBuf<unsigned long long> k1, k2; DevBuf<int> dcount;
+        CK(dsl.ensure(2 * (size_t)n)); CK(k1.ensure(n)); CK(k2.ensure(n)); CK(dcount.ensure(4));
+        int r = slots_to_device(e, 2 * (long long)n, pairs, dsl.p, "exclusion list");
+        if (r != CLB_OK) { dsl.release(); k1.release(); k2.release(); dcount.release(); return r; }
+        k_excl_keys<<<ceil_div(n, 256), 256, 0, e->stream>>>(n, dsl.p, k1.p);
+        size_t tb = 0;
+        cub::DeviceRadixSort::SortKeys(nullptr, tb, k1.p, k2.p, (int)n, 0, 64, e->stream);
+        CK(e->cubtmp2.ensure(tb + 256));
+        cub::DeviceRadixSort::SortKeys(e->cubtmp2.p, tb, k1.p, k2.p, (int)n, 0, 64, e->stream);
+        size_t tb2 = 0;
+        cub::DeviceSelect::Unique(nullptr, tb2, k2.p, k1.p, dcount.p, (int)n, e->stream);
+        CK(e->cubtmp2.ensure(tb2 + 256));
+        cub::DeviceSelect::Unique(e->cubtmp2.p, tb2, k2.p, k1.p, dcount.p, (int)n, e->stream);
+        int nu = 0;
+        CK(cudaMemcpyAsync(&nu, dcount.p, 4, cudaMemcpyDeviceToHost, e->stream));
+        CK(cudaMemsetAsync(dcount.p + 1, 0, 4, e->stream));
+        CK(cudaStreamSynchronize(e->stream));
+        if (nu > 0) k_excl_unpack<<<ceil_div(nu, 256), 256, 0, e->stream>>>(nu, k1.p, e->excl_pairs.p, dcount.p + 1);
+        int nvalid = 0;
+        CK(cudaMemcpyAsync(&nvalid, dcount.p + 1, 4, cudaMemcpyDeviceToHost, e->stream));
+        CK(cudaStreamSynchronize(e->stream));
+        e->nexcl = nvalid;
+        dsl.release(); k1.release(); k2.release(); dcount.release();
     }
-    if (!std::is_sorted(keys.begin(), keys.end())) std::sort(keys.begin(), keys.end());
-    keys.erase(std::unique(keys.begin(), keys.end()), keys.end());
-    std::vector<int2> h(keys.size());
-    for (size_t k = 0; k < keys.size(); ++k) h[k] = make_int2((int)(keys[k] >> 32), (int)(keys[k] & 0xffffffffu));
-    e->nexcl = (long long)h.size();
-    CK(e->excl_pairs.ensure(h.size() * 2 + (size_t)e->n + 1024));
-    if (!h.empty()) CK(cudaMemcpy(e->excl_pairs.p, h.data(), h.size() * sizeof(int2), cudaMemcpyHostToDevice));
     e->excl_dirty = true; e->lists_valid = false; e->cont_ok = false;
     return CLB_OK;
 }
@@ -932,9 +1068,12 @@ int clb_engine::upload_potentials() {
     // differ); rows {A_i, B_i} as for tab2, windows chosen in configure_tables()
     tab3_ok = 0;
     {
+        // one dx for all tables; first abscissae may differ by whole rows (shipped dacron tables start at r = 0.002 or at r = 0)
         bool same_grid = !tm.empty() && geo.cubic && all_tab;
-        for (size_t k = 1; k < tm.size() && same_grid; ++k) same_grid = tm[k].x0 == tm[0].x0 && tm[k].dx == tm[0].dx;
-        const double k0 = same_grid ? tm[0].x0 / tm[0].dx : 0.5;
+        double x0min = same_grid ? tm[0].x0 : 0.0;
+        for (size_t k = 1; k < tm.size() && same_grid; ++k) { same_grid = tm[k].dx == tm[0].dx; x0min = std::min(x0min, tm[k].x0); }
+        for (size_t k = 0; k < tm.size() && same_grid; ++k) { const double sh = (tm[k].x0 - x0min) / tm[0].dx; same_grid = fabs(sh - rint(sh)) < 1e-9 && rint(sh) < 1024; }
+        const double k0 = same_grid ? x0min / tm[0].dx : 0.5;
         if (same_grid && fabs(k0 - rint(k0)) < 1e-9 && rint(k0) < 1e6) {
             const double q = geo.q[0];
             t3_rows.assign(frows.size(), make_double2(0.0, 0.0));
@@ -952,7 +1091,7 @@ int clb_engine::upload_potentials() {
                 // lower window edge: the first row a pair can reach thermally (U - U_min < 30 kT); without a thermostat: row 0
                 int w0 = 0;
                 if (lang_on && kT > 0) { while (w0 < m.n - 1 && erows[m.off + w0].x - emin > 30.0 * kT) ++w0; w0 = std::max(0, w0 - 2); }
-                clb_engine::T3Slot sl3 = {m.off, m.n, w0, m.n, 0.0, -1};
+                clb_engine::T3Slot sl3 = {m.off, m.n, w0, m.n, 0.0, -1, (int)rint((m.x0 - x0min) / m.dx)};
                 t3_slots.push_back(sl3);
             }
             if (same_grid) {
@@ -969,7 +1108,7 @@ int clb_engine::upload_potentials() {
                     rcmax[slot_i] = std::max(rcmax[slot_i], pp[a][b].rc);
                 }
                 for (size_t z = 0; z < tm.size(); ++z) {
-                    int w1 = (int)floor((rcmax[z] - tm[z].x0) / tm[z].dx) + 2;
+                    int w1 = (int)floor((rcmax[z] - tm[z].x0) / tm[z].dx) + 2;      // in rows of THIS table
                     t3_slots[z].w1 = std::max(t3_slots[z].w0 + 1, std::min(tm[z].n, w1));
                 }
                 CK(d_rows2.ensure(t3_rows.size()));
@@ -1067,10 +1206,9 @@ extern "C" int clb_list_add(clb_engine* e, int list, int64_t n, const int64_t* i
     if (!e || list < 0 || list >= (int)e->lists.size() || n < 0 || (n && !ids)) return e ? e->fail(CLB_ERR_ARG, "clb_list_add: bad argument") : CLB_ERR_ARG;
     cudaSetDevice(e->device);
     HostList& l = e->lists[list];
-    std::vector<int> h((size_t)n * l.arity);
-    for (size_t k = 0; k < h.size(); ++k) { int s = e->slot_of(ids[k]); if (s < 0) return e->fail(CLB_ERR_ARG, "tuple names unknown particle id %lld", (long long)ids[k]); h[k] = s; }
     TRY(e->list_reserve(list, l.n + n));
-    if (n) CK(cudaMemcpy(l.d.p + (size_t)l.n * l.arity, h.data(), h.size() * 4, cudaMemcpyHostToDevice));
+    // ids -> slots straight into the tuple array (on the device for dense ids)
+    TRY(slots_to_device(e, (long long)n * l.arity, ids, e->lists[list].d.p + (size_t)l.n * l.arity, "tuple list"));
     l.n += n;
     e->terms_dirty = true; e->forces_valid = false; e->cont_ok = false;
     if (l.arity == 2 && l.tm_observed) e->topo_dirty = true;
@@ -1279,8 +1417,9 @@ int clb_engine::configure_tables(size_t budget_bytes, int rlog) {
         if (z >= 0) {
             const T3Slot& sl = t3_slots[z];
             d.rc2 = t3_pair_rc2[k];
-            gm[k] = make_int2(sl.off, sl.n - 1);
-            if (sl.srow >= 0) { d.soff = (sl.srow - sl.w0) * R; d.w0 = (unsigned short)sl.w0; d.wn = (unsigned short)(sl.w1 - sl.w0); }
+            // the kernel computes ONE row index ix on the common grid; this table's row is ix - shift
+            gm[k] = make_int2(sl.off - sl.shift, (sl.shift << 20) | (sl.n - 1));
+            if (sl.srow >= 0) { d.soff = (sl.srow - sl.w0 - sl.shift) * R; d.w0 = (unsigned short)(sl.w0 + sl.shift); d.wn = (unsigned short)(sl.w1 - sl.w0); }
         }
         pd3[k] = d;
         one = one && z >= 0 && z == t3_pair_slot[0] && t3_pair_rc2[k] == t3_pair_rc2[0];
@@ -1306,16 +1445,17 @@ int clb_engine::configure_pair_launch() {
         if (pair_warps_user > 0) npw = pair_warps_user;
         npw = std::min(npw, 16);
         const int tile_cap = (tile_max + 3) & ~3;
-        const size_t vcb = (size_t)(CLB_TILE_CELLS + 4 + CLB_TILE_CELLS) * sizeof(int) + (size_t)tile_cap * sizeof(int4);
+        const size_t vcb = 32 + (size_t)tile_cap * sizeof(int4);          // [mbarrier 16 B][TileMeta 16 B][tile positions]
         size_t want_rows = 0;
         bool single = true;
         for (const T3Slot& sl : t3_slots) want_rows += (size_t)(sl.w1 - sl.w0);
         for (size_t k = 0; k < t3_pair_slot.size(); ++k) single = single && t3_pair_slot[k] >= 0 && t3_pair_slot[k] == t3_pair_slot[0] && t3_pair_rc2[k] == t3_pair_rc2[0];
         const size_t fixed = single ? 0 : (size_t)nt_dev * nt_dev * sizeof(ClbPairDesc3);
-        // replication: 8 conflict-free copies when ONE table serves every pair and the copies leave room for >= 3 tiles
+        // replication (8 conflict-free copies of the windows) is opt-in: measured on B200 (1M-bead melt, one table) the copies
+        // cost two of five resident tiles and the kernel, which is latency-bound rather than wavefront-bound, gets 20 % slower
+        // (profiles/r2b_sweep_c2.log: 0.334 -> 0.403 ms)
         int rlog = 0;
-        if (pair_rep_user >= 8) rlog = 3;
-        else if (pair_rep_user < 0 && single && fixed + (want_rows << 3) * sizeof(double2) + 3 * vcb <= (size_t)smem_optin) rlog = 3;
+        if (pair_rep_user >= 8 && single) rlog = 3;
         // table budget: everything that is wanted, but at least 3 tiles (virtual CTAs) must stay resident
         const int nv_keep = 3;
         size_t budget = (size_t)smem_optin > fixed + nv_keep * vcb ? (size_t)smem_optin - fixed - nv_keep * vcb : 0;
@@ -1323,20 +1463,24 @@ int clb_engine::configure_pair_launch() {
         budget = std::min(budget, (want_rows << rlog) * sizeof(double2));
         if (t3_dirty || rlog != tab3_rlog || ((size_t)tab3_nsrows << tab3_rlog) * sizeof(double2) > budget) { int r = configure_tables(budget, rlog); if (r != CLB_OK) return r; }
         const size_t shared_part = fixed + ((size_t)tab3_nsrows << tab3_rlog) * sizeof(double2);
+        tab3_fb = pair_fb_user >= 0 ? pair_fb_user : (tab3_resident_weight < 0.999 ? 1 : 0);
+        if (tab3_onepd) tab3_fb = 0;
+        if (tab3_fb && !pair_ni_user) pair_ni = 2;          // the inline global gather needs the registers of two interleaved pairs
+        else if (!pair_ni_user) pair_ni = 4;
         int best_nv = 1, best_nb = 1; double best_w = -1;
         const int nv_max = pair_nv_user > 0 ? pair_nv_user : 15;
         for (int nv = (pair_nv_user > 0 ? pair_nv_user : 1); nv <= nv_max; ++nv) {
             if (nv * npw * 32 > 1024) break;
-            size_t smem = shared_part + nv * vcb;
+            size_t smem = shared_part + nv * vcb + (size_t)nv * npw * 32 * 32;      // + two 16-byte entry slots per thread
             if ((int)smem > smem_optin) break;
             int nb = 0;
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, pair_kernel_tab3(tab3_onepd, tab3_rlog, pair_ni), nv * npw * 32, smem);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, pair_kernel_tab3(tab3_onepd, tab3_rlog, pair_ni, tab3_fb), nv * npw * 32, smem);
             double w = (double)nb * nv * npw;
             if (w > best_w * 1.001) { best_w = w; best_nv = nv; best_nb = std::max(nb, 1); }
         }
         pair_nv = best_nv; pair_vc_bytes = (int)vcb;
         pair_split = 1; pair_npw = npw; pair_threads = best_nv * npw * 32;
-        pair_smem = (int)(shared_part + best_nv * vcb);
+        pair_smem = (int)(shared_part + best_nv * vcb + (size_t)best_nv * npw * 32 * 32);
         tabs_smem = tab3_nsrows > 0;
         if (pair_smem > smem_optin) return fail(CLB_ERR_UNSUPPORTED, "pair kernel needs %d B of shared memory: lower block_cells", pair_smem);
         pair_grid = std::min(ceil_div(grid.nblocks, best_nv), best_nb * nsm);
@@ -1421,7 +1565,7 @@ int clb_engine::rebuild() {
     if (nranks > 1) {
         // ghosts are dropped, owned particles that left the slab move to the neighbour ranks (engine_comm.inl)
         CK(cudaMemsetAsync(id2idx.p, 0xff, (size_t)n * sizeof(int), stream));
-        TRY(comm_migrate());
+        TRY(peer_active() ? comm_migrate_peer() : comm_migrate());
     }
     if (!bx_user && !bx_auto_done) {
         // row-block length from the mean cell occupancy: a tile (9 rows of bx+2 cells) of about 1800 beads keeps several
@@ -1438,11 +1582,11 @@ int clb_engine::rebuild() {
     size_t tb = cubtmp.n;
     cub::DeviceRadixSort::SortPairs(cubtmp.p, tb, key.p, key2.p, val.p, val2.p, ns, 0, bits, stream);
     k_gather<<<ceil_div(std::max(ns, 1), 256), 256, 0, stream>>>(ns, val2.p, pos.p, vel.p, slot.p, pos2.p, vel2.p, slot2.p, xref.p, id2idx.p);
-    std::swap(pos.p, pos2.p); std::swap(vel.p, vel2.p); std::swap(slot.p, slot2.p);
+    std::swap(pos, pos2); std::swap(vel, vel2); std::swap(slot, slot2);      // whole handles (pointer, capacity and block size)
     if (nranks > 1) {
         // boundary planes of the sorted owned range -> neighbours' ghost planes, appended behind the owned range
         k_cell_start<<<ceil_div(ns + 1, 256), 256, 0, stream>>>(ns, key2.p, grid.ncell, cell_start.p);
-        TRY(comm_exchange_ghosts());
+        TRY(peer_active() ? comm_exchange_ghosts_peer() : comm_exchange_ghosts());
         ns = nstored;
     }
     k_cell_start<<<ceil_div(ns + 1, 256), 256, 0, stream>>>(ns, key2.p, grid.ncell, cell_start.p);
@@ -1524,7 +1668,7 @@ void clb_engine::launch_pair(int b0, int seg0, int b1, int nidx) {
         A.cap = nl_cap; A.ntypes = nt_dev; A.nsrows = tab3_nsrows; A.fstride = ncap; A.npw = pair_npw;
         A.invdx = tab2_invdx; A.cmagic = tab2_cmagic; A.one = tab3_one; A.one_g = tab3_one_g;
         A.b0 = b0; A.seg0 = seg0; A.b1 = b1; A.nidx = nidx; A.nv = pair_nv; A.vc_bytes = pair_vc_bytes;
-        pair_kernel_tab3(tab3_onepd, tab3_rlog, pair_ni)<<<std::max(1, std::min(pair_grid, ceil_div(nidx, pair_nv))), pair_threads, pair_smem, stream>>>(grid, A);
+        pair_kernel_tab3(tab3_onepd, tab3_rlog, pair_ni, tab3_fb)<<<std::max(1, std::min(pair_grid, ceil_div(nidx, pair_nv))), pair_threads, pair_smem, stream>>>(grid, A);
     } else if (pair_kernel_active == 2) {
         ClbPairArgs2 A;
         A.cell_start = cell_start.p; A.pos = pos.p; A.entries = nl_entries.p; A.nl_count = nl_count.p;
@@ -1765,7 +1909,11 @@ static int run_impl(clb_engine* e, int64_t nsteps, bool cont) {
                 if (pend) e->enqueue_integrate(CLB_INT_SECOND, (uint64_t)(e->step + s - 1));
                 e->enqueue_integrate(CLB_INT_FIRST, 0);
             }
-            if (e->nranks > 1 && (e->overlap_user > 0 || (e->overlap_user < 0 && e->nranks >= 4))) {
+            if (e->peer_active()) {
+                // peer mailboxes: push boundary planes + displacement maximum over NVLink, wait for the neighbours, resort check
+                TRY(e->comm_step_peer(e->stream, (int)(s - i)));
+                e->enqueue_forces();
+            } else if (e->nranks > 1 && (e->overlap_user > 0 || (e->overlap_user < 0 && e->nranks >= 4))) {
                 // global max displacement + position halo travel on the comm stream while the interior planes compute
                 cudaEventRecord(e->ev_int, e->stream);
                 cudaStreamWaitEvent(e->comm_stream, e->ev_int, 0);

@@ -11,35 +11,42 @@
 #include "clb_common.cuh"
 #include "clb_kernels.cuh"
 
+// Process-wide cache of released device blocks (per device): cudaMalloc / cudaFree synchronise the device and cost from
+// 0.1 ms to (measured on the B200 box, after large host allocations were freed) > 100 ms per call, so a block released by
+// one engine is handed to the next request of similar size instead of going back to the driver.  clb_trim_cache() frees it.
+cudaError_t clb_cache_alloc(void** p, size_t bytes, size_t* got);
+void clb_cache_free(void* p, size_t bytes);
+
 template <typename T>
 struct DevBuf {
     T* p = nullptr;
     size_t n = 0;
+    size_t bytes = 0;      // size of the underlying block (>= n * sizeof(T))
     // grow-only; contents are NOT preserved
     cudaError_t ensure(size_t need) {
         if (need <= n && p) return cudaSuccess;
-        // regrowth is geometric: cudaFree/cudaMalloc synchronise the device and cost milliseconds
+        // regrowth is geometric: device allocation is expensive
         size_t cap = p ? need + need / 2 + 64 : (need ? need : 1);
-        if (p) cudaFree(p);
-        p = nullptr; n = 0;
-        cudaError_t e = cudaMalloc((void**)&p, cap * sizeof(T));
-        if (e == cudaSuccess) n = cap;
+        release();
+        size_t got = 0;
+        cudaError_t e = clb_cache_alloc((void**)&p, cap * sizeof(T), &got);
+        if (e == cudaSuccess) { bytes = got; n = got / sizeof(T); }
         return e;
     }
     // grow and keep the first `keep` elements
     cudaError_t ensure_keep(size_t need, size_t keep, cudaStream_t st) {
         if (need <= n && p) return cudaSuccess;
         T* q = nullptr;
-        size_t cap = need + need / 2 + 16;
-        cudaError_t e = cudaMalloc((void**)&q, cap * sizeof(T));
+        size_t cap = need + need / 2 + 16, got = 0;
+        cudaError_t e = clb_cache_alloc((void**)&q, cap * sizeof(T), &got);
         if (e != cudaSuccess) return e;
         if (p && keep) { e = cudaMemcpyAsync(q, p, keep * sizeof(T), cudaMemcpyDeviceToDevice, st); if (e != cudaSuccess) return e; }
         e = cudaStreamSynchronize(st);
-        if (p) cudaFree(p);
-        p = q; n = cap;
+        release();
+        p = q; bytes = got; n = got / sizeof(T);
         return e;
     }
-    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    void release() { if (p) clb_cache_free(p, bytes); p = nullptr; n = 0; bytes = 0; }
 };
 
 struct HostTable { int n, interp; double x0, dx; std::vector<double> e, f; };
@@ -116,13 +123,13 @@ struct clb_engine {
     unsigned tab2_nm1 = 0;
     int pair_nv = 1, pair_nv_user = 0, pair_vc_bytes = 0;
     // windowed multi-table kernel (k_pair_forces_tab3)
-    struct T3Slot { int off, n, w0, w1; double weight; int srow; };
+    struct T3Slot { int off, n, w0, w1; double weight; int srow; int shift; };   // shift: rows between the common grid origin and this table's first row
     std::vector<T3Slot> t3_slots;               // one per uploaded table slot (premixed rows)
     std::vector<int> t3_pair_slot;              // [nt*nt] slot of the type pair, -1: no potential
     std::vector<double> t3_pair_rc2;            // [nt*nt] cutoff^2 in lattice^2
     std::vector<double2> t3_rows;               // host copy of all {A_i, B_i} rows
     DevBuf<ClbPairDesc3> d_pd3; DevBuf<int2> d_gmeta; DevBuf<double2> d_swin; DevBuf<unsigned long long> d_hist;
-    int tab3_ok = 0, tab3_onepd = 0, tab3_nsrows = 0, tab3_rlog = 0, tab3_resident = 0, pair_rep_user = -1, pair_table_kb_user = -1;
+    int tab3_fb = 0, pair_fb_user = -1, pair_ni_user = 0, tab3_ok = 0, tab3_onepd = 0, tab3_nsrows = 0, tab3_rlog = 0, tab3_resident = 0, pair_rep_user = -1, pair_table_kb_user = -1;
     double tab3_resident_weight = 0;
     bool t3_dirty = true;
     ClbPairDesc3 tab3_one; int2 tab3_one_g;
@@ -161,6 +168,7 @@ struct clb_engine {
     std::vector<int64_t> react_counters;
     struct ReactDev;
     ReactDev* rd = nullptr;
+    int R_prealloc_n = -1;
 
     // timers / counters
     cudaEvent_t ev_a[CLB_NBUCKET], ev_b[CLB_NBUCKET];
@@ -192,6 +200,13 @@ struct clb_engine {
     int comm_max_displacement(cudaStream_t st);
     int comm_step(cudaStream_t st);
     int comm_group_user = 1;
+    int peer_user = -1;       // -1 auto (peer mailboxes when cudaIpc works), 0 = NCCL on the step path
+    int comm_peer_setup();
+    void comm_peer_teardown();
+    int comm_step_peer(cudaStream_t st, int step_index);
+    int comm_migrate_peer();
+    int comm_exchange_ghosts_peer();
+    bool peer_active() const;
     int pending_step_index = 0;
     int comm_allreduce_sum(double* v, int n);
     int comm_allreduce_sum_dev(double* d, size_t n);

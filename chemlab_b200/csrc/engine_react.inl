@@ -118,10 +118,30 @@ int clb_engine::upload_reactions() {
         CK(cudaMemsetAsync(rd->counters.p, 0, CLB_MAX_REACTIONS * 8, stream));
         rd->slot_arrays_init = true;
     }
+    // every buffer of a reaction pass is allocated here, at set-up time: device allocation inside the first pass cost up to
+    // 0.4 s on the B200 box (bench.py times one pass on its own)
+    if (!reactions.empty()) {
+        if (R_prealloc_n != n) {
+            ReactDev& R = *rd;
+            if (R.candcap == 0) R.candcap = std::max<size_t>(65536, (size_t)n / 4);
+            const size_t cc = R.candcap;
+            CK(R.cands.ensure(cc)); CK(R.cands_sorted.ensure(cc)); CK(R.ckey.ensure(cc)); CK(R.ckey2.ensure(cc)); CK(R.cval.ensure(cc)); CK(R.cval2.ensure(cc));
+            CK(R.alive.ensure(cc)); CK(R.surv.ensure(cc)); CK(R.status.ensure(cc)); CK(R.ev.ensure(cc)); CK(R.erank.ensure(cc)); CK(R.iota.ensure(cc));
+            CK(R.evpairs.ensure(2 * cc)); CK(R.flag.ensure(4)); CK(R.touched.ensure(cc * 8));
+            CK(R.lists.ensure(CLB_MAX_LISTS)); CK(R.list_n.ensure(CLB_MAX_LISTS)); CK(R.list_cnt.ensure(CLB_MAX_LISTS));
+            if (!R.adj.p) { CK(R.adj.ensure((size_t)n * CLB_MAXDEG)); CK(R.deg.ensure(n)); CK(cudaMemsetAsync(R.deg.p, 0, (size_t)n * 4, stream)); }
+            size_t tb = 0, tb2 = 0;
+            cub::DeviceRadixSort::SortPairs(nullptr, tb, R.ckey.p, R.ckey2.p, R.cval.p, R.cval2.p, (int)cc, 0, 64, stream);
+            cub::DeviceSelect::Flagged(nullptr, tb2, R.iota.p, R.alive.p, R.surv.p, (int*)R.scalars.p, (int)cc, stream);
+            CK(cubtmp2.ensure(std::max(tb, tb2) + 256));
+            CK(excl_pairs.ensure_keep((size_t)nexcl + cc + 1024, (size_t)nexcl, stream));
+            R_prealloc_n = n;
+        }
+    }
     CK(cudaStreamSynchronize(stream));
     // lists that reactions append to (bond targets, registered angle/dihedral lists): capacity up front
-    for (auto& r : reactions) TRY(list_reserve(r.list, lists[r.list].n + 1));
-    for (auto& g : tmregs) TRY(list_reserve(g.list, lists[g.list].n + 1));
+    for (auto& r : reactions) TRY(list_reserve(r.list, lists[r.list].n + std::max<long long>(1, n / 8)));
+    for (auto& g : tmregs) TRY(list_reserve(g.list, lists[g.list].n + std::max<long long>(1, n / 8)));
     react_dirty = false;
     return CLB_OK;
 }

@@ -46,6 +46,9 @@ int clb_create(clb_engine **out, int device, const double box[3], double rc_max,
 void clb_destroy(clb_engine *e);
 const char *clb_last_error(const clb_engine *e); /* e may be NULL: error of the failed clb_create */
 int clb_abi_version(void);
+/* Device blocks released by destroyed engines are cached per process (allocation on a busy device costs milliseconds);
+ * this hands them back to the CUDA driver.  No reference counterpart (memory management of the engine). */
+int clb_trim_cache(void);
 
 /* Generic numeric options (name -> double).  Known names:
  *   "resort_criterion"  0 = reference rule (sum over steps of the per-step max displacement > skin/2,
