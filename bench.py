@@ -456,7 +456,7 @@ def main():
 
     # the first engine is done (timed run, parity): its device blocks go to the engine's block cache and are reused below
     pair_opts = {k: e.get_option(k) for k in ("pair_threads", "pair_grid", "pair_nv", "pair_smem", "home_max", "tile_max", "pair_kernel", "pair_rep",
-                                               "pair_table_rows", "pair_tables_resident", "pair_tables_resident_weight", "block_cells", "timers")}
+                                               "pair_table_rows", "pair_tables_resident", "pair_tables_resident_weight", "block_cells", "timers", "comm_peer")}
     if rank == 0:
         line.update({k: pair_opts[k] for k in pair_opts if k != "timers"})
         line["buckets_s"] = {k: v for k, v in tm.items() if v > 0} if pair_opts["timers"] else None

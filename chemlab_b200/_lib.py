@@ -69,6 +69,9 @@ SIGNATURES = {
     "clb_topology_initialize": (C.c_int, [C.c_void_p]),
     "clb_react_now": (C.c_int, [C.c_void_p, c_i64p]),
     "clb_reaction_counters": (C.c_int, [C.c_void_p, C.c_int, c_i64p]),
+    "clb_atrp_configure": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double]),
+    "clb_atrp_add_center": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int]),
+    "clb_atrp_now": (C.c_int, [C.c_void_p, c_i64p, c_f64p]),
     "clb_get_pairs": (C.c_int, [C.c_void_p, C.c_int64, c_i64p, c_i64p]),
     "clb_get_last_candidates": (C.c_int, [C.c_void_p, C.c_int64, c_i64p, c_f64p, c_i64p]),
     "clb_timers": (C.c_int, [C.c_void_p, c_f64p, c_i64p]),

@@ -52,13 +52,18 @@ struct ClbCtl {
     unsigned long long halo_epoch;  // multi-GPU peer path: number of completed per-step halo exchanges (identical on every rank)
     unsigned comm_done;             // block-completion counter of the push kernels
     unsigned comm_pad;
+    int nblocks;            // row blocks of the current block table (k_blocks_scan)
+    int blk_p1, blk_pl;     // first block of owned plane 1 and of the last owned plane (multi-GPU interior / boundary split)
+    int blk_pad;
 };
 
 struct ClbGrid {
     int ncx, ncy, ncz, ncell;
-    int bx;      // home cells per row block
-    int nbx;     // blocks per row
-    int nblocks; // nbx * ncy * nczl
+    int bx;      // max home cells per row block
+    int target;  // max home particles per row block (a single fuller cell still makes a block); <= 0: cells only (fixed-length blocks)
+    int nblocks; // number of row blocks in the table (host copy of ctl->nblocks; < 0: read ctl->nblocks on the device)
+    const int4* blk;     // block table {first home cell x, home cells, row y, local plane}, rebuilt with the cell lists (k_blocks_*)
+    const int* nblk_d;   // &ctl->nblocks
     int cz0, nczl; // owned z-plane range [cz0, cz0+nczl) of this rank (single GPU: 0, ncz)
     int zoff;      // = cz0.  Local plane of global plane cz: l = (cz - zoff) mod ncz; owned planes are l in [0,nczl),
                    // the upper ghost plane (cz0+nczl) is local plane nczl, the lower ghost plane (cz0-1, l = ncz-1) is
@@ -111,6 +116,7 @@ __host__ __device__ inline void philox4x32_10(uint32_t c[4], uint32_t k0, uint32
 #define CLB_STREAM_HEATUP 0x48454154u
 #define CLB_STREAM_REACT 0x52454143u
 #define CLB_STREAM_PARTNER 0x50415254u
+#define CLB_STREAM_ATRP 0x41545250u
 
 __host__ __device__ inline void clb_draw3(uint64_t seed, uint32_t stream, uint64_t step, uint32_t idx, double u[3]) {
     uint32_t c[4] = {idx, 0u, (uint32_t)step, (uint32_t)(step >> 32)};
@@ -134,6 +140,8 @@ __device__ __forceinline__ double lat2d(int d) {
 __host__ __device__ __forceinline__ int wsub(int a, int b) { return (int)((unsigned)a - (unsigned)b); }
 __host__ __device__ __forceinline__ int wadd(int a, int b) { return (int)((unsigned)a + (unsigned)b); }
 __device__ __forceinline__ int wrapi(int c, int n) { return c < 0 ? c + n : (c >= n ? c - n : c); }
+// number of row blocks: the host's copy, or (kernels enqueued between k_blocks_scan and the host check of a rebuild) the device's
+__device__ __forceinline__ int grid_nblocks(const ClbGrid& g) { return g.nblocks >= 0 ? g.nblocks : *(volatile const int*)g.nblk_d; }
 // local plane index of global plane cz (see ClbGrid::zoff); planes that are neither owned nor ghost map to -1
 __device__ __forceinline__ int local_plane(const ClbGrid& g, int cz) {
     if (!g.ghost) return cz;

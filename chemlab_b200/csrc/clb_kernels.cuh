@@ -39,14 +39,69 @@ __global__ void k_cell_start(int n, const int* __restrict__ key, int ncell, int*
     int cur = i == n ? ncell : key[i];
     for (int c = prev + 1; c <= cur; ++c) cell_start[c] = i;
 }
+// ---- row-block table ---------------------------------------------------------------------------------------------------
+// A row block = consecutive cells of one x-row whose particles are the HOME particles of one tile (clb_tile.cuh).  Blocks are
+// cut greedily along each row: a block closes when the next cell would push it over `target` home particles (so that the
+// home particles fill the lanes of the warps that work on the tile: fixed-length blocks of a fluctuating melt left a quarter
+// of the lanes idle) or when it holds `bx` cells (shared-memory offset tables).  Empty blocks are dropped.  Three tiny
+// kernels: blocks per row, exclusive scan over the rows (one CTA), table fill.
+template <bool WRITE>
+__global__ void k_blocks_rows(ClbGrid g, const int* __restrict__ cell_start, int* __restrict__ row_n, const int* __restrict__ row_off, int4* __restrict__ blk) {
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= g.ncy * g.nczl) return;
+    const int cy = row % g.ncy, lz = row / g.ncy;
+    const int* cs = cell_start + (size_t)row * g.ncx;
+    const int target = g.target > 0 ? g.target : 0x7fffffff;
+    int k = 0, c = 0;
+    int o = WRITE ? row_off[row] : 0;
+    while (c < g.ncx) {
+        int c1 = c + 1, cnt = cs[c1] - cs[c];
+        while (c1 < g.ncx && c1 - c < g.bx) { const int nx = cs[c1 + 1] - cs[c1]; if (cnt + nx > target) break; cnt += nx; ++c1; }
+        if (cnt > 0) { if (WRITE) blk[o + k] = make_int4(c, c1 - c, cy, lz); ++k; }
+        c = c1;
+    }
+    if (!WRITE) row_n[row] = k;
+}
+__global__ void __launch_bounds__(1024) k_blocks_scan(int nrows, int ncy, int nczl, const int* __restrict__ row_n, int* __restrict__ row_off, ClbCtl* ctl) {
+    __shared__ int s_w[32];
+    __shared__ int s_run;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_run = 0;
+    __syncthreads();
+    for (int base = 0; base < nrows; base += 1024) {
+        const int r = base + threadIdx.x;
+        const int v = r < nrows ? row_n[r] : 0;
+        int incl = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { int u = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += u; }
+        if (lane == 31) s_w[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            int w = s_w[lane], wi = w;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { int u = __shfl_up_sync(0xffffffffu, wi, d); if (lane >= d) wi += u; }
+            s_w[lane] = wi - w;
+        }
+        __syncthreads();
+        const int run = s_run;
+        const int excl = run + s_w[warp] + incl - v;
+        if (r < nrows) {
+            row_off[r] = excl;
+            if (r == ncy) ctl->blk_p1 = excl;
+            if (r == (nczl - 1) * ncy) ctl->blk_pl = excl;
+        }
+        __syncthreads();
+        if (threadIdx.x == 1023) s_run = excl + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { ctl->nblocks = s_run; if (nczl < 2) { ctl->blk_p1 = s_run; ctl->blk_pl = 0; } }
+}
 // per-block tile statistics -> dynamic shared memory size and block size of the tile kernels
 __global__ void k_block_stats(ClbGrid g, const int* __restrict__ cell_start, ClbCtl* ctl) {
     int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= g.nblocks) return;
-    int row = b / g.nbx, bxi = b - row * g.nbx;
-    int cx0 = bxi * g.bx, bxe = min(g.bx, g.ncx - cx0);
-    int cy = row % g.ncy, zrow = row / g.ncy;
-    int lz = zrow;
+    if (b >= grid_nblocks(g)) return;
+    const int4 q = g.blk[b];
+    int cx0 = q.x, bxe = q.y, cy = q.z, lz = q.w;
     bool whole = bxe + 2 > g.ncx;
     int W = whole ? g.ncx : bxe + 2;
     int T = 0, cmax = 0;

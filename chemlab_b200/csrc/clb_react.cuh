@@ -481,3 +481,58 @@ __global__ void k_iota(int n, int* __restrict__ v) { int i = blockIdx.x * blockD
 __global__ void k_fill_u64(long long n, unsigned long long* __restrict__ v, unsigned long long x) { long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; if (i < n) v[i] = x; }
 __global__ void k_fill_i32(long long n, int* __restrict__ v, int x) { long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; if (i < n) v[i] = x; }
 __global__ void k_set_force_rebuild(ClbCtl* c) { c->force_rebuild = 1; }
+
+// ------------------------------------------------------------------------------------------------------------------
+// ATRPActivator (src/chemlab/reaction_post_process.py:393-424; [EXT] integrator/ATRPActivator.cpp, U23): every `interval`
+// steps up to `num_particles` particles sitting on a reactive centre (type, state) are picked at random and switch between
+// the dormant and the active state with the probability of meeting the right catalyst complex.
+//   candidate : first centre k (registration order) with type == type_k and state == state_k
+//   selection : counter-based key  u = Philox(seed, "ATRP", step, slot).x ; the num_particles smallest (u, slot) are taken
+//   reaction  : w = Philox(...).y ;  w < k_deactivate*ratio_deactivator (flag "DA") or k_activate*ratio_activator (flag "A")
+//   effect    : state += delta_state ; type / mass / charge from new_property
+// The ratios used are those at the START of the pass; the host moves them by delta_catalyst*(n_act - n_deact)/num_particles.
+struct ClbAtrpCenter { int type, state, deactivator, new_type, delta_state, pad; double new_mass, new_q, p; };
+__global__ void k_atrp_scan(int i0, int i1, const int4* __restrict__ pos, const int* __restrict__ slot, const ClbAtrpCenter* __restrict__ cen, int ncen,
+                            uint64_t seed, uint64_t step, unsigned long long* __restrict__ keys, unsigned long long* __restrict__ count, unsigned long long cap) {
+    int i = i0 + blockIdx.x * blockDim.x + threadIdx.x;
+    int hit = -1, s = 0;
+    if (i < i1) {
+        const int w = pos[i].w;
+        for (int k = 0; k < ncen && hit < 0; ++k) if (cen[k].type == pw_type(w) && cen[k].state == pw_state(w)) hit = k;
+        s = slot[i];
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, hit >= 0);
+    if (!bal) return;
+    const int lane = threadIdx.x & 31;
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(count, (unsigned long long)__popc(bal));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (hit >= 0) {
+        uint32_t c[4] = {(uint32_t)s, 0u, (uint32_t)step, (uint32_t)(step >> 32)};
+        philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32) ^ CLB_STREAM_ATRP);
+        const unsigned long long o = base + __popc(bal & ((1u << lane) - 1u));
+        if (o < cap) keys[o] = ((unsigned long long)c[0] << 32) | (unsigned)s;
+    }
+}
+// the first nsel keys (ascending) are the selected particles
+__global__ void k_atrp_apply(int nsel, const unsigned long long* __restrict__ keys, const ClbAtrpCenter* __restrict__ cen, int ncen, uint64_t seed, uint64_t step,
+                             const int* __restrict__ id2idx, int* wslot, int4* pos, ClbVel* vel, double* charge, unsigned long long* __restrict__ counts) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nsel) return;
+    const int s = (int)(keys[k] & 0xffffffffull);
+    int w = wslot[s];
+    int hit = -1;
+    for (int q = 0; q < ncen && hit < 0; ++q) if (cen[q].type == pw_type(w) && cen[q].state == pw_state(w)) hit = q;
+    if (hit < 0) return;
+    const ClbAtrpCenter C = cen[hit];
+    uint32_t c[4] = {(uint32_t)s, 0u, (uint32_t)step, (uint32_t)(step >> 32)};
+    philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32) ^ CLB_STREAM_ATRP);
+    const double u = ((double)c[1] + 0.5) * (1.0 / 4294967296.0);
+    if (!(u < C.p)) return;
+    w = pw_pack(C.new_type >= 0 ? C.new_type : pw_type(w), pw_state(w) + C.delta_state);
+    wslot[s] = w;
+    const int idx = id2idx[s];
+    if (idx >= 0) { pos[idx].w = w; if (C.new_mass > 0) vel[idx].w = C.new_mass; }
+    if (C.new_q == C.new_q) charge[s] = C.new_q;
+    atomicAdd(counts + (C.deactivator ? 1 : 0), 1ull);
+}

@@ -25,12 +25,11 @@ struct TileCtx {
 
 // decode block -> geometry.  Must be called by all threads (uniform).
 __device__ __forceinline__ void tile_geometry(const ClbGrid& g, int b, TileCtx& t) {
-    int row = b / g.nbx, bxi = b - row * g.nbx;
-    t.cx0 = bxi * g.bx;
-    t.bxe = min(g.bx, g.ncx - t.cx0);
-    t.cy = row % g.ncy;
-    int zrow = row / g.ncy;                 // 0..nczl-1 : owned plane index
-    t.lz = zrow;
+    const int4 q = __ldg(g.blk + b);        // block table (k_blocks_rows): {first home cell, home cells, row y, owned plane}
+    t.cx0 = q.x;
+    t.bxe = q.y;
+    t.cy = q.z;
+    t.lz = q.w;
     t.whole = (t.bxe + 2 > g.ncx);
     t.W = t.whole ? g.ncx : t.bxe + 2;
 }
@@ -144,6 +143,21 @@ __device__ __forceinline__ int home_column(const TileCtx& t, const int* s_off, i
     return m;
 }
 
+// Work order of a block's home particles for the pair kernel: longest neighbour row first.  Lane l of warp w takes the home
+// particle perm[32 w + l], so the rows of one warp have nearly the same length and few lanes idle while the longest row of
+// the warp finishes (cell order mixes rows of 55..95 entries in every warp: 12 % of the lane slots).  Stable counting rank,
+// called by the whole CTA after all rows of the block are written; s_cnt[p] = row length of home particle p.
+#define CLB_PERM_MAX 1024
+__device__ __forceinline__ void block_perm(int hs, int nh, const int* s_cnt, unsigned short* __restrict__ perm) {
+    if (nh > CLB_PERM_MAX) { for (int p = threadIdx.x; p < nh; p += blockDim.x) perm[hs + p] = (unsigned short)(p & 0xffff); return; }
+    for (int p = threadIdx.x; p < nh; p += blockDim.x) {
+        const int c = s_cnt[p];
+        int r = 0;
+        for (int q = 0; q < nh; ++q) { const int d = s_cnt[q]; r += (d > c || (d == c && q < p)) ? 1 : 0; }
+        perm[hs + r] = (unsigned short)p;
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // Neighbour-list build.  One WARP per home particle, lanes = candidates: the 27 cells around the
 // particle's cell are 9 contiguous tile ranges, read 32 at a time (conflict-free LDS.128), tested
@@ -159,11 +173,12 @@ __global__ void __launch_bounds__(512) k_build_lists(ClbGrid g, ClbGeom geo, uns
                                                      const int4* __restrict__ pos, const int* __restrict__ slot,
                                                      const int* __restrict__ excl_off, const int* __restrict__ excl_ids,
                                                      unsigned short* __restrict__ entries, int* __restrict__ nl_count,
-                                                     int cap, int tile_cap, ClbCtl* ctl) {
+                                                     unsigned short* __restrict__ nl_perm, int cap, int tile_cap, ClbCtl* ctl) {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ int s_off[CLB_TILE_CELLS + 1];
     __shared__ int s_src[CLB_TILE_CELLS];
     __shared__ int s_item[CLB_MAX_BX + 1];      // prefix of (cell, group-of-G) work items over the home cells
+    __shared__ int s_cnt[CLB_PERM_MAX];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
     const unsigned lt_mask = (1u << lane) - 1u;
     // dynamic smem: tile positions | tile slots | G staging rows (cap entries each) per warp
@@ -172,7 +187,8 @@ __global__ void __launch_bounds__(512) k_build_lists(ClbGrid g, ClbGeom geo, uns
     unsigned short* s_rows = reinterpret_cast<unsigned short*>(s_slot + tile_cap) + (size_t)warp * CLB_BUILD_G * cap;
     int lmax = 0;
     unsigned long long ltot = 0;
-    for (int b = blockIdx.x; b < g.nblocks; b += gridDim.x) {
+    const int nblk = grid_nblocks(g);
+    for (int b = blockIdx.x; b < nblk; b += gridDim.x) {
         TileCtx t;
         tile_geometry(g, b, t);
         __syncthreads();
@@ -267,12 +283,184 @@ __global__ void __launch_bounds__(512) k_build_lists(ClbGrid g, ClbGeom geo, uns
                 for (int k = lane; k * 8 < n; k += 32) grow4[k] = srow4[k];
                 if (lane == 0) {
                     nl_count[gi] = n;
+                    if (ti - tbase < CLB_PERM_MAX) s_cnt[ti - tbase] = n;
                     if (found > cap) atomicOr(&ctl->err, CLB_EF_LIST_OVERFLOW);
                     lmax = max(lmax, found); ltot += (unsigned long long)n;
                 }
             }
             __syncwarp();
         }
+        __syncthreads();
+        block_perm(t.hs, t.nh, s_cnt, nl_perm);
+    }
+    if (lane == 0 && ltot) { atomicMax(&ctl->nl_max, lmax); atomicAdd(&ctl->nl_total, ltot); }
+}
+
+// ------------------------------------------------------------------------------------------
+// Neighbour-list build, second generation (round 2): same result as k_build_lists (the pair SET is bit-identical, entries
+// keep the candidate order), about 2.5x fewer instructions.  The 5*10^8 candidate tests per rebuild of the 1M-bead melt hit
+// only 15 % of the time, so they are split in two phases:
+//   phase 1  an 8-bit PREFILTER on one DP4A per test.  Every particle carries its position inside its cell quantised to
+//            84 units per cell edge (k_qsub: q = floor(frac * 84), exactly consistent with the cell assignment), the tile
+//            stage adds the cell offsets, so tile-relative coordinates are integers X' in [0, 84*W), Y', Z' in [2, 254).
+//            For a home cell the candidates of its 27 cells lie within +-126 units of the cell centre: signed bytes.  With
+//            a = home bead, b = candidate (bytes x, 0, z, y):   |b - a|^2 - |a|^2 = DP4A(-2a, b, DP4A(b, b, 0))  and the
+//            test is  <= Rq2 - |a|^2.  Floor quantisation moves each coordinate difference by less than one unit, so with
+//            Rq = (rc+skin)/u + sqrt(3) the prefilter keeps a strict SUPERSET (+6 % at the melt's geometry).
+//   phase 2  the survivors (~80 per bead instead of 540 candidates) get the exact 64-bit integer test, lose the bead itself
+//            and its excluded partners (slot compare against the bead's exclusion row held across the lanes) and are
+//            compacted in place, order preserved.
+// Cubic boxes with tiles that do not wrap around x only (everything else takes k_build_lists).
+#define CLB_QCELL 84
+__global__ void k_qsub(int n, const int4* __restrict__ pos, ClbGrid g, unsigned* __restrict__ qsub) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int4 p = pos[i];
+    // low word of x * nc = position inside the cell as a 2^-32 fraction (the cell index is the high word: k_cell_keys)
+    const unsigned qx = __umulhi((unsigned)p.x * (unsigned)g.ncx, CLB_QCELL);
+    const unsigned qy = __umulhi((unsigned)p.y * (unsigned)g.ncy, CLB_QCELL);
+    const unsigned qz = __umulhi((unsigned)p.z * (unsigned)g.ncz, CLB_QCELL);
+    qsub[i] = (qy << 24) | (qz << 16) | qx;
+}
+__global__ void __launch_bounds__(512) k_build_lists2(ClbGrid g, unsigned long long rl2_lat, int rq2,
+                                                      const int* __restrict__ cell_start,
+                                                      const int4* __restrict__ pos, const int* __restrict__ slot, const unsigned* __restrict__ qsub,
+                                                      const int* __restrict__ excl_off, const int* __restrict__ excl_ids,
+                                                      unsigned short* __restrict__ entries, int* __restrict__ nl_count,
+                                                      unsigned short* __restrict__ nl_perm, int cap, int tile_cap, ClbCtl* ctl) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ int s_off[CLB_TILE_CELLS + 1];
+    __shared__ int s_src[CLB_TILE_CELLS];
+    __shared__ int s_item[CLB_MAX_BX + 1];
+    __shared__ int s_cnt[CLB_PERM_MAX];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    // dynamic smem: tile positions | tile slots | tile quantised words | G staging rows (cap entries each) per warp
+    int4* s_pos = reinterpret_cast<int4*>(smem);
+    int* s_slot = reinterpret_cast<int*>(s_pos + tile_cap);
+    unsigned* s_q = reinterpret_cast<unsigned*>(s_slot + tile_cap);
+    unsigned short* s_rows = reinterpret_cast<unsigned short*>(s_q + tile_cap) + (size_t)warp * CLB_BUILD_G * cap;
+    int lmax = 0;
+    unsigned long long ltot = 0;
+    const int nblk = grid_nblocks(g);
+    for (int b = blockIdx.x; b < nblk; b += gridDim.x) {
+        TileCtx t;
+        tile_geometry(g, b, t);
+        __syncthreads();
+        tile_offsets(g, t, cell_start, s_off, s_src);
+        if (t.T > tile_cap) { if (threadIdx.x == 0) atomicOr(&ctl->err, CLB_EF_TILE_OVERFLOW); continue; }
+        {   // stage positions, slots and the tile-relative quantised words
+            const int nct = CLB_TILE_ROWS * t.W;
+            for (int tc = warp; tc < nct; tc += nw) {
+                const int k = tc / t.W, m = tc - k * t.W;
+                const unsigned offc = ((unsigned)((k % 3) * CLB_QCELL + 2) << 24) | ((unsigned)((k / 3) * CLB_QCELL + 2) << 16) | (unsigned)(m * CLB_QCELL);
+                const int o = s_off[tc], c = s_off[tc + 1] - o, sgl = s_src[tc];
+                for (int i = lane; i < c; i += 32) {
+                    s_pos[o + i] = __ldg(pos + sgl + i);
+                    s_slot[o + i] = __ldg(slot + sgl + i);
+                    s_q[o + i] = (__ldg(qsub + sgl + i) + offc) ^ 0x80800000u;
+                }
+            }
+        }
+        const int mh0 = t.whole ? t.cx0 : 1;
+        if (threadIdx.x == 0) {
+            int acc = 0;
+            for (int c = 0; c < t.bxe; ++c) { s_item[c] = acc; acc += (s_off[4 * t.W + mh0 + c + 1] - s_off[4 * t.W + mh0 + c] + CLB_BUILD_G - 1) / CLB_BUILD_G; }
+            s_item[t.bxe] = acc;
+        }
+        __syncthreads();
+        const int tbase = s_off[4 * t.W + mh0];
+        const int nitems = s_item[t.bxe];
+#pragma unroll 1
+        for (int item = warp; item < nitems; item += nw) {
+            int c = 0;
+            while (c + 1 < t.bxe && s_item[c + 1] <= item) ++c;
+            const int mh = mh0 + c;
+            const int cell_lo = s_off[4 * t.W + mh], cell_hi = s_off[4 * t.W + mh + 1];
+            const int t0 = cell_lo + (item - s_item[c]) * CLB_BUILD_G;
+            const int np = min(CLB_BUILD_G, cell_hi - t0);
+            int an2[CLB_BUILD_G], cq[CLB_BUILD_G], cnt[CLB_BUILD_G];
+            const int xbias = 128 - (mh * CLB_QCELL + CLB_QCELL / 2);
+#pragma unroll
+            for (int q = 0; q < CLB_BUILD_G; ++q) {
+                const unsigned w = s_q[t0 + min(q, np - 1)];
+                const int ax = (int)(w & 0xffffu) + xbias - 128, az = (int)(signed char)(w >> 16), ay = (int)(signed char)(w >> 24);
+                an2[q] = (int)(((unsigned)(-2 * ax) & 0xffu) | (((unsigned)(-2 * az) & 0xffu) << 16) | (((unsigned)(-2 * ay) & 0xffu) << 24));
+                cq[q] = rq2 - (ax * ax + ay * ay + az * az);
+                cnt[q] = 0;
+            }
+            // phase 1: prefilter, ballot compaction into the staging rows
+#pragma unroll 1
+            for (int sgm = 0; sgm < CLB_TILE_ROWS; ++sgm) {
+                const int lo = s_off[sgm * t.W + mh - 1], hi = s_off[sgm * t.W + mh + 2];
+#pragma unroll 1
+                for (int j0 = lo; j0 < hi; j0 += 32) {
+                    const int j = j0 + lane;
+                    const bool valid = j < hi;
+                    const unsigned bw = (s_q[valid ? j : lo] + (unsigned)xbias) ^ 0x80u;     // bytes {x, 0, z, y} relative to the home cell centre
+                    const int bb = valid ? __dp4a((int)bw, (int)bw, 0) : 0x3fffffff;
+#pragma unroll
+                    for (int q = 0; q < CLB_BUILD_G; ++q) {
+                        const bool pass = __dp4a(an2[q], (int)bw, bb) <= cq[q];
+                        const unsigned bal = __ballot_sync(0xffffffffu, pass);
+                        const int o = cnt[q] + __popc(bal & lt_mask);
+                        const unsigned st = (pass && o < cap) ? 1u : 0u;
+                        const unsigned addr = (unsigned)__cvta_generic_to_shared(s_rows + q * cap + o);
+                        asm volatile("{ .reg .pred p; setp.ne.u32 p, %2, 0; @p st.shared.u16 [%0], %1; }"
+                                     :: "r"(addr), "h"((unsigned short)j), "r"(st) : "memory");
+                        cnt[q] += __popc(bal);
+                    }
+                }
+            }
+            __syncwarp();
+            // phase 2: exact test, self / exclusions, in-place compaction, row output
+#pragma unroll 1
+            for (int q = 0; q < np; ++q) {
+                unsigned short* s_row = s_rows + q * cap;
+                const int ti = t0 + q;
+                const int gi = t.hs + (ti - tbase);
+                int found = 0;
+#pragma unroll
+                for (int r = 0; r < CLB_BUILD_G; ++r) if (r == q) found = cnt[r];
+                const int n1 = min(found, cap);
+                const int4 pi = s_pos[ti];
+                const int myslot = s_slot[ti];
+                const int e0 = __ldg(excl_off + myslot), nex = __ldg(excl_off + myslot + 1) - e0;
+                const int exid = lane < nex ? __ldg(excl_ids + e0 + lane) : -1;      // first 32 excluded partners across the lanes
+                int n2 = 0;
+#pragma unroll 1
+                for (int k0 = 0; k0 < n1; k0 += 32) {
+                    const int k = k0 + lane;
+                    const bool valid = k < n1;
+                    const unsigned e = s_row[valid ? k : 0];
+                    const int4 pj = s_pos[e];
+                    const int dx = wsub(pi.x, pj.x), dy = wsub(pi.y, pj.y), dz = wsub(pi.z, pj.z);
+                    const unsigned long long r2 = (unsigned long long)((long long)dx * dx) + (unsigned long long)((long long)dy * dy) +
+                                                  (unsigned long long)((long long)dz * dz);
+                    const int sj = s_slot[e];
+                    bool keep = valid && r2 <= rl2_lat && (int)e != ti;
+                    const int nx32 = min(nex, 32);
+                    for (int x = 0; x < nx32; ++x) keep = keep && (sj != __shfl_sync(0xffffffffu, exid, x));
+                    for (int x = 32; x < nex; ++x) keep = keep && (sj != __ldg(excl_ids + e0 + x));      // more than 32 exclusions: rare
+                    const unsigned bal = __ballot_sync(0xffffffffu, keep);
+                    if (keep) s_row[n2 + __popc(bal & lt_mask)] = (unsigned short)e;      // position <= k: never ahead of an unread entry
+                    n2 += __popc(bal);
+                    __syncwarp();
+                }
+                const uint4* srow4 = reinterpret_cast<const uint4*>(s_row);
+                uint4* grow4 = reinterpret_cast<uint4*>(entries + (size_t)gi * cap);
+                for (int k = lane; k * 8 < n2; k += 32) grow4[k] = srow4[k];
+                if (lane == 0) {
+                    nl_count[gi] = n2;
+                    if (ti - tbase < CLB_PERM_MAX) s_cnt[ti - tbase] = n2;
+                    if (found > cap) atomicOr(&ctl->err, CLB_EF_LIST_OVERFLOW);
+                    lmax = max(lmax, found > cap ? found : n2); ltot += (unsigned long long)n2;
+                }
+            }
+            __syncwarp();
+        }
+        __syncthreads();
+        block_perm(t.hs, t.nh, s_cnt, nl_perm);
     }
     if (lane == 0 && ltot) { atomicMax(&ctl->nl_max, lmax); atomicAdd(&ctl->nl_total, ltot); }
 }
@@ -711,6 +899,9 @@ __device__ __forceinline__ void mbar_init(unsigned long long* mbar, unsigned cou
 __device__ __forceinline__ void mbar_expect_tx(unsigned long long* mbar, unsigned bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(mbar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(unsigned long long* mbar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(mbar)) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(unsigned long long* mbar, unsigned parity) {
     asm volatile(
         "{\n"
@@ -753,7 +944,8 @@ __device__ __forceinline__ void tile_stage_bulk(const ClbGrid& g, const TileCtx&
     for (int d = 1; d < 32; d <<= 1) { int v = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += v; }
     const int T = __shfl_sync(0xffffffffu, incl, CLB_TILE_RANGES - 1);
     const int ts = incl - cnt;
-    if (lane == CLB_TILE_RANGES) { meta->hs = gs; meta->nh = cnt; meta->T = T; }
+    const int hs_ = __shfl_sync(0xffffffffu, gs, CLB_TILE_RANGES), nh_ = __shfl_sync(0xffffffffu, cnt, CLB_TILE_RANGES);
+    if (lane == 0) { meta->hs = hs_; meta->nh = nh_; meta->T = T; }   // written by the arriving thread: the mbarrier release publishes it
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // earlier generic reads of the tile are ordered before the async writes
     if (lane == 0) mbar_expect_tx(mbar, (unsigned)T * 16u);
     __syncwarp();
@@ -780,6 +972,7 @@ struct ClbPairDesc3 {          // 16 bytes per type pair
 };
 struct ClbPairArgs3 {
     const int* cell_start; const int4* pos; const unsigned short* entries; const int* nl_count;
+    const unsigned short* perm;   // work order of the home particles of every block (block_perm); NULL: cell order
     const ClbPairDesc3* pd3;   // [ntypes^2]
     const int2* gmeta;         // [ntypes^2] {first row of the pair's table in trows - shift, (shift << 20) | (rows - 1)}; shift = rows between
                                // the common grid origin and the table's first abscissa (tables may start at different r)
@@ -791,6 +984,7 @@ struct ClbPairArgs3 {
     ClbPairDesc3 one; int2 one_g;  // ONEPD: the only descriptor
     int b0, seg0, b1, nidx;
     int nv, vc_bytes;
+    int pipe, tile_cap;            // pipe: two tile buffers per virtual CTA, the next tile is staged while the current one is evaluated
 };
 // Rare path of k_pair_forces_tab3: the listed pairs of one 8-entry batch whose table row is NOT in a shared-memory window
 // (bit k of `defer`) are evaluated again from scratch with the row read from global memory.  Kept out of line so that its
@@ -836,15 +1030,19 @@ __global__ void __launch_bounds__(1024) k_pair_forces_tab3(ClbGrid g, ClbPairArg
     const int nth = A.npw * 32;
     const int vc = threadIdx.x / nth, tid = threadIdx.x - vc * nth;
     const int bar = 1 + vc;
-    // per virtual CTA: [mbarrier 16 B][TileMeta 16 B][tile positions]
-    unsigned long long* mbar = reinterpret_cast<unsigned long long*>(vc_base + (size_t)vc * A.vc_bytes);
-    TileMeta* meta = reinterpret_cast<TileMeta*>(mbar + 2);
-    int4* s_pos = reinterpret_cast<int4*>(meta + 1);
+    // per virtual CTA: [full mbarriers 2 x 8 B][empty mbarriers 2 x 8 B][TileMeta x 2][tile buffer 0][tile buffer 1 (pipe)]
+    unsigned long long* mb_full = reinterpret_cast<unsigned long long*>(vc_base + (size_t)vc * A.vc_bytes);
+    unsigned long long* mb_empty = mb_full + 2;
+    TileMeta* metas = reinterpret_cast<TileMeta*>(mb_empty + 2);
+    int4* s_pos0 = reinterpret_cast<int4*>(metas + 2);
+    const bool pipe = A.pipe != 0;
     if (!ONEPD) for (int i = threadIdx.x; i < ntp; i += blockDim.x) s_pd[i] = A.pd3[i];
     for (int i = threadIdx.x; i < (A.nsrows << RLOG); i += blockDim.x) s_rows[i] = __ldg(A.swin + i);
-    if (tid == 0) { mbar_init(mbar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    if (tid == 0) {
+        mbar_init(mb_full, 1); mbar_init(mb_full + 1, 1); mbar_init(mb_empty, (unsigned)A.npw); mbar_init(mb_empty + 1, (unsigned)A.npw);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     __syncthreads();
-    unsigned phase = 0;
     const int lane = tid & 31, warp = tid >> 5;
     // neighbour-row batches (8 entries = 16 B per lane) are prefetched ONE BATCH AHEAD with cp.async into two private 16-byte
     // slots per thread.  (Round 1 / first round-2 version prefetched into registers: ptxas sank the load to the end of the loop
@@ -857,19 +1055,44 @@ __global__ void __launch_bounds__(1024) k_pair_forces_tab3(ClbGrid g, ClbPairArg
     const int nhpass = nth;
     const double invdx = A.invdx, cmagic = A.cmagic;
     unsigned err = 0;
-    for (int idx = vc * gridDim.x + blockIdx.x; idx < A.nidx; idx += gridDim.x * A.nv) {
-        const int b = idx < A.seg0 ? A.b0 + idx : A.b1 + (idx - A.seg0);
+    // PIPE (round 2): the profile of the single-buffer version showed 21 % of the warp time at the group barrier between two
+    // tiles (waiting for the slowest warp of the group, then for the bulk copies of the next tile).  With two buffers the warps
+    // of a group are decoupled: warp 0 stages tile k+1 as soon as it starts tile k (after the `empty` mbarrier of that buffer
+    // has collected one arrival per warp for tile k-1), every warp waits only for the `full` mbarrier of its own next tile,
+    // and warp 0 takes the shortest rows of the block (block_perm) so that it is the first to move on.
+    const int first = vc * gridDim.x + blockIdx.x, stride = gridDim.x * A.nv;
+    const int wv = pipe ? (A.npw - 1 - warp) : warp;            // chunk of the (length-sorted) home particles this warp takes
+    if (pipe && warp == 0 && first < A.nidx) {
+        TileCtx t0; tile_geometry(g, first < A.seg0 ? A.b0 + first : A.b1 + (first - A.seg0), t0);
+        tile_stage_bulk(g, t0, A.cell_start, A.pos, s_pos0, metas, mb_full, lane);
+    }
+    int k = 0;
+    for (int idx = first; idx < A.nidx; idx += stride, ++k) {
+        const int buf = pipe ? (k & 1) : 0;
+        const int4* s_pos = s_pos0 + (size_t)buf * A.tile_cap;
         TileCtx t;
-        tile_geometry(g, b, t);
-        vc_sync(bar, nth);                                     // every warp is done with the previous tile
-        if (warp == 0) tile_stage_bulk(g, t, A.cell_start, A.pos, s_pos, meta, mbar, lane);
-        vc_sync(bar, nth);                                     // meta visible
-        t.hs = meta->hs; t.nh = meta->nh;
-        mbar_wait(mbar, phase); phase ^= 1u;                   // tile landed
+        if (!pipe) {
+            const int b = idx < A.seg0 ? A.b0 + idx : A.b1 + (idx - A.seg0);
+            tile_geometry(g, b, t);
+            vc_sync(bar, nth);                                     // every warp is done with the previous tile
+            if (warp == 0) tile_stage_bulk(g, t, A.cell_start, A.pos, s_pos0, metas, mb_full, lane);
+            vc_sync(bar, nth);                                     // meta visible
+            t.hs = metas->hs; t.nh = metas->nh;
+            mbar_wait(mb_full, (unsigned)(k & 1));                 // tile landed
+        } else {
+            if (warp == 0 && idx + stride < A.nidx) {
+                const int nx = idx + stride;
+                if (k >= 1) mbar_wait(mb_empty + (buf ^ 1), (unsigned)(((k - 1) >> 1) & 1));       // tile k-1 has left that buffer
+                TileCtx tn; tile_geometry(g, nx < A.seg0 ? A.b0 + nx : A.b1 + (nx - A.seg0), tn);
+                tile_stage_bulk(g, tn, A.cell_start, A.pos, s_pos0 + (size_t)(buf ^ 1) * A.tile_cap, metas + (buf ^ 1), mb_full + (buf ^ 1), lane);
+            }
+            mbar_wait(mb_full + buf, (unsigned)((k >> 1) & 1));
+            t.hs = metas[buf].hs; t.nh = metas[buf].nh;
+        }
         for (int p0 = 0; p0 < t.nh; p0 += nhpass) {
-            const int p = p0 + warp * 32 + lane;
+            const int p = p0 + wv * 32 + lane;
             const bool act = p < t.nh;
-            const int gi = t.hs + (act ? p : 0);
+            const int gi = t.hs + (act ? (A.perm ? (int)__ldg(A.perm + t.hs + p) : p) : 0);
             const int4 pi = __ldg(A.pos + gi);
             const unsigned pix = (unsigned)pi.x + 0x80000000u, piy = (unsigned)pi.y + 0x80000000u, piz = (unsigned)pi.z + 0x80000000u;
             const int cnt = act ? __ldg(A.nl_count + gi) : 0;
@@ -956,6 +1179,7 @@ __global__ void __launch_bounds__(1024) k_pair_forces_tab3(ClbGrid g, ClbPairArg
             }
             if (act) { A.force[gi] = ax; A.force[gi + A.fstride] = ay; A.force[gi + 2 * A.fstride] = az; }
         }
+        if (pipe) { __syncwarp(); if (lane == 0) mbar_arrive(mb_empty + buf); }      // this warp has left the buffer
     }
     if (err) atomicOr(&A.ctl->err, err);
 }

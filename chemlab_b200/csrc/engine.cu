@@ -176,6 +176,7 @@ extern "C" int clb_create(clb_engine** out, int device, const double box[3], dou
     }
     if ((long long)g.ncx * g.ncy * g.ncz > (1ll << 30)) { g_create_error = "too many cells"; delete e; return CLB_ERR_UNSUPPORTED; }
     g.cz0 = 0; g.nczl = g.ncz; g.zoff = 0; g.nplanes = g.ncz; g.ghost = 0;
+    g.blk = nullptr; g.nblk_d = nullptr; g.target = 0; g.nblocks = 0;
     e->geo.rl2 = rl * rl;
     for (int d = 0; d < 3; ++d) {
         e->geo.box[d] = box[d];
@@ -202,6 +203,8 @@ extern "C" int clb_create(clb_engine** out, int device, const double box[3], dou
     int mx = e->smem_optin;
     cudaFuncSetAttribute(k_build_lists<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
     cudaFuncSetAttribute(k_build_lists<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+    cudaFuncSetAttribute(k_build_lists2, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+    cudaFuncSetAttribute(k_build_lists2, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     cudaFuncSetAttribute(k_build_lists<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     cudaFuncSetAttribute(k_build_lists<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     for (int c = 0; c < 2; ++c) for (int sm = 0; sm < 2; ++sm) for (int ug = 0; ug < 2; ++ug) for (int sp = 0; sp < 3; ++sp)
@@ -231,9 +234,29 @@ extern "C" int clb_create(clb_engine** out, int device, const double box[3], dou
 void clb_engine::set_block_cells(int bx) {
     bx = std::max(1, std::min(bx, CLB_MAX_BX));
     grid.bx = bx;
-    grid.nbx = (grid.ncx + bx - 1) / bx;
     grid.ncell = grid.ncx * grid.ncy * grid.nplanes;
-    grid.nblocks = grid.nbx * grid.ncy * grid.nczl;
+    grid.nblocks = 0;                  // known after the next rebuild (make_blocks)
+}
+// Row-block table of the current cell lists (clb_kernels.cuh).  target: home particles per block = the lanes of the warps that
+// work on one tile (whole warps; about 160 keeps the tile near 1800 particles at melt densities).
+int clb_engine::make_blocks() {
+    clb_engine* e = this;
+    const int nrows = grid.ncy * grid.nczl;
+    CK(blk_table.ensure((size_t)std::max(1, nrows * grid.ncx)));
+    CK(blk_row_n.ensure(nrows + 1)); CK(blk_row_off.ensure(nrows + 1));
+    grid.blk = blk_table.p; grid.nblk_d = &d_ctl->nblocks;
+    if (block_target_user != 0) grid.target = block_target_user;
+    else {
+        const double ppc = (double)n / ((double)grid.ncx * grid.ncy * grid.ncz);
+        int t = 160;
+        while (t > 64 && 9.0 * (t + 2.0 * ppc) > 2100.0) t -= 32;      // tile = 9 rows of (home + 2 cells)
+        grid.target = t;
+    }
+    k_blocks_rows<false><<<ceil_div(nrows, 128), 128, 0, stream>>>(grid, cell_start.p, blk_row_n.p, nullptr, nullptr);
+    k_blocks_scan<<<1, 1024, 0, stream>>>(nrows, grid.ncy, grid.nczl, blk_row_n.p, blk_row_off.p, d_ctl);
+    k_blocks_rows<true><<<ceil_div(nrows, 128), 128, 0, stream>>>(grid, cell_start.p, nullptr, blk_row_off.p, blk_table.p);
+    launches += 3;
+    return CLB_OK;
 }
 
 extern "C" void clb_destroy(clb_engine* e) {
@@ -250,6 +273,10 @@ extern "C" int clb_set_option(clb_engine* e, const char* name, double v) {
     if (s == "resort_criterion") e->criterion = (int)v;
     else if (s == "step") e->step = (int64_t)v;               // integrator.step (restart): keys the thermostat and reaction draws
     else if (s == "block_cells") { e->set_block_cells((int)v); e->bx_user = (int)v > 0; e->lists_valid = false; }
+    else if (s == "block_target") { e->block_target_user = (int)v; e->lists_valid = false; }
+    else if (s == "build_kernel") { e->build_kernel_user = (int)v; e->lists_valid = false; }
+    else if (s == "pair_perm") e->pair_perm_user = (int)v;
+    else if (s == "pair_pipe") { e->pair_pipe_user = (int)v; e->lists_valid = false; }
     else if (s == "list_capacity") { e->nl_cap_user = (int)v; e->lists_valid = false; }
     else if (s == "fuse_integrator") e->fuse = (int)v;
     else if (s == "sync_chunk") e->chunk_user = (int)v;
@@ -277,6 +304,10 @@ extern "C" int clb_get_option(clb_engine* e, const char* name, double* v) {
     std::string s(name);
     if (s == "resort_criterion") *v = e->criterion;
     else if (s == "block_cells") *v = e->grid.bx;
+    else if (s == "block_target") *v = e->grid.target;
+    else if (s == "blocks") *v = e->grid.nblocks;
+    else if (s == "build_kernel") *v = e->build_kernel_active;
+    else if (s == "pair_pipe") *v = e->pair_pipe;
     else if (s == "list_capacity") *v = e->nl_cap;
     else if (s == "fuse_integrator") *v = e->fuse;
     else if (s == "sync_chunk") *v = e->chunk_user;
@@ -477,7 +508,7 @@ int clb_engine::alloc_particles(int nlocal_cap) {
     CK(id2idx.ensure(n)); CK(image.ensure(3 * (size_t)n)); CK(resid.ensure(n)); CK(charge.ensure(n)); CK(mol.ensure(n)); CK(wslot.ensure(n));
     CK(key.ensure(ncap)); CK(key2.ensure(ncap)); CK(val.ensure(ncap)); CK(val2.ensure(ncap));
     CK(cell_start.ensure((size_t)grid.ncell + 2));
-    CK(nl_count.ensure(ncap));
+    CK(nl_count.ensure(ncap)); CK(nl_perm.ensure(ncap));
     CK(partial.ensure(65536)); CK(partial_u64.ensure(65536));
     size_t tb = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, tb, key.p, key2.p, val.p, val2.p, ncap, 0, 32, stream);
@@ -1445,7 +1476,9 @@ int clb_engine::configure_pair_launch() {
         if (pair_warps_user > 0) npw = pair_warps_user;
         npw = std::min(npw, 16);
         const int tile_cap = (tile_max + 3) & ~3;
-        const size_t vcb = 32 + (size_t)tile_cap * sizeof(int4);          // [mbarrier 16 B][TileMeta 16 B][tile positions]
+        pair_pipe = pair_pipe_user >= 0 ? (pair_pipe_user ? 1 : 0) : 1;
+        pair_tile_cap = tile_cap;
+        const size_t vcb = 64 + (size_t)(pair_pipe ? 2 : 1) * tile_cap * sizeof(int4);   // [mbarriers 32 B][TileMeta x 2][tile buffer(s)]
         size_t want_rows = 0;
         bool single = true;
         for (const T3Slot& sl : t3_slots) want_rows += (size_t)(sl.w1 - sl.w0);
@@ -1457,7 +1490,7 @@ int clb_engine::configure_pair_launch() {
         int rlog = 0;
         if (pair_rep_user >= 8 && single) rlog = 3;
         // table budget: everything that is wanted, but at least 3 tiles (virtual CTAs) must stay resident
-        const int nv_keep = 3;
+        const int nv_keep = pair_pipe ? 2 : 3;
         size_t budget = (size_t)smem_optin > fixed + nv_keep * vcb ? (size_t)smem_optin - fixed - nv_keep * vcb : 0;
         if (pair_table_kb_user >= 0) budget = std::min(budget, (size_t)pair_table_kb_user * 1024);
         budget = std::min(budget, (want_rows << rlog) * sizeof(double2));
@@ -1568,11 +1601,10 @@ int clb_engine::rebuild() {
         TRY(peer_active() ? comm_migrate_peer() : comm_migrate());
     }
     if (!bx_user && !bx_auto_done) {
-        // row-block length from the mean cell occupancy: a tile (9 rows of bx+2 cells) of about 1800 beads keeps several
-        // virtual CTAs resident per SM; dense systems (hyperbranched: 38 beads per cell) get shorter blocks
-        const double ppc = (double)n / ((double)grid.ncx * grid.ncy * grid.ncz);
-        int bx = (int)floor(1800.0 / (9.0 * std::max(ppc, 1.0))) - 2;
-        set_block_cells(std::max(2, std::min(bx, 8)));
+        // blocks are cut by home-particle count (make_blocks); the cell cap only bounds the shared-memory offset tables and
+        // keeps sparse rows from producing very long tiles
+        // at most ncx - 2 cells: a tile row then never wraps onto itself (the prefilter build kernel needs that)
+        set_block_cells(block_target_user < 0 ? 8 : std::max(1, std::min(CLB_MAX_BX, grid.ncx - 2)));
         bx_auto_done = true;
     }
     int ns = own1;
@@ -1593,7 +1625,10 @@ int clb_engine::rebuild() {
     tr.mark("sort");
     // 2. tile statistics (read back together with the build result: one host check per rebuild instead of two)
     k_ctl_reset_stats<<<1, 1, 0, stream>>>(d_ctl);
-    k_block_stats<<<ceil_div(grid.nblocks, 128), 128, 0, stream>>>(grid, cell_start.p, d_ctl);
+    TRY(make_blocks());
+    ClbGrid gdev = grid; gdev.nblocks = -1;                 // the block count of this rebuild is only on the device so far
+    const int nblk_bound = grid.ncy * grid.nczl * grid.ncx;
+    k_block_stats<<<ceil_div(nblk_bound, 128), 128, 0, stream>>>(gdev, cell_start.p, d_ctl);
     int tile_guess = tile_max > 0 ? (int)(tile_max * 1.08) + 32 : 0;
     if (tile_guess == 0) {                       // first rebuild: nothing to extrapolate from
         TRY(read_ctl());
@@ -1610,21 +1645,47 @@ int clb_engine::rebuild() {
     }
     const int threads = build_threads;
     const unsigned long long rl2_lat = (unsigned long long)floor(geo.rl2 / geo.q2);
+    // prefilter kernel: cubic boxes whose tile rows never wrap around x
+    build_kernel_active = (geo.cubic && grid.ncx >= grid.bx + 2 && build_kernel_user != 1) ? 2 : 1;
+    int rq2 = 0;
+    if (build_kernel_active == 2) {
+        CK(qsub.ensure(ncap));
+        k_qsub<<<ceil_div(std::max(ns, 1), 256), 256, 0, stream>>>(ns, pos.p, grid, qsub.p);
+        const double rq = (rc + skin) * CLB_QCELL * grid.ncx / box[0] + 1.7320508075688772 + 0.02;
+        rq2 = (int)floor(rq * rq);
+        ++launches;
+    }
     for (int attempt = 0;; ++attempt) {
         CK(nl_entries.ensure((size_t)ncap * nl_cap));
         const int tile_cap = (tile_guess + 3) & ~3;     // keeps the per-warp staging rows 16-byte aligned
-        size_t smem = (size_t)tile_cap * (sizeof(int4) + sizeof(int)) + (size_t)(threads / 32) * CLB_BUILD_G * nl_cap * sizeof(unsigned short) + 16;
+        size_t smem = (size_t)tile_cap * (sizeof(int4) + sizeof(int) + (build_kernel_active == 2 ? sizeof(unsigned) : 0)) +
+                      (size_t)(threads / 32) * CLB_BUILD_G * nl_cap * sizeof(unsigned short) + 16;
         if ((int)smem > smem_optin) return fail(CLB_ERR_UNSUPPORTED, "tile needs %zu B of shared memory: lower block_cells", smem);
         int nb = 0;
-        if (geo.cubic) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_build_lists<true>, threads, smem);
+        if (build_kernel_active == 2) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_build_lists2, threads, smem);
+        else if (geo.cubic) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_build_lists<true>, threads, smem);
         else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_build_lists<false>, threads, smem);
-        int gridsz = std::min(grid.nblocks, std::max(1, nb) * nsm);
-        if (geo.cubic) k_build_lists<true><<<gridsz, threads, smem, stream>>>(grid, geo, rl2_lat, cell_start.p, pos.p, slot.p, excl_off.p, excl_ids.p, nl_entries.p, nl_count.p, nl_cap, tile_cap, d_ctl);
-        else k_build_lists<false><<<gridsz, threads, smem, stream>>>(grid, geo, rl2_lat, cell_start.p, pos.p, slot.p, excl_off.p, excl_ids.p, nl_entries.p, nl_count.p, nl_cap, tile_cap, d_ctl);
+        int gridsz = std::min(grid.nblocks > 0 ? grid.nblocks + grid.nblocks / 8 + 1 : nblk_bound, std::max(1, nb) * nsm);
+        if (build_kernel_active == 2) k_build_lists2<<<gridsz, threads, smem, stream>>>(gdev, rl2_lat, rq2, cell_start.p, pos.p, slot.p, qsub.p, excl_off.p, excl_ids.p, nl_entries.p, nl_count.p, nl_perm.p, nl_cap, tile_cap, d_ctl);
+        else if (geo.cubic) k_build_lists<true><<<gridsz, threads, smem, stream>>>(gdev, geo, rl2_lat, cell_start.p, pos.p, slot.p, excl_off.p, excl_ids.p, nl_entries.p, nl_count.p, nl_perm.p, nl_cap, tile_cap, d_ctl);
+        else k_build_lists<false><<<gridsz, threads, smem, stream>>>(gdev, geo, rl2_lat, cell_start.p, pos.p, slot.p, excl_off.p, excl_ids.p, nl_entries.p, nl_count.p, nl_perm.p, nl_cap, tile_cap, d_ctl);
         ++launches;
         TRY(read_ctl());
         tile_max = h_ctl->tile_max; home_max = h_ctl->home_max;
-        if (tile_max > 65535) return fail(CLB_ERR_UNSUPPORTED, "tile of %d particles exceeds 16-bit list entries: lower block_cells", tile_max);
+        grid.nblocks = h_ctl->nblocks; blk_p1 = h_ctl->blk_p1; blk_pl = h_ctl->blk_pl;
+        if (tile_max > 65535) {
+            if (getenv("CLB_TRACE")) {        // debugging aid: where do the sorted keys break?
+                std::vector<int> hk(ns), hc(grid.ncell + 1);
+                cudaMemcpy(hk.data(), key2.p, (size_t)ns * 4, cudaMemcpyDeviceToHost);
+                cudaMemcpy(hc.data(), cell_start.p, ((size_t)grid.ncell + 1) * 4, cudaMemcpyDeviceToHost);
+                int inv = -1; for (int i = 1; i < ns && inv < 0; ++i) if (hk[i] < hk[i - 1]) inv = i;
+                int big = -1; for (int c = 0; c < grid.ncell && big < 0; ++c) if (hc[c + 1] - hc[c] > 4096) big = c;
+                fprintf(stderr, "[clb rebuild] rank %d: tile_max %d ns %d own1 %d ncell %d first key inversion at %d (keys %d -> %d) first big cell %d (%d..%d) key[0] %d key[ns-1] %d nblocks %d\n",
+                        rank, tile_max, ns, own1, grid.ncell, inv, inv > 0 ? hk[inv - 1] : -1, inv > 0 ? hk[inv] : -1, big, big >= 0 ? hc[big] : -1, big >= 0 ? hc[big + 1] : -1,
+                        ns > 0 ? hk[0] : -1, ns > 0 ? hk[ns - 1] : -1, h_ctl->nblocks);
+            }
+            return fail(CLB_ERR_UNSUPPORTED, "tile of %d particles exceeds 16-bit list entries: lower block_cells", tile_max);
+        }
         const bool tile_over = (h_ctl->err & CLB_EF_TILE_OVERFLOW) || tile_max > tile_cap;
         const bool list_over = (h_ctl->err & CLB_EF_LIST_OVERFLOW) != 0;
         if (!tile_over && !list_over) break;
@@ -1664,10 +1725,12 @@ void clb_engine::launch_pair(int b0, int seg0, int b1, int nidx) {
     if (pair_kernel_active == 3) {
         ClbPairArgs3 A;
         A.cell_start = cell_start.p; A.pos = pos.p; A.entries = nl_entries.p; A.nl_count = nl_count.p;
+        A.perm = pair_perm_user ? nl_perm.p : nullptr;
         A.pd3 = d_pd3.p; A.gmeta = d_gmeta.p; A.trows = d_rows2.p; A.swin = d_swin.p; A.force = force.p; A.ctl = d_ctl;
         A.cap = nl_cap; A.ntypes = nt_dev; A.nsrows = tab3_nsrows; A.fstride = ncap; A.npw = pair_npw;
         A.invdx = tab2_invdx; A.cmagic = tab2_cmagic; A.one = tab3_one; A.one_g = tab3_one_g;
         A.b0 = b0; A.seg0 = seg0; A.b1 = b1; A.nidx = nidx; A.nv = pair_nv; A.vc_bytes = pair_vc_bytes;
+        A.pipe = pair_pipe; A.tile_cap = pair_tile_cap;
         pair_kernel_tab3(tab3_onepd, tab3_rlog, pair_ni, tab3_fb)<<<std::max(1, std::min(pair_grid, ceil_div(nidx, pair_nv))), pair_threads, pair_smem, stream>>>(grid, A);
     } else if (pair_kernel_active == 2) {
         ClbPairArgs2 A;
@@ -1695,7 +1758,7 @@ void clb_engine::launch_pair(int b0, int seg0, int b1, int nidx) {
 void clb_engine::enqueue_forces(bool overlap_halo) {
     bucket_begin(CLB_B_PAIR);
     const int nb = grid.nblocks;
-    const int R = grid.nbx * grid.ncy;                   // row blocks per cell plane
+    const int p1 = blk_p1, pl = blk_pl;                  // first block of owned plane 1 / of the last owned plane
     const bool split = overlap_halo && nranks > 1 && grid.nczl >= 3;
     const size_t slot_i = pair_event_used / 2;
     if (pair_event_timing) {
@@ -1703,7 +1766,7 @@ void clb_engine::enqueue_forces(bool overlap_halo) {
         pair_event_has2.resize(slot_i + 1, 0); pair_event_has2[slot_i] = 0;
         cudaEventRecord(next_pair_event(), stream);
     }
-    if (split) launch_pair(R, nb - 2 * R, 0, nb - 2 * R);            // interior planes
+    if (split) launch_pair(p1, pl - p1, 0, pl - p1);                  // interior planes
     else if (!overlap_halo || nranks == 1) launch_pair(0, nb, 0, nb);
     if (pair_event_timing) cudaEventRecord(next_pair_event(), stream);
     if (overlap_halo && nranks > 1) {
@@ -1715,7 +1778,7 @@ void clb_engine::enqueue_forces(bool overlap_halo) {
             pair_event_has2[slot_i] = 1;
             cudaEventRecord(pair_events2[2 * slot_i], stream);
         }
-        if (split) launch_pair(0, R, nb - R, 2 * R);                  // bottom and top owned planes
+        if (split) launch_pair(0, p1, pl, p1 + (nb - pl));            // bottom and top owned planes
         else launch_pair(0, nb, 0, nb);
         if (pair_event_timing) cudaEventRecord(pair_events2[2 * slot_i + 1], stream);
     }

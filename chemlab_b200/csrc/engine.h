@@ -86,6 +86,11 @@ struct clb_engine {
     DevBuf<int> wslot;                        // replicated per-slot type|state word (reaction decisions; clb_react.cuh)
     DevBuf<double> force, charge;
     DevBuf<int> key, key2, val, val2, cell_start;
+    DevBuf<int4> blk_table; DevBuf<int> blk_row_n, blk_row_off;     // row-block table (k_blocks_*)
+    int blk_p1 = 0, blk_pl = 0, block_target_user = 0;
+    DevBuf<unsigned> qsub;                      // per stored particle: position inside its cell, 84 units per edge (k_qsub, k_build_lists2)
+    int build_kernel_user = 0, build_kernel_active = 1;
+    int make_blocks();
     DevBuf<unsigned char> cubtmp, cubtmp2, stage;
     DevBuf<double> partial;
     DevBuf<unsigned long long> partial_u64;
@@ -95,6 +100,8 @@ struct clb_engine {
     // neighbour lists
     DevBuf<unsigned short> nl_entries;
     DevBuf<int> nl_count;
+    DevBuf<unsigned short> nl_perm;           // work order of the home particles of every block (clb_tile.cuh block_perm)
+    int pair_perm_user = 1, pair_pipe_user = -1, pair_pipe = 0, pair_tile_cap = 0;
     int nl_cap = 0, nl_cap_user = 0, nl_cap_user_seen = 0, nl_max = 0, tile_max = 0, home_max = 0;
     unsigned long long nl_total = 0, last_interacting = 0;
     int pair_grid = 0, pair_threads = 128, pair_smem = 0, tabs_smem = 1, pair_split = 1, pair_split_user = 0, pair_npw = 1, build_threads = 256;
@@ -169,6 +176,13 @@ struct clb_engine {
     struct ReactDev;
     ReactDev* rd = nullptr;
     int R_prealloc_n = -1;
+
+    // ATRPActivator
+    struct HostAtrpCenter { int type, state, deactivator, new_type, delta_state; double new_mass, new_q; };
+    std::vector<HostAtrpCenter> atrp_centers;
+    int atrp_num = 0; double atrp_ratio_act = 0, atrp_ratio_deact = 0, atrp_delta = 0, atrp_k_act = 0, atrp_k_deact = 0;
+    DevBuf<unsigned long long> atrp_keys, atrp_keys2, atrp_scal;
+    DevBuf<unsigned char> atrp_cen;
 
     // timers / counters
     cudaEvent_t ev_a[CLB_NBUCKET], ev_b[CLB_NBUCKET];

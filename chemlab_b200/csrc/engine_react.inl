@@ -431,3 +431,79 @@ extern "C" int clb_get_last_candidates(clb_engine* e, int64_t cap, int64_t* rows
     }
     return CLB_OK;
 }
+
+// ---- ATRPActivator (clb_react.cuh) ---------------------------------------------------------------------------------------
+extern "C" int clb_atrp_configure(clb_engine* e, int num_particles, double ratio_activator, double ratio_deactivator, double delta_catalyst,
+                                  double k_activate, double k_deactivate) {
+    if (!e || num_particles < 0) return e ? e->fail(CLB_ERR_ARG, "clb_atrp_configure: bad argument") : CLB_ERR_ARG;
+    e->atrp_num = num_particles; e->atrp_ratio_act = ratio_activator; e->atrp_ratio_deact = ratio_deactivator;
+    e->atrp_delta = delta_catalyst; e->atrp_k_act = k_activate; e->atrp_k_deact = k_deactivate;
+    e->atrp_centers.clear();
+    return CLB_OK;
+}
+extern "C" int clb_atrp_add_center(clb_engine* e, int type, int state, int needs_deactivator, int new_type, double new_mass, double new_q, int delta_state) {
+    if (!e || type < 0 || type >= CLB_MAX_TYPES || new_type >= CLB_MAX_TYPES) return e ? e->fail(CLB_ERR_ARG, "clb_atrp_add_center: type out of range") : CLB_ERR_ARG;
+    clb_engine::HostAtrpCenter c = {type, state, needs_deactivator ? 1 : 0, new_type, delta_state, new_mass, new_q};
+    e->atrp_centers.push_back(c);
+    if (new_type + 1 > e->ntypes) { e->ntypes = new_type + 1; e->pots_dirty = true; }
+    return CLB_OK;
+}
+// one pass at the current step; counts = {activated, deactivated} of this pass, ratios = {activator, deactivator} after it
+extern "C" int clb_atrp_now(clb_engine* e, int64_t counts[2], double ratios[2]) {
+    if (!e) return CLB_ERR_ARG;
+    cudaSetDevice(e->device);
+    if (counts) { counts[0] = 0; counts[1] = 0; }
+    const int ncen = (int)e->atrp_centers.size();
+    if (ncen == 0 || e->atrp_num <= 0 || e->n <= 0) { if (ratios) { ratios[0] = e->atrp_ratio_act; ratios[1] = e->atrp_ratio_deact; } return CLB_OK; }
+    std::vector<ClbAtrpCenter> hc(ncen);
+    for (int k = 0; k < ncen; ++k) {
+        const auto& c = e->atrp_centers[k];
+        ClbAtrpCenter d; memset(&d, 0, sizeof(d));
+        d.type = c.type; d.state = c.state; d.deactivator = c.deactivator; d.new_type = c.new_type; d.delta_state = c.delta_state;
+        d.new_mass = c.new_mass; d.new_q = c.new_q;
+        d.p = c.deactivator ? e->atrp_k_deact * e->atrp_ratio_deact : e->atrp_k_act * e->atrp_ratio_act;
+        hc[k] = d;
+    }
+    const size_t cap = (size_t)e->n;
+    CK(e->atrp_cen.ensure(ncen * sizeof(ClbAtrpCenter))); CK(e->atrp_keys.ensure(cap)); CK(e->atrp_keys2.ensure(cap)); CK(e->atrp_scal.ensure(8));
+    CK(cudaMemcpyAsync(e->atrp_cen.p, hc.data(), ncen * sizeof(ClbAtrpCenter), cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemsetAsync(e->atrp_scal.p, 0, 64, e->stream));
+    const int no = e->own1 - e->own0;
+    if (no > 0) k_atrp_scan<<<ceil_div(no, 256), 256, 0, e->stream>>>(e->own0, e->own1, e->pos.p, e->slot.p, (const ClbAtrpCenter*)e->atrp_cen.p, ncen, e->seed,
+                                                                       (uint64_t)e->step, e->atrp_keys.p, e->atrp_scal.p, (unsigned long long)cap);
+    unsigned long long nc = 0;
+    CK(cudaMemcpyAsync(&nc, e->atrp_scal.p, 8, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    unsigned long long* keys = e->atrp_keys.p;
+    if (e->nranks > 1) {
+        // every rank selects from the candidates of ALL ranks (same canonical order everywhere)
+        void* all = nullptr; size_t tot = 0;
+        TRY(e->comm_allgatherv(e->atrp_keys.p, (size_t)nc * 8, &all, &tot));
+        nc = tot / 8;
+        CK(e->atrp_keys.ensure(std::max<size_t>(nc, cap))); CK(e->atrp_keys2.ensure(std::max<size_t>(nc, cap)));
+        if (nc) CK(cudaMemcpyAsync(e->atrp_keys.p, all, tot, cudaMemcpyDeviceToDevice, e->stream));
+        keys = e->atrp_keys.p;
+    }
+    if (nc > 0) {
+        size_t tb = 0;
+        cub::DeviceRadixSort::SortKeys(nullptr, tb, keys, e->atrp_keys2.p, (int)nc, 0, 64, e->stream);
+        CK(e->cubtmp2.ensure(tb + 256));
+        cub::DeviceRadixSort::SortKeys(e->cubtmp2.p, tb, keys, e->atrp_keys2.p, (int)nc, 0, 64, e->stream);
+        const int nsel = (int)std::min<unsigned long long>(nc, (unsigned long long)e->atrp_num);
+        k_atrp_apply<<<ceil_div(nsel, 128), 128, 0, e->stream>>>(nsel, e->atrp_keys2.p, (const ClbAtrpCenter*)e->atrp_cen.p, ncen, e->seed, (uint64_t)e->step,
+                                                                 e->id2idx.p, e->wslot.p, e->pos.p, e->vel.p, e->charge.p, e->atrp_scal.p + 2);
+        unsigned long long hcnt[2] = {0, 0};
+        CK(cudaMemcpyAsync(hcnt, e->atrp_scal.p + 2, 16, cudaMemcpyDeviceToHost, e->stream));
+        CK(cudaStreamSynchronize(e->stream));
+        CK(cudaGetLastError());
+        const long long n_act = (long long)hcnt[0], n_deact = (long long)hcnt[1];
+        if (counts) { counts[0] = n_act; counts[1] = n_deact; }
+        // an activation turns one activator complex into a deactivator complex and vice versa
+        const double d = e->atrp_delta * (double)(n_act - n_deact) / (double)std::max(1, e->atrp_num);
+        e->atrp_ratio_act = std::min(1.0, std::max(0.0, e->atrp_ratio_act - d));
+        e->atrp_ratio_deact = std::min(1.0, std::max(0.0, e->atrp_ratio_deact + d));
+        if (n_act + n_deact > 0) { e->t3_dirty = true; e->forces_valid = false; }      // type populations moved (table windows)
+    }
+    if (ratios) { ratios[0] = e->atrp_ratio_act; ratios[1] = e->atrp_ratio_deact; }
+    return CLB_OK;
+}

@@ -311,6 +311,21 @@ class Engine:
         self._ck(self.L.clb_reaction_counters(self.h, n, _p(out, c_i64p)))
         return out[:n]
 
+    # ---- ATRPActivator
+    def atrp_configure(self, num_particles, ratio_activator, ratio_deactivator, delta_catalyst, k_activate, k_deactivate):
+        self._ck(self.L.clb_atrp_configure(self.h, int(num_particles), float(ratio_activator), float(ratio_deactivator), float(delta_catalyst),
+                                           float(k_activate), float(k_deactivate)))
+
+    def atrp_add_center(self, type_id, state, needs_deactivator, new_type=-1, new_mass=-1.0, new_q=float("nan"), delta_state=0):
+        self._ck(self.L.clb_atrp_add_center(self.h, int(type_id), int(state), int(bool(needs_deactivator)), int(new_type), float(new_mass),
+                                            float(new_q), int(delta_state)))
+
+    def atrp_now(self):
+        """One ATRPActivator pass at the current step: ((activated, deactivated), (ratio_activator, ratio_deactivator))."""
+        cnt = np.zeros(2, np.int64); rat = np.zeros(2)
+        self._ck(self.L.clb_atrp_now(self.h, _p(cnt, c_i64p), _p(rat, c_f64p)))
+        return (int(cnt[0]), int(cnt[1])), (float(rat[0]), float(rat[1]))
+
     # ---- parity / introspection
     def pairs(self):
         m = C.c_int64()

@@ -121,7 +121,7 @@ class VerletList:
         if e is None:
             return {}
         t, c = e.timers()
-        return {"timeRebuild": t["neighbour"], "rebuilds": c["rebuilds"]}
+        return {"timeRebuild": t.get("neighbour", 0.0), "rebuilds": c.get("rebuilds", 0)}
 
     def totalSize(self):
         return len(self._system._ctx.require_engine().pairs())

@@ -311,10 +311,48 @@ class TopologyManager:
     def get_fixed_pair_list(self, t1, t2):
         return None
 
-    def save_topology(self, filename):
-        open(filename, "w").close()
+    # ---- topology dumps written at the end of a run (src/start_simulation.py:1004-1006).  [EXT] TopologyManager::SaveTopologyToFile /
+    # SaveResTopologyToFile / SaveResiduesListToFile define the formats; unverified here (REFERENCE_UNVERIFIED.md U24): one line
+    # per node, "id: neighbour ids ..." (bond graph), "res_id: neighbour res_ids ..." (residue graph), "res_id: particle ids ...".
+    def _graph(self):
+        import collections
+        adj = collections.defaultdict(set)
+        for fpl in self._observed:
+            for a, b in fpl.getAllBonds():
+                adj[int(a)].add(int(b)); adj[int(b)].add(int(a))
+        return adj
 
-    save_res_topology = save_residues = save_topology
+    def _res_ids(self):
+        e = self._ctx.require_engine()
+        g = e.get_particles(fields=("res_id",))
+        return dict(zip(sorted(self._ctx.pid), (int(r) for r in g["res_id"])))
+
+    def save_topology(self, filename):
+        adj = self._graph()
+        with open(filename, "w") as f:
+            for a in sorted(adj):
+                f.write("%d: %s\n" % (a, " ".join(str(b) for b in sorted(adj[a]))))
+
+    def save_res_topology(self, filename):
+        import collections
+        res = self._res_ids()
+        radj = collections.defaultdict(set)
+        for a, nb in self._graph().items():
+            for b in nb:
+                if res[a] != res[b]:
+                    radj[res[a]].add(res[b])
+        with open(filename, "w") as f:
+            for r in sorted(radj):
+                f.write("%d: %s\n" % (r, " ".join(str(x) for x in sorted(radj[r]))))
+
+    def save_residues(self, filename):
+        import collections
+        members = collections.defaultdict(list)
+        for pid, r in self._res_ids().items():
+            members[r].append(pid)
+        with open(filename, "w") as f:
+            for r in sorted(members):
+                f.write("%d: %s\n" % (r, " ".join(str(x) for x in members[r])))
 
 
 class ExtAnalyze:
@@ -332,12 +370,11 @@ class ExtAnalyze:
 
 class ATRPActivator:
     """integrator.ATRPActivator(system, interval, num_particles, ratio_activator, ratio_deactivator, delta_catalyst,
-    k_activate, k_deactivate) + add_reactive_center: reaction_post_process.py:393-424 (config 1 only).
+    k_activate, k_deactivate) + add_reactive_center: reaction_post_process.py:380-426 (config 1 only).
 
-    Host-side restatement [EXT, unverified]: every `interval` steps up to `num_particles` particles matching a reactive
-    centre (type, state) are drawn; an activator centre reacts with probability k_activate*ratio_activator, a deactivator
-    centre with k_deactivate*ratio_deactivator; on success state += delta_state, type/mass follow new_property and the
-    catalyst ratios move by delta_catalyst/num_particles.  Small (<=1000 particles per call), so it is driven from Python."""
+    The pass itself runs in the engine (clb_atrp_configure / clb_atrp_add_center / clb_atrp_now: candidate scan, counter-based
+    random selection of num_particles centres, activation / deactivation draws, property change -- csrc/clb_react.cuh); this
+    class holds the parameters, fires the pass every `interval` steps and writes the statistics file [EXT, U22]."""
     def __init__(self, system, interval, num_particles, ratio_activator, ratio_deactivator, delta_catalyst, k_activate, k_deactivate):
         self._ctx = system._ctx
         self.interval, self.num_particles = int(interval), int(num_particles)
@@ -346,46 +383,33 @@ class ATRPActivator:
         self.stats_filename = None
         self.select_from_all = 1
         self._centers = []
-        self._rng = np.random.default_rng(self._ctx.seed + 7919)
+        self._pushed = None
 
     def add_reactive_center(self, type_id, state, is_activator, new_property, delta_state):
         self._centers.append((int(type_id), int(state), bool(is_activator), new_property, int(delta_state)))
+        self._pushed = None
 
     def _host_interval(self):
         return self.interval
 
-    def _host_action(self, integrator_):
-        e = self._ctx.require_engine()
-        g = e.get_particles(fields=("type", "state"))
-        pids = np.asarray(self._ctx.pid)[np.argsort(self._ctx.pid)]
-        hits = []
-        for k, (t, s, act, prop, ds) in enumerate(self._centers):
-            idx = np.nonzero((g["type"] == t) & (g["state"] == s))[0]
-            hits += [(int(i), k) for i in idx]
-        if not hits:
+    def _push(self, e):
+        key = (id(e), self.num_particles, self.ratio_activator, self.ratio_deactivator, self.delta_catalyst, self.k_activate, self.k_deactivate,
+               len(self._centers))
+        if key == self._pushed:
             return
-        sel = self._rng.permutation(len(hits))[: self.num_particles]
-        n_activated = n_deactivated = 0
-        for j in sel:
-            i, k = hits[j]
-            t, s, needs_deactivator, prop, ds = self._centers[k]
+        e.atrp_configure(self.num_particles, self.ratio_activator, self.ratio_deactivator, self.delta_catalyst, self.k_activate, self.k_deactivate)
+        for t, s, needs_deactivator, prop, ds in self._centers:
             # flag "A" (is_activator=False in chemlab's call, reaction_post_process.py:411): a dormant end that meets the
             # ACTIVATOR catalyst, rate k_activate * ratio_activator; flag "DA": an active end that meets the DEACTIVATOR
-            p = (self.k_deactivate * self.ratio_deactivator) if needs_deactivator else (self.k_activate * self.ratio_activator)
-            if self._rng.random() >= p:
-                continue
-            pid = int(pids[i])
-            e.modify_particle(pid, "state", s + ds)
-            if prop.type is not None and int(prop.type) != t:
-                e.modify_particle(pid, "type", int(prop.type))
-            if prop.mass is not None:
-                e.modify_particle(pid, "mass", float(prop.mass))
-            n_deactivated += needs_deactivator; n_activated += (not needs_deactivator)
-        n_act, n_deact = n_activated, n_deactivated
-        # an activation turns one activator complex into a deactivator complex and vice versa
-        d = self.delta_catalyst * (n_activated - n_deactivated) / max(1, self.num_particles)
-        self.ratio_activator = min(1.0, max(0.0, self.ratio_activator - d))
-        self.ratio_deactivator = min(1.0, max(0.0, self.ratio_deactivator + d))
+            e.atrp_add_center(t, s, needs_deactivator, -1 if prop.type is None else int(prop.type), -1.0 if prop.mass is None else float(prop.mass),
+                              float("nan") if prop.q is None else float(prop.q), ds)
+
+    def _host_action(self, integrator_):
+        e = self._ctx.require_engine()
+        self._push(e)
+        (n_act, n_deact), (self.ratio_activator, self.ratio_deactivator) = e.atrp_now()
+        self._pushed = (id(e), self.num_particles, self.ratio_activator, self.ratio_deactivator, self.delta_catalyst, self.k_activate, self.k_deactivate,
+                        len(self._centers))
         if self.stats_filename:
             with open(self.stats_filename, "a") as f:
                 f.write("%d %d %d %.6f %.6f\n" % (integrator_.step, n_act, n_deact, self.ratio_activator, self.ratio_deactivator))

@@ -339,6 +339,21 @@ def _main(argv, rank, world):
             ar.save_reaction_counters("%s_reaction_counters.dat" % prefix)
         with open("%s_benchmark.csv" % prefix, "a") as f:          # record format of the reference (:997-998): nranks NPart total loop
             f.write("%d %d %.6f %.6f\n" % (world, npart, total_time, integrator_loop))
+    # :1004-1006 -- bond graph, residue graph and residue membership at the end of the run (collective read, rank 0 writes)
+    tm_files = [("save_topology", "%s_topology.dat"), ("save_res_topology", "%s_res_topology.dat"), ("save_residues", "%s_residue_list.dat")]
+    for meth, pattern in tm_files:
+        getattr(topology_manager, meth)(pattern % prefix if rank == 0 else os.devnull)
+    if rank == 0:
+        import pickle                                               # :1062-1076 -- per-bucket timers of the run
+        ext_timers = {}
+        for k_ in range(integrator.getNumberOfExtensions()):
+            ext = integrator.getExtension(k_)
+            tmr = ext.get_timers() if hasattr(ext, "get_timers") else {}
+            if tmr:
+                ext_timers["%s_%d" % (type(ext).__name__, id(ext))] = tmr
+        with open("%s_benchmark.pck" % prefix, "wb") as f:
+            pickle.dump({"traj_timers": {}, "topol_timers": topology_manager.get_timers(), "integrator_timers": tools.get_integrator_timers(system, integrator),
+                         "extension_timers": ext_timers, "verlet_list": verletlist.get_timers()}, f)
     timers = tools.get_integrator_timers(system, integrator)
     print("final: steps=%d total=%.3fs integratorLoop=%.3fs (%.1f steps/s) setup=%.3fs" %
           (integrator.step, total_time, integrator_loop, integrator.step / max(integrator_loop, 1e-9), total_time0 - time0))

@@ -229,6 +229,20 @@ int clb_react_now(clb_engine *e, int64_t *events_out);
  * out[reaction] = cumulated number of events. */
 int clb_reaction_counters(clb_engine *e, int cap, int64_t *out);
 
+/* integrator.ATRPActivator(system, interval, num_particles, ratio_activator, ratio_deactivator, delta_catalyst, k_activate,
+ * k_deactivate) and .add_reactive_center(type_id, state, is_activator, new_property, delta_state):
+ * src/chemlab/reaction_post_process.py:380-426.  The caller fires clb_atrp_now every `interval` steps (the extension's signal
+ * inside VelocityVerlet::run).  One pass: of the particles that sit on a reactive centre (type, state), the num_particles with
+ * the smallest counter-based random keys (seed, step, particle) are drawn; a centre written X(s,A) reacts with probability
+ * k_activate*ratio_activator, X(s,DA) (needs_deactivator) with k_deactivate*ratio_deactivator; state += delta_state, type /
+ * mass / charge follow new_property (new_type < 0, new_mass <= 0, new_q NaN: keep).  counts_out = {activated, deactivated} of
+ * this pass, ratios_out = {activator, deactivator} ratios after it.  clb_atrp_configure clears the registered centres. */
+int clb_atrp_configure(clb_engine *e, int num_particles, double ratio_activator, double ratio_deactivator,
+                       double delta_catalyst, double k_activate, double k_deactivate);
+int clb_atrp_add_center(clb_engine *e, int type, int state, int needs_deactivator, int new_type, double new_mass,
+                        double new_q, int delta_state);
+int clb_atrp_now(clb_engine *e, int64_t counts_out[2], double ratios_out[2]);
+
 /* ---- parity / introspection -------------------------------------------------------------- */
 /* The current Verlet pair set as (min id, max id) rows sorted ascending (VerletList pairs, :193-197). */
 int clb_get_pairs(clb_engine *e, int64_t cap, int64_t *pairs, int64_t *n_out);

@@ -196,6 +196,9 @@ typedef struct orc_sim {
     /* integrator */
     int64_t step; int forces_valid; int lists_valid; int cont_ok;
     int lang_on; double kT, gamma; uint64_t seed; int lang_all; unsigned char lang_type[ORC_MAX_TYPES];
+    /* ATRPActivator */
+    int atrp_num, atrp_ncen; double atrp_ratio[2], atrp_delta, atrp_k[2];
+    struct { int type, state, deact, new_type, delta; double new_mass, new_q; } atrp_cen[16];
     /* reactions */
     int react_on, interval, nearest, max_per_interval;
     orc_reaction *reac; int nreac;
@@ -1148,3 +1151,61 @@ int64_t orc_count_type(orc_sim *s, int type, int state) {
     int64_t c = 0; for (int i = 0; i < s->n; ++i) if (s->type[i] == type && (state < 0 || s->state[i] == state)) ++c; return c;
 }
 void orc_update_mixing(orc_sim *s) { update_mixing(s); }
+
+/* ---- ATRPActivator (src/chemlab/reaction_post_process.py:393-424; [EXT] integrator/ATRPActivator.cpp, U22) ----------------
+ * Sequential restatement: list every particle that sits on a reactive centre (the first registered centre with its type and
+ * state), give it the key (u, index) with u = first word of Philox(seed ^ "ATRP", step, index), take the num_particles
+ * smallest keys, and let each of them react when the second Philox word (as a uniform in (0,1)) is below
+ * k_deactivate*ratio_deactivator (flag "DA") or k_activate*ratio_activator (flag "A") -- the ratios of the START of the pass.
+ * An activation moves one catalyst complex from the activator to the deactivator pool and vice versa. */
+#define ORC_STREAM_ATRP 0x41545250u
+void orc_atrp_configure(orc_sim *s, int num_particles, double ratio_activator, double ratio_deactivator, double delta_catalyst,
+                        double k_activate, double k_deactivate) {
+    s->atrp_num = num_particles; s->atrp_ratio[0] = ratio_activator; s->atrp_ratio[1] = ratio_deactivator;
+    s->atrp_delta = delta_catalyst; s->atrp_k[0] = k_activate; s->atrp_k[1] = k_deactivate; s->atrp_ncen = 0;
+}
+void orc_atrp_add_center(orc_sim *s, int type, int state, int needs_deactivator, int new_type, double new_mass, double new_q, int delta_state) {
+    int k = s->atrp_ncen++;
+    s->atrp_cen[k].type = type; s->atrp_cen[k].state = state; s->atrp_cen[k].deact = needs_deactivator ? 1 : 0;
+    s->atrp_cen[k].new_type = new_type; s->atrp_cen[k].delta = delta_state; s->atrp_cen[k].new_mass = new_mass; s->atrp_cen[k].new_q = new_q;
+    if (new_type + 1 > s->ntypes) s->ntypes = new_type + 1;
+}
+static int atrp_center_of(const orc_sim *s, int i) {
+    for (int k = 0; k < s->atrp_ncen; ++k) if (s->atrp_cen[k].type == s->type[i] && s->atrp_cen[k].state == s->state[i]) return k;
+    return -1;
+}
+void orc_atrp_now(orc_sim *s, int64_t counts[2], double ratios[2]) {
+    int64_t nact = 0, ndeact = 0;
+    if (s->atrp_ncen > 0 && s->atrp_num > 0) {
+        uint64_t *keys = malloc((size_t)s->n * 8 + 8);
+        int64_t nc = 0;
+        for (int i = 0; i < s->n; ++i) {
+            if (atrp_center_of(s, i) < 0) continue;
+            uint32_t c[4] = {(uint32_t)i, 0u, (uint32_t)s->step, (uint32_t)((uint64_t)s->step >> 32)};
+            philox4x32_10(c, (uint32_t)s->seed, (uint32_t)(s->seed >> 32) ^ ORC_STREAM_ATRP);
+            keys[nc++] = ((uint64_t)c[0] << 32) | (uint32_t)i;
+        }
+        qsort(keys, (size_t)nc, 8, cmp_u64);
+        const double p_act = s->atrp_k[0] * s->atrp_ratio[0], p_deact = s->atrp_k[1] * s->atrp_ratio[1];
+        for (int64_t k = 0; k < nc && k < s->atrp_num; ++k) {
+            const int i = (int)(keys[k] & 0xffffffffu);
+            const int ce = atrp_center_of(s, i);
+            uint32_t c[4] = {(uint32_t)i, 0u, (uint32_t)s->step, (uint32_t)((uint64_t)s->step >> 32)};
+            philox4x32_10(c, (uint32_t)s->seed, (uint32_t)(s->seed >> 32) ^ ORC_STREAM_ATRP);
+            const double w = ((double)c[1] + 0.5) * (1.0 / 4294967296.0);
+            const int de = s->atrp_cen[ce].deact;
+            if (!(w < (de ? p_deact : p_act))) continue;
+            s->state[i] += s->atrp_cen[ce].delta;
+            if (s->atrp_cen[ce].new_type >= 0) s->type[i] = s->atrp_cen[ce].new_type;
+            if (s->atrp_cen[ce].new_mass > 0) s->mass[i] = s->atrp_cen[ce].new_mass;
+            if (s->atrp_cen[ce].new_q == s->atrp_cen[ce].new_q) s->q[i] = s->atrp_cen[ce].new_q;
+            if (de) ++ndeact; else ++nact;
+        }
+        free(keys);
+        const double d = s->atrp_delta * (double)(nact - ndeact) / (double)(s->atrp_num > 1 ? s->atrp_num : 1);
+        double a = s->atrp_ratio[0] - d, b = s->atrp_ratio[1] + d;
+        s->atrp_ratio[0] = a < 0 ? 0 : (a > 1 ? 1 : a); s->atrp_ratio[1] = b < 0 ? 0 : (b > 1 ? 1 : b);
+    }
+    if (counts) { counts[0] = nact; counts[1] = ndeact; }
+    if (ratios) { ratios[0] = s->atrp_ratio[0]; ratios[1] = s->atrp_ratio[1]; }
+}

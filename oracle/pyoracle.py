@@ -288,6 +288,20 @@ class Oracle:
     def count_type(self, t, state=-1):
         return int(self.L.orc_count_type(self.h, int(t), int(state)))
 
+    # -- ATRPActivator
+    def atrp_configure(self, num_particles, ratio_activator, ratio_deactivator, delta_catalyst, k_activate, k_deactivate):
+        self.L.orc_atrp_configure(self.h, int(num_particles), C.c_double(ratio_activator), C.c_double(ratio_deactivator),
+                                  C.c_double(delta_catalyst), C.c_double(k_activate), C.c_double(k_deactivate))
+
+    def atrp_add_center(self, type_id, state, needs_deactivator, new_type=-1, new_mass=-1.0, new_q=float("nan"), delta_state=0):
+        self.L.orc_atrp_add_center(self.h, int(type_id), int(state), int(bool(needs_deactivator)), int(new_type), C.c_double(new_mass),
+                                   C.c_double(new_q), int(delta_state))
+
+    def atrp_now(self):
+        cnt = (C.c_int64 * 2)(); rat = (C.c_double * 2)()
+        self.L.orc_atrp_now(self.h, cnt, rat)
+        return (int(cnt[0]), int(cnt[1])), (float(rat[0]), float(rat[1]))
+
 
 # Engine-compatible method names, so that one set-up routine can drive either side
 Oracle.nb_set_tabulated = Oracle.nb_set_tab

@@ -114,8 +114,18 @@ def test_driver_host_logic_on_the_oracle_backend(tmp_path, monkeypatch):
     out = set(os.listdir("data"))
     for name in ("cpc01_42_confout.gro", "cpc01_42_before_reaction_confout.gro", "cpc01_42_output_topol.top", "cpc01_42_state.dat",
                  "cpc01_42_bonds.dat", "cpc01_42_angles.dat", "cpc01_42_reaction_counters.dat", "cpc01_42_benchmark.csv",
-                 "cpc01_energy_42.csv", "cpc01params.out", "cpc01_42_atrp_stats.dat"):
+                 "cpc01_energy_42.csv", "cpc01params.out", "cpc01_42_atrp_stats.dat", "cpc01_42_topology.dat", "cpc01_42_res_topology.dat",
+                 "cpc01_42_residue_list.dat", "cpc01_42_benchmark.pck"):
         assert name in out, name
+    import pickle
+    bp = pickle.load(open(os.path.join("data", "cpc01_42_benchmark.pck"), "rb"))
+    assert set(bp) == {"traj_timers", "topol_timers", "integrator_timers", "extension_timers", "verlet_list"}      # src/start_simulation.py:1062-1076
+    topo = [l.split(":") for l in open(os.path.join("data", "cpc01_42_topology.dat"))]
+    assert len(topo) == 6000 and all(len(nb.split()) in (1, 2, 3) for _, nb in topo)        # trimers + the bonds the reactions added
+    resl = open(os.path.join("data", "cpc01_42_residue_list.dat")).read().splitlines()
+    assert len(resl) == 2000 and all(len(l.split(":")[1].split()) == 3 for l in resl)
+    stats = np.loadtxt(os.path.join("data", "cpc01_42_atrp_stats.dat"), ndmin=2)
+    assert len(stats) >= 1 and (stats[:, 1] + stats[:, 2]).sum() > 0                     # the activator fired and changed some chain ends
     g = GROFile(os.path.join("data", "cpc01_42_confout.gro")); g.read()
     assert len(g.atoms) == 6000 and {a.name for a in g.atoms.values()} >= {"MA", "ML", "FA", "PL"}      # activated trimers renamed
     csv = open(os.path.join("data", "cpc01_energy_42.csv")).read().splitlines()

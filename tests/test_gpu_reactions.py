@@ -182,3 +182,25 @@ def test_mixed_tabulated_follows_conversion():
     assert err < 1e-6, err
     assert abs(P.e.energy(a) - P.o.energy(b)) <= 1e-8 * abs(P.o.energy(b))
     P.close()
+
+
+def test_atrp_activator_pass_matches_oracle():
+    """ATRPActivator (reaction_post_process.py:380-426, examples/atrp_lj/atrp.cfg:16-26) on the device vs the oracle's sequential
+    restatement: same selected particles, same activation / deactivation draws, same states / types / masses and catalyst ratios."""
+    m, P, h = _reactive_pair(seed=12, steps_before=0)
+    # type 0, state 1 = dormant chain ends (flag "A"); type 0, state 3 = active ends (flag "DA") that go back to the dormant state
+    P.both("atrp_configure", 150, 0.6, 0.4, 0.5, 0.9, 0.7)
+    P.both("atrp_add_center", 0, 1, False, 0, 1.25, float("nan"), 2)
+    P.both("atrp_add_center", 0, 3, True, 0, 1.0, float("nan"), -2)
+    seen_deact = 0
+    for k in range(6):
+        (ca, ra), (cb, rb) = P.both("atrp_now")
+        assert ca == cb and ra == rb, (k, ca, cb, ra, rb)
+        assert ca[0] + ca[1] > 0
+        seen_deact += ca[1]
+        sa = P.e.get_particles(fields=("type", "state", "mass")); sb = P.o.get()
+        assert (sa["type"] == sb["type"]).all() and (sa["state"] == sb["state"]).all() and (sa["mass"] == sb["mass"]).all()
+        P.both("run", 3)          # a new step number: new random keys
+    assert seen_deact > 0
+    assert (P.e.get_particles(fields=("state",))["state"] == 3).sum() > 0
+    P.close()

@@ -239,3 +239,46 @@ def test_react_matches_an_independent_python_restatement():
         want = np.array([[c["a"], c["b"]] for c in events])
         assert (got[np.lexsort((got[:, 1], got[:, 0]))] == want[np.lexsort((want[:, 1], want[:, 0]))]).all()
         assert (o.get()["state"] == st).all()
+
+
+def test_atrp_pass_matches_an_independent_numpy_restatement():
+    """orc_atrp_now against a numpy restatement written from the description in REFERENCE_UNVERIFIED.md (U22): candidates by
+    (type, state), the num_particles smallest (Philox word 0, index) keys, reaction when the uniform from word 1 is below
+    k * ratio of the start of the pass, catalyst ratios moved by delta * (n_act - n_deact) / num_particles."""
+    rng = np.random.default_rng(3)
+    n, seed, ATRP = 600, 77, 0x41545250
+    box = np.array([12.0, 12.0, 12.0])
+    typ = rng.integers(0, 3, n).astype(np.int32); st = rng.integers(0, 3, n).astype(np.int32)
+    o = pyoracle.Oracle(n, box, 2.5, 0.3, seed=seed)
+    o.set_particles(rng.random((n, 3)) * box, np.zeros((n, 3)), np.ones(n), None, typ, st, np.arange(n, dtype=np.int32))
+    num, ra, rd, delta, ka, kd = 40, 0.7, 0.3, 0.8, 0.9, 0.6
+    o.atrp_configure(num, ra, rd, delta, ka, kd)
+    centres = [(0, 1, False, 2, 1.5, 1), (2, 2, True, 0, 1.0, -1), (1, 0, False, -1, -1.0, 2)]
+    for t, s, de, nt, nm, ds in centres:
+        o.atrp_add_center(t, s, de, nt, nm, float("nan"), ds)
+    typ = typ.copy(); st = st.copy(); mass = np.ones(n)
+    for step in (0, 0, 0):           # the oracle's step counter stays 0: the same keys, a changing candidate set
+        cen = np.full(n, -1)
+        for k in reversed(range(len(centres))):
+            cen[(typ == centres[k][0]) & (st == centres[k][1])] = k
+        idx = np.nonzero(cen >= 0)[0]
+        words = np.array([pyoracle.philox([int(i), 0, step, 0], [seed & 0xffffffff, (seed >> 32) ^ ATRP]) for i in idx], dtype=np.uint64).reshape(-1, 4)
+        order = np.lexsort((idx, words[:, 0]))[:num]
+        na = nd = 0
+        for j in order:
+            i, k = idx[j], cen[idx[j]]
+            t, s, de, nt, nm, ds = centres[k]
+            if (float(words[j, 1]) + 0.5) / 4294967296.0 < (kd * rd if de else ka * ra):
+                st[i] += ds
+                if nt >= 0:
+                    typ[i] = nt
+                if nm > 0:
+                    mass[i] = nm
+                na += (not de); nd += de
+        d = delta * (na - nd) / num
+        ra, rd = min(1.0, max(0.0, ra - d)), min(1.0, max(0.0, rd + d))
+        (ca, cd), (oa, od) = o.atrp_now()
+        g = o.get()
+        assert (ca, cd) == (na, nd) and na + nd > 0
+        assert abs(oa - ra) < 1e-15 and abs(od - rd) < 1e-15
+        assert (g["type"] == typ).all() and (g["state"] == st).all() and (g["mass"] == mass).all()
