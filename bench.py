@@ -200,10 +200,36 @@ def cpu_run(wl, s, steps, warmup, threads, reactions=True):
         t0 = time.perf_counter(); o.run(m); dt = time.perf_counter() - t0
         total += dt; rates.append(m / dt)
     return {"value": steps / total, "unit": "steps/s", "cores": threads, "kind": "port",
-            "sample": "%d MD steps (after %d warm-up steps, %.2fs incl. the list build) of the same %d-bead workload from the same state (fp64 C restatement, OpenMP x%d, pinned threads)"
-                      % (steps, max(1, warmup), t_warm, s["n"], threads),
+            "sample": "%d MD steps (after %d warm-up steps, %.2fs incl. the list build) of the same %d-bead workload from the same state (fp64 C restatement, OpenMP x%d, pinned threads; %s)"
+                      % (steps, max(1, warmup), t_warm, s["n"], threads, "reaction passes at their interval" if reactions else "no reaction pass, like the GPU arm's timed window"),
             "seconds": total, "steps": steps, "segment_rates": rates, "median_rate": float(np.median(rates)),
             "spread": (max(rates) - min(rates)) / float(np.median(rates)) if len(rates) > 1 else 0.0}
+
+
+def cpu_leg_subprocess(a, snap, steps, warmup, reactions=True):
+    """The cpu_baseline leg in its own process (same interpreter, same workload flags, `--impl cpu_leg`): pinned OpenMP threads
+    there, none of the pinning in the process that drives the GPU."""
+    import pickle
+    import subprocess
+    import tempfile
+    d = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else None
+    fd, path = tempfile.mkstemp(suffix=".pkl", prefix="clb_snap_", dir=d)
+    try:
+        with os.fdopen(fd, "wb") as f:
+            pickle.dump({k: (np.array(v) if isinstance(v, np.ndarray) else v) for k, v in snap.items() if k != "_keep"}, f, protocol=4)
+        env = {k: v for k, v in os.environ.items() if not k.startswith("OMP_")}
+        cmd = [sys.executable, os.path.abspath(__file__), "--impl", "cpu_leg", "--state", path, "--steps", str(steps), "--warmup", str(warmup),
+               "--workload", a.workload, "--scale", str(a.scale), "--n_side", str(a.n_side)] + ([] if reactions else ["--no_reactions"])
+        r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=1800)
+        for ln in reversed(r.stdout.splitlines()):
+            if ln.startswith("{"):
+                return json.loads(ln)
+        return {"error": "cpu_leg failed: " + (r.stderr or r.stdout)[-400:]}
+    finally:
+        try:
+            os.unlink(path)
+        except OSError:
+            pass
 
 
 def bounded_cpu_steps(wl, n, threads, seconds):
@@ -227,10 +253,11 @@ def rel_force_err(f, fref):
     return float((d / np.maximum(nr, rms)).max())
 
 
-def parity_block(e, wl, sysd, h, rank, threads, do_reaction=True):
+def parity_block(e, wl, sysd, h, rank, threads, do_reaction=True, barrier=None):
     """GPU engine vs CPU oracle on the engine's CURRENT (benchmarked) state.  Collective on a multi-rank engine: every rank
     makes the engine calls, rank 0 runs the oracle and compares.  Returns (dict on rank 0 | None, reaction_pass_seconds)."""
     t_start = time.perf_counter()
+    e.decompose()                                    # lists of the CURRENT positions (the run's last rebuild is a few steps old)
     snap = snapshot(e, sysd, h)
     pe = e.pairs()                                   # canonical sorted (id_a < id_b) rows
     e.compute_forces()
@@ -243,19 +270,28 @@ def parity_block(e, wl, sysd, h, rank, threads, do_reaction=True):
         ko = sorted_pair_keys(o.pairs_raw())
         ke = (pe[:, 0].astype(np.uint64) << np.uint64(32)) | pe[:, 1].astype(np.uint64)
         pairs_equal = bool(len(ko) == len(ke) and np.array_equal(ko, ke))
+        pair_diff = None
+        if not pairs_equal:                         # diagnostics: which side lists what the other does not
+            miss = np.setdiff1d(ko, ke, assume_unique=False); extra = np.setdiff1d(ke, ko, assume_unique=False)
+            dup = int(len(ke) - len(np.unique(ke)))
+            pair_diff = {"oracle_pairs": int(len(ko)), "missing_in_engine": int(len(miss)), "extra_in_engine": int(len(extra)), "duplicates_in_engine": dup,
+                         "first_missing": [[int(k >> np.uint64(32)), int(k & np.uint64(0xffffffff))] for k in miss[:4]],
+                         "first_extra": [[int(k >> np.uint64(32)), int(k & np.uint64(0xffffffff))] for k in extra[:4]]}
         o.compute_forces()
         fo = o.get_particles(fields=("force",))["force"]
         en_o = {k: o.energy(v) for k, v in ho["energies"].items()}
         e_err = max(abs(en_e[k] - en_o[k]) / max(abs(en_o[k]), 1e-300) for k in en_o if en_o[k] != 0.0 or en_e[k] != 0.0) if en_o else 0.0
         out = {"state": "benchmarked state after the timed steps (%d beads, step %d)" % (snap["n"], snap["step"]),
-               "pairs": int(len(ke)), "pairs_equal": pairs_equal, "force_rel_err": rel_force_err(fe, fo), "force_bar": 1e-6,
+               "pairs": int(len(ke)), "pairs_equal": pairs_equal, "pair_diff": pair_diff, "force_rel_err": rel_force_err(fe, fo), "force_bar": 1e-6,
                "energy_rel_err": float(e_err), "energy_bar": 1e-8, "energies": {k: en_e[k] for k in en_e}}
     t_react = None
     if do_reaction:
         e.reaction_general(1, wl.interval, 1 if wl.nearest else 0, 0)
+        if barrier is not None:
+            barrier()                                 # rank 0 has just run the oracle: the other ranks must not time their wait for it
         t0 = time.perf_counter()
         nev = e.react_now()
-        t_react = time.perf_counter() - t0
+        t_react_first = time.perf_counter() - t0
         st = e.get_particles(fields=("type", "state", "mass"))
         lists_e = {k: e.list_get(v, a) for k, (v, a) in h["lists"].items()}
         ex_e = e.get_exclusions()
@@ -272,6 +308,16 @@ def parity_block(e, wl, sysd, h, rank, threads, do_reaction=True):
                                "types_equal": bool(np.array_equal(st["type"], so["type"])), "states_equal": bool(np.array_equal(st["state"], so["state"])),
                                "masses_equal": bool(np.array_equal(st["mass"], so["mass"])),
                                "exclusions_equal": bool(np.array_equal(canon(ex_e), canon(o.get_exclusions())))}
+    if do_reaction:
+        # the pass compared above is the first one of this engine when the timed window held none (buffers grow to their working
+        # size, the replicated tile yields 3x the events of any later pass): a second pass is the one that is timed
+        if barrier is not None:
+            barrier()
+        t0 = time.perf_counter()
+        e.react_now()
+        t_react = time.perf_counter() - t0
+        if rank == 0:
+            out["reaction"]["first_pass_ms"] = 1e3 * t_react_first
     if rank == 0:
         r = out.get("reaction", {})
         out["green"] = bool(out["pairs_equal"] and out["force_rel_err"] < 1e-6 and out["energy_rel_err"] < 1e-8 and
@@ -297,17 +343,33 @@ def main():
     ap.add_argument("--no_parity", action="store_true")
     ap.add_argument("--cpu_seconds", type=float, default=15.0)
     ap.add_argument("--option", action="append", default=[], help="engine option name=value")
+    ap.add_argument("--state", default=None, help="(--impl cpu_leg) pickled host snapshot written by the GPU arm")
+    ap.add_argument("--no_reactions", action="store_true", help="(--impl cpu_leg) MD steps only: the GPU arm's timed window held no reaction pass")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     threads = host_threads()
-    # the CPU arms use every core this process may run on, pinned (set before libgomp loads)
+    # the CPU arms use every core this process may run on (set before libgomp loads).  Thread PINNING is for the processes that
+    # only run the CPU restatement (`--impl reference`, `--impl cpu_leg`): in a process that drives a GPU, OMP_PROC_BIND pins the
+    # main thread to the first core and every thread created later (NCCL proxy, CUDA workers) inherits that single-core mask --
+    # measured on the 2-GPU box as a constant 8 ms (one scheduler slice) per NCCL round and 0.4 s reaction passes.
     os.environ["OMP_NUM_THREADS"] = str(threads)
-    os.environ.setdefault("OMP_PROC_BIND", "close")
-    os.environ.setdefault("OMP_PLACES", "cores")
+    if a.impl in ("reference", "cpu_leg"):
+        os.environ.setdefault("OMP_PROC_BIND", "close")
+        os.environ.setdefault("OMP_PLACES", "cores")
+    else:
+        os.environ.setdefault("OMP_WAIT_POLICY", "passive")      # the parity oracle's idle workers must not spin beside the CUDA host thread
     wl = make_workload(a)
     config = wl.config(a.gpus)
+
+    if a.impl == "cpu_leg":
+        # child of the GPU arm: the cpu_baseline leg on the pickled snapshot, alone in its process with pinned threads
+        import pickle
+        with open(a.state, "rb") as f:
+            snap = pickle.load(f)
+        print(json.dumps(cpu_run(wl, snap, a.steps, a.warmup, threads, reactions=not a.no_reactions)))
+        return 0
 
     if a.impl == "reference":
         if rank != 0:
@@ -409,9 +471,11 @@ def main():
     # parity on the benchmarked state (+ one reaction pass on both sides, which is also the timed reaction pass)
     parity, t_react = (None, None)
     if not a.no_parity:
-        parity, t_react = parity_block(e, wl, sysd, h, rank, threads)
+        parity, t_react = parity_block(e, wl, sysd, h, rank, threads, barrier=barrier)
     else:
         e.reaction_general(1, wl.interval, 1 if wl.nearest else 0, 0)
+        e.react_now()                     # first pass of this engine (buffers grow, 3x the events): untimed
+        barrier()
         t0 = time.perf_counter(); e.react_now(); t_react = time.perf_counter() - t0
     if dist is not None and t_react is not None:
         tt = torch.tensor([t_react], dtype=torch.float64, device="cuda")
@@ -527,7 +591,7 @@ def main():
 
     if world == 1 and rank == 0 and not a.no_cpu_baseline:
         ksteps = bounded_cpu_steps(wl, n, threads, a.cpu_seconds)
-        line["cpu_baseline"] = cpu_run(wl, snap, ksteps, 3, threads)
+        line["cpu_baseline"] = cpu_leg_subprocess(a, snap, ksteps, 3, reactions=cn["reaction_passes"] > 0)
     if rank == 0:
         print(json.dumps(line))
     if dist is not None:

@@ -440,8 +440,8 @@ __global__ void __launch_bounds__(512) k_build_lists2(ClbGrid g, unsigned long l
                     const int sj = s_slot[e];
                     bool keep = valid && r2 <= rl2_lat && (int)e != ti;
                     const int nx32 = min(nex, 32);
-                    for (int x = 0; x < nx32; ++x) keep = keep && (sj != __shfl_sync(0xffffffffu, exid, x));
-                    for (int x = 32; x < nex; ++x) keep = keep && (sj != __ldg(excl_ids + e0 + x));      // more than 32 exclusions: rare
+                    for (int x = 0; x < nx32; ++x) { const int xid = __shfl_sync(0xffffffffu, exid, x); keep = keep && (sj != xid); }   // all lanes shuffle
+                    for (int x = 32; x < nex; ++x) { const int xid = __ldg(excl_ids + e0 + x); keep = keep && (sj != xid); }          // more than 32 exclusions: rare
                     const unsigned bal = __ballot_sync(0xffffffffu, keep);
                     if (keep) s_row[n2 + __popc(bal & lt_mask)] = (unsigned short)e;      // position <= k: never ahead of an unread entry
                     n2 += __popc(bal);

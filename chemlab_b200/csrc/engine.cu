@@ -1476,7 +1476,7 @@ int clb_engine::configure_pair_launch() {
         if (pair_warps_user > 0) npw = pair_warps_user;
         npw = std::min(npw, 16);
         const int tile_cap = (tile_max + 3) & ~3;
-        pair_pipe = pair_pipe_user >= 0 ? (pair_pipe_user ? 1 : 0) : 1;
+        pair_pipe = pair_pipe_user > 0 ? 1 : 0;     // opt-in: measured slower on B200 (two buffers halve the resident tiles; profiles/r2k_pipe_c2.log)
         pair_tile_cap = tile_cap;
         const size_t vcb = 64 + (size_t)(pair_pipe ? 2 : 1) * tile_cap * sizeof(int4);   // [mbarriers 32 B][TileMeta x 2][tile buffer(s)]
         size_t want_rows = 0;

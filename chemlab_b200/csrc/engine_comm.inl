@@ -576,7 +576,10 @@ int clb_engine::comm_peer_setup() {
     CommDev& c = *cd;
     if (peer_user == 0) { c.peer_ok = 0; return CLB_OK; }
     const int plane_cap = (int)(2.0 * n / std::max(1, grid.ncz)) + 8192;
-    const int mig_cap = std::max(16384, ncap / 8);
+    // the layout must be the SAME on every rank (a sender addresses slot 1 of its neighbour's block with its own copy of the
+    // layout): sizes come from global quantities only.  (ncap differs between ranks with 19 and 18 planes: at 1M beads the migrants
+    // of one rank landed 0.3 MB beside the slot the receiver read.)
+    const int mig_cap = std::max(16384, plane_cap / 2);
     if (c.mb && plane_cap <= c.plane_cap && mig_cap <= c.mig_cap) return CLB_OK;
     comm_peer_teardown();
     if (nranks > CLB_MAX_RANKS) { c.peer_ok = 0; return CLB_OK; }
