@@ -247,9 +247,11 @@ int clb_engine::make_blocks() {
     grid.blk = blk_table.p; grid.nblk_d = &d_ctl->nblocks;
     if (block_target_user != 0) grid.target = block_target_user;
     else {
+        // measured (profiles/r2k_pipe_c2.log, r2t_sweep_c{3,5}.log): one-table melts are flat between 160 and 256 (160 keeps 5 tiles
+        // resident); many-table systems, whose table windows take half of the shared memory, run best with 7-warp blocks
         const double ppc = (double)n / ((double)grid.ncx * grid.ncy * grid.ncz);
-        int t = 160;
-        while (t > 64 && 9.0 * (t + 2.0 * ppc) > 2100.0) t -= 32;      // tile = 9 rows of (home + 2 cells)
+        int t = t3_slots.size() > 1 ? 224 : 160;
+        while (t > 64 && 9.0 * (t + 2.0 * ppc) > 2900.0) t -= 32;      // tile = 9 rows of (home + 2 cells), at most ~46 KB
         grid.target = t;
     }
     k_blocks_rows<false><<<ceil_div(nrows, 128), 128, 0, stream>>>(grid, cell_start.p, blk_row_n.p, nullptr, nullptr);
@@ -1491,7 +1493,8 @@ int clb_engine::configure_pair_launch() {
         if (pair_rep_user >= 8 && single) rlog = 3;
         // table budget: everything that is wanted, but at least 3 tiles (virtual CTAs) must stay resident
         const int nv_keep = pair_pipe ? 2 : 3;
-        size_t budget = (size_t)smem_optin > fixed + nv_keep * vcb ? (size_t)smem_optin - fixed - nv_keep * vcb : 0;
+        const size_t per_vc = vcb + (size_t)npw * 32 * 32;          // tile buffer(s) + the two 16-byte entry slots of its threads
+        size_t budget = (size_t)smem_optin > fixed + nv_keep * per_vc ? (size_t)smem_optin - fixed - nv_keep * per_vc : 0;
         if (pair_table_kb_user >= 0) budget = std::min(budget, (size_t)pair_table_kb_user * 1024);
         budget = std::min(budget, (want_rows << rlog) * sizeof(double2));
         if (t3_dirty || rlog != tab3_rlog || ((size_t)tab3_nsrows << tab3_rlog) * sizeof(double2) > budget) { int r = configure_tables(budget, rlog); if (r != CLB_OK) return r; }

@@ -574,7 +574,9 @@ static ClbPeers make_peers(clb_engine* e) {
 int clb_engine::comm_peer_setup() {
     clb_engine* e = this;
     CommDev& c = *cd;
-    if (peer_user == 0) { c.peer_ok = 0; return CLB_OK; }
+    // auto: mailboxes from 3 ranks on.  Measured on the 1M-bead melt (profiles/r2q_*, r2o_*): 2 ranks 1918 (mailboxes) vs 2161 steps/s
+    // (NCCL: both planes of a rank go to the same peer, one grouped NCCL kernel does it all), 4 ranks 2987 vs 2740, 8 ranks 4060 vs 3870
+    if (peer_user == 0 || (peer_user < 0 && nranks < 3)) { c.peer_ok = 0; return CLB_OK; }
     const int plane_cap = (int)(2.0 * n / std::max(1, grid.ncz)) + 8192;
     // the layout must be the SAME on every rank (a sender addresses slot 1 of its neighbour's block with its own copy of the
     // layout): sizes come from global quantities only.  (ncap differs between ranks with 19 and 18 planes: at 1M beads the migrants
