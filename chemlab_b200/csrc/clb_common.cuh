@@ -54,7 +54,9 @@ struct ClbCtl {
     unsigned comm_pad;
     int nblocks;            // row blocks of the current block table (k_blocks_scan)
     int blk_p1, blk_pl;     // first block of owned plane 1 and of the last owned plane (multi-GPU interior / boundary split)
-    int blk_pad;
+    int maybe;              // resort criterion 2: the global maximum passed skin/2 -> the per-cell bound decides (k_cell_*)
+    int maybe_step;         // step index of that check
+    int blk_pad[3];
 };
 
 struct ClbGrid {

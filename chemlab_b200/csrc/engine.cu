@@ -272,7 +272,7 @@ extern "C" void clb_destroy(clb_engine* e) {
 extern "C" int clb_set_option(clb_engine* e, const char* name, double v) {
     if (!e || !name) return CLB_ERR_ARG;
     std::string s(name);
-    if (s == "resort_criterion") e->criterion = (int)v;
+    if (s == "resort_criterion") { e->criterion_user = (int)v; e->criterion = e->resort_criterion(); }
     else if (s == "step") e->step = (int64_t)v;               // integrator.step (restart): keys the thermostat and reaction draws
     else if (s == "block_cells") { e->set_block_cells((int)v); e->bx_user = (int)v > 0; e->lists_valid = false; }
     else if (s == "block_target") { e->block_target_user = (int)v; e->lists_valid = false; }
@@ -304,7 +304,7 @@ extern "C" int clb_set_option(clb_engine* e, const char* name, double v) {
 extern "C" int clb_get_option(clb_engine* e, const char* name, double* v) {
     if (!e || !name || !v) return CLB_ERR_ARG;
     std::string s(name);
-    if (s == "resort_criterion") *v = e->criterion;
+    if (s == "resort_criterion") *v = e->resort_criterion();
     else if (s == "block_cells") *v = e->grid.bx;
     else if (s == "block_target") *v = e->grid.target;
     else if (s == "blocks") *v = e->grid.nblocks;
@@ -1380,7 +1380,7 @@ int clb_engine::read_ctl() {
 }
 __global__ void k_ctl_reset_stats(ClbCtl* c) { c->tile_max = 0; c->home_max = 0; c->cell_max = 0; c->nl_max = 0; c->nl_total = 0; c->err &= ~(CLB_EF_LIST_OVERFLOW | CLB_EF_TILE_OVERFLOW); }
 __global__ void k_ctl_reset_after_overflow(ClbCtl* c) { c->nl_max = 0; c->nl_total = 0; c->err &= ~(CLB_EF_LIST_OVERFLOW | CLB_EF_TILE_OVERFLOW); }
-__global__ void k_ctl_after_rebuild(ClbCtl* c) { c->stall = 0; c->accum_maxdist = 0.0; c->maxdisp2_bits = 0u; c->force_rebuild = 0; }
+__global__ void k_ctl_after_rebuild(ClbCtl* c) { c->stall = 0; c->accum_maxdist = 0.0; c->maxdisp2_bits = 0u; c->force_rebuild = 0; c->maybe = 0; }
 
 int clb_engine::setup_sync() {
     if (n <= 0) return fail(CLB_ERR_STATE, "no particles");
@@ -1934,6 +1934,8 @@ static int run_impl(clb_engine* e, int64_t nsteps, bool cont) {
     if (!e || nsteps < 0) return CLB_ERR_ARG;
     cudaSetDevice(e->device);
     cont = cont && e->cont_ok && e->lists_valid;
+    e->criterion = e->resort_criterion();          // 2 (per-cell bound) on one GPU, 1 (global maximum) across ranks, unless set by the caller
+    if (e->criterion == 2) { if (e->nranks > 1) e->criterion = 1; else CK(e->cell_disp.ensure((size_t)e->grid.ncell + 1)); }
     ClbTrace trr(e->stream, "run");
     if (cont) {
         // list / term / exclusion updates left by a reaction pass are picked up at the forced rebuild of the first step
@@ -1996,6 +1998,13 @@ static int run_impl(clb_engine* e, int64_t nsteps, bool cont) {
                 }
                 k_check_resort<<<1, 1, 0, e->stream>>>(e->d_ctl, e->criterion, half_skin, (int)(s - i));
                 ++e->launches;
+                if (e->criterion == 2) {
+                    // the per-cell bound (clb_kernels.cuh): both kernels return at once unless the global maximum is past skin/2
+                    const int nc = e->grid.ncell;
+                    k_cell_disp<<<ceil_div(nc, 128), 128, 0, e->stream>>>(e->d_ctl, nc, e->cell_start.p, e->pos.p, e->xref.p, e->geo.q[0], e->geo.q[1], e->geo.q[2], e->cell_disp.p);
+                    k_cell_pairs<<<ceil_div(nc, 128), 128, 0, e->stream>>>(e->d_ctl, e->grid.ncx, e->grid.ncy, e->grid.ncz, e->cell_disp.p, (float)e->skin);
+                    e->launches += 2;
+                }
                 e->enqueue_forces();
             }
             pend = true;

@@ -281,7 +281,15 @@ void orc_set_particles(orc_sim *s, const double *x, const double *v, const doubl
     s->forces_valid = 0; s->lists_valid = 0; s->cont_ok = 0;
 }
 void orc_set_positions(orc_sim *s, const double *x) {
-    memcpy(s->x, x, 3 * (size_t)s->n * 8); s->forces_valid = 0; s->lists_valid = 0; s->cont_ok = 0;
+    /* folded into the box (the cell binning of orc_rebuild expects [0, L)); a coordinate outside the box moves the image counter
+     * like fold() does, a folded coordinate leaves it alone */
+    for (int i = 0; i < s->n; ++i) for (int d = 0; d < 3; ++d) {
+        double L = s->box[d], xx = x[3 * i + d], im = floor(xx / L);
+        xx -= im * L;
+        if (xx >= L) { xx -= L; im += 1.0; }
+        s->x[3 * i + d] = xx; s->image[3 * i + d] += (int)im;
+    }
+    s->forces_valid = 0; s->lists_valid = 0; s->cont_ok = 0;
 }
 void orc_set_velocities(orc_sim *s, const double *v) { memcpy(s->v, v, 3 * (size_t)s->n * 8); }
 void orc_get(orc_sim *s, double *x, double *v, double *f, int *type, int *state, double *mass, int *image) {

@@ -279,3 +279,30 @@ def test_run_is_bit_reproducible():
         res.append((st["pos"].copy(), st["vel"].copy(), st["force"].copy()))
         P.close()
     assert (res[0][0] == res[1][0]).all() and (res[0][1] == res[1][1]).all() and (res[0][2] == res[1][2]).all()
+
+
+def test_cell_pair_resort_criterion():
+    """resort_criterion=2 (option): when the fastest bead has moved more than skin/2 the lists are kept as long as
+    D(c) + D(c') <= skin for all cells within two of each other.  The lists must stay COMPLETE: at every step the forces from
+    the current (possibly old) lists equal the oracle's forces on the same positions, and rebuilds are rarer than with the
+    global-maximum rule."""
+    rebuilds = {}
+    for crit in (1, 2):
+        m, P = _md_pair(n_side=16, langevin=True, dt=0.005, crit=crit)
+        P.e.set_langevin(1, 1.3, 1.0)                   # a warm melt: fast beads, frequent resorts
+        assert P.e.get_option("resort_criterion") == crit
+        worst = 0.0
+        for k in range(40):
+            P.e.run_continue(1) if k else P.e.run(1)
+            if crit == 2:
+                st = P.e.get_particles(fields=("pos",))
+                P.e.compute_forces()                                              # lists valid -> no rebuild: pair + bonded forces from the lists as they are
+                fe = P.e.get_particles(fields=("force",))["force"]
+                P.o.set_positions(st["pos"])
+                P.o.compute_forces()
+                worst = max(worst, util.rel_force_err(fe, P.o.get()["force"]))
+        if crit == 2:
+            assert worst < 1e-6, worst
+        rebuilds[crit] = P.e.timers()[1]["rebuilds"]
+        P.close()
+    assert rebuilds[2] <= rebuilds[1], rebuilds
