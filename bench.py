@@ -491,11 +491,11 @@ def main():
         pair_bytes = (40.0 + 4.0 * lh) * n_per_gpu            # pos 16 + list 4*L_half + force 24 per particle
         step_bytes = (128.0 + 4.0 * lh) * n_per_gpu
         t_pair = (pair_ms * 1e-3 / pair_launches) if pair_launches else None
-        traffic, traffic_src = profiled_traffic(wl, world)
+        traffic, traffic_src = profiled_traffic(wl, world, n)
         roof = {"bound": "hbm", "kernel": "k_pair_forces", "achieved": (pair_bytes / t_pair / 1e9) if t_pair else None, "peak": peak,
                 "unit": "GB/s", "frac": (pair_bytes / t_pair / 1e9 / peak) if t_pair else None,
                 "traffic": traffic, "traffic_source": traffic_src,
-                "binding_roof": "shared-memory gather wavefronts (two random 16-byte gathers per listed pair) and fp64 issue; not HBM (DESIGN.md 3.1)",
+                "binding_roof": "issue slots (55 instructions per listed pair around 16 fp64 operations, 60 % issue utilisation at 25 warps/SM) and shared-memory gather wavefronts; not HBM (DESIGN.md 3.1)",
                 "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": pair_bytes, "kernel_ms": (t_pair * 1e3) if t_pair else None, "launches_timed": pair_launches,
                 "kernel_share_of_step": (pair_ms * 1e-3 / t_dev) if t_dev else None,
@@ -599,14 +599,14 @@ def main():
     return 0
 
 
-def profiled_traffic(wl, world):
+def profiled_traffic(wl, world, n=None):
     """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the pair kernel on this workload, from the committed
     `ncu --set full` capture named in profiles/traffic.json (a profile cannot be taken inside a timed run)."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     try:
         t = json.load(open(p))
         ent = t.get("%s_n%d" % (wl.name, world))
-        if ent:
+        if ent and (n is None or ent.get("n_beads") in (None, n)):
             return float(ent["bytes_per_launch"]), "from profile: " + ent["source"]
     except Exception:
         pass

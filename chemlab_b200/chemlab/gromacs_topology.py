@@ -294,6 +294,14 @@ def set_nonbonded_interactions(system, gt, vl, lj_cutoff, qq_cutoff=None, tab_cu
         system.addInteraction(lj, "lj")
     if used["tab"]:
         system.addInteraction(tab, "lj-tab")
+    # :866-878 -- the `coulomb` term: registered whenever the cutoff is positive, zero for the (neutral) coarse-grained beads
+    fudge_qq = float(defaults.get("fudgeQQ", 1.0))
+    if qq_cutoff is not None and float(qq_cutoff) > 0.0 and 138.935485 * fudge_qq > 0.0:
+        pot_qq = espressopp.interaction.CoulombTruncated(prefactor=138.935485 * fudge_qq, cutoff=float(qq_cutoff))
+        coul = espressopp.interaction.VerletListCoulombTruncated(vl)
+        for n1, n2 in pairs:
+            coul.setPotential(type1=sym2id[n1], type2=sym2id[n2], potential=pot_qq)
+        system.addInteraction(coul, "coulomb")
     return cr_observs, []
 
 

@@ -1758,7 +1758,7 @@ void clb_engine::launch_pair(int b0, int seg0, int b1, int nidx) {
 // Pair + bonded forces of the owned particles.  overlap_halo (multi-GPU steps): the row blocks of the interior planes
 // need no ghost, so they are launched first while the halo of this step is still in flight on the comm stream; the
 // caller then makes the main stream wait for the halo (k_check_resort in between) and the two boundary planes follow.
-void clb_engine::enqueue_forces(bool overlap_halo) {
+void clb_engine::enqueue_forces(bool overlap_halo, bool resort_checked) {
     bucket_begin(CLB_B_PAIR);
     const int nb = grid.nblocks;
     const int p1 = blk_p1, pl = blk_pl;                  // first block of owned plane 1 / of the last owned plane
@@ -1774,8 +1774,10 @@ void clb_engine::enqueue_forces(bool overlap_halo) {
     if (pair_event_timing) cudaEventRecord(next_pair_event(), stream);
     if (overlap_halo && nranks > 1) {
         cudaStreamWaitEvent(stream, ev_comm, 0);                      // halo + global max displacement have arrived
-        k_check_resort<<<1, 1, 0, stream>>>(d_ctl, criterion, 0.5 * skin, pending_step_index);
-        ++launches;
+        if (!resort_checked) {                                        // (the peer-mailbox path checks on the comm stream: k_check_resort_peer)
+            k_check_resort<<<1, 1, 0, stream>>>(d_ctl, criterion, 0.5 * skin, pending_step_index);
+            ++launches;
+        }
         if (pair_event_timing) {
             while (pair_events2.size() < 2 * (slot_i + 1)) { cudaEvent_t ev; cudaEventCreate(&ev); pair_events2.push_back(ev); }
             pair_event_has2[slot_i] = 1;
@@ -1978,9 +1980,20 @@ static int run_impl(clb_engine* e, int64_t nsteps, bool cont) {
                 e->enqueue_integrate(CLB_INT_FIRST, 0);
             }
             if (e->peer_active()) {
-                // peer mailboxes: push boundary planes + displacement maximum over NVLink, wait for the neighbours, resort check
-                TRY(e->comm_step_peer(e->stream, (int)(s - i)));
-                e->enqueue_forces();
+                // peer mailboxes: push boundary planes + displacement maximum over NVLink, wait for the neighbours, resort check.
+                // With >= 3 owned planes the exchange runs on the comm stream while the interior planes (whose tiles hold no
+                // ghost) are evaluated; the two boundary planes follow once the neighbours' planes have landed.
+                if (e->overlap_user != 0 && e->grid.nczl >= 3) {
+                    cudaEventRecord(e->ev_int, e->stream);
+                    cudaStreamWaitEvent(e->comm_stream, e->ev_int, 0);
+                    TRY(e->comm_step_peer(e->comm_stream, (int)(s - i)));
+                    cudaEventRecord(e->ev_comm, e->comm_stream);
+                    e->pending_step_index = (int)(s - i);
+                    e->enqueue_forces(true, true);
+                } else {
+                    TRY(e->comm_step_peer(e->stream, (int)(s - i)));
+                    e->enqueue_forces();
+                }
             } else if (e->nranks > 1 && (e->overlap_user > 0 || (e->overlap_user < 0 && e->nranks >= 4))) {
                 // global max displacement + position halo travel on the comm stream while the interior planes compute
                 cudaEventRecord(e->ev_int, e->stream);

@@ -247,7 +247,7 @@ struct clb_engine {
     int setup_sync();
     int rebuild();
     int configure_pair_launch();
-    void enqueue_forces(bool overlap_halo = false);
+    void enqueue_forces(bool overlap_halo = false, bool resort_checked = false);
     void launch_pair(int b0, int seg0, int b1, int nidx);
     void enqueue_integrate(int mode, uint64_t key_step);
     ClbIntegParams integ_params(uint64_t key_step) const;

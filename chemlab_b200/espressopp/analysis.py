@@ -35,6 +35,8 @@ class PotentialEnergy(_Obs):
 
     def compute(self):
         e = self._ctx.require_engine()
+        if getattr(self._inter, "_zero_energy", False):         # the `coulomb` term of an all-neutral system
+            return 0.0
         if getattr(self._inter, "_h", None) is None:
             self._inter._attach(e)
         return float(e.energy(self._inter._h))

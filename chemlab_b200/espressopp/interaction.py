@@ -233,11 +233,44 @@ FixedTripleListTypesAngularHarmonic = FixedTripleListTypesTabulatedAngular = Fix
 FixedQuadrupleListTabulatedDihedral = FixedQuadrupleListDihedralHarmonic = _FixedListInteraction
 FixedQuadrupleListTypesTabulatedDihedral = FixedQuadrupleListTypesDihedralHarmonic = _TypedFixedListInteraction
 
+class CoulombTruncated(_Pot):
+    """CoulombTruncated(prefactor, cutoff): gromacs_topology.py:866-878 (prefactor 138.935485 * fudgeQQ)."""
+    kind = "CoulombTruncated"
+
+    def __init__(self, prefactor=1.0, cutoff=None, **kw):
+        self.prefactor, self.cutoff = float(prefactor), cutoff
+
+
+class VerletListCoulombTruncated:
+    """The `coulomb` interaction chemlab registers whenever coulomb_cutoff > 0 (gromacs_topology.py:866-878; rim135, dacron,
+    pccg_lj ship coulomb_cutoff=0.9).  Every shipped coarse-grained system is NEUTRAL bead by bead (all q = 0), so the term is
+    identically zero: this class keeps the label and the energy column (0.0) without touching the pair kernel.  A system with a
+    non-zero charge raises NotImplementedError at set-up: charged pairs are outside north_star."""
+    def __init__(self, vl):
+        self._vl = vl
+        self._ctx = vl._system._ctx
+        self._h = None
+        self._pots = {}
+        self._zero_energy = True
+
+    def setPotential(self, type1, type2, potential):
+        self._pots[(int(type1), int(type2))] = potential
+
+    def _attach(self, e):
+        q = np.asarray(self._ctx.props.get("q", []), float)
+        if q.size and np.any(q != 0.0):
+            raise NotImplementedError("VerletListCoulombTruncated: the system holds charged particles (%d with q != 0); Coulomb pair "
+                                      "forces are outside the scope of the B200 engine (SURVEY 8f rank 3)" % int((q != 0.0).sum()))
+
+    def computeEnergy(self):
+        return 0.0
+
+
 # constructible, NotImplementedError when attached/used (SURVEY 2.3 E21; gromacs_topology.py:513-514 builds two of them always)
 for _n in ("VerletListTabulatedCapped", "VerletListLennardJonesEnergyCapped", "VerletListMultiTabulated", "VerletListMultiMixedTabulated",
-           "VerletListScaleTabulated", "VerletListCoulombTruncated", "VerletListDynamicResolutionTabulated",
+           "VerletListScaleTabulated", "VerletListDynamicResolutionTabulated",
            "VerletListDynamicResolutionLennardJones", "TabulatedCapped", "LennardJonesEnergyCapped", "MultiTabulated",
-           "MultiMixedTabulated", "ScaleTabulated", "CoulombTruncated", "FixedPairListLambdaHarmonic", "FixedPairListLambdaTabulated",
+           "MultiMixedTabulated", "ScaleTabulated", "FixedPairListLambdaHarmonic", "FixedPairListLambdaTabulated",
            "FixedTripleListLambdaAngularHarmonic", "FixedTripleListLambdaTabulatedAngular", "FixedQuadrupleListLambdaTabulatedDihedral",
            "DihedralRB", "DihedralHarmonicNCos", "FixedQuadrupleListDihedralRB", "FixedQuadrupleListDihedralHarmonicNCos",
            "FixedQuadrupleListTypesDihedralRB", "FixedQuadrupleListTypesDihedralHarmonicNCos", "ParticlePairScaling"):

@@ -133,3 +133,30 @@ def test_driver_host_logic_on_the_oracle_backend(tmp_path, monkeypatch):
     assert open(os.path.join("data", "cpc01_42_benchmark.csv")).read().split()[:2] == ["1", "6000"]
     gt = GromacsTopology(os.path.join("data", "cpc01_42_output_topol.top")).read()
     assert len(gt.atoms) == 6000 and len(gt.bonds) >= 4000 and len(gt.angles) >= 2000
+
+
+def test_coulomb_label_for_neutral_systems():
+    """gromacs_topology.py:866-878: with coulomb_cutoff > 0 the reference registers a `coulomb` interaction for every type pair.
+    All shipped coarse-grained beads carry q = 0, so the term is identically zero: the label and the energy column exist, a
+    charged system is refused (Coulomb pair forces are outside north_star)."""
+    from chemlab_b200 import espressopp
+    from chemlab_b200.espressopp import interaction as I, analysis as A
+
+    def build(q):
+        system = espressopp.System()
+        system.bc = espressopp.bc.OrthorhombicBC(system.rng, (10.0, 10.0, 10.0))
+        system.skin = 0.3
+        system.storage = espressopp.storage.DomainDecomposition(system, (1, 1, 1), (3, 3, 3))
+        system.storage.addParticles([[1, 0, espressopp.Real3D(1, 1, 1), 1.0, q], [2, 0, espressopp.Real3D(2, 1, 1), 1.0, 0.0]], "id", "type", "pos", "mass", "q")
+        vl = espressopp.VerletList(system, cutoff=2.5)
+        c = I.VerletListCoulombTruncated(vl)
+        c.setPotential(type1=0, type2=0, potential=I.CoulombTruncated(prefactor=138.935485, cutoff=0.9))
+        system.addInteraction(c, "coulomb")
+        return system, c
+    system, c = build(0.0)
+    c._attach(None)                                   # neutral: nothing to upload
+    assert c.computeEnergy() == 0.0 and system.getNameOfInteraction(0) == "coulomb"
+    assert A.PotentialEnergy(system, c)._inter is c
+    system, c = build(0.5)
+    with pytest.raises(NotImplementedError):
+        c._attach(None)
