@@ -1981,9 +1981,11 @@ static int run_impl(clb_engine* e, int64_t nsteps, bool cont) {
             }
             if (e->peer_active()) {
                 // peer mailboxes: push boundary planes + displacement maximum over NVLink, wait for the neighbours, resort check.
-                // With >= 3 owned planes the exchange runs on the comm stream while the interior planes (whose tiles hold no
-                // ghost) are evaluated; the two boundary planes follow once the neighbours' planes have landed.
-                if (e->overlap_user != 0 && e->grid.nczl >= 3) {
+                // Option overlap_halo=1: with >= 3 owned planes the exchange runs on the comm stream while the interior planes (whose
+                // tiles hold no ghost) are evaluated; the two boundary planes follow once the neighbours' planes have landed.
+                // Off by default: measured at 4 ranks the split launch costs more than the exchange it hides (3252 vs 3443 steps/s,
+                // profiles/r2z_n4_ov{1,0}.json).
+                if (e->overlap_user > 0 && e->grid.nczl >= 3) {
                     cudaEventRecord(e->ev_int, e->stream);
                     cudaStreamWaitEvent(e->comm_stream, e->ev_int, 0);
                     TRY(e->comm_step_peer(e->comm_stream, (int)(s - i)));

@@ -188,6 +188,11 @@ extern "C" int clb_comm_init(clb_engine* e, int rank, int nranks, const void* nc
     for (int r2 = 0; r2 < nranks; ++r2) NC(g_nccl.Broadcast(cd->cnt.p + 16 + (r2 == rank ? 0 : 1), cd->cnt.p + 18, 4, ncclChar, r2, cd->comm, e->stream));
     NC(g_nccl.GroupEnd());
     NC(g_nccl.AllReduce(cd->cnt.p + 24, cd->cnt.p + 24, 2, ncclDouble, ncclSum, cd->comm, e->stream));
+    // ... and the large-message protocol of the collective read-back (get_particles sums an [n x 15] matrix over the ranks): its
+    // channels are set up at the first large all-reduce (110 ms inside the first download at 8 ranks, profiles/r2q_n8_default.json)
+    CK(cd->red.ensure((size_t)1 << 21));
+    CK(cudaMemsetAsync(cd->red.p, 0, ((size_t)1 << 21) * sizeof(double), e->stream));
+    NC(g_nccl.AllReduce(cd->red.p, cd->red.p, (size_t)1 << 21, ncclDouble, ncclSum, cd->comm, e->stream));
     CK(cudaStreamSynchronize(e->stream));
     return CLB_OK;
 }
