@@ -399,7 +399,8 @@ def main():
     if world > 1:
         import torch.distributed as dist
         torch.cuda.set_device(local)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        if not dist.is_initialized():         # the recorded chemlab driver of the c3/c4/c5 workloads may have joined the group already
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     device = local
 
     sysd = wl.system()

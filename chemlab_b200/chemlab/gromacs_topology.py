@@ -435,9 +435,55 @@ def set_dihedral_interactions(system, gt, dynamic_type_ids, change_dihedral_type
 
 
 def set_pair_interactions(system, gt, args, dynamic_type_ids):
-    if gt.pairs:
-        raise NotImplementedError("1-4 [pairs] interactions are outside the scope of the B200 engine (SURVEY 8f rank 3)")
-    return {}, []
+    """1-4 `[ pairs ]` as Lennard-Jones on pair lists (gromacs_topology.py:1314-1411): pairs whose types can change in a reaction
+    go to ONE FixedPairListTypesLennardJones (`dyn_lj14_<k>`: sigma/epsilon by the combination rule, epsilon scaled by fudgeLJ);
+    the other pairs are grouped by their parameters into FixedPairListLennardJones interactions `lj14_<k>` -- (sigma, epsilon)
+    written on the pair line, else the combination rule with fudgeLJ when `gen-pairs` is set.  (The reference calls
+    `combination` with three arguments on that static branch, :1358, and would stop there; the parameters are used as given
+    instead.)  The Coulomb part of the 1-4 term needs charged particles and stays outside the scope (all shipped CG beads are neutral)."""
+    if not gt.pairs:
+        return None, []
+    defaults, atomparams = gt.gt.defaults, gt.gt.atomtypes
+    cr = int(defaults.get("combinationrule", 1))
+    fudge = float(defaults.get("fudgeLJ", 1.0))
+    cutoff = float(args.lj_cutoff)
+    id2sym = {v: k for k, v in gt.atomsym_atomtype.items()}
+    static, dynamic = {}, []
+    for b, parameters in gt.pairs.items():
+        ptypes = [gt.atoms[x]["type_id"] for x in b]
+        if set(ptypes) & set(dynamic_type_ids):
+            dynamic.append(b)
+            continue
+        params = tuple(float(x) for x in parameters[1:])
+        if not params:
+            if not defaults.get("gen-pairs"):
+                raise RuntimeError("pair %s has no parameters and [ defaults ] gen-pairs is off" % (b,))
+            n1, n2 = id2sym[ptypes[0]], id2sym[ptypes[1]]
+            sig, eps = combination(atomparams[n1]["sigma"], atomparams[n1]["epsilon"], atomparams[n2]["sigma"], atomparams[n2]["epsilon"], cr)
+            params = (sig, fudge * eps)
+        static.setdefault(params[:2], []).append(b)
+    static_fpls, count = [], 0
+    for (sig, eps), b_list in sorted(static.items()):
+        fpl = espressopp.FixedPairList(system.storage)
+        fpl.addBonds(b_list)
+        inter = espressopp.interaction.FixedPairListLennardJones(system, fpl, espressopp.interaction.LennardJones(epsilon=eps, sigma=sig, cutoff=cutoff))
+        system.addInteraction(inter, "lj14_%d" % count)
+        static_fpls.append(fpl)
+        count += 1
+    dfpl = espressopp.FixedPairList(system.storage)
+    if dynamic:
+        dfpl.addBonds(dynamic)
+    type_pairs = sorted({tuple(sorted((a, b))) for a in gt.used_atomsym_atomtype for b in gt.used_atomsym_atomtype
+                         if gt.used_atomsym_atomtype[a] in dynamic_type_ids or gt.used_atomsym_atomtype[b] in dynamic_type_ids})
+    if type_pairs:
+        print("Set up 1-4 pair interactions")
+        inter = espressopp.interaction.FixedPairListTypesLennardJones(system, dfpl)
+        for n1, n2 in type_pairs:
+            sig, eps = combination(atomparams[n1]["sigma"], atomparams[n1]["epsilon"], atomparams[n2]["sigma"], atomparams[n2]["epsilon"], cr)
+            inter.setPotential(type1=gt.used_atomsym_atomtype[n1], type2=gt.used_atomsym_atomtype[n2],
+                               potential=espressopp.interaction.LennardJones(sigma=sig, epsilon=fudge * eps, cutoff=cutoff))
+        system.addInteraction(inter, "dyn_lj14_%d" % count)
+    return dfpl, static_fpls
 
 
 def set_coulomb_interactions(system, gt, args):

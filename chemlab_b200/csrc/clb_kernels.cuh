@@ -319,6 +319,9 @@ __device__ __forceinline__ void bpot_eval(const ClbBPot* p, double x, const ClbB
         case 9: { double d = x - p->p[1], xx = d / p->p[2], sr2 = p->p[3] * p->p[3] / (x * x), sr6 = sr2 * sr2 * sr2;          // FENE + LJ (func 9)
                   F = -p->p[0] * d / (1.0 - xx * xx) + 24.0 * p->p[4] * (2.0 * sr6 * sr6 - sr6) / x;
                   E = -0.5 * p->p[0] * p->p[2] * p->p[2] * log(1.0 - xx * xx) + 4.0 * p->p[4] * (sr6 * sr6 - sr6); break; }
+        case 10: { if (x > p->p[2]) { F = 0.0; E = 0.0; break; }                                               // LennardJones on a pair list (1-4 pairs)
+                   double sr2 = p->p[1] * p->p[1] / (x * x), sr6 = sr2 * sr2 * sr2;
+                   F = 24.0 * p->p[0] * (2.0 * sr6 * sr6 - sr6) / x; E = 4.0 * p->p[0] * (sr6 * sr6 - sr6) - p->p[3]; break; }
         case 8: { double d = x - p->p[1]; d -= 6.283185307179586 * rint(d / 6.283185307179586);
                   F = -2.0 * p->p[0] * d; E = p->p[0] * d * d; break; }                                      // DihedralHarmonic
         case 2: case 4: case 5: {                                                                            // tables

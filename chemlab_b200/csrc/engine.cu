@@ -1282,7 +1282,7 @@ extern "C" int clb_bonded_set_potential(clb_engine* e, int inter, int t1, int t2
     if (!e || inter < 0 || inter >= (int)e->inters.size() || e->inters[inter].bonded < 0) return e ? e->fail(CLB_ERR_ARG, "bad bonded interaction handle") : CLB_ERR_ARG;
     HostBonded& b = e->bondeds[e->inters[inter].bonded];
     int ar = e->lists[b.list].arity;
-    bool ok = (ar == 2 && (kind == CLB_POT_HARMONIC || kind == CLB_POT_TABULATED || kind == CLB_POT_FENE || kind == CLB_POT_FENE_LJ)) ||
+    bool ok = (ar == 2 && (kind == CLB_POT_HARMONIC || kind == CLB_POT_TABULATED || kind == CLB_POT_FENE || kind == CLB_POT_FENE_LJ || kind == CLB_POT_LENNARD_JONES)) ||
               (ar == 3 && (kind == CLB_POT_ANGULAR_HARMONIC || kind == CLB_POT_TABULATED_ANGULAR || kind == CLB_POT_COSINE)) ||
               (ar == 4 && (kind == CLB_POT_TABULATED_DIHEDRAL || kind == CLB_POT_DIHEDRAL_HARMONIC));
     if (!ok) return e->fail(CLB_ERR_ARG, "potential kind %d does not fit a list of arity %d", kind, ar);

@@ -33,7 +33,7 @@ def _p(a, t):
 
 # potential kinds (CLB_POT_*), non-bonded kinds (CLB_NB_*)
 POT = dict(Harmonic=1, Tabulated=2, AngularHarmonic=3, TabulatedAngular=4, TabulatedDihedral=5, Cosine=6, FENE=7,
-           DihedralHarmonic=8, FENELennardJones=9)
+           DihedralHarmonic=8, FENELennardJones=9, LennardJones=10)
 NB = dict(Tabulated=1, LennardJones=2, MixedTabulated=3)
 
 

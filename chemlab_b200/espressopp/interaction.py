@@ -46,6 +46,12 @@ class LennardJones(_Pot):
     def __init__(self, epsilon=1.0, sigma=1.0, cutoff=2.5, shift="auto", **kw):
         self.epsilon, self.sigma, self.cutoff, self.shift = float(epsilon), float(sigma), float(cutoff), shift
 
+    def params(self):
+        """as a pair-list potential (1-4 pairs): {epsilon, sigma, cutoff, shift}; shift 'auto' = U_LJ(cutoff)."""
+        sr6 = (self.sigma / self.cutoff) ** 6
+        shift = 4.0 * self.epsilon * (sr6 * sr6 - sr6) if self.shift == "auto" else float(self.shift or 0.0)
+        return (self.epsilon, self.sigma, self.cutoff, shift)
+
 
 class MixedTabulated(_Pot):
     """MixedTabulated(itype, tab1, tab2, cr_obs | mix_value, cutoff): gromacs_topology.py:757-790."""
@@ -226,8 +232,8 @@ class _TypedFixedListInteraction(_FixedListInteraction):
     _typed = 1
 
 
-FixedPairListHarmonic = FixedPairListTabulated = FixedPairListFENE = FixedPairListFENELennardJones = _FixedListInteraction
-FixedPairListTypesHarmonic = FixedPairListTypesTabulated = FixedPairListTypesFENE = FixedPairListTypesFENELennardJones = _TypedFixedListInteraction
+FixedPairListHarmonic = FixedPairListTabulated = FixedPairListFENE = FixedPairListFENELennardJones = FixedPairListLennardJones = _FixedListInteraction
+FixedPairListTypesHarmonic = FixedPairListTypesTabulated = FixedPairListTypesFENE = FixedPairListTypesFENELennardJones = FixedPairListTypesLennardJones = _TypedFixedListInteraction
 FixedTripleListAngularHarmonic = FixedTripleListTabulatedAngular = FixedTripleListCosine = _FixedListInteraction
 FixedTripleListTypesAngularHarmonic = FixedTripleListTypesTabulatedAngular = FixedTripleListTypesCosine = _TypedFixedListInteraction
 FixedQuadrupleListTabulatedDihedral = FixedQuadrupleListDihedralHarmonic = _FixedListInteraction

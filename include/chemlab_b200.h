@@ -141,13 +141,15 @@ int clb_list_get(clb_engine *e, int list, int64_t cap, int64_t *ids, int64_t *n_
 #define CLB_POT_FENE 7               /* FENE(K, r0, rMax)                          gromacs_topology.py:949-961 */
 #define CLB_POT_DIHEDRAL_HARMONIC 8  /* DihedralHarmonic(K, phi0): K (phi-phi0)^2  gromacs_topology.py:1206-1224 */
 #define CLB_POT_FENE_LJ 9            /* FENELennardJones(K, r0, rMax, sigma, epsilon) gromacs_topology.py:935-961  */
+#define CLB_POT_LENNARD_JONES 10     /* LennardJones(epsilon, sigma, cutoff) on a pair list: the 1-4 [ pairs ]        gromacs_topology.py:1314-1411;
+                                      * params {epsilon, sigma, cutoff, shift}: U = 4 eps [(s/r)^12 - (s/r)^6] - shift for r <= cutoff, 0 beyond */
 /* interaction.FixedPairList<Pot>(system, fpl, pot) (typed=0: one potential for the whole list) or
  * interaction.FixedPairListTypes<Pot>(system, fpl) (typed=1: potential chosen by particle types);
  * same for Triple/Quadruple lists.  Returns the interaction handle (system.addInteraction order). */
 int clb_add_bonded(clb_engine *e, int list, int typed, int *interaction_out);
 /* setPotential(type1, type2[, type3[, type4]], potential); for typed=0 the types are ignored.
  * params: HARMONIC {K, r0}; ANGULAR_HARMONIC {K, theta0}; COSINE {K, theta0}; FENE {K, r0, rMax};
- * DIHEDRAL_HARMONIC {K, phi0}; FENE_LJ {K, r0, rMax, sigma, epsilon}; TABULATED* {} with table handle. Unused types = -1. */
+ * DIHEDRAL_HARMONIC {K, phi0}; FENE_LJ {K, r0, rMax, sigma, epsilon}; LENNARD_JONES {epsilon, sigma, cutoff, shift}; TABULATED* {} with table handle. Unused types = -1. */
 int clb_bonded_set_potential(clb_engine *e, int interaction, int t1, int t2, int t3, int t4,
                              int pot_kind, const double *params, int nparams, int table);
 

@@ -152,7 +152,7 @@ typedef struct {
 } orc_pairpot;
 
 enum { POT_HARMONIC = 1, POT_TAB = 2, POT_ANG_HARM = 3, POT_TAB_ANG = 4, POT_TAB_DIH = 5,
-       POT_COSINE = 6, POT_FENE = 7, POT_DIH_HARM = 8, POT_FENE_LJ = 9 };
+       POT_COSINE = 6, POT_FENE = 7, POT_DIH_HARM = 8, POT_FENE_LJ = 9, POT_LJ = 10 };
 typedef struct { int kind, table; double p[6]; } orc_bpot;
 typedef struct { int t[4]; orc_bpot pot; } orc_typed_pot;
 
@@ -677,6 +677,11 @@ static int bond_eval(orc_sim *s, const orc_bpot *p, double r, double *F, double 
                          *F = -p->p[0] * (r - p->p[1]) / (1 - x * x); return 0; }
         /* FENE + LJ bond, [ bondtypes ] func 9 (doc/topology.rst:72-79, gromacs_topology.py:935-944): p = {K, r0, rMax, sigma, epsilon};
          * U = -K rMax^2/2 ln(1 - ((r-r0)/rMax)^2) + 4 eps [(sigma/r)^12 - (sigma/r)^6], no cutoff on the LJ part (formula as documented) */
+        /* 1-4 [ pairs ]: FixedPairList[Types]LennardJones with LennardJones(epsilon, sigma, cutoff), shift 'auto'
+         * (gromacs_topology.py:1314-1411); p = {epsilon, sigma, cutoff, shift}; no force and no energy beyond the cutoff */
+        case POT_LJ: { if (r > p->p[2]) { *E = 0; *F = 0; return 0; }
+                       double sr2 = p->p[1] * p->p[1] / (r * r), sr6 = sr2 * sr2 * sr2;
+                       *E = 4 * p->p[0] * (sr6 * sr6 - sr6) - p->p[3]; *F = 24 * p->p[0] * (2 * sr6 * sr6 - sr6) / r; return 0; }
         case POT_FENE_LJ: { double x = (r - p->p[1]) / p->p[2], sr2 = p->p[3] * p->p[3] / (r * r), sr6 = sr2 * sr2 * sr2;
                             *E = -0.5 * p->p[0] * p->p[2] * p->p[2] * log(1 - x * x) + 4 * p->p[4] * (sr6 * sr6 - sr6);
                             *F = -p->p[0] * (r - p->p[1]) / (1 - x * x) + 24 * p->p[4] * (2 * sr6 * sr6 - sr6) / r; return 0; }

@@ -160,3 +160,36 @@ def test_coulomb_label_for_neutral_systems():
     system, c = build(0.5)
     with pytest.raises(NotImplementedError):
         c._attach(None)
+
+
+def test_14_pairs_become_lj_pair_lists(tmp_path, monkeypatch):
+    """[ pairs ] -> lj14_<k> / dyn_lj14_<k> interactions (gromacs_topology.py:1314-1411): parameters from the pair line or from
+    the combination rule with fudgeLJ; pairs touching a reactive type go to the type-dispatched list."""
+    from chemlab_b200 import espressopp
+    from chemlab_b200.chemlab import gromacs_topology as G
+
+    class Args:
+        lj_cutoff = 1.2
+
+    class GT:       # the few attributes set_pair_interactions reads
+        pass
+    gt = GT(); gt.gt = GT()
+    gt.gt.defaults = {"combinationrule": 2, "fudgeLJ": 0.5, "gen-pairs": True}
+    gt.gt.atomtypes = {"A": {"sigma": 0.3, "epsilon": 1.0}, "B": {"sigma": 0.5, "epsilon": 4.0}, "R": {"sigma": 0.4, "epsilon": 1.0}}
+    gt.atomsym_atomtype = {"A": 0, "B": 1, "R": 2}
+    gt.used_atomsym_atomtype = dict(gt.atomsym_atomtype)
+    gt.atoms = {1: {"type_id": 0}, 2: {"type_id": 1}, 3: {"type_id": 0}, 4: {"type_id": 2}, 5: {"type_id": 1}}
+    gt.pairs = {(1, 2): ["1"], (3, 5): ["1"], (1, 3): ["1", "0.35", "0.7"], (2, 4): ["1"]}
+    system = espressopp.System()
+    system.bc = espressopp.bc.OrthorhombicBC(system.rng, (10.0, 10.0, 10.0))
+    system.storage = espressopp.storage.DomainDecomposition(system, (1, 1, 1), (3, 3, 3))
+    dfpl, static = G.set_pair_interactions(system, gt, Args(), {2})
+    names = [system.getNameOfInteraction(k) for k in range(system.getNumberOfInteractions())]
+    assert names == ["lj14_0", "lj14_1", "dyn_lj14_2"]
+    assert sorted(map(tuple, dfpl.getAllBonds())) == [(2, 4)] and len(static) == 2
+    inters = system.getAllInteractions() if hasattr(system, "getAllInteractions") else None
+    # explicit parameters are used as given; generated ones follow rule 2 (arithmetic sigma, geometric epsilon) times fudgeLJ
+    pots = sorted((i._pot.sigma, i._pot.epsilon) for i, _ in system._ctx.interactions if getattr(i, "_pot", None) is not None)
+    assert pots[0] == (0.35, 0.7) and abs(pots[1][0] - 0.4) < 1e-12 and abs(pots[1][1] - 0.5 * 2.0) < 1e-12
+    gt.pairs = {}
+    assert G.set_pair_interactions(system, gt, Args(), set()) == (None, [])

@@ -167,7 +167,13 @@ def test_bonded_forces_all_kinds():
     # Kremer-Grest bonds of examples/pccg_lj: FENE (func 7) and FENE + LJ (func 9, gromacs_topology.py:935-961)
     l6 = P.add_list(2, m["bonds"][:250]); i6 = P.add_bonded(l6); P.bonded_pot(i6, (), "FENE", (30.0, 0.0, 1.5))
     l7 = P.add_list(2, m["bonds"][250:]); i7 = P.add_bonded(l7); P.bonded_pot(i7, (), "FENELennardJones", (30.0, 0.0, 1.5, 1.0, 1.0))
-    _compare_forces(P, [ib, ia, iq, i1, i2, i3, i4, i5, i6, i7])
+    # 1-4 [ pairs ]: Lennard-Jones on a pair list with a cutoff and the 'auto' shift (gromacs_topology.py:1314-1411); the 1-3 pairs of
+    # the trimers serve as the pair list (r ~ 1.9: inside the cutoff 2.2 for most, beyond it for the stretched ones)
+    p13 = np.array([(a[0], a[2]) for a in m["angles"]], np.int64)
+    sr6 = (1.1 / 2.2) ** 6
+    l8 = P.add_list(2, p13); i8 = P.add_bonded(l8); P.bonded_pot(i8, (), "LennardJones", (0.8, 1.1, 2.2, 4 * 0.8 * (sr6 * sr6 - sr6)))
+    l9 = P.add_list(2, p13); i9 = P.add_bonded(l9, typed=1); P.bonded_pot(i9, (0, 0), "LennardJones", (0.5, 1.0, 1.9, 0.0))
+    _compare_forces(P, [ib, ia, iq, i1, i2, i3, i4, i5, i6, i7, i8, i9])
     P.close()
 
 

@@ -96,10 +96,12 @@ def test_bonded_forces_are_energy_gradient():
     o2 = pyoracle.Oracle(n, m["box"], 2.5, 0.3, seed=7)
     o2.set_particles(m["pos"], None, np.ones(n), None, m["type"])
     for ar, ids, kind, par in ((2, m["bonds"], 1, (30.0, 0.97)), (3, m["angles"], 3, (1.25, 2.6)), (4, quads, 8, (2.0, 0.7)),
-                               (2, m["bonds"][:40], 7, (30.0, 0.0, 1.5)), (2, m["bonds"][40:90], 9, (30.0, 0.0, 1.5, 1.0, 1.0))):
+                               (2, m["bonds"][:40], 7, (30.0, 0.0, 1.5)), (2, m["bonds"][40:90], 9, (30.0, 0.0, 1.5, 1.0, 1.0)),
+                               # 1-4 pairs: LJ on a pair list (kind 10) with cutoff 5 (everything inside) and a shift
+                               (2, np.array([(a[0], a[2]) for a in m["angles"]], np.int64), 10, (0.8, 1.1, 5.0, 0.01))):
         l = o2.add_list(ar); o2.list_add(l, ids)
         o2.bonded_set_potential(o2.add_bonded(l), (), kind, par)
-    _fd_check(o2, [0, 1, 2, 3, 4], n, probes=(0, 1, 2, 3, 10, 11), tol=1e-6)
+    _fd_check(o2, [0, 1, 2, 3, 4, 5], n, probes=(0, 1, 2, 3, 10, 11), tol=1e-6)
     f = o.get()["force"]
     assert np.abs(f.sum(0)).max() < 1e-9  # Newton's third law
 
