@@ -53,6 +53,7 @@ SIGNATURES = {
     "clb_count_type": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_i64p]),
     "clb_set_dt": (C.c_int, [C.c_void_p, C.c_double]),
     "clb_set_langevin": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_int, c_i32p]),
+    "clb_set_cap_force": (C.c_int, [C.c_void_p, C.c_double]),
     "clb_run": (C.c_int, [C.c_void_p, C.c_int64]),
     "clb_run_continue": (C.c_int, [C.c_void_p, C.c_int64]),
     "clb_step": (C.c_int64, [C.c_void_p]),

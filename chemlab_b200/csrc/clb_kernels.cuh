@@ -199,6 +199,14 @@ __global__ void __launch_bounds__(256) k_integrate(ClbIntegParams P, int4* __res
         }
     }
 }
+// integrator.CapForce (src/start_simulation.py:320-324) [EXT, U26]: force vectors longer than `cap` are scaled back to that length
+__global__ void k_cap_force(int i0, int i1, double* __restrict__ force, int fstride, double cap, const ClbCtl* ctl) {
+    if (*(volatile const int*)&ctl->stall) return;
+    int i = i0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= i1) return;
+    const double fx = force[i], fy = force[i + fstride], fz = force[i + 2 * fstride], f2 = fx * fx + fy * fy + fz * fz;
+    if (f2 > cap * cap) { const double k = cap / sqrt(f2); force[i] = fx * k; force[i + fstride] = fy * k; force[i + 2 * fstride] = fz * k; }
+}
 // LangevinThermostat at run entry (recalc1/updateForces/recalc2 with heatUp: pref2 *= sqrt(3))
 __global__ void k_thermalize(ClbIntegParams P, double scale, uint32_t stream, const int4* __restrict__ pos,
                              const ClbVel* __restrict__ vel, const int* __restrict__ slot, double* __restrict__ force,

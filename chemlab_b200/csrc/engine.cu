@@ -1797,6 +1797,11 @@ void clb_engine::enqueue_forces(bool overlap_halo, bool resort_checked) {
         bucket_end(CLB_B_BONDED);
         ++launches;
     }
+    if (cap_force > 0) {
+        int no = own1 - own0;
+        k_cap_force<<<ceil_div(no, 256), 256, 0, stream>>>(own0, own1, force.p, ncap, cap_force, d_ctl);
+        ++launches;
+    }
 }
 
 int clb_engine::check_device_errors(const char* where) {
@@ -1904,6 +1909,12 @@ extern "C" int clb_set_langevin(clb_engine* e, int enabled, double kT, double ga
     e->lang_on = enabled; e->kT = kT; e->gamma = gamma;
     if (ntypes <= 0) e->lang_mask = ~0ull;
     else { e->lang_mask = 0; for (int i = 0; i < ntypes; ++i) if (types[i] >= 0 && types[i] < 64) e->lang_mask |= 1ull << types[i]; }
+    return CLB_OK;
+}
+extern "C" int clb_set_cap_force(clb_engine* e, double cap) {
+    if (!e) return CLB_ERR_ARG;
+    if (cap != e->cap_force) { e->forces_valid = false; e->cont_ok = false; }
+    e->cap_force = cap;
     return CLB_OK;
 }
 extern "C" int64_t clb_step(const clb_engine* e) { return e ? e->step : 0; }

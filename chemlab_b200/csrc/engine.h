@@ -166,6 +166,7 @@ struct clb_engine {
     int64_t step = 0;
     int lang_on = 0;
     double kT = 1.0, gamma = 1.0;
+    double cap_force = -1.0;      // integrator.CapForce: <= 0 off
     unsigned long long lang_mask = ~0ull;
     int last_interval = 0;
     int64_t last_rebuild_step = 0;

@@ -253,6 +253,10 @@ class Engine:
     def run(self, n):
         self._ck(self.L.clb_run(self.h, int(n)))
 
+    def set_cap_force(self, cap):
+        """integrator.CapForce(system, cap): cap <= 0 switches it off."""
+        self._ck(self.L.clb_set_cap_force(self.h, float(cap)))
+
     def run_continue(self, n):
         """Next chunk of the same integrator.run(n): no run-entry force recalculation / heat-up (clb_run_continue)."""
         self._ck(self.L.clb_run_continue(self.h, int(n)))

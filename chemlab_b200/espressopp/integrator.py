@@ -55,6 +55,8 @@ class VelocityVerlet:
             thermo[-1]._push(e)
         else:
             e.set_langevin(0, 1.0, 1.0)
+        caps = [x for x in self._extensions if isinstance(x, CapForce)]
+        e.set_cap_force(caps[-1].capForce if caps else -1.0)
         react = [x for x in self._extensions if isinstance(x, ChemicalReaction) and x._connected]
         for x in self._extensions:
             if isinstance(x, ChemicalReaction):
@@ -415,7 +417,15 @@ class ATRPActivator:
                 f.write("%d %d %d %.6f %.6f\n" % (integrator_.step, n_act, n_deact, self.ratio_activator, self.ratio_deactivator))
 
 
-for _n in ("StochasticVelocityRescaling", "BerendsenThermostat", "Isokinetic", "LangevinBarostat", "BerendsenBarostat", "CapForce",
+class CapForce:
+    """integrator.CapForce(system, capForce): src/start_simulation.py:320-324 (--max_force).  Force vectors longer than capForce
+    are scaled back to that length after every force evaluation, before the thermostat (clb_set_cap_force, U26)."""
+    def __init__(self, system, capForce, **kw):
+        self._system = system
+        self.capForce = float(capForce)
+
+
+for _n in ("StochasticVelocityRescaling", "BerendsenThermostat", "Isokinetic", "LangevinBarostat", "BerendsenBarostat",
            "FixedListDynamicResolution", "BasicDynamicResolution", "FixDistances", "PostProcessReleaseParticles",
            "PostProcessJoinParticles", "PostProcessRemoveNeighbourBond", "PostProcessChangePropertyByTopologyManager",
            "ChangeInRegion", "ChangeParticleType", "ReactionConstraintNeighbourState"):

@@ -193,6 +193,11 @@ def _main(argv, rank, world):
     gromacs_topology.set_pair_interactions(system, gt, args, dynamic_types)
     print("Interactions: %s" % ", ".join(system.getNameOfInteraction(k) for k in range(system.getNumberOfInteractions())))
 
+    # ---- cap force (:320-324)
+    if getattr(args, "max_force", -1) is not None and float(getattr(args, "max_force", -1)) > -1:
+        integrator.addExtension(espressopp.integrator.CapForce(system, float(args.max_force)))
+        print("Cap force to %s" % args.max_force)
+
     # ---- thermostat (:326-376)
     if args.thermostat != "lv":
         raise NotImplementedError("thermostat %r: only the Langevin thermostat (lv) is inside the engine's scope (SURVEY E20)" % args.thermostat)

@@ -168,6 +168,9 @@ int clb_set_dt(clb_engine *e, double dt);
  * src/start_simulation.py:330-336,353-354.  ntypes == 0: all types thermalised. */
 int clb_set_langevin(clb_engine *e, int enabled, double kT, double gamma, int ntypes,
                      const int32_t *types);
+/* integrator.CapForce(system, capForce) added with --max_force (src/start_simulation.py:320-324): after every force evaluation a
+ * force vector longer than cap is scaled back to that length (before the thermostat acts).  cap <= 0: off. */
+int clb_set_cap_force(clb_engine *e, double cap);
 /* integrator.run(n): src/start_simulation.py:780.  Synchronous. */
 int clb_run(clb_engine *e, int64_t nsteps);
 /* Continuation of the previous clb_run inside ONE integrator.run(n) of the reference: ExtAnalyze and

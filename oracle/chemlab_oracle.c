@@ -196,6 +196,7 @@ typedef struct orc_sim {
     /* integrator */
     int64_t step; int forces_valid; int lists_valid; int cont_ok;
     int lang_on; double kT, gamma; uint64_t seed; int lang_all; unsigned char lang_type[ORC_MAX_TYPES];
+    double cap_force;   /* CapForce: <= 0 off */
     /* ATRPActivator */
     int atrp_num, atrp_ncen; double atrp_ratio[2], atrp_delta, atrp_k[2];
     struct { int type, state, deact, new_type, delta; double new_mass, new_q; } atrp_cen[16];
@@ -789,8 +790,19 @@ void orc_compute_forces(orc_sim *s) {
     nonbonded_forces(s, fbuf);
     bonded_forces(s, fbuf);
     reduce_force_buffers(s, fbuf);
+    /* integrator.CapForce(system, capForce) (src/start_simulation.py:320-324) [EXT, U26]: after the force calculation every
+     * particle's force vector longer than capForce is scaled back to that length; the thermostat (added to the integrator
+     * after CapForce) acts on the capped forces */
+    if (s->cap_force > 0) {
+#pragma omp parallel for num_threads(s->nthreads) schedule(static)
+        for (int i = 0; i < s->n; ++i) {
+            double *f = s->f + 3 * (size_t)i, f2 = f[0] * f[0] + f[1] * f[1] + f[2] * f[2];
+            if (f2 > s->cap_force * s->cap_force) { double k = s->cap_force / sqrt(f2); f[0] *= k; f[1] *= k; f[2] *= k; }
+        }
+    }
     s->forces_valid = 1;
 }
+void orc_set_cap_force(orc_sim *s, double cap) { s->cap_force = cap; s->forces_valid = 0; }
 double orc_energy(orc_sim *s, int inter) {
     if (!s->forces_valid) orc_compute_forces(s);
     return s->inter_energy[inter];

@@ -288,6 +288,9 @@ class Oracle:
     def count_type(self, t, state=-1):
         return int(self.L.orc_count_type(self.h, int(t), int(state)))
 
+    def set_cap_force(self, cap):
+        self.L.orc_set_cap_force(self.h, C.c_double(cap))
+
     # -- ATRPActivator
     def atrp_configure(self, num_particles, ratio_activator, ratio_deactivator, delta_catalyst, k_activate, k_deactivate):
         self.L.orc_atrp_configure(self.h, int(num_particles), C.c_double(ratio_activator), C.c_double(ratio_deactivator),

@@ -312,3 +312,22 @@ def test_cell_pair_resort_criterion():
         rebuilds[crit] = P.e.timers()[1]["rebuilds"]
         P.close()
     assert rebuilds[2] <= rebuilds[1], rebuilds
+
+
+def test_cap_force():
+    """integrator.CapForce (src/start_simulation.py:320-324): forces longer than the cap are scaled back to it, on the engine as in
+    the oracle; a short run with the cap and the thermostat tracks the oracle."""
+    m, P = _md_pair(n_side=10, langevin=True)
+    P.both("set_cap_force", 12.0)
+    P.e.compute_forces(); P.o.compute_forces()
+    fe = P.e.get_particles(fields=("force",))["force"]; fo = P.o.get()["force"]
+    assert util.rel_force_err(fe, fo) < 1e-6
+    nf = np.linalg.norm(fe, axis=1)
+    assert nf.max() <= 12.0 * (1 + 1e-12) and (np.abs(nf - 12.0) < 1e-9).sum() > 10          # some forces were capped
+    P.both("run", 30)
+    a = P.e.get_particles(); b = P.o.get()
+    assert np.abs(_unfolded(a, m["box"]) - _unfolded(b, m["box"])).max() < 2e-4
+    P.both("set_cap_force", -1.0)
+    P.e.compute_forces(); P.o.compute_forces()
+    assert np.linalg.norm(P.e.get_particles(fields=("force",))["force"], axis=1).max() > 12.0
+    P.close()
