@@ -1,0 +1,9 @@
+#!/bin/bash
+# usage: gpuretry.sh <logfile> <gpurun args...>   -- retries while the pod answers "transient" (nothing charged)
+log=$1; shift
+for i in $(seq 1 40); do
+  /usr/local/graft/bin/gpurun "$@" > "$log" 2>&1
+  if grep -q "status=transient" "$log"; then sleep 60; continue; fi
+  break
+done
+tail -n 30 "$log"
