@@ -178,6 +178,9 @@ def _main(argv, rank, world):
         sc = reaction_setup.SetupReactions(system, verletlist, gt, topology_manager, cfg, args)
         ar, chem_fpls, reactions, ext_to_integrator = sc.setup_reactions()
         ar_interval = sc.ar_interval
+        if rank == 0:                                            # :261-263
+            import shutil
+            shutil.copyfile(args.reactions, "%s_%s" % (prefix, os.path.basename(args.reactions)))
         integrator_step = min(integrator_step, ar_interval)      # :265-267
         print("Set up %d reactions in %d groups, interval %d" % (len(reactions), len(chem_fpls), ar_interval))
     sim_step = args.run // integrator_step                       # :103,:268 (Python-2 integer division)
@@ -247,6 +250,11 @@ def _main(argv, rank, world):
     energy_collect = max(1, args.energy_collect)
     integrator.addExtension(espressopp.integrator.ExtAnalyze(monitor, energy_collect))
 
+    if getattr(args, "gro_trj_collect", None):                   # :684-696
+        dump_trj = espressopp.io.DumpGRO(system, integrator, filename=("%s_traj.gro" % prefix) if rank == 0 else os.devnull, unfolded=True, append=True)
+        integrator.addExtension(espressopp.integrator.ExtAnalyze(dump_trj, int(args.gro_trj_collect)))
+        print("Set gro trajectory saver, save every %d steps" % int(args.gro_trj_collect))
+
     maximum_conversion = []
     if args.maximum_conversion:
         maximum_conversion = tools.get_maximum_conversion(args, system, chem_fpls, gt, cr_observs)
@@ -256,6 +264,8 @@ def _main(argv, rank, world):
     k_stop_reactions = (args.stop_ar // integrator_step) if (ar is not None and getattr(args, "stop_ar", None)) else -1
     print("Running %d steps as %d x integrator.run(%d); reactions start at outer step %d" % (args.run, sim_step, integrator_step, k_enable_reactions))
     espressopp.analysis.CMVelocity(system).reset()
+
+    rate_file = open("%s_new_rates.csv" % prefix, "w") if (getattr(args, "rate_arrhenius", False) and rank == 0) else None     # :712-714
 
     # ---- main loop (:728-797)
     total_time0 = time.time()
@@ -302,11 +312,15 @@ def _main(argv, rank, world):
                 energy_delta = (monitor.potential_energy - energy0) / float(delta_bonds)
                 new_rate = math.exp(-energy_delta / temperature)
                 print("%d\tChange reaction rate, delta_E=%s, new_k=%s, delta_bonds=%d" % (k * integrator_step, energy_delta, new_rate, delta_bonds))
+                if rate_file is not None:
+                    rate_file.write("%d %e\n" % (k * integrator_step, new_rate))
                 for r_ in reactions:
                     r_.rate = new_rate
         if "hook_at_step" in hooks:
             hooks["hook_at_step"](system, integrator, ar, gt, args, k * integrator_step)     # :783
     total_time = time.time() - total_time0
+    if rate_file is not None:
+        rate_file.close()
     monitor.dump()
     monitor.info()
 
@@ -340,10 +354,17 @@ def _main(argv, rank, world):
         rows = dict(tuple_rows)
         gt.gt.write_system("%s_output_topol.top" % prefix, top_atoms, list(rows["bonds"]) + [tuple(b_) for bb in chem_bonds for b_ in bb.tolist()],
                            rows["angles"], rows["dihedrals"], {v: k_ for k_, v in gt.atomsym_atomtype.items()})
-        if ar is not None:
-            ar.save_reaction_counters("%s_reaction_counters.dat" % prefix)
+        if ar is not None:                                           # :1027-1036
+            ar.save_reaction_counters("%s_reaction_counters" % prefix)
+            with open("%s_reaction_counters" % prefix, "a") as f:
+                f.write("\n\nReaction index\n")
+                for ridx in sorted(sc.reaction_index):
+                    f.write("%s %s\n" % (ridx, sc.reaction_index[ridx]))
+            ar.save_intra_inter_counter("%s_intra_inter_counters" % prefix)
         with open("%s_benchmark.csv" % prefix, "a") as f:          # record format of the reference (:997-998): nranks NPart total loop
             f.write("%d %d %.6f %.6f\n" % (world, npart, total_time, integrator_loop))
+    # :1014-1017 -- the whole configuration through io.DumpGRO (collective read, rank 0 writes)
+    espressopp.io.DumpGRO(system, integrator, filename=("%s_whole_confout.gro" % prefix) if rank == 0 else os.devnull, unfolded=False, append=False).dump()
     # :1004-1006 -- bond graph, residue graph and residue membership at the end of the run (collective read, rank 0 writes)
     tm_files = [("save_topology", "%s_topology.dat"), ("save_res_topology", "%s_res_topology.dat"), ("save_residues", "%s_residue_list.dat")]
     for meth, pattern in tm_files:

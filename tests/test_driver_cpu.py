@@ -113,7 +113,8 @@ def test_driver_host_logic_on_the_oracle_backend(tmp_path, monkeypatch):
     assert r["steps"] == 600
     out = set(os.listdir("data"))
     for name in ("cpc01_42_confout.gro", "cpc01_42_before_reaction_confout.gro", "cpc01_42_output_topol.top", "cpc01_42_state.dat",
-                 "cpc01_42_bonds.dat", "cpc01_42_angles.dat", "cpc01_42_reaction_counters.dat", "cpc01_42_benchmark.csv",
+                 "cpc01_42_bonds.dat", "cpc01_42_angles.dat", "cpc01_42_reaction_counters", "cpc01_42_intra_inter_counters", "cpc01_42_benchmark.csv",
+                 "cpc01_42_atrp.cfg", "cpc01_42_whole_confout.gro",
                  "cpc01_energy_42.csv", "cpc01params.out", "cpc01_42_atrp_stats.dat", "cpc01_42_topology.dat", "cpc01_42_res_topology.dat",
                  "cpc01_42_residue_list.dat", "cpc01_42_benchmark.pck"):
         assert name in out, name

@@ -49,7 +49,7 @@ def test_atrp_lj_driver_gpu_matches_oracle(tmp_path):
     a = _run(str(tmp_path), "gpu", steps)
     assert a["steps"] == steps
     # products of the reference driver (src/start_simulation.py:800-1081): final .gro, energy CSV, counters, benchmark record
-    for suffix in ("_confout.gro", "_energy_42.csv", "_reaction_counters.dat", "_benchmark.csv", "params.out"):
+    for suffix in ("_confout.gro", "_energy_42.csv", "_reaction_counters", "_benchmark.csv", "_whole_confout.gro", "params.out"):
         assert any(f.endswith(suffix) for f in a["files"]), (suffix, a["files"])
     assert 0.8 < a["T"] < 1.25
     t = a["g"]["type"]
