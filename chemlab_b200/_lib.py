@@ -63,6 +63,7 @@ SIGNATURES = {
     "clb_add_reaction": (C.c_int, [C.c_void_p, C.POINTER(ReactionSpec), C.POINTER(C.c_int)]),
     "clb_reaction_set_rate": (C.c_int, [C.c_void_p, C.c_int, C.c_double]),
     "clb_reaction_set_active": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "clb_reaction_define_connections": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, c_i64p]),
     "clb_reaction_add_change": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int]),
     "clb_topology_observe": (C.c_int, [C.c_void_p, C.c_int]),
     "clb_topology_register_triplet": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]),

@@ -95,13 +95,14 @@ class SetupReactions:
 
     def _reaction(self, r, fpl):
         """integrator.Reaction from one [reaction_*] section (reaction_setup.py:71-165)."""
-        if r["reaction_type"] != REACTION_NORMAL or r.get("connectivity_map") or "sigma" in r:
-            raise NotImplementedError("reaction %r: reverse/exchange/restricted reactions and random cut-offs are outside "
+        if r["reaction_type"] != REACTION_NORMAL or "sigma" in r:
+            raise NotImplementedError("reaction %r: reverse/exchange reactions and random cut-offs are outside "
                                       "the scope of the B200 engine (SURVEY E21)" % r["equation"])
         rl = r["reactant_list"]
         a, b = rl["type_1"], rl["type_2"]
         t1, t2 = self.name2type[a["name"]], self.name2type[b["name"]]
-        reaction = espressopp.integrator.Reaction(
+        r_class = espressopp.integrator.RestrictReaction if r.get("connectivity_map") else espressopp.integrator.Reaction   # :74-77
+        reaction = r_class(
             type_1=t1, type_2=t2, delta_1=int(a["delta"]), delta_2=int(b["delta"]), min_state_1=int(a["min"]), max_state_1=int(a["max"]),
             min_state_2=int(b["min"]), max_state_2=int(b["max"]), rate=float(r["rate"]), fpl=fpl, cutoff=float(r["cutoff"]))
         self.dynamic_types.update((t1, t2))
@@ -111,6 +112,18 @@ class SetupReactions:
         if "min_cutoff" in r:
             reaction.get_reaction_cutoff().min_cutoff = float(r["min_cutoff"])
         reaction.active = r.get("active", True)
+        if r.get("connectivity_map"):                                   # :115-126
+            print("Reading connectivity map %s, reaction will be restricted to form connections only from the map" % r["connectivity_map"])
+            ex_list = set()
+            with open(r["connectivity_map"]) as f:
+                for l in f:
+                    if l.strip():
+                        b1, b2 = (int(x) for x in l.split())
+                        ex_list.add(tuple(sorted((b1, b2))))
+            for b1, b2 in sorted(ex_list):
+                reaction.define_connection(b1, b2)
+            self.exclusions_list.extend(sorted(ex_list))
+            print("Restricted to %d connections" % len(ex_list))
         n1, n2 = self.name2type[a["new_type"]], self.name2type[b["new_type"]]
         for side, old, new, new_name in (("type_1", t1, n1, a["new_type"]), ("type_2", t2, n2, b["new_type"])):
             if old != new:       # PostProcessChangeProperty: reactant type/mass/charge rewrite (:137-163)

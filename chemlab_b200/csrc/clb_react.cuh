@@ -17,7 +17,8 @@ namespace cg = cooperative_groups;
 struct ClbReactSpec {
     int type_1, type_2, delta_1, delta_2, min1, max1, min2, max2;
     double cutoff2, min_cutoff2, p;
-    int list, intramolecular, intraresidual, is_virtual, active, pad;
+    int list, intramolecular, intraresidual, is_virtual, active;
+    int conn_n, conn_off, pad;     // RestrictReaction: conn_n >= 0 -> only pairs among conn[conn_off, conn_off + conn_n) may react; -1 unrestricted
 };
 struct ClbCand { int a, b, r, accepted; double d2; unsigned long long rnd; };
 struct ClbChange { int reaction, side, nb_level, old_type, new_type, state_mode, state_value, pad; double new_mass, new_q; };
@@ -32,6 +33,14 @@ template <int N> struct ClbTupLess {
     }
 };
 
+// RestrictReaction.define_connection (reaction_setup.py:115-126): sorted keys (lower slot << 32 | higher slot) per reaction
+__device__ __forceinline__ bool conn_has(const unsigned long long* __restrict__ conn, int off, int n, int lo, int hi) {
+    const unsigned long long key = ((unsigned long long)(unsigned)lo << 32) | (unsigned)hi;
+    int a = 0, b = n;
+    while (a < b) { const int m = (a + b) >> 1; if (__ldg(conn + off + m) < key) a = m + 1; else b = m; }
+    return a < n && __ldg(conn + off + a) == key;
+}
+
 __device__ __forceinline__ bool side_ok(const ClbReactSpec& r, int wa, int wb) {
     int sa = pw_state(wa), sb = pw_state(wb);
     return pw_type(wa) == r.type_1 && pw_type(wb) == r.type_2 && sa >= r.min1 && sa < r.max1 && sb >= r.min2 && sb < r.max2;
@@ -43,6 +52,7 @@ __global__ void __launch_bounds__(512) k_react_scan(ClbGrid g, ClbGeom geo, cons
                                                     const int* __restrict__ nl_count, int cap,
                                                     const ClbReactSpec* __restrict__ specs, int nspec,
                                                     const int* __restrict__ resid, const int* __restrict__ mol,
+                                                    const unsigned long long* __restrict__ conn,
                                                     uint64_t seed, uint64_t step, ClbCand* __restrict__ cands,
                                                     unsigned long long candcap, ClbCtl* ctl) {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -96,6 +106,7 @@ __global__ void __launch_bounds__(512) k_react_scan(ClbGrid g, ClbGeom geo, cons
                         if (!(d2 >= r.min_cutoff2 && d2 < r.cutoff2)) continue;               // U3
                         if (!r.intraresidual && __ldg(resid + A) == __ldg(resid + B)) continue; // U10
                         if (!r.intramolecular && __ldg(mol + A) == __ldg(mol + B)) continue;
+                        if (r.conn_n >= 0 && !conn_has(conn, r.conn_off, r.conn_n, si, sj)) continue;   // si < sj
                         uint32_t w[4], h[4];
                         clb_draw_pair(seed, CLB_STREAM_REACT, step, (uint32_t)si, (uint32_t)sj, (uint32_t)ri, w);
                         clb_draw_pair(seed, CLB_STREAM_PARTNER, step, (uint32_t)si, (uint32_t)sj, (uint32_t)ri, h);

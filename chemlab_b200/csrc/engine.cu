@@ -433,6 +433,7 @@ extern "C" int clb_set_particles(clb_engine* e, int64_t n, const int64_t* id, co
         }
     }
     e->n = (int)n;
+    for (char c : e->react_restricted) if (c) e->react_dirty = true;     // connectivity maps are resolved to slots at upload
     ClbTrace tr(e->stream, "set_particles");
     tr.mark("ids");
     // per-slot arrays are full size on every rank

@@ -178,6 +178,8 @@ struct clb_engine {
     std::vector<HostTmReg> tmregs;
     bool react_dirty = true, topo_dirty = true, topo_initialized = false;
     std::vector<int64_t> react_counters;
+    std::vector<std::vector<int64_t>> react_conn;   // RestrictReaction: connectivity map per reaction, [n][2] particle ids
+    std::vector<char> react_restricted;
     struct ReactDev;
     ReactDev* rd = nullptr;
     int R_prealloc_n = -1;

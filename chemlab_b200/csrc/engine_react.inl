@@ -6,7 +6,7 @@ struct clb_engine::ReactDev {
     DevBuf<ClbTmReg> regs;
     DevBuf<ClbListDev> lists;
     DevBuf<ClbCand> cands, cands_sorted;
-    DevBuf<unsigned long long> ckey, ckey2, best1, best2, claim, counters, scalars;
+    DevBuf<unsigned long long> ckey, ckey2, best1, best2, claim, counters, scalars, conn;
     DevBuf<int> cval, cval2, alive, surv, status, ev, erank, asA, inB, adj, deg, ev_of_slot, list_n, list_cnt, touched, evpairs, flag, iota;
     size_t candcap = 0;
     long long ncand_last = 0;
@@ -17,7 +17,7 @@ void clb_engine::react_free() {
     if (!rd) return;
     ReactDev& R = *rd;
     R.specs.release(); R.chg.release(); R.regs.release(); R.lists.release(); R.cands.release(); R.cands_sorted.release();
-    R.ckey.release(); R.ckey2.release(); R.best1.release(); R.best2.release(); R.claim.release(); R.counters.release(); R.scalars.release();
+    R.ckey.release(); R.ckey2.release(); R.best1.release(); R.best2.release(); R.claim.release(); R.counters.release(); R.scalars.release(); R.conn.release();
     R.cval.release(); R.cval2.release(); R.alive.release(); R.surv.release(); R.status.release(); R.ev.release(); R.erank.release();
     R.asA.release(); R.inB.release(); R.adj.release(); R.deg.release(); R.ev_of_slot.release(); R.list_n.release(); R.list_cnt.release();
     R.touched.release(); R.evpairs.release(); R.flag.release(); R.iota.release();
@@ -39,6 +39,8 @@ extern "C" int clb_add_reaction(clb_engine* e, const clb_reaction_spec* s, int* 
     if (s->cutoff > e->rc * (1 + 1e-12)) return e->fail(CLB_ERR_ARG, "reaction cutoff %g exceeds the Verlet cutoff %g", s->cutoff, e->rc);
     e->reactions.push_back(*s);
     e->react_counters.push_back(0);
+    e->react_conn.emplace_back();
+    e->react_restricted.push_back(0);
     e->ntypes = std::max(e->ntypes, std::max(s->type_1, s->type_2) + 1);
     *out = (int)e->reactions.size() - 1;
     e->react_dirty = true;
@@ -51,6 +53,15 @@ extern "C" int clb_reaction_set_rate(clb_engine* e, int r, double rate) {
 extern "C" int clb_reaction_set_active(clb_engine* e, int r, int a) {
     if (!e || r < 0 || r >= (int)e->reactions.size()) return CLB_ERR_ARG;
     e->reactions[r].active = a; e->react_dirty = true; return CLB_OK;
+}
+extern "C" int clb_reaction_define_connections(clb_engine* e, int r, int64_t n, const int64_t* pairs) {
+    if (!e || r < 0 || r >= (int)e->reactions.size() || n < 0 || (n && !pairs)) return e ? e->fail(CLB_ERR_ARG, "clb_reaction_define_connections: bad argument") : CLB_ERR_ARG;
+    for (int64_t k = 0; k < 2 * n; ++k)
+        if (e->slot_of(pairs[k]) < 0) return e->fail(CLB_ERR_ARG, "connectivity map names unknown particle id %lld", (long long)pairs[k]);
+    e->react_conn[r].assign(pairs, pairs + 2 * n);     // kept as ids: slots are resolved at upload (set_particles may follow)
+    e->react_restricted[r] = 1;
+    e->react_dirty = true;
+    return CLB_OK;
 }
 extern "C" int clb_reaction_add_change(clb_engine* e, int reaction, int side, int nb_level, int old_type, int new_type, double new_mass,
                                        double new_q, int state_mode, int state_value) {
@@ -86,6 +97,7 @@ int clb_engine::upload_reactions() {
     clb_engine* e = this;
     if (!rd) rd = new ReactDev();
     std::vector<ClbReactSpec> hs(std::max<size_t>(reactions.size(), 1));
+    std::vector<unsigned long long> hconn;       // connectivity maps of the restricted reactions, one sorted range each
     for (size_t k = 0; k < reactions.size(); ++k) {
         const clb_reaction_spec& s = reactions[k];
         ClbReactSpec d; memset(&d, 0, sizeof(d));
@@ -94,8 +106,24 @@ int clb_engine::upload_reactions() {
         d.cutoff2 = s.cutoff * s.cutoff; d.min_cutoff2 = s.min_cutoff * s.min_cutoff;
         d.p = s.rate * dt * react_interval;                      // U5
         d.list = s.list; d.intramolecular = s.intramolecular; d.intraresidual = s.intraresidual; d.is_virtual = s.is_virtual; d.active = s.active;
+        d.conn_n = -1;
+        if (react_restricted[k]) {
+            const std::vector<int64_t>& cp = react_conn[k];
+            std::vector<unsigned long long> keys(cp.size() / 2);
+            for (size_t q = 0; q < keys.size(); ++q) {
+                const int a = slot_of(cp[2 * q]), b = slot_of(cp[2 * q + 1]);
+                if (a < 0 || b < 0) return fail(CLB_ERR_ARG, "connectivity map of reaction %d names an unknown particle id", (int)k);
+                keys[q] = ((unsigned long long)(unsigned)std::min(a, b) << 32) | (unsigned)std::max(a, b);
+            }
+            std::sort(keys.begin(), keys.end());
+            keys.erase(std::unique(keys.begin(), keys.end()), keys.end());
+            d.conn_off = (int)hconn.size(); d.conn_n = (int)keys.size();
+            hconn.insert(hconn.end(), keys.begin(), keys.end());
+        }
         hs[k] = d;
     }
+    CK(rd->conn.ensure(std::max<size_t>(hconn.size(), 1)));
+    if (!hconn.empty()) CK(cudaMemcpyAsync(rd->conn.p, hconn.data(), hconn.size() * 8, cudaMemcpyHostToDevice, stream));
     std::vector<ClbChange> hc(std::max<size_t>(changes.size(), 1));
     for (size_t k = 0; k < changes.size(); ++k) {
         const HostChange& c = changes[k];
@@ -229,7 +257,7 @@ int clb_engine::react_pass(int64_t* events_out) {
     for (;;) {
         CK(cudaMemsetAsync(&d_ctl->ncand, 0, 8, stream));
         k_react_scan<<<gridsz, 256, smem, stream>>>(grid, geo, cell_start.p, pos.p, slot.p, nl_entries.p, nl_count.p, nl_cap, R.specs.p, (int)reactions.size(),
-                                                            resid.p, mol.p, seed, (uint64_t)step, R.cands.p, (unsigned long long)R.candcap, d_ctl);
+                                                            resid.p, mol.p, R.conn.p, seed, (uint64_t)step, R.cands.p, (unsigned long long)R.candcap, d_ctl);
         ++launches;
         TRY(read_ctl());
         nc = (long long)h_ctl->ncand;

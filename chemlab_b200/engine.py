@@ -288,6 +288,11 @@ class Engine:
     def reaction_set_active(self, r, active):
         self._ck(self.L.clb_reaction_set_active(self.h, int(r), int(active)))
 
+    def reaction_define_connections(self, r, pairs):
+        """RestrictReaction.define_connection for every pair of the connectivity map (reaction_setup.py:115-126)."""
+        p = np.ascontiguousarray(np.asarray(pairs, np.int64).reshape(-1, 2))
+        self._ck(self.L.clb_reaction_define_connections(self.h, int(r), len(p), _p(p, c_i64p)))
+
     def reaction_add_change(self, reaction, side, nb_level, old_type, new_type, new_mass=-1.0, new_q=float("nan"),
                             state_mode=0, state_value=0):
         self._ck(self.L.clb_reaction_add_change(self.h, int(reaction), int(side), int(nb_level), int(old_type), int(new_type),

@@ -176,6 +176,9 @@ class Reaction:
     def add_postprocess(self, pp, which="both"):
         self._post.append((pp, which))
 
+    def _attach_more(self, e):
+        pass
+
     def _attach(self, e):
         if self._h is not None:
             return
@@ -186,6 +189,7 @@ class Reaction:
                                  min_cutoff=self._cutoff.min_cutoff, intramolecular=int(bool(self.intramolecular)),
                                  intraresidual=int(bool(self.intraresidual)), is_virtual=int(bool(self.is_virtual)),
                                  active=int(self._active))
+        self._attach_more(e)
         side_of = {"type_1": 1, "type_2": 2, "both": 3, None: 3}
         for pp, which in self._post:
             if not isinstance(pp, PostProcessChangeProperty):
@@ -197,7 +201,27 @@ class Reaction:
                                       new_q=float(p.q) if p.q is not None else float("nan"), state_mode=mode, state_value=val)
 
 
-RestrictReaction = not_in_scope("integrator.RestrictReaction")
+class RestrictReaction(Reaction):
+    """integrator.RestrictReaction(...): a Reaction that forms bonds only between the particle pairs named with
+    define_connection(b1, b2) -- one call per line of the group's `connectivity_map` (reaction_setup.py:74-75,115-126;
+    examples/dacron/restrict/reaction.cfg:26 + connections.list).  `revert` is only set for dissociation reactions
+    (:127-128), which stay outside the scope of the engine."""
+    def __init__(self, *a, **kw):
+        super().__init__(*a, **kw)
+        self._connections = set()
+        self.revert = False
+
+    def define_connection(self, b1, b2):
+        self._connections.add((min(int(b1), int(b2)), max(int(b1), int(b2))))
+        if self._h is not None:
+            self._engine.reaction_define_connections(self._h, sorted(self._connections))
+
+    def _attach_more(self, e):
+        if self.revert:
+            raise NotImplementedError("RestrictReaction.revert (dissociation) is outside the scope of the B200 engine")
+        e.reaction_define_connections(self._h, sorted(self._connections))
+
+
 DissociationReaction = not_in_scope("integrator.DissociationReaction")
 ReactionCutoffRandom = not_in_scope("integrator.ReactionCutoffRandom")
 

@@ -150,7 +150,18 @@ def prepare_example(src_dir, dst_dir, example):
             write("table_a%d.pot" % k, th, 0.5 * K * (th - t0) ** 2, -K * (th - t0))
         for k in range(8):
             write("table_d%d.pot" % k, ph, 2.0 * (1 + np.cos(2 * ph - 0.3 * k)), 4.0 * np.sin(2 * ph - 0.3 * k))
-    if example == "dacron":
+    if example == "dacron_restrict":
+        # examples/dacron/restrict: the includes, the exclusion list and every table are byte-identical to no_water/test_1 and come
+        # from that fixture.  Dropped as out of scope, exactly like there: the dummy-water type Z with its
+        # func-11 (dynamic-resolution) rows -- only the unused ReleaseMolecule extension would create Z particles.
+        base = os.path.join(os.path.dirname(src_dir), "dacron")
+        for f in ("diol_cg.itp", "ter_cg.itp", "exclusion_topol.list", "tables.npz"):
+            shutil.copy(os.path.join(base, f), os.path.join(dst_dir, f))
+        top = os.path.join(dst_dir, "topol.top")
+        lines = open(top).read().split("\n")
+        with open(top, "w") as fh:
+            fh.write("\n".join((";" + l) if (l.split()[:1] == ["Z"] or l.split()[1:2] == ["Z"]) else l for l in lines))
+    if example in ("dacron", "dacron_restrict"):
         for k in range(2):
             write("table_d%d.pot" % k, ph, 1.5 * (1 + np.cos(3 * ph - 0.4 * k)), 4.5 * np.sin(3 * ph - 0.4 * k))
     npz = os.path.join(dst_dir, "tables.npz")

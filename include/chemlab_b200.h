@@ -209,6 +209,12 @@ int clb_add_reaction(clb_engine *e, const clb_reaction_spec *spec, int *reaction
 /* r.rate = ..., r.active = ... mid-run (src/start_simulation.py:785-796) */
 int clb_reaction_set_rate(clb_engine *e, int reaction, double rate);
 int clb_reaction_set_active(clb_engine *e, int reaction, int active);
+/* integrator.RestrictReaction(...).define_connection(b1, b2) for every line of the group's `connectivity_map`
+ * (src/chemlab/reaction_setup.py:74-75,115-126; examples/dacron/restrict/reaction.cfg:26, connections.list): the
+ * reaction forms a bond only between particle pairs named in the map (either order).  pairs = [n][2] particle ids;
+ * the call REPLACES the map of this reaction; n = 0 leaves a restricted reaction that accepts no pair.  A reaction
+ * that never received this call is unrestricted. */
+int clb_reaction_define_connections(clb_engine *e, int reaction, int64_t n, const int64_t *pairs);
 
 /* PostProcessChangeProperty().add_change_property(old_type, TopologyParticleProperties(type, mass, q
  * [, state | incr_state])) + reaction.add_postprocess(pp, 'type_1'|'type_2'|both):

@@ -168,6 +168,9 @@ typedef struct {
     double rate, cutoff, min_cutoff;
     int list, intramolecular, intraresidual, is_virtual, active;
     int64_t counter;
+    /* RestrictReaction.define_connection (reaction_setup.py:74-75,115-126): nconn >= 0 -> only the pairs of the
+     * connectivity map (sorted keys lower index << 32 | higher index) may react; -1 = plain Reaction */
+    int64_t nconn; uint64_t *conn;
 } orc_reaction;
 typedef struct {
     int reaction, side, nb_level, old_type, new_type, state_mode, state_value;
@@ -238,6 +241,7 @@ void orc_destroy(orc_sim *s) {
     for (int i = 0; i < s->nlists; ++i) free(s->lists[i].ids);
     free(s->lists);
     for (int i = 0; i < s->nbonded; ++i) free(s->bonded[i].tp);
+    for (int i = 0; i < s->nreac; ++i) free(s->reac[i].conn);
     free(s->bonded); free(s->reac); free(s->chg); free(s->tmreg);
     free(s);
 }
@@ -913,9 +917,26 @@ int orc_add_reaction(orc_sim *s, int type_1, int type_2, int delta_1, int delta_
                      int is_virtual, int active) {
     s->reac = realloc(s->reac, sizeof(orc_reaction) * (s->nreac + 1));
     orc_reaction r = {type_1, type_2, delta_1, delta_2, min1, max1, min2, max2, rate, cutoff, min_cutoff, list,
-                      intramolecular, intraresidual, is_virtual, active, 0};
+                      intramolecular, intraresidual, is_virtual, active, 0, -1, NULL};
     s->reac[s->nreac] = r;
     return s->nreac++;
+}
+/* the call replaces the map; pairs = [n][2] dense indices, either order */
+void orc_reaction_define_connections(orc_sim *s, int r, int64_t n, const int *pairs) {
+    orc_reaction *R = &s->reac[r];
+    free(R->conn);
+    R->conn = malloc(sizeof(uint64_t) * (size_t)(n > 0 ? n : 1));
+    for (int64_t k = 0; k < n; ++k) {
+        int a = pairs[2 * k], b = pairs[2 * k + 1];
+        R->conn[k] = ((uint64_t)(uint32_t)(a < b ? a : b) << 32) | (uint32_t)(a < b ? b : a);
+    }
+    qsort(R->conn, (size_t)n, sizeof(uint64_t), cmp_u64);
+    R->nconn = n;
+}
+static int conn_allows(const orc_reaction *r, int i, int j) {
+    if (r->nconn < 0) return 1;
+    uint64_t key = ((uint64_t)(uint32_t)(i < j ? i : j) << 32) | (uint32_t)(i < j ? j : i);
+    return bsearch(&key, r->conn, (size_t)r->nconn, sizeof(uint64_t), cmp_u64) != NULL;
 }
 void orc_reaction_set_rate(orc_sim *s, int r, double rate) { s->reac[r].rate = rate; }
 void orc_reaction_set_active(orc_sim *s, int r, int a) { s->reac[r].active = a; }
@@ -1006,6 +1027,7 @@ void orc_react(orc_sim *s) {
             else continue;
             if (!r->intraresidual && s->resid[A] == s->resid[B]) continue; /* U10 */
             if (!r->intramolecular && mol_find(s, A) == mol_find(s, B)) continue;
+            if (!conn_allows(r, i, j)) continue;
             if (d2 < 0) d2 = dist2(s, i, j, d);
             if (!(d2 >= r->min_cutoff * r->min_cutoff && d2 < r->cutoff * r->cutoff)) continue; /* U3 */
             uint32_t w[4]; draw_pair(s->seed, STREAM_REACT, step, (uint32_t)i, (uint32_t)j, (uint32_t)ri, w);

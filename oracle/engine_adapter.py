@@ -83,6 +83,9 @@ class OracleEngine:
     def get_exclusions(self):
         return self.ids[self.o.get_exclusions()]
 
+    def reaction_define_connections(self, r, pairs):
+        self.o.reaction_define_connections(r, self._ix(np.asarray(pairs, np.int64).reshape(-1, 2)))
+
     def list_add(self, lst, ids):
         ids = np.asarray(ids, np.int64)
         if ids.size:

@@ -251,6 +251,10 @@ class Oracle:
                                            C.c_double(rate), C.c_double(cutoff), C.c_double(min_cutoff), int(lst),
                                            int(intramolecular), int(intraresidual), int(is_virtual), int(active)))
 
+    def reaction_define_connections(self, r, pairs):
+        p = _i(np.asarray(pairs).reshape(-1, 2))
+        self.L.orc_reaction_define_connections(self.h, int(r), C.c_int64(len(p)), _p(p, C.c_int))
+
     def reaction_set_rate(self, r, rate):
         self.L.orc_reaction_set_rate(self.h, int(r), C.c_double(rate))
 

@@ -106,7 +106,24 @@ def pack_dacron():
     print("dacron: %d tables packed: %s" % (len(arrays), " ".join(sorted(arrays))))
 
 
+# dacron/restrict: the RestrictReaction example (group key `connectivity_map:connections.list`, reaction_setup.py:74-75,115-126).
+# Only the files that differ from no_water/test_1 are stored (coordinates, topology, arg-file, reaction config, the connectivity map);
+# the two .itp includes, the exclusion list and every table are byte-identical to the dacron fixture and are taken from it by
+# chemlab_b200.synthetic.prepare_example.
+def pack_dacron_restrict():
+    src = os.path.join(REF, "examples", "dacron", "restrict")
+    dst = os.path.join(HERE, "dacron_restrict")
+    os.makedirs(dst, exist_ok=True)
+    for f in ("conf.gro", "topol.top", "params", "reaction.cfg", "connections.list"):
+        shutil.copy(os.path.join(src, f), os.path.join(dst, f))
+        os.chmod(os.path.join(dst, f), 0o644)
+    for f in ("diol_cg.itp", "ter_cg.itp", "exclusion_topol.list"):
+        assert open(os.path.join(src, f), "rb").read() == open(os.path.join(HERE, "dacron", f), "rb").read(), f
+    print("dacron_restrict: copied")
+
+
 if __name__ == "__main__":
     pack_rim135()
     pack_hyperbranched()
     pack_dacron()
+    pack_dacron_restrict()

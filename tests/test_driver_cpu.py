@@ -194,3 +194,48 @@ def test_14_pairs_become_lj_pair_lists(tmp_path, monkeypatch):
     assert pots[0] == (0.35, 0.7) and abs(pots[1][0] - 0.4) < 1e-12 and abs(pots[1][1] - 0.5 * 2.0) < 1e-12
     gt.pairs = {}
     assert G.set_pair_interactions(system, gt, Args(), set()) == (None, [])
+
+
+def run_dacron_restrict(tmp, backend, steps, seed="7"):
+    """examples/dacron/restrict through the driver (shared by the CPU test below and tests/test_gpu_zz_restrict.py): the shipped
+    connectivity map, topology, coordinates and arg-file; the reaction interval is shortened to 100 steps and the rate raised so
+    that every allowed pair inside the cut-off reacts (the shipped p = 0.005 per pass is meant for 2e7-step runs)."""
+    import sys
+    sys.path.insert(0, HERE)
+    from chemlab_b200 import synthetic
+    import chemlab_b200.espressopp._context as C
+    from chemlab_b200 import start_simulation as S
+    d = synthetic.prepare_example(os.path.join(GOLD, "dacron_restrict"), os.path.join(tmp, "restrict_" + backend), "dacron_restrict")
+    cwd = os.getcwd()
+    os.chdir(d)
+    real = C.Engine
+    try:
+        cfg = open("reaction.cfg").read()
+        assert "connectivity_map:connections.list" in cfg and cfg.count("rate: 0.005") == 2
+        open("reaction.cfg", "w").write(cfg.replace("interval: 1000", "interval: 100").replace("rate: 0.005", "rate: 100.0"))
+        if backend == "oracle":
+            from oracle.engine_adapter import OracleEngine
+            C.Engine = OracleEngine
+        r = S.main(["@params", "--run", str(steps), "--rng_seed", seed, "--t_hybrid_bond", "0", "--gen_velocity", "True",
+                    "--int_step", "100", "--energy_collect", "100"])
+        e = r["system"]._ctx.engine
+        g = e.get_particles(fields=("type", "state", "mass"))
+        bonds = np.concatenate([np.asarray(f.fpl.getAllBonds(), np.int64).reshape(-1, 2) for f in r["chem_fpls"]])
+        conn = {tuple(sorted(int(x) for x in l.split())) for l in open("connections.list") if l.strip()}
+        names = [r["system"].getNameOfInteraction(k) for k in range(r["system"].getNumberOfInteractions())]
+        return dict(g=g, bonds=bonds, conn=conn, steps=r["steps"], names=names, reactions=r.get("reactions"))
+    finally:
+        C.Engine = real
+        os.chdir(cwd)
+
+
+def test_dacron_restrict_driver_on_the_oracle_backend(tmp_path):
+    """RestrictReaction end to end (reaction_setup.py:74-75,115-126; examples/dacron/restrict): every bond the reactions form is
+    a line of connections.list, and the run forms at least one (1998 allowed pairs among 4000 beads: about one pair per pass
+    comes within the 0.48 nm cut-off)."""
+    a = run_dacron_restrict(str(tmp_path), "oracle", 400)
+    assert a["steps"] == 400 and len(a["conn"]) == 1998
+    assert len(a["bonds"]) >= 1
+    assert all(tuple(sorted(b)) in a["conn"] for b in a["bonds"].tolist())
+    t = a["g"]["type"]
+    assert (t >= 3).sum() >= 1          # products C / E exist

@@ -180,7 +180,9 @@ def test_react_matches_an_independent_python_restatement():
     list and Philox draws: candidate rows, acceptance, UniqueA -> UniqueB (nearest and random), one reaction per particle,
     max_per_interval, state deltas and the bond list must equal what the C oracle does."""
     STREAM_REACT, STREAM_PARTNER = 0x52454143, 0x50415254
-    for nearest, cap in ((1, 0), (0, 0), (1, 25)):
+    # last case: reaction 0 is a RestrictReaction (reaction_setup.py:74-75,115-126) whose connectivity map names every third
+    # Verlet pair (given in either order, with duplicates) -- a pair outside the map is no candidate of that reaction
+    for nearest, cap, restrict in ((1, 0, 0), (0, 0, 0), (1, 25, 0), (0, 0, 1)):
         m = util.melt(10, seed=21)
         n = len(m["pos"]); box = m["box"]; seed = 77; dt = 0.004; interval = 10
         state = np.where(m["type"] == 0, 1, 0).astype(np.int32)
@@ -196,6 +198,10 @@ def test_react_matches_an_independent_python_restatement():
             o.add_reaction(s["t1"], s["t2"], s["d1"], s["d2"], s["w1"][0], s["w1"][1], s["w2"][0], s["w2"][1], s["rate"], s["rc"], rl,
                            intramolecular=1, intraresidual=0)
         pairs = o.pairs()
+        if restrict:
+            cmap = pairs[::3]
+            specs[0]["conn"] = {(int(min(a, b)), int(max(a, b))) for a, b in cmap}
+            o.reaction_define_connections(0, np.concatenate([cmap[:, ::-1], cmap[:50]]))
         typ, st, resid, pos = m["type"].copy(), state.copy(), m["resid"], m["pos"]
         step = o.step()
 
@@ -212,6 +218,7 @@ def test_react_matches_an_independent_python_restatement():
                 elif side_ok(s, j, i): a, b = j, i
                 else: continue
                 if resid[a] == resid[b] or not (d2 < s["rc"] ** 2): continue
+                if "conn" in s and (int(min(i, j)), int(max(i, j))) not in s["conn"]: continue
                 w = draw(STREAM_REACT, int(i), int(j), r); h = draw(STREAM_PARTNER, int(i), int(j), r)
                 cands.append(dict(a=int(a), b=int(b), r=r, d2=d2, acc=(w[0] / 4294967296.0) < s["rate"] * dt * interval, rnd=(h[0] << 32) | h[1]))
         cands.sort(key=lambda c: (c["a"], c["b"], c["r"]))
@@ -234,6 +241,11 @@ def test_react_matches_an_independent_python_restatement():
         nev = o.react()
         rows, d2o = o.candidates()
         assert len(rows) == len(cands) > 100
+        if not restrict:
+            n_unrestricted = sum(c["r"] == 0 for c in cands)
+        else:
+            assert 0 < sum(c["r"] == 0 for c in cands) < 0.5 * n_unrestricted
+            assert all((min(c["a"], c["b"]), max(c["a"], c["b"])) in specs[0]["conn"] for c in cands if c["r"] == 0)
         assert (rows == np.array([[c["a"], c["b"], c["r"], int(c["acc"])] for c in cands])).all()
         assert np.allclose(d2o, [c["d2"] for c in cands], rtol=1e-13)
         assert nev == len(events) > (10 if not cap else 0) and (not cap or nev == cap)
