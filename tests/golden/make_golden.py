@@ -122,8 +122,31 @@ def pack_dacron_restrict():
     print("dacron_restrict: copied")
 
 
+# mf/espp_cg_1: melamine-formaldehyde network, one bead type, A(0,3) + A(0,3) -> A(1):A(1) with intramolecular: 0 (every bead binds
+# up to three others, never inside its own molecule), harmonic reaction bonds; inputs as shipped, table_A_A.xvg converted with
+# the reference's converter logic and packed like the other examples.
+def pack_mf():
+    import sys
+    import tempfile
+    import numpy as np
+    sys.path.insert(0, os.path.join(HERE, "..", ".."))
+    from chemlab_b200.espressopp.tools.convert.gromacs import convertTable
+    src = os.path.join(REF, "examples", "mf", "espp_cg_1")
+    dst = os.path.join(HERE, "mf")
+    os.makedirs(dst, exist_ok=True)
+    for f in ("conf.gro", "topol.top", "params", "reaction.cfg"):
+        shutil.copy(os.path.join(src, f), os.path.join(dst, f))
+        os.chmod(os.path.join(dst, f), 0o644)
+    with tempfile.TemporaryDirectory() as tmp:
+        pot = os.path.join(tmp, "table_A_A.pot")
+        convertTable(os.path.join(src, "table_A_A.xvg"), pot)
+        np.savez_compressed(os.path.join(dst, "tables.npz"), table_A_A=np.loadtxt(pot))
+    print("mf: packed")
+
+
 if __name__ == "__main__":
     pack_rim135()
     pack_hyperbranched()
     pack_dacron()
     pack_dacron_restrict()
+    pack_mf()

@@ -239,3 +239,49 @@ def test_dacron_restrict_driver_on_the_oracle_backend(tmp_path):
     assert all(tuple(sorted(b)) in a["conn"] for b in a["bonds"].tolist())
     t = a["g"]["type"]
     assert (t >= 3).sum() >= 1          # products C / E exist
+
+
+def run_mf(tmp, backend, steps, seed="3"):
+    """examples/mf/espp_cg_1 as shipped through the driver (shared with tests/test_gpu_zz_restrict.py)."""
+    import sys
+    sys.path.insert(0, HERE)
+    from chemlab_b200 import synthetic
+    import chemlab_b200.espressopp._context as C
+    from chemlab_b200 import start_simulation as S
+    d = synthetic.prepare_example(os.path.join(GOLD, "mf"), os.path.join(tmp, "mf_" + backend), "mf")
+    cwd = os.getcwd()
+    os.chdir(d)
+    real = C.Engine
+    try:
+        if backend == "oracle":
+            from oracle.engine_adapter import OracleEngine
+            C.Engine = OracleEngine
+        r = S.main(["@params", "--run", str(steps), "--rng_seed", seed, "--start_ar", "0"])
+        g = r["system"]._ctx.engine.get_particles(fields=("type", "state", "mass"))
+        bonds = np.concatenate([np.asarray(f.fpl.getAllBonds(), np.int64).reshape(-1, 2) for f in r["chem_fpls"]])
+        return dict(g=g, bonds=bonds, steps=r["steps"])
+    finally:
+        C.Engine = real
+        os.chdir(cwd)
+
+
+def test_mf_driver_on_the_oracle_backend(tmp_path):
+    """examples/mf/espp_cg_1 as shipped: 1000 single-bead molecules, A(0,3) + A(0,3) -> A(1):A(1), cutoff 0.5, intramolecular: 0,
+    interval 1000 (reaction.cfg).  Size-independent properties of the result: a bead's state counts its new bonds and stays below
+    3, and -- because a bond inside one molecule is forbidden and molecule ids merge with every bond -- the bond graph is a forest."""
+    a = run_mf(str(tmp_path), "oracle", 3000)
+    b = a["bonds"]
+    assert a["steps"] == 3000 and len(b) > 20
+    deg = np.bincount(b.ravel(), minlength=1001)
+    st = a["g"]["state"]
+    assert deg.max() <= 3 and (deg[1:] == st).all()
+    parent = list(range(1001))
+
+    def find(x):
+        while parent[x] != x:
+            parent[x] = parent[parent[x]]; x = parent[x]
+        return x
+    for i, j in b.tolist():
+        ri, rj = find(i), find(j)
+        assert ri != rj, "a reaction closed a ring inside one molecule (%d, %d)" % (i, j)
+        parent[ri] = rj

@@ -67,3 +67,15 @@ def test_dacron_restrict_driver_gpu_matches_oracle(tmp_path):
     assert all(tuple(sorted(x)) in a["conn"] for x in a["bonds"].tolist())
     assert (a["g"]["type"] == b["g"]["type"]).all() and (a["g"]["state"] == b["g"]["state"]).all()
     assert np.array_equal(a["g"]["mass"], b["g"]["mass"])
+
+
+def test_mf_driver_gpu_matches_oracle(tmp_path):
+    """examples/mf/espp_cg_1 as shipped (one bead type, A(0,3) + A(0,3) -> A(1):A(1), intramolecular: 0 -> molecule ids merge
+    with every bond and later passes must see them): GPU run == oracle run, bond for bond."""
+    from test_driver_cpu import run_mf
+    a = run_mf(str(tmp_path), "gpu", 3000)
+    b = run_mf(str(tmp_path), "oracle", 3000)
+    srt = lambda x: x[np.lexsort((x[:, 1], x[:, 0]))]
+    assert len(b["bonds"]) > 20 and a["bonds"].shape == b["bonds"].shape
+    assert (srt(np.sort(a["bonds"], 1)) == srt(np.sort(b["bonds"], 1))).all()
+    assert (a["g"]["state"] == b["g"]["state"]).all() and (a["g"]["type"] == b["g"]["type"]).all()
