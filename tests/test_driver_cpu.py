@@ -241,8 +241,9 @@ def test_dacron_restrict_driver_on_the_oracle_backend(tmp_path):
     assert (t >= 3).sum() >= 1          # products C / E exist
 
 
-def run_mf(tmp, backend, steps, seed="3"):
-    """examples/mf/espp_cg_1 as shipped through the driver (shared with tests/test_gpu_zz_restrict.py)."""
+def run_mf(tmp, backend, steps, seed="3", interval=None):
+    """examples/mf/espp_cg_1 as shipped through the driver (shared with tests/test_gpu_zz_restrict.py, which shortens the
+    reaction interval so that several passes fall inside the time over which two fp64 trajectories stay together)."""
     import sys
     sys.path.insert(0, HERE)
     from chemlab_b200 import synthetic
@@ -256,7 +257,13 @@ def run_mf(tmp, backend, steps, seed="3"):
         if backend == "oracle":
             from oracle.engine_adapter import OracleEngine
             C.Engine = OracleEngine
-        r = S.main(["@params", "--run", str(steps), "--rng_seed", seed, "--start_ar", "0"])
+        extra = []
+        if interval:
+            cfg = open("reaction.cfg").read()
+            assert "interval: 1000" in cfg
+            open("reaction.cfg", "w").write(cfg.replace("interval: 1000", "interval: %d" % interval))
+            extra = ["--int_step", str(interval)]
+        r = S.main(["@params", "--run", str(steps), "--rng_seed", seed, "--start_ar", "0"] + extra)
         g = r["system"]._ctx.engine.get_particles(fields=("type", "state", "mass"))
         bonds = np.concatenate([np.asarray(f.fpl.getAllBonds(), np.int64).reshape(-1, 2) for f in r["chem_fpls"]])
         return dict(g=g, bonds=bonds, steps=r["steps"])
