@@ -92,6 +92,53 @@ class ChemicalConversionTypeState(_Obs):
         return self._ctx.require_engine().count_type(self.type_id, self.state) / self.total
 
 
+class AngleDistribution(_Obs):
+    """analysis.AngleDistribution(system) + .load_from_topology_manager(tm) + .compute(nbins): the user hook of
+    examples/pccg_lj/chemical_reactions/hooks.py:44-56 accumulates it at every outer step.  [EXT] semantics restated (U28): every
+    angle i-j-k spanned by two bonds that meet at j in the TopologyManager's bond graph (the observed pair lists, reaction bonds
+    included) is binned over [0, pi) into `nbins` equal bins; the raw counts are returned.  An analysis observable outside the hot
+    path: bonds and positions are read back through the C-ABI (clb_list_get, clb_get_particles) and binned with numpy."""
+    def __init__(self, system):
+        super().__init__(system)
+        self._tm = None
+
+    def load_from_topology_manager(self, tm):
+        self._tm = tm
+
+    def compute(self, nbins):
+        nbins = int(nbins)
+        hist = np.zeros(nbins, np.int64)
+        tm = self._tm if self._tm is not None else getattr(self._ctx, "topology_manager", None)
+        if tm is None:
+            return hist.tolist()
+        e = self._ctx.require_engine()
+        bonds = [np.asarray(f.getAllBonds(), np.int64).reshape(-1, 2) for f in tm._observed]
+        bonds = np.concatenate(bonds) if bonds else np.zeros((0, 2), np.int64)
+        if len(bonds) == 0:
+            return hist.tolist()
+        ids, inv = np.unique(bonds, return_inverse=True)
+        inv = inv.reshape(-1, 2)
+        pos = np.asarray(e.get_particles(ids=ids, fields=("pos",))["pos"], float)
+        box = np.asarray(self._system.bc.boxL, float)
+        # half-edges sorted by their centre j; all unordered pairs of half-edges of one centre span an angle
+        centre = np.concatenate([inv[:, 0], inv[:, 1]]); other = np.concatenate([inv[:, 1], inv[:, 0]])
+        order = np.argsort(centre, kind="stable")
+        centre, other = centre[order], other[order]
+        start = np.flatnonzero(np.r_[True, centre[1:] != centre[:-1]])
+        count = np.diff(np.r_[start, len(centre)])
+        for deg in np.unique(count[count >= 2]):
+            rows = start[count == deg]
+            nb = other[rows[:, None] + np.arange(deg)[None, :]]                 # [centres][deg]
+            c = pos[centre[rows]]
+            v = pos[nb] - c[:, None, :]
+            v -= box * np.rint(v / box)
+            v /= np.linalg.norm(v, axis=2, keepdims=True)
+            a, b = np.triu_indices(deg, 1)
+            cos = np.clip(np.einsum("nkd,nkd->nk", v[:, a, :], v[:, b, :]), -1.0, 1.0)
+            hist += np.histogram(np.arccos(cos).ravel(), bins=nbins, range=(0.0, np.pi))[0]
+        return hist.tolist()
+
+
 class CMVelocity(_Obs):
     """analysis.CMVelocity(system).reset(): removes the centre-of-mass velocity (src/start_simulation.py:680-682)."""
     def compute(self):

@@ -32,6 +32,13 @@ def _load_hooks(path="hooks.py"):
     hooks = {}
     if os.path.exists(path):
         ns = {"espressopp": espressopp, "__name__": "hooks"}
+        # user hook files start with `import espressopp` (examples/*/hooks.py): inside this driver that name is this package's
+        # surface, unless a real espressopp has already been imported by the caller
+        import sys
+        sys.modules.setdefault("espressopp", espressopp)
+        for sub in ("analysis", "integrator", "interaction", "storage", "bc", "esutil", "io", "tools"):
+            if hasattr(espressopp, sub):
+                sys.modules.setdefault("espressopp." + sub, getattr(espressopp, sub))
         with open(path) as f:
             try:
                 code = compile(f.read(), path, "exec")
@@ -39,7 +46,9 @@ def _load_hooks(path="hooks.py"):
                 raise RuntimeError("%s is not valid Python 3 (%s, line %s): port the hook file (print statements, "
                                    "random.sample on sets, ...)" % (path, e.msg, e.lineno)) from e
             exec(code, ns)
-        for name in ("hook_init_reaction", "hook_at_step", "hook_postsetup_interaction", "hook_setup_interactions", "hook_end"):
+        # the five hooks of the reference (:215-228) plus two names earlier versions of this driver accepted
+        for name in ("hook_init_reaction", "hook_postsetup_reaction", "hook_at_step", "hook_before_sim", "hook_end",
+                     "hook_postsetup_interaction", "hook_setup_interactions"):
             if callable(ns.get(name)):
                 hooks[name] = ns[name]
         print("Loaded hooks: %s" % ", ".join(sorted(hooks)))
@@ -183,6 +192,8 @@ def _main(argv, rank, world):
             shutil.copyfile(args.reactions, "%s_%s" % (prefix, os.path.basename(args.reactions)))
         integrator_step = min(integrator_step, ar_interval)      # :265-267
         print("Set up %d reactions in %d groups, interval %d" % (len(reactions), len(chem_fpls), ar_interval))
+        if "hook_postsetup_reaction" in hooks:                   # :272
+            hooks["hook_postsetup_reaction"](system, integrator, gt, args, ar)
     sim_step = args.run // integrator_step                       # :103,:268 (Python-2 integer division)
     dynamic_types = sc.dynamic_types if sc else set()
 
@@ -270,6 +281,8 @@ def _main(argv, rank, world):
     # ---- main loop (:728-797)
     total_time0 = time.time()
     integrator_loop = 0.0
+    if "hook_before_sim" in hooks:                               # :726
+        hooks["hook_before_sim"](system, integrator, ar, gt)
     reactions_enabled = False
     stop_simulation = False
     for k in range(sim_step):
@@ -286,8 +299,10 @@ def _main(argv, rank, world):
                 before.update_position(system, unfolded=False)
                 if rank == 0:
                     before.write(with_velocity=True)
-            if "hook_init_reaction" in hooks:
-                hooks["hook_init_reaction"](system, integrator, ar, gt, args)
+            if "hook_init_reaction" in hooks:                    # :748-750
+                print("Processing hook_init_reaction")
+                if not hooks["hook_init_reaction"](system, integrator, ar, gt, args):
+                    raise RuntimeError("hook_init_reaction return False")
         if reactions_enabled and maximum_conversion:
             reached = [obs.compute() >= stop for obs, stop in maximum_conversion]
             if all(reached):

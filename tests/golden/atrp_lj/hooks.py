@@ -28,3 +28,4 @@ def hook_init_reaction(system, integrator, ar, topol, args):
                 system.storage.modifyParticle(pid, "mass", topol.gt.atomtypes["PL"]["mass"])
                 system.storage.modifyParticle(pid, "state", 2)
     print("Activated %d trimers" % len(chosen))
+    return True      # the driver stops when the hook does not return a true value (src/start_simulation.py:749-750)

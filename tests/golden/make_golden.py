@@ -144,9 +144,23 @@ def pack_mf():
     print("mf: packed")
 
 
+# pccg_lj/chemical_reactions: Kremer-Grest-like divinyl monomers in solvent (15,200 beads), pair-specific LJ, FENE + LJ bonds
+# ([ bonds ] func 9) also for the reaction bonds, Cosine angles (func 11) generated by the TopologyManager, ATRP activator.
+# Inputs as shipped; hooks.py of the fixture is a Python-3 re-authoring (the shipped one is Python 2) and is NOT copied.
+def pack_pccg_lj():
+    src = os.path.join(REF, "examples", "pccg_lj", "chemical_reactions")
+    dst = os.path.join(HERE, "pccg_lj")
+    os.makedirs(dst, exist_ok=True)
+    for f in ("conf.gro", "topol.top", "solvent.itp", "atrp.cfg", "params", "exclusion_topol.list"):
+        shutil.copy(os.path.join(src, f), os.path.join(dst, f))
+        os.chmod(os.path.join(dst, f), 0o644)
+    print("pccg_lj: copied")
+
+
 if __name__ == "__main__":
     pack_rim135()
     pack_hyperbranched()
     pack_dacron()
     pack_dacron_restrict()
     pack_mf()
+    pack_pccg_lj()

@@ -292,3 +292,62 @@ def test_mf_driver_on_the_oracle_backend(tmp_path):
         ri, rj = find(i), find(j)
         assert ri != rj, "a reaction closed a ring inside one molecule (%d, %d)" % (i, j)
         parent[ri] = rj
+
+
+def run_pccg_lj(tmp, backend, steps, seed="3"):
+    """examples/pccg_lj/chemical_reactions as shipped (hooks.py re-authored for Python 3) through the driver."""
+    import shutil
+    import sys
+    sys.path.insert(0, HERE)
+    import chemlab_b200.espressopp._context as C
+    from chemlab_b200 import start_simulation as S
+    d = os.path.join(tmp, "pccg_" + backend)
+    shutil.copytree(os.path.join(GOLD, "pccg_lj"), d)
+    cwd = os.getcwd()
+    os.chdir(d)
+    real = C.Engine
+    try:
+        if backend == "oracle":
+            from oracle.engine_adapter import OracleEngine
+            C.Engine = OracleEngine
+        r = S.main(["@params", "--run", str(steps), "--rng_seed", seed, "--energy_collect", "200"])
+        system = r["system"]
+        g = system._ctx.engine.get_particles(fields=("pos", "type", "state", "mass"))
+        bonds = np.concatenate([np.asarray(f.fpl.getAllBonds(), np.int64).reshape(-1, 2) for f in r["chem_fpls"]])
+        names = [system.getNameOfInteraction(k) for k in range(system.getNumberOfInteractions())]
+        return dict(g=g, bonds=bonds, steps=r["steps"], names=names, dir=d, system=system, files=sorted(os.listdir(os.path.join(d, "data"))))
+    finally:
+        C.Engine = real
+        os.chdir(cwd)
+
+
+def test_pccg_lj_driver_on_the_oracle_backend(tmp_path):
+    """examples/pccg_lj/chemical_reactions: pair-specific Lennard-Jones, FENE + LJ bonds for the monomers and for the reaction bonds
+    (group potential FENELennardJones), Cosine angles generated by the TopologyManager, ATRPActivator, all five user hooks of the
+    reference driver (src/start_simulation.py:215-228) incl. `import espressopp` inside hooks.py and analysis.AngleDistribution."""
+    import chemlab_b200.espressopp as es
+    a = run_pccg_lj(str(tmp_path), "oracle", 600)
+    assert a["steps"] == 600 and a["names"][:2] == ["chem_fpl_reaction_1", "lj"] and "dyn_angles_0" in a["names"]
+    assert len(a["bonds"]) >= 3
+    assert any(f.endswith("_atrp_stats.dat") for f in a["files"])
+    hist = np.loadtxt(os.path.join(a["dir"], "output_angle.csv"))           # hook_before_sim + hook_at_step + hook_end ran
+    assert hist.shape == (100, 2) and hist[:, 1].sum() > 0
+    # AngleDistribution against a direct loop over the bond graph (monomer bonds + reaction bonds) at the final positions
+    system = a["system"]
+    obs = es.analysis.AngleDistribution(system); obs.load_from_topology_manager(system.topology_manager)
+    got = np.array(obs.compute(100))
+    tm_bonds = np.concatenate([np.asarray(f.getAllBonds(), np.int64).reshape(-1, 2) for f in system.topology_manager._observed])
+    assert len(tm_bonds) == 2000 + len(a["bonds"])
+    adj = {}
+    for i, j in tm_bonds.tolist():
+        adj.setdefault(i, []).append(j); adj.setdefault(j, []).append(i)
+    pos, box = a["g"]["pos"], 26.150192
+    want = np.zeros(100, np.int64)
+    for j, nb in adj.items():
+        for x in range(len(nb)):
+            for y in range(x + 1, len(nb)):
+                u = pos[nb[x] - 1] - pos[j - 1]; v = pos[nb[y] - 1] - pos[j - 1]
+                u -= box * np.rint(u / box); v -= box * np.rint(v / box)
+                th = np.arccos(np.clip(u @ v / np.sqrt((u @ u) * (v @ v)), -1, 1))
+                want[min(int(th / (np.pi / 100)), 99)] += 1
+    assert want.sum() > 0 and (got == want).all()

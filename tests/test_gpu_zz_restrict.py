@@ -1,4 +1,6 @@
-"""RestrictReaction on the device (reaction_setup.py:74-75,115-126; examples/dacron/restrict): a reaction that
+"""Added after the last full GPU run of round 2 (the file sorts last on purpose).
+
+RestrictReaction on the device (reaction_setup.py:74-75,115-126; examples/dacron/restrict): a reaction that
 carries a connectivity map takes candidates only among the pairs named in it.  Candidate rows, events, bond lists and the
 resulting types/states must equal the oracle's bit-exactly; the map can be replaced between passes; an empty map switches
 the reaction off; other reactions of the same pass are not affected.  (The file sorts last on purpose: it was added after the
@@ -79,3 +81,16 @@ def test_mf_driver_gpu_matches_oracle(tmp_path):
     assert len(b["bonds"]) > 5 and a["bonds"].shape == b["bonds"].shape
     assert (srt(np.sort(a["bonds"], 1)) == srt(np.sort(b["bonds"], 1))).all()
     assert (a["g"]["state"] == b["g"]["state"]).all() and (a["g"]["type"] == b["g"]["type"]).all()
+
+
+def test_pccg_lj_driver_gpu_matches_oracle(tmp_path):
+    """examples/pccg_lj/chemical_reactions (15,200 beads: pair-specific LJ, FENE + LJ monomer and reaction bonds, Cosine angles from the
+    TopologyManager, ATRPActivator, the five user hooks): GPU run == oracle run."""
+    from test_driver_cpu import run_pccg_lj
+    a = run_pccg_lj(str(tmp_path), "gpu", 600)
+    b = run_pccg_lj(str(tmp_path), "oracle", 600)
+    srt = lambda x: x[np.lexsort((x[:, 1], x[:, 0]))]
+    assert len(b["bonds"]) >= 3 and a["bonds"].shape == b["bonds"].shape
+    assert (srt(np.sort(a["bonds"], 1)) == srt(np.sort(b["bonds"], 1))).all()
+    assert (a["g"]["state"] == b["g"]["state"]).all() and (a["g"]["type"] == b["g"]["type"]).all()
+    assert a["names"] == b["names"]
