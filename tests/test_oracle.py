@@ -296,3 +296,161 @@ def test_atrp_pass_matches_an_independent_numpy_restatement():
         assert (ca, cd) == (na, nd) and na + nd > 0
         assert abs(oa - ra) < 1e-15 and abs(od - rd) < 1e-15
         assert (g["type"] == typ).all() and (g["state"] == st).all() and (g["mass"] == mass).all()
+
+
+def test_velocity_verlet_and_langevin_match_an_independent_numpy_restatement():
+    """VelocityVerlet::run + LangevinThermostat (SURVEY 3.2, U11) restated in numpy for non-interacting particles plus harmonic
+    bonds evaluated by the restatement itself: run-entry heat-up kick (sqrt 3, its own stream), half kick, drift, fold with image
+    counters, force, friction + noise  -gamma m v + sqrt(24 kT gamma / dt) sqrt(m) (u - 1/2)  with u = (word + 1/2) / 2^32 from
+    Philox(seed ^ stream; particle, 0, step), thermostat restricted to a type list, second half kick.  Two consecutive runs (the
+    step counter keys the draws of the second)."""
+    LANG, HEAT = 0x4c414e47, 0x48454154
+    rng = np.random.default_rng(11)
+    n, seed, dt, kT, gamma = 60, 4242, 0.004, 1.3, 0.7
+    box = np.array([6.0, 7.0, 8.0])
+    pos = rng.uniform(0, 1, (n, 3)) * box
+    vel = rng.normal(0, 1, (n, 3))
+    mass = rng.uniform(0.5, 3.0, n)
+    typ = rng.integers(0, 3, n).astype(np.int32)
+    bonds = np.array([[2 * k, 2 * k + 1] for k in range(n // 2)], np.int64)
+    pos[bonds[:, 1]] = pos[bonds[:, 0]] + rng.normal(0, 0.4, (n // 2, 3))           # partners close by, some across the box faces
+    K, r0 = 17.0, 0.8
+    o = pyoracle.Oracle(n, box, 2.5, 0.3, seed=seed)
+    o.set_particles(pos, vel, mass, None, typ, None, None)
+    bl = o.add_list(2); o.list_add(bl, bonds)
+    ib = o.add_bonded(bl, 0); o.bonded_set_potential(ib, (), 1, (K, r0))
+    o.set_dt(dt); o.set_langevin(1, kT, gamma, types=(0, 2))                        # type 1 is not thermalised
+
+    x, v = pos.copy(), vel.copy()
+    img = np.zeros((n, 3), np.int64)
+    im = np.floor(x / box); x -= im * box; img += im.astype(np.int64)               # set_particles folds
+
+    def bonded(x):
+        f = np.zeros((n, 3))
+        d = x[bonds[:, 0]] - x[bonds[:, 1]]; d -= box * np.rint(d / box)
+        r = np.linalg.norm(d, axis=1)
+        fr = (-2.0 * K * (r - r0) / r)[:, None] * d                                  # U = K (r - r0)^2
+        np.add.at(f, bonds[:, 0], fr); np.add.at(f, bonds[:, 1], -fr)
+        return f
+
+    def thermo(f, v, stream, step, scale):
+        pref2 = np.sqrt(24.0 * kT * gamma / dt) * scale
+        for i in range(n):
+            if typ[i] == 1:
+                continue
+            w = pyoracle.philox([i, 0, step & 0xffffffff, step >> 32], [seed & 0xffffffff, (seed >> 32) ^ stream])
+            u = (np.array(w[:3], float) + 0.5) / 4294967296.0
+            f[i] += -gamma * mass[i] * v[i] + pref2 * np.sqrt(mass[i]) * (u - 0.5)
+
+    step = 0
+    for nsteps in (7, 5):
+        f = bonded(x); thermo(f, v, HEAT, step, np.sqrt(3.0))
+        for it in range(nsteps):
+            v += (0.5 * dt / mass)[:, None] * f
+            x += dt * v
+            f = bonded(x); thermo(f, v, LANG, step + it, 1.0)
+            v += (0.5 * dt / mass)[:, None] * f
+        step += nsteps
+        o.run(nsteps)
+        g = o.get()
+        assert o.step() == step
+        assert np.abs(g["vel"] - v).max() < 1e-12
+        # the oracle folds at rebuilds only: stored position + image * L is the unfolded coordinate at any time
+        assert np.abs(g["pos"] + g["image"] * box - (x + img * box)).max() < 1e-12
+
+
+def test_topology_manager_tuples_match_path_enumeration_on_the_final_graph():
+    """TopologyManager after a reaction pass against a formulation that shares nothing with the oracle's
+    per-event emission: the new angles (dihedrals) must be exactly the simple paths of 3 (4) particles in the FINAL bond graph
+    that run through at least one bond created in this pass and whose FINAL type tuple, read in either direction, is registered --
+    each once, in the list of the first matching registration; a DynamicExcludeList observing those lists gains (first, last)
+    of every new tuple and (a, b) of every new bond.  The neighbour-property rule (U18) is checked too: a particle exactly one
+    bond from the type_1-side reactant whose type matches takes the new type.  Two passes: in the second, ends that already
+    carry a reaction bond react again, so paths run through old reaction bonds as well."""
+    m = util.melt(9, seed=5)
+    n = len(m["pos"]); box = m["box"]
+    state = np.where(m["type"] == 0, 1, 0).astype(np.int32)
+    o = pyoracle.Oracle(n, box, 2.5, 0.3, seed=3)
+    o.set_particles(m["pos"], np.zeros((n, 3)), np.ones(n), None, m["type"], state, m["resid"])
+    ex0 = util.exclusions_from(m["bonds"], m["angles"])
+    o.set_exclusions(ex0)
+    bl = o.add_list(2); o.list_add(bl, m["bonds"])
+    rl = o.add_list(2)
+    al = o.add_list(3); o.list_add(al, m["angles"])
+    al2 = o.add_list(3)
+    ql = o.add_list(4)
+    o.set_dt(0.004); o.reaction_general(1, 10, 1, 0)
+    for lst in (rl, al, al2, ql):
+        o.excl_observe(lst)
+    o.tm_observe(bl); o.tm_observe(rl)
+    # types: 0 = A (end), 1 = L (middle), 3 = middle bead whose neighbour reacted as type_1
+    regs3 = [(al2, (3, 0, 0)), (al, (3, 0, 0)), (al, (1, 0, 0)), (al2, (0, 0, 0))]            # (al, (3,0,0)) is shadowed by the entry before it
+    regs4 = [(ql, (3, 0, 0, 3)), (ql, (3, 0, 0, 1)), (ql, (1, 0, 0, 1)), (ql, (0, 1, 0, 0)), (ql, (0, 3, 0, 0)), (ql, (0, 0, 0, 0)),
+             (ql, (3, 0, 0, 0))]                                                             # (1,0,0,0) is left unregistered
+    for lst, t in regs3 + regs4:
+        o.tm_register(lst, t)
+    o.tm_initialize()
+    r = o.add_reaction(0, 0, 1, 1, 1, 3, 1, 3, 1e6, 1.25, rl, intramolecular=1, intraresidual=0)      # every end may bind twice
+    o.reaction_add_change(r, 1, 1, 1, 3)                     # neighbours of the type_1 reactant: L -> 3
+    canon = lambda t: tuple(t) if t[0] < t[-1] else tuple(t[::-1])
+    have = {al: {canon(t) for t in m["angles"].tolist()}, al2: set(), ql: set()}
+    old_b = np.zeros((0, 2), np.int64)
+    want_t = m["type"].copy()
+    want_ex = {tuple(p) for p in ex0.tolist()}
+    seen_kinds = set()
+    for pas in range(2):
+        nev = o.react()
+        allb = o.list_get(rl, 2).astype(np.int64)
+        newb = allb[len(old_b):]
+        assert nev == len(newb) and nev > (30 if pas == 0 else 3)
+        old_b = allb
+        typ = o.get()["type"]
+        adj = {i: set() for i in range(n)}
+        for a, b in np.concatenate([m["bonds"], allb]).tolist():
+            adj[a].add(b); adj[b].add(a)
+        for a in newb[:, 0].tolist():
+            for q in adj[a]:
+                if want_t[q] == 1:
+                    want_t[q] = 3
+        assert (typ == want_t).all()
+        new_edges = {(min(a, b), max(a, b)) for a, b in newb.tolist()}
+        is_new = lambda a, b: (min(a, b), max(a, b)) in new_edges
+
+        def first_match(regs, ids):
+            ty = tuple(int(typ[i]) for i in ids)
+            for lst, t in regs:
+                if t == ty or t == ty[::-1]:
+                    seen_kinds.add(t)
+                    return lst
+            return None
+        want = {al: set(), al2: set(), ql: set()}
+        for j in range(n):
+            for i in adj[j]:
+                for k in adj[j]:
+                    if i < k and (is_new(i, j) or is_new(j, k)):
+                        lst = first_match(regs3, (i, j, k))
+                        if lst is not None:
+                            want[lst].add(canon((i, j, k)))
+        for j in range(n):
+            for k in adj[j]:
+                if j < k:
+                    for i in adj[j] - {k}:
+                        for l in adj[k] - {j, i}:
+                            if is_new(i, j) or is_new(j, k) or is_new(k, l):
+                                lst = first_match(regs4, (i, j, k, l))
+                                if lst is not None:
+                                    want[lst].add(canon((i, j, k, l)))
+        want_ex |= new_edges
+        for lst, ar in ((al, 3), (al2, 3), (ql, 4)):
+            rows = [canon(t) for t in o.list_get(lst, ar).tolist()]
+            assert len(rows) == len(set(rows)), "a tuple was emitted twice"
+            got_new = set(rows) - have[lst]
+            assert len(rows) == len(have[lst]) + len(got_new)
+            assert want[lst].isdisjoint(have[lst])           # a path through a bond of this pass cannot have existed before
+            assert got_new == want[lst], (pas, lst, len(got_new), len(want[lst]))
+            have[lst] |= got_new
+            want_ex |= {(min(t[0], t[-1]), max(t[0], t[-1])) for t in got_new}
+        got_ex = {(min(a, b), max(a, b)) for a, b in o.get_exclusions().tolist()}
+        assert got_ex == want_ex
+    assert len(have[al]) > len(m["angles"]) + 10 and len(have[al2]) > 10 and len(have[ql]) > 10
+    assert {(3, 0, 0), (1, 0, 0), (0, 0, 0), (0, 0, 0, 0)} <= seen_kinds          # the second pass produced paths through old reaction bonds
