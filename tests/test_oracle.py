@@ -454,3 +454,39 @@ def test_topology_manager_tuples_match_path_enumeration_on_the_final_graph():
         assert got_ex == want_ex
     assert len(have[al]) > len(m["angles"]) + 10 and len(have[al2]) > 10 and len(have[ql]) > 10
     assert {(3, 0, 0), (1, 0, 0), (0, 0, 0), (0, 0, 0, 0)} <= seen_kinds          # the second pass produced paths through old reaction bonds
+
+
+@pytest.mark.parametrize("criterion", [0, 1])
+def test_verlet_list_stays_complete_between_rebuilds(criterion):
+    """Skin/2 resort rule: at any step of a Langevin run the Verlet list in use -- built at the last rebuild with
+    radius rc + skin -- must contain every non-excluded pair that is now within rc.  Checked with numpy O(N^2) distances at
+    several points of a hot melt run, for the reference's criterion (sum of per-step maxima, 0) and the true-displacement one (1);
+    and the rule must not be trivially satisfied by rebuilding at every step."""
+    m = util.melt(9, seed=8)
+    n = len(m["pos"]); box = m["box"]; rc = 2.5
+    o = pyoracle.Oracle(n, box, rc, 0.3, seed=5)
+    rng = np.random.default_rng(2)
+    o.set_particles(m["pos"], rng.normal(0, 1.2, (n, 3)), np.ones(n), None, m["type"], None, m["resid"])
+    ex = util.exclusions_from(m["bonds"], m["angles"])
+    o.set_exclusions(ex)
+    r, e, f = util.lj_table()
+    tab = o.add_table(r, e, f, 1)
+    nb = o.add_nonbonded(1)
+    for t1, t2 in util.type_pairs(2):
+        o.nb_set_tab(nb, t1, t2, tab, rc)
+    bl = o.add_list(2); o.list_add(bl, m["bonds"])
+    ib = o.add_bonded(bl, 0); o.bonded_set_potential(ib, (), 1, (30.0, 0.97))
+    o.set_option("resort_criterion", criterion)
+    o.set_dt(0.004); o.set_langevin(1, 1.5, 1.0)
+    exs = {tuple(p) for p in ex.tolist()}
+    iu = np.triu_indices(n, 1)
+    steps = 0
+    for chunk in (3, 4, 5, 7, 9, 11):
+        o.run(chunk); steps += chunk
+        x = o.get()["pos"]
+        d = x[iu[0]] - x[iu[1]]; d -= box * np.rint(d / box)
+        close = (d * d).sum(1) <= rc * rc
+        need = {(int(a), int(b)) for a, b in zip(iu[0][close], iu[1][close])} - exs
+        have = {tuple(p) for p in o.pairs().tolist()}
+        assert need <= have, (steps, len(need - have))
+    assert 1 <= o.nrebuild() < steps // 2
