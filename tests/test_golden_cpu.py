@@ -48,3 +48,39 @@ def test_oracle_table_matches_numpy_interp():
         assert not bad
         assert abs(ee - np.interp(x, r, e)) <= 1e-9 * max(1, abs(ee))
         assert abs(ff - np.interp(x, r, f)) <= 1e-9 * max(1, abs(ff))
+
+
+def test_table_tools_command_line(tmp_path, monkeypatch):
+    """The three table tools of the reference's tools/ directory as `python -m chemlab_b200.tools.<name>`: the converter's command
+    line reproduces a shipped .pot byte for byte; fix_table repairs zero forces at the table ends in place; mix_table writes
+    x*tab1 + (1-x)*tab2 (and the geometric variant) for every func-9 row of the topology (tools/mix_table.py:107-123)."""
+    import subprocess
+    import sys
+    root = os.path.dirname(HERE)
+    env = dict(os.environ, PYTHONPATH=root)
+    out = tmp_path / "b0.pot"
+    subprocess.check_call([sys.executable, "-m", "chemlab_b200.tools.convert_gromacs2espp", os.path.join(GOLD, "table_b0.xvg"), str(out)], env=env)
+    assert out.read_bytes() == open(os.path.join(GOLD, "table_b0.pot"), "rb").read()
+    # fix_table
+    from chemlab_b200.tools import fix_table, mix_table
+    t = np.column_stack([np.arange(1, 6) * 0.1, np.arange(5) * 1.0, [0.0, 2.0, 3.0, 4.0, 0.0]])
+    p = tmp_path / "t.pot"
+    np.savetxt(p, t)
+    fix_table.main([str(p)])
+    d = np.loadtxt(p)
+    assert d[0, 2] == 2.0 and d[-1, 2] == 4.0 and (d[1:-1] == t[1:-1]).all()
+    # mix_table on two shipped-format tables of different length
+    monkeypatch.chdir(tmp_path)
+    xa = np.loadtxt(os.path.join(GOLD, "table_A_A.xvg"))
+    xb = xa[:-7].copy(); xb[:, 3:] *= 0.5
+    np.savetxt("table_MO_MO.xvg", xa); np.savetxt("table_PO_PO.xvg", xb)
+    open("topol.top", "w").write("[ defaults ]\n1 1 no 1.0 1.0\n\n[ atomtypes ]\nMO 1.0 0.0 A 1.0 1.0\nPO 1.0 0.0 A 1.0 1.0\n\n"
+                                 "[ nonbond_params ]\nMO PO 9 tabA tabB PO 100 0.0 0.5\n\n[ moleculetype ]\nM 1\n\n[ atoms ]\n1 MO 1 M A1 1 0.0 1.0\n\n"
+                                 "[ system ]\nx\n\n[ molecules ]\nM 1\n")
+    assert mix_table.main(["--scaling", "0.25"]) == ["table_tabB_tabA.pot"]
+    m = np.loadtxt("table_tabB_tabA.pot")
+    ra, rb = mix_table.xvg_to_ref(xa), mix_table.xvg_to_ref(xb)
+    assert len(m) == len(xb) and np.allclose(m[:, 1], 0.25 * ra[:len(xb), 1] + 0.75 * rb[:, 1], rtol=1e-9, atol=1e-12)
+    assert np.allclose(m[:, 2], (0.25 + 0.75 * 0.5) * ra[:len(xb), 2], rtol=1e-9, atol=1e-12)
+    g = mix_table.mix_geometric(np.array([[0.1, 4.0, 1.0]]), np.array([[0.1, 9.0, 2.0]]), 0.5, 0.0)
+    assert np.allclose(g[0], [0.1, 2.0 + 3.0, 0.5 * 0.5 * 1.0 + 0.5 * (1.0 / 3.0) * 2.0])
