@@ -6,14 +6,6 @@ from .. import espressopp
 _RE_TS = re.compile(r"(?P<type>[A-Za-z0-9-]+)\(?(?P<state>\d?)\)?")
 
 
-class _SumObs:
-    def __init__(self, parts, total):
-        self.parts, self.total = parts, total
-
-    def compute(self):
-        return sum(p.compute() for p in self.parts)
-
-
 def get_maximum_conversion(args, system, chem_fpls, gt, cr_observs=None):
     """--maximum_conversion 'SYM(state):max:total[,…]' ; 'A-B:max:total' counts bonds of a reaction list; 'A+B:…' sums types
     (src/tools.py:102-180).  Returns [(observable, stop_value)]."""
@@ -30,16 +22,23 @@ def get_maximum_conversion(args, system, chem_fpls, gt, cr_observs=None):
                     out.append((espressopp.analysis.NFixedPairListEntries(system, f.fpl), max_n))
                     break
             continue
-        parts = []
-        for s in sym.split("+"):
-            m = _RE_TS.match(s).groupdict()
-            state = int(m["state"]) if m["state"] else None
-            key = (ids[m["type"]], tot, state)
-            if key not in cr_observs:
-                cr_observs[key] = (espressopp.analysis.ChemicalConversion(system, key[0], tot) if state is None
-                                   else espressopp.analysis.ChemicalConversionTypeState(system, key[0], state, tot))
-            parts.append(cr_observs[key])
-        out.append((parts[0] if len(parts) == 1 else _SumObs(parts, tot), float(max_n) / tot))
+        if "+" in sym:                                        # :141-158: one observable counting every summand, column cr_<A>_<B>_...
+            obs = espressopp.analysis.ChemicalConversionTypeState(system, total_count=tot)
+            names = []
+            for s in sym.split("+"):
+                m = _RE_TS.match(s).groupdict()
+                obs.count_type(ids[m["type"]], int(m["state"]) if m["state"] else None)
+                names.append(m["type"])
+            cr_observs[(tuple(names), tot, None)] = obs
+            out.append((obs, float(max_n) / tot))
+            continue
+        m = _RE_TS.match(sym).groupdict()                      # :159-178
+        state = int(m["state"]) if m["state"] else None
+        key = (ids[m["type"]], tot, state)
+        if key not in cr_observs:
+            cr_observs[key] = (espressopp.analysis.ChemicalConversion(system, key[0], tot) if state is None
+                               else espressopp.analysis.ChemicalConversionTypeState(system, key[0], state, tot))
+        out.append((cr_observs[key], float(max_n) / tot))
     return out
 
 

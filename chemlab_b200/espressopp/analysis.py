@@ -84,12 +84,23 @@ class ChemicalConversion(_Obs):
 
 
 class ChemicalConversionTypeState(_Obs):
-    def __init__(self, system, type_id, state, total=None):
+    """ChemicalConversionTypeState(system, type, state, total): N(type in state)/total; or, as src/tools.py:142-158 uses it for
+    'A+B(1)+...' stop criteria, ChemicalConversionTypeState(system, total_count=total) followed by count_type(type, state | None)
+    for every summand."""
+    def __init__(self, system, type_id=None, state=None, total=None, total_count=None):
         super().__init__(system)
-        self.type_id, self.state, self.total = int(type_id), int(state), (float(total) if total else 1.0)
+        tot = total if total is not None else total_count
+        self.total = float(tot) if tot else 1.0
+        self._counted = []
+        if type_id is not None:
+            self.count_type(type_id, state)
+
+    def count_type(self, type_id, state=None):
+        self._counted.append((int(type_id), -1 if state is None else int(state)))
 
     def compute(self):
-        return self._ctx.require_engine().count_type(self.type_id, self.state) / self.total
+        e = self._ctx.require_engine()
+        return sum(e.count_type(t, s) for t, s in self._counted) / self.total
 
 
 class AngleDistribution(_Obs):

@@ -199,6 +199,9 @@ def _main(argv, rank, world):
 
     # ---- force field (:298-310)
     cr_observs = dict(sc.cr_observs) if sc else {}
+    maximum_conversion = []                                      # :280-287: its observables join cr_observs, hence the energy CSV
+    if args.maximum_conversion:
+        maximum_conversion = tools.get_maximum_conversion(args, system, chem_fpls, gt, cr_observs)
     cr_observs, _ = gromacs_topology.set_nonbonded_interactions(system, gt, verletlist, lj_cutoff, getattr(args, "coulomb_cutoff", None),
                                                                 cg_cutoff, tables=getattr(args, "table_groups", None), cr_observs=cr_observs)
     dyn_fpl, static_fpl, _ = gromacs_topology.set_bonded_interactions(system, gt, dynamic_types)
@@ -245,30 +248,51 @@ def _main(argv, rank, world):
     topology_manager.initialize_topology()
     integrator.addExtension(topology_manager)
 
-    # ---- observables (:446-569)
+    # ---- observables (:446-569): same columns, in the same order, as the reference's energy CSV
     energy_file = "%s_energy_%s.csv" % (args.output_prefix, rng_seed)
     monitor = espressopp.analysis.SystemMonitor(system, integrator, espressopp.analysis.SystemMonitorOutputCSV(energy_file))
     temp_obs = espressopp.analysis.Temperature(system)
+    monitor_filter = args.system_monitor_filter.split(",") if getattr(args, "system_monitor_filter", None) else None   # :458-460
     monitor.add_observable("T", temp_obs)
     monitor.add_observable("Ekin", espressopp.analysis.KineticEnergy(system, temp_obs))
-    for k in range(system.getNumberOfInteractions()):
-        label = system.getNameOfInteraction(k)
-        monitor.add_observable(label, espressopp.analysis.PotentialEnergy(system, system.getInteraction(k)), visible=label.startswith("lj"))
-    for (cr_type, cr_total, cr_state), obs in cr_observs.items():
-        monitor.add_observable("cr_%s_%s" % (cr_type, cr_state if cr_state is not None else "x"), obs)
+    if getattr(args, "store_pressure", False):
+        print("Note: store_pressure is ignored (analysis.Pressure is outside the engine's scope, SURVEY E20)")
+    for label, interaction in sorted(system.getAllInteractions().items()):       # :471-480: sorted by label; the filter only hides columns from info()
+        visible = True if not monitor_filter else any(v in label for v in monitor_filter)
+        monitor.add_observable(label, espressopp.analysis.PotentialEnergy(system, interaction), visible)
+    for (cr_type, _, ts), obs in cr_observs.items():                             # :481-489
+        name = "cr_" + "_".join(str(x) for x in (cr_type if isinstance(cr_type, (tuple, list)) else [cr_type]))
+        monitor.add_observable(name if ts is None else "%s_%s" % (name, ts), obs)
     for i, f in enumerate(chem_fpls):
         monitor.add_observable("count_%d" % i, espressopp.analysis.NFixedPairListEntries(system, f.fpl))
-    energy_collect = max(1, args.energy_collect)
-    integrator.addExtension(espressopp.integrator.ExtAnalyze(monitor, energy_collect))
+    if getattr(args, "count_tuples", False):                                     # :503-538
+        A = espressopp.analysis
+        for prefix_, statics, dynamics, cls in (("bcount", static_fpl, dyn_fpl, A.NFixedPairListEntries), ("acount", static_ftl, dyn_ftl, A.NFixedTripleListEntries),
+                                                ("qcount", static_fql, dyn_fql, A.NFixedQuadrupleListEntries)):
+            for n_, lst in enumerate(list(statics) + list(dynamics.values())):
+                monitor.add_observable("%s_%d" % (prefix_, n_), cls(system, lst))
+        monitor.add_observable("vl_excl", A.NExcludeListEntries(system, verletlist))
+    if getattr(args, "count_types", None):                                       # :544-549
+        for sym in args.count_types.split(","):
+            tid = gt.atomsym_atomtype[sym]
+            print("Observer %-9s (%s)" % (sym, tid))
+            monitor.add_observable("num_type_%s_%s" % (sym, tid), espressopp.analysis.ChemicalConversion(system, tid))
+    if getattr(args, "count_types_state", None) is not None:                     # :551-559
+        for ts in args.count_types_state.split(","):
+            type_name, state = ts.split(":")
+            monitor.add_observable("st_%s_%d" % (type_name, int(state)),
+                                   espressopp.analysis.ChemicalConversionTypeState(system, gt.atomsym_atomtype[type_name], int(state)))
+    # :565-569: data are collected every min(reaction interval | integrator step, energy_collect) steps
+    cr_interval = ar_interval if ar is not None else integrator_step
+    if args.energy_collect > 0:
+        energy_collect = min(cr_interval, args.energy_collect)
+        integrator.addExtension(espressopp.integrator.ExtAnalyze(monitor, energy_collect))
+        print("Configured system analysis, collect data every %d steps" % energy_collect)
 
     if getattr(args, "gro_trj_collect", None):                   # :684-696
         dump_trj = espressopp.io.DumpGRO(system, integrator, filename=("%s_traj.gro" % prefix) if rank == 0 else os.devnull, unfolded=True, append=True)
         integrator.addExtension(espressopp.integrator.ExtAnalyze(dump_trj, int(args.gro_trj_collect)))
         print("Set gro trajectory saver, save every %d steps" % int(args.gro_trj_collect))
-
-    maximum_conversion = []
-    if args.maximum_conversion:
-        maximum_conversion = tools.get_maximum_conversion(args, system, chem_fpls, gt, cr_observs)
 
     # ---- start/stop of the reactions in units of outer iterations (:700-721)
     k_enable_reactions = (args.start_ar // integrator_step) if ar is not None else -1
@@ -278,52 +302,57 @@ def _main(argv, rank, world):
 
     rate_file = open("%s_new_rates.csv" % prefix, "w") if (getattr(args, "rate_arrhenius", False) and rank == 0) else None     # :712-714
 
-    # ---- main loop (:728-797)
+    # ---- main loop (:705-800)
+    monitor.dump()                                               # :705 -- the row of step 0
+    eq_run = int(args.eq_steps / sim_step) if (maximum_conversion and getattr(args, "eq_steps", 0) > 0 and sim_step) else 0      # :286-287
     total_time0 = time.time()
     integrator_loop = 0.0
     if "hook_before_sim" in hooks:                               # :726
         hooks["hook_before_sim"](system, integrator, ar, gt)
     reactions_enabled = False
     stop_simulation = False
+    energy0, bonds0 = 0.0, 0
     for k in range(sim_step):
         monitor.info()
-        if k == k_enable_reactions and ar is not None:
+        if k == k_enable_reactions and ar is not None:           # :735-755
             print("Enabling chemical reactions at step %d" % integrator.step)
             integrator.addExtension(ar)
             for ext in ext_to_integrator:
                 integrator.addExtension(ext)
             reactions_enabled = True
-            if getattr(args, "save_before_reaction", False):       # :743-746
-                before = files_io.GROFile("%s_before_reaction_confout.gro" % prefix)
-                before.box, before.title, before.atoms = box, "before reaction, step %d" % integrator.step, dict(conf.atoms)
-                before.update_position(system, unfolded=False)
-                if rank == 0:
-                    before.write(with_velocity=True)
+            before = files_io.GROFile("%s_before_reaction_confout.gro" % prefix)      # :742-746 (written unconditionally, unfolded)
+            before.box, before.title, before.atoms = box, "before reaction, step %d" % integrator.step, dict(conf.atoms)
+            before.update_position(system, unfolded=True)
+            if rank == 0:
+                before.write(with_velocity=True)
             if "hook_init_reaction" in hooks:                    # :748-750
                 print("Processing hook_init_reaction")
                 if not hooks["hook_init_reaction"](system, integrator, ar, gt, args):
                     raise RuntimeError("hook_init_reaction return False")
-        if reactions_enabled and maximum_conversion:
-            reached = [obs.compute() >= stop for obs, stop in maximum_conversion]
-            if all(reached):
-                print("Maximum conversion reached at step %d" % integrator.step)
-                stop_simulation = True
-        if reactions_enabled and (k == k_stop_reactions or stop_simulation):
-            ar.disconnect()
-            reactions_enabled = False
-            if stop_simulation and not getattr(args, "eq_steps", 0):
-                break
-        if getattr(args, "rate_arrhenius", False) and reactions_enabled:
-            bonds0 = sum(f.fpl.totalSize() for f in chem_fpls)
-            monitor.perform_action()
-            energy0 = monitor.potential_energy
+        if reactions_enabled:                                    # :757-776
+            if not stop_simulation:
+                for obs, stop_value in maximum_conversion:
+                    val = obs.compute()
+                    if val >= stop_value:
+                        print("Reaches %s of the conversion => Stop simulation" % val)
+                        stop_simulation = True
+            if stop_simulation:
+                if eq_run == 0:
+                    break
+                eq_run -= 1
+            if getattr(args, "rate_arrhenius", False):
+                bonds0 = sum(f.fpl.totalSize() for f in chem_fpls)
+                energy0 = monitor.potential_energy
+            if k == k_stop_reactions or stop_simulation:
+                ar.disconnect()
         t0 = time.time()
         integrator.run(integrator_step)                           # :780 -- 100 % of the compute
         integrator_loop += time.time() - t0
+        if "hook_at_step" in hooks:
+            hooks["hook_at_step"](system, integrator, ar, gt, args, k * integrator_step)     # :783
         if getattr(args, "rate_arrhenius", False) and reactions_enabled:      # :785-796: k = exp(-dE/kT) per new bond
             delta_bonds = sum(f.fpl.totalSize() for f in chem_fpls) - bonds0
             if delta_bonds > 0:
-                monitor.perform_action()
                 energy_delta = (monitor.potential_energy - energy0) / float(delta_bonds)
                 new_rate = math.exp(-energy_delta / temperature)
                 print("%d\tChange reaction rate, delta_E=%s, new_k=%s, delta_bonds=%d" % (k * integrator_step, energy_delta, new_rate, delta_bonds))
@@ -331,13 +360,12 @@ def _main(argv, rank, world):
                     rate_file.write("%d %e\n" % (k * integrator_step, new_rate))
                 for r_ in reactions:
                     r_.rate = new_rate
-        if "hook_at_step" in hooks:
-            hooks["hook_at_step"](system, integrator, ar, gt, args, k * integrator_step)     # :783
     total_time = time.time() - total_time0
     if rate_file is not None:
         rate_file.close()
-    monitor.dump()
-    monitor.info()
+    if "hook_end" in hooks:                                      # :800
+        hooks["hook_end"](system, integrator, ar, gt, args)
+    monitor.info()                                               # :802
 
     # ---- outputs (:800-1081)
     e = system._ctx.require_engine()
@@ -399,8 +427,6 @@ def _main(argv, rank, world):
     print("final: steps=%d total=%.3fs integratorLoop=%.3fs (%.1f steps/s) setup=%.3fs" %
           (integrator.step, total_time, integrator_loop, integrator.step / max(integrator_loop, 1e-9), total_time0 - time0))
     print("engine timers/counters: %s" % {k: (round(v, 4) if isinstance(v, float) else v) for k, v in timers.items()})
-    if "hook_end" in hooks:
-        hooks["hook_end"](system, integrator, ar, gt, args)
     return dict(system=system, integrator=integrator, ar=ar, topology=gt, chem_fpls=chem_fpls, reactions=reactions, prefix=prefix,
                 steps=integrator.step, integrator_loop=integrator_loop, monitor=monitor)
 

@@ -130,7 +130,12 @@ def test_driver_host_logic_on_the_oracle_backend(tmp_path, monkeypatch):
     g = GROFile(os.path.join("data", "cpc01_42_confout.gro")); g.read()
     assert len(g.atoms) == 6000 and {a.name for a in g.atoms.values()} >= {"MA", "ML", "FA", "PL"}      # activated trimers renamed
     csv = open(os.path.join("data", "cpc01_energy_42.csv")).read().splitlines()
-    assert csv[0].split("\t")[:4] == ["step", "time", "T", "Ekin"] and len(csv) == 1 + 3 + 1                  # 3 collections + final dump
+    # columns and rows of the reference's SystemMonitor (src/start_simulation.py:446-569,705): T, Ekin, the interactions sorted by
+    # label, the conversion observers (cr_<type id>_<state> of maximum_conversion=PL(1):...), count_<k> per reaction list; the row
+    # of step 0 is dumped before the loop, then one row every min(reaction interval, energy_collect) steps
+    assert csv[0].split("\t") == ["step", "time", "T", "Ekin", "chem_fpl_reaction_1", "dyn_angles_0", "dyn_bonds_0", "lj", "cr_6_1", "count_0"]
+    assert [int(l.split("\t")[0]) for l in csv[1:]] == [0, 200, 400, 600]
+    assert "cpc01_42_before_reaction_confout.gro" in out                               # written unconditionally (:742-746)
     assert open(os.path.join("data", "cpc01_42_benchmark.csv")).read().split()[:2] == ["1", "6000"]
     gt = GromacsTopology(os.path.join("data", "cpc01_42_output_topol.top")).read()
     assert len(gt.atoms) == 6000 and len(gt.bonds) >= 4000 and len(gt.angles) >= 2000
@@ -351,3 +356,31 @@ def test_pccg_lj_driver_on_the_oracle_backend(tmp_path):
                 th = np.arccos(np.clip(u @ v / np.sqrt((u @ u) * (v @ v)), -1, 1))
                 want[min(int(th / (np.pi / 100)), 99)] += 1
     assert want.sum() > 0 and (got == want).all()
+
+
+def test_maximum_conversion_stops_the_run_like_the_reference(tmp_path, monkeypatch):
+    """src/start_simulation.py:757-770 + src/tools.py:102-180: the run ends as soon as ANY stop criterion is reached (checked at the
+    top of an outer iteration once the reactions are on); `A+B(1)` criteria are ONE observable whose column is cr_<A>_<B>; with
+    eq_steps the loop goes on for int(eq_steps / number of outer iterations) more iterations with the reactions disconnected."""
+    import shutil
+    import sys
+    sys.path.insert(0, HERE)
+    import chemlab_b200.espressopp._context as C
+    from oracle.engine_adapter import OracleEngine
+    from chemlab_b200 import start_simulation as S
+    monkeypatch.setattr(C, "Engine", OracleEngine)
+    res = {}
+    for tag, extra in (("stop", []), ("eq", ["--eq_steps", "16"])):
+        d = str(tmp_path / tag)
+        shutil.copytree(os.path.join(GOLD, "atrp_lj"), d)
+        monkeypatch.chdir(d)
+        # 3 PL beads are in state 1 after the pass at step 600 (see the test above): the first criterion can never be met, the second is
+        r = S.main(["@params", "--rng_seed", "42", "--run", "1600", "--start_ar", "200", "--energy_collect", "200",
+                    "--maximum_conversion", "MA:5000:6000,PL(1)+FA(7):2:2000"] + extra)
+        hdr = open(os.path.join("data", "cpc01_energy_42.csv")).readline().split()
+        assert "cr_0" in hdr and "cr_PL_FA" in hdr
+        bonds = np.concatenate([np.asarray(f.fpl.getAllBonds(), np.int64).reshape(-1, 2) for f in r["chem_fpls"]])
+        res[tag] = (r["steps"], len(bonds))
+    assert res["stop"] == (600, 3)
+    # 8 outer iterations -> eq_run = int(16 / 8) = 2 more iterations, without reactions: the bond count stays
+    assert res["eq"] == (1000, 3)
