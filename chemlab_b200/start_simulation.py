@@ -227,7 +227,8 @@ def _main(argv, rank, world):
 
     # ---- dynamic exclusions and topology bookkeeping (:378-444)
     for f in chem_fpls:
-        dynamic_exclude.observe_tuple(f.fpl)
+        if not getattr(args, "do_not_exclude_bonds", False):     # :425-430
+            dynamic_exclude.observe_tuple(f.fpl)
         topology_manager.observe_tuple(f.fpl)
     for lst in list(dyn_fpl.values()) + list(static_fpl):
         topology_manager.observe_tuple(lst)
