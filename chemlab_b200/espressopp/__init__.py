@@ -10,6 +10,41 @@ from . import esutil, bc, storage, interaction, integrator, analysis, io, tools 
 pmi = None
 
 
+class Version:
+    """espressopp.Version().info(): printed by the example scripts (examples/atrp_lj/polymer_melt.py:48)."""
+    name = "chemlab_b200.espressopp"
+
+    def info(self):
+        return "%s: espressopp surface of the B200 reactive-MD engine (C-ABI include/chemlab_b200.h)" % self.name
+
+
+class _CommWorld:
+    """MPI.COMM_WORLD.size / .rank as the driver and user scripts read them (src/start_simulation.py:155-157,998,1078): one rank
+    per GPU under torchrun, else a single rank."""
+    @property
+    def size(self):
+        try:
+            import torch.distributed as dist
+            return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        except Exception:
+            return 1
+
+    @property
+    def rank(self):
+        try:
+            import torch.distributed as dist
+            return dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
+        except Exception:
+            return 0
+
+
+class _MPI:
+    COMM_WORLD = _CommWorld()
+
+
+MPI = _MPI()
+
+
 class Real3D(tuple):
     """espressopp.Real3D(x, y, z): indexable 3-vector (files_io.py:268-279 reads pos[0..2])."""
     def __new__(cls, x=0.0, y=0.0, z=0.0):
