@@ -53,6 +53,46 @@ def substitute_defines(lines, defines):
     return out
 
 
+def _py2_str_hash(s):
+    """hash() of a str in CPython 2.7 on a 64-bit build without -R (Objects/stringobject.c:string_hash), as unsigned 64 bit."""
+    if not s:
+        return 0
+    m = (1 << 64) - 1
+    x = (ord(s[0]) << 7) & m
+    for ch in s:
+        x = ((1000003 * x) & m) ^ ord(ch)
+    x ^= len(s)
+    return m - 1 if x == m else x
+
+
+def py2_dict_order(keys):
+    """Iteration order of a CPython-2.7 dict into which the str `keys` were inserted in this order (no deletions):
+    open addressing with the perturbed probe sequence of Objects/dictobject.c, 8 slots at first, resize to the first power of two
+    above 4 * used once two thirds are filled; iteration runs over the slots.  chemlab's type ids depend on it (see _prepare)."""
+    def insert(table, k, h):
+        mask = len(table) - 1
+        i, perturb = h & mask, h
+        while table[i & mask] is not None:
+            if table[i & mask][0] == k:
+                return False
+            i = (i << 2) + i + perturb + 1
+            perturb >>= 5
+        table[i & mask] = (k, h)
+        return True
+    table, fill = [None] * 8, 0
+    for k in keys:
+        if insert(table, k, _py2_str_hash(k)):
+            fill += 1
+            if fill * 3 >= len(table) * 2:
+                size = 8
+                while size <= (2 if fill > 50000 else 4) * fill:
+                    size <<= 1
+                old, table = [e for e in table if e is not None], [None] * size
+                for kk, hh in old:
+                    insert(table, kk, hh)
+    return [e[0] for e in table if e is not None]
+
+
 def convertc6c12(c6, c12, cr):
     """(c6, c12) -> (sigma, epsilon) for combination rule 1 only (gromacs_topology.py:110-121)."""
     if cr != 1:
@@ -141,9 +181,12 @@ class GromacsTopology:
         for v in gt.nonbond_params.values():
             if v["func"] == 1 and cr == 1 and v["params"]:
                 v["params"][0], v["params"][1] = convertc6c12(float(v["params"][0]), float(v["params"][1]), cr)
-        # remaining [atomtypes] of the master file get ids too (reaction products may not appear in any molecule);
-        # Python-3 dict order = file order, which pins what was hash order in the Python-2 reference (appendix A)
-        all_types = dict(self.master_topol.atom_name2atomnr)
+        # remaining [atomtypes] of the master file get ids too (reaction products may not appear in any molecule).  The reference
+        # walks `master_topol.atomtypes.items()` (:260), a Python-2 dict: the ids follow CPython 2.7's hash order of the type
+        # names, reproduced by py2_dict_order -- this gives the ids of the shipped run log examples/atrp_lj/single:199-205
+        # (MA0 ML1 DA2 FA3 PA4 RA5 PL6 for the file order MA ML PA FA DA RA PL; tests/test_runlog_cpu.py)
+        master = self.master_topol.atom_name2atomnr
+        all_types = {name: master[name] for name in py2_dict_order(list(master))}
         for name, nr in gt.atom_name2atomnr.items():      # also the types that arrive through #include files
             all_types.setdefault(name, nr)
         for name, nr in all_types.items():

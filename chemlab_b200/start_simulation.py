@@ -196,6 +196,7 @@ def _main(argv, rank, world):
             hooks["hook_postsetup_reaction"](system, integrator, gt, args, ar)
     sim_step = args.run // integrator_step                       # :103,:268 (Python-2 integer division)
     dynamic_types = sc.dynamic_types if sc else set()
+    print("Dynamic type ids: %s" % sorted(dynamic_types))       # :276
 
     # ---- force field (:298-310)
     cr_observs = dict(sc.cr_observs) if sc else {}
