@@ -148,4 +148,9 @@ def parse_config(path):
             if group not in config["reactions"]:
                 raise RuntimeError("Wrong order, first reaction groups and then referring reactions")
             config["reactions"][group]["reaction_list"].append(data)
+    # the reference keeps the groups in a plain Python-2 dict (reaction_parser.py:239) and SetupReactions walks `.items()`
+    # (reaction_setup.py:434): the order of the reaction lists (chem_fpl index, count_<k> column, reaction index) is CPython 2.7's
+    # hash order of the group names -- e.g. reaction_2 before reaction_1 for examples/rim135/reaction.cfg
+    from .py2compat import py2_dict_order
+    config["reactions"] = {k: config["reactions"][k] for k in py2_dict_order(list(config["reactions"]))}
     return config

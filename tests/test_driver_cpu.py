@@ -384,3 +384,17 @@ def test_maximum_conversion_stops_the_run_like_the_reference(tmp_path, monkeypat
     assert res["stop"] == (600, 3)
     # 8 outer iterations -> eq_run = int(16 / 8) = 2 more iterations, without reactions: the bond count stays
     assert res["eq"] == (1000, 3)
+
+
+def test_python2_dict_order_of_the_reference_is_reproduced():
+    """Where the Python-2 reference iterates a plain dict, the order shows in its results.  Known answer: the type ids of the
+    shipped run log examples/atrp_lj/single:199-205 (MA0 ML1 DA2 FA3 PA4 RA5 PL6) for the [ atomtypes ] file order MA ML PA FA DA RA PL
+    (examples/atrp_activator/topol.top:3-11 without the later row I).  The same rule orders the reaction groups."""
+    from chemlab_b200.chemlab.py2compat import py2_dict_order
+    from chemlab_b200.chemlab import reaction_parser as rp
+    assert py2_dict_order(["MA", "ML", "PA", "FA", "DA", "RA", "PL"]) == ["MA", "ML", "DA", "FA", "PA", "RA", "PL"]
+    assert py2_dict_order(["a", "a", "b"]) in (["a", "b"], ["b", "a"])                 # re-insertion keeps one entry
+    big = ["k%d" % i for i in range(200)]
+    assert sorted(py2_dict_order(big)) == sorted(big)                                 # several resizes, nothing lost
+    c = rp.parse_config(os.path.join(GOLD, "rim135", "reaction.cfg"))
+    assert list(c["reactions"]) == ["reaction_2", "reaction_1"]
