@@ -391,9 +391,34 @@ def _main(argv, rank, world):
         np.savetxt("%s_state.dat" % prefix, np.column_stack([ids, g["type"], g["state"], g["res_id"]]), fmt="%d", header="id type state res_id")
         for i, bonds_i in enumerate(chem_bonds):
             np.savetxt("%s_bonds_chem_%d.dat" % (prefix, i), bonds_i, fmt="%d")
-        for label, rows in tuple_rows:
-            if rows:
-                np.savetxt("%s_%s.dat" % (prefix, label), np.asarray(rows, np.int64), fmt="%d")
+        # :897-988 -- one row per tuple: ids, func, parameters and where it comes from (static list, type-dispatched "dynamic" list,
+        # reaction list); a tuple whose current types have no parameters is flagged like in the reference
+        type_of = {pid: int(g["type"][k]) for k, pid in enumerate(ids)}
+        name_of = lambda pid: id2type.get(type_of[pid], "?")
+
+        def lookup(params, tup):
+            key = tuple(type_of[x] for x in tup)
+            return params.get(key) or params.get(key[::-1])
+        written = {}
+        for label, getter, statics, dynamics, params in (("bonds", "getAllBonds", static_fpl, dyn_fpl, gt.bondparams), ("angles", "getAllTriples", static_ftl, dyn_ftl, gt.angleparams),
+                                                         ("dihedrals", "getAllQuadruples", static_fql, dyn_fql, gt.dihedralparams)):
+            lines = []
+            for lst in statics:
+                func, pr = lst.params
+                lines += [[*t, func, *pr, "; static"] for t in getattr(lst, getter)()]
+            for lst in dynamics.values():
+                for t in getattr(lst, getter)():
+                    q = lookup(params, t)
+                    lines.append([*t, q["func"], *q["params"], "; dynamic"] if q else [*t, "; MISSING params type: %s dynamic" % "-".join(name_of(x) for x in t)])
+            if label == "bonds":
+                for bonds_i in chem_bonds:
+                    for t in bonds_i.tolist():
+                        q = lookup(params, t)
+                        names = "-".join(name_of(x) for x in t)
+                        lines.append([*t, ("%s %s ; chem %s" % (q["func"], " ".join(str(x) for x in q["params"]), names)) if q else ("; chem MISSING params type: %s" % names)])
+            written[label] = len(lines)
+            with open("%s_%s.dat" % (prefix, label), "w") as f:
+                f.writelines(" ".join(str(x) for x in row) + "\n" for row in lines)
         # final topology (:834-994): current types, the static lists and everything the reactions added
         top_atoms = {pid: dict(gt.atoms[pid], type_id=int(g["type"][k])) for k, pid in enumerate(ids) if pid in gt.atoms}
         rows = dict(tuple_rows)

@@ -118,6 +118,12 @@ def test_driver_host_logic_on_the_oracle_backend(tmp_path, monkeypatch):
                  "cpc01_energy_42.csv", "cpc01params.out", "cpc01_42_atrp_stats.dat", "cpc01_42_topology.dat", "cpc01_42_res_topology.dat",
                  "cpc01_42_residue_list.dat", "cpc01_42_benchmark.pck"):
         assert name in out, name
+    # _bonds.dat / _angles.dat rows: ids, func, parameters, origin (src/start_simulation.py:897-988)
+    brow = [l.split() for l in open(os.path.join("data", "cpc01_42_bonds.dat"))]
+    assert len(brow) >= 4000 and brow[0] == ["1", "2", "1", "0.97", "60.0", ";", "dynamic"]
+    assert all(r[-2:] == [";", "dynamic"] or r[-3:-1] == [";", "chem"] for r in brow) and not any("MISSING" in r for r in brow)
+    arow = [l.split() for l in open(os.path.join("data", "cpc01_42_angles.dat"))]
+    assert len(arow) >= 2000 and arow[0] == ["1", "2", "3", "1", "180.0", "2.5", ";", "dynamic"]
     import pickle
     bp = pickle.load(open(os.path.join("data", "cpc01_42_benchmark.pck"), "rb"))
     assert set(bp) == {"traj_timers", "topol_timers", "integrator_timers", "extension_timers", "verlet_list"}      # src/start_simulation.py:1062-1076
