@@ -44,14 +44,18 @@ class GROFile:
                 self.atoms[pid] = self.atoms[pid]._replace(position=p, velocity=g["vel"][k])
 
     def write(self, file_name=None, force=False, with_velocity=False):
-        out = ["%s\n" % self.title, "%d\n" % len(self.atoms)]
+        # the reference's own writer (files_io.py:216-257): title (default 'XXX of molecules'), '%d' atoms, fixed-width rows with
+        # '%8.3f' positions AND velocities, box as '%f %f %f'.  The shipped conf.gro of dacron, hyperbranched, rim135,
+        # chain_growth_catalytic and pccg_lj were written by it and round-trip byte for byte (tests/test_golden_cpu.py).
+        # Ids above 99999 wrap like in GROMACS instead of widening the column.
+        out = ["%s\n" % (self.title if self.title else "XXX of molecules"), "%d\n" % len(self.atoms)]
         for aid in sorted(self.atoms):
             a = self.atoms[aid]
             row = "%5d%-5s%5s%5d%8.3f%8.3f%8.3f" % (a.chain_idx % 100000, a.chain_name[:5], a.name[:5], aid % 100000, *a.position)
             if with_velocity and a.velocity is not None:
-                row += "%8.4f%8.4f%8.4f" % tuple(a.velocity)
+                row += "%8.3f%8.3f%8.3f" % tuple(a.velocity)
             out.append(row + "\n")
-        out.append("%10.5f%10.5f%10.5f\n" % tuple(self.box))
+        out.append("%f %f %f\n" % tuple(self.box))
         with open(file_name or self.file_name, "w") as f:
             f.writelines(out)
 
