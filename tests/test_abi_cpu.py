@@ -56,3 +56,26 @@ def test_product_does_not_import_oracle():
                 if re.search(r"^\s*(from|import)\s+oracle\b|oracle/|liboracle", src, flags=re.M):
                     bad.append(f)
     assert not bad, "product files reference the oracle: %s" % bad
+
+
+def test_every_entry_point_rejects_a_null_engine():
+    """Error convention of the boundary: a call on a NULL engine handle returns an error code (or 0 / NULL for the value
+    getters) instead of touching memory.  Runs without a GPU, in a child process so that a crash is reported as a failure."""
+    import subprocess
+    import sys
+    import textwrap
+    code = textwrap.dedent("""
+        import sys, ctypes as C
+        sys.path.insert(0, %r)
+        from chemlab_b200 import _lib
+        L = _lib.load()
+        for name, (res, args) in _lib.SIGNATURES.items():
+            vals = [a(0) if a in (C.c_int, C.c_int64, C.c_double, C.c_uint64, C.c_int32) else None for a in args]
+            print(name, flush=True)
+            r = getattr(L, name)(*vals)
+            if name.startswith("clb_") and res is C.c_int and args and args[0] is C.c_void_p and name not in ("clb_nccl_unique_id",):
+                assert r != 0, (name, r)
+        print("NULL_OK")
+        """ % ROOT)
+    p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+    assert p.returncode == 0 and "NULL_OK" in p.stdout, (p.stdout.splitlines()[-2:], p.stderr[-1500:])
