@@ -490,3 +490,28 @@ def test_verlet_list_stays_complete_between_rebuilds(criterion):
         have = {tuple(p) for p in o.pairs().tolist()}
         assert need <= have, (steps, len(need - have))
     assert 1 <= o.nrebuild() < steps // 2
+
+
+def test_cell_list_equals_numpy_brute_force_on_random_boxes():
+    """Randomised: non-cubic boxes from barely 2 cut-offs wide to many cells, densities from dilute to dense, particles given
+    outside the box (several images away), random exclusions.  The Verlet pair set must equal an O(N^2) numpy minimum-image
+    search with the inclusive rule r^2 <= (rc + skin)^2 (U1), and the image counters must fold every particle into [0, L)."""
+    rng = np.random.default_rng(123)
+    for trial in range(12):
+        rc, skin = float(rng.uniform(0.8, 2.5)), float(rng.uniform(0.05, 0.5))
+        box = (rc + skin) * rng.uniform(2.05, 6.0, 3)
+        n = int(rng.integers(30, 400))
+        pos = rng.uniform(-2.0, 3.0, (n, 3)) * box                       # up to two images below, three above
+        o = pyoracle.Oracle(n, box, rc, skin, seed=1)
+        o.set_particles(pos, None, np.ones(n), None, np.zeros(n, np.int32), None, None)
+        iu = np.triu_indices(n, 1)
+        ex = np.column_stack(iu)[rng.random(len(iu[0])) < 0.02]
+        o.set_exclusions(ex)
+        got = {tuple(p) for p in o.pairs().tolist()}
+        d = pos[iu[0]] - pos[iu[1]]; d -= box * np.rint(d / box)
+        close = (d * d).sum(1) <= (rc + skin) ** 2
+        want = {(int(a), int(b)) for a, b in zip(iu[0][close], iu[1][close])} - {tuple(p) for p in ex.tolist()}
+        assert got == want, (trial, len(got), len(want), box, rc, skin)
+        g = o.get()
+        assert (g["pos"] >= 0).all() and (g["pos"] < box).all()
+        assert np.abs(g["pos"] + g["image"] * box - pos).max() < 1e-9
