@@ -404,3 +404,41 @@ def test_python2_dict_order_of_the_reference_is_reproduced():
     assert sorted(py2_dict_order(big)) == sorted(big)                                 # several resizes, nothing lost
     c = rp.parse_config(os.path.join(GOLD, "rim135", "reaction.cfg"))
     assert list(c["reactions"]) == ["reaction_2", "reaction_1"]
+
+
+def test_driver_calls_bind_to_the_cuda_engine_signatures(tmp_path, monkeypatch):
+    """The CPU suite drives the oracle adapter; on the GPU box the same driver drives chemlab_b200.Engine.  Every call the driver
+    makes here (method name, positional and keyword arguments) must bind to the signature of the ctypes mirror of the C-ABI, so a
+    driver path that was only ever exercised on the oracle cannot fail on the GPU for a missing method or argument."""
+    import inspect
+    import oracle.engine_adapter as EA
+    from chemlab_b200.engine import Engine
+    calls = {}
+    real = EA.OracleEngine
+
+    class Proxy:
+        def __init__(self, *a, **k):
+            inspect.signature(Engine.__init__).bind(None, *a, **k)
+            object.__setattr__(self, "_o", real(*a, **k))
+
+        def __getattr__(self, name):
+            attr = getattr(self._o, name)
+            if not callable(attr):
+                return attr
+
+            def f(*a, **k):
+                calls.setdefault(name, []).append((a, k))
+                return attr(*a, **k)
+            return f
+
+        def __setattr__(self, k, v):
+            setattr(self._o, k, v)
+    monkeypatch.setattr(EA, "OracleEngine", Proxy)
+    run_pccg_lj(str(tmp_path), "oracle", 200)
+    run_dacron_restrict(str(tmp_path), "oracle", 100)
+    assert len(calls) >= 35 and {"reaction_define_connections", "atrp_now", "set_cap_force", "get_particles", "energy"} <= set(calls)
+    for name, lst in calls.items():
+        m = getattr(Engine, name, None)
+        assert m is not None, "Engine has no method %s" % name
+        for a, k in lst[:40]:
+            inspect.signature(m).bind(None, *a, **k)
