@@ -64,9 +64,13 @@ def _init_ranks():
     import torch
     import torch.distributed as dist
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
     if not dist.is_initialized():
+        # the engine itself needs the GPU (clb_create fails without one); a process group that the caller initialised beforehand
+        # (e.g. gloo in the CPU tests of the driver's multi-rank host logic) is used as it is
+        torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    elif torch.cuda.is_available():
+        torch.cuda.set_device(local)
     return dist.get_rank(), world
 
 

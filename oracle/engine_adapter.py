@@ -133,6 +133,9 @@ class OracleEngine:
     def set_option(self, name, value):
         self.o.set_option(name, value)       # the oracle knows "resort_criterion" and "step"; everything else is ignored there
 
+    def join(self):
+        """multi-rank driver runs on the checker: every rank simulates the whole system (no decomposition on the CPU side)"""
+
     def close(self):
         pass
 

@@ -30,3 +30,11 @@ def test_gloo_world2_decomposition_matches_oracle():
            "--master-port", "29533", os.path.join(HERE, "gloo_worker.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, OMP_NUM_THREADS="2"))
     assert r.returncode == 0 and "GLOO_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
+
+
+def test_gloo_world2_driver_host_logic(tmp_path):
+    """The driver under torchrun with two ranks (tests/gloo_driver_worker.py): common seed, identical end state, rank 0 alone writes."""
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29547", os.path.join(HERE, "gloo_driver_worker.py"), str(tmp_path)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, OMP_NUM_THREADS="2"))
+    assert r.returncode == 0 and "GLOO_DRIVER_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
