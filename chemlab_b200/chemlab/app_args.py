@@ -88,3 +88,14 @@ def parse(argv=None):
     if a.rng_seed is None or a.rng_seed == -1:
         a.rng_seed = random.randint(1000, 10000)
     return a
+
+
+class RegexpFilter:
+    """logging filter of `--debug name:regex` (src/app_args.py:60-68): a record passes when its message or the name of the
+    function that logged it matches the expression."""
+    def __init__(self, regexp):
+        import re
+        self._rx = re.compile(regexp)
+
+    def filter(self, record):
+        return bool(self._rx.match(str(record.msg)) or self._rx.match(record.funcName or ""))

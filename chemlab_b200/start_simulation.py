@@ -101,6 +101,18 @@ def _main(argv, rank, world):
     dt = args.dt
     time0 = time.time()
 
+    if getattr(args, "debug", None):                            # :65-72 -- `--debug logger[:regex],...`; the engine's own stage timer
+        import logging                                             # is the environment variable CLB_TRACE=1 (csrc/engine.cu)
+        logging.basicConfig()
+        for item in args.debug.split(","):
+            name_filter = item.split(":")
+            print("Activating logger %s" % name_filter[0])
+            logging.getLogger(name_filter[0].strip()).setLevel(logging.DEBUG)
+            if len(name_filter) == 2:
+                logging.getLogger(name_filter[0].strip()).addFilter(app_args.RegexpFilter(name_filter[1]))
+    if getattr(args, "check_topology", False):                  # :74-75
+        import logging
+        logging.getLogger("TopologyManager").setLevel(logging.WARN)
     has_excl_file = args.exclusion_list is not None and os.path.exists(args.exclusion_list)
     gt = gromacs_topology.GromacsTopology(args.top, generate_exclusions=not has_excl_file).read()
     conf = files_io.GROFile(args.conf)
