@@ -313,8 +313,10 @@ def _main(argv, rank, world):
         print("Set gro trajectory saver, save every %d steps" % int(args.gro_trj_collect))
 
     # ---- start/stop of the reactions in units of outer iterations (:700-721)
-    k_enable_reactions = (args.start_ar // integrator_step) if ar is not None else -1
-    k_stop_reactions = (args.stop_ar // integrator_step) if (ar is not None and getattr(args, "stop_ar", None)) else -1
+    # :636-640, :661-665 -- rounded UP to whole outer iterations
+    k_enable_reactions = int(math.ceil(args.start_ar / float(integrator_step))) if (ar is not None and args.start_ar >= 0) else -1
+    stop_ar = getattr(args, "stop_ar", -1)
+    k_stop_reactions = int(math.ceil(stop_ar / float(integrator_step))) if (ar is not None and stop_ar is not None and stop_ar >= 0) else -1
     print("Running %d steps as %d x integrator.run(%d); reactions start at outer step %d" % (args.run, sim_step, integrator_step, k_enable_reactions))
     espressopp.analysis.CMVelocity(system).reset()
 
