@@ -292,13 +292,10 @@ def set_nonbonded_interactions(system, gt, vl, lj_cutoff, qq_cutoff=None, tab_cu
             print("Set LJ potential %s-%s, eps=%s, sig=%s, cutoff=%s" % (n1, n2, eps, sig, lj_cutoff))
             lj.setPotential(type1=t1, type2=t2, potential=espressopp.interaction.LennardJones(epsilon=eps, sigma=sig, cutoff=lj_cutoff))
             used["lj"] = True
+    # registration order of the reference: lj-mix_tab (:757-790), coulomb (:866-878), lj, lj-tab (:883-893)
     if used["mixed"]:
         system.addInteraction(mixed, "lj-mix_tab")
-    if used["lj"]:
-        system.addInteraction(lj, "lj")
-    if used["tab"]:
-        system.addInteraction(tab, "lj-tab")
-    # :866-878 -- the `coulomb` term: registered whenever the cutoff is positive, zero for the (neutral) coarse-grained beads
+    # the `coulomb` term: registered whenever the cutoff is positive, zero for the (neutral) coarse-grained beads
     fudge_qq = float(defaults.get("fudgeQQ", 1.0))
     if qq_cutoff is not None and float(qq_cutoff) > 0.0 and 138.935485 * fudge_qq > 0.0:
         pot_qq = espressopp.interaction.CoulombTruncated(prefactor=138.935485 * fudge_qq, cutoff=float(qq_cutoff))
@@ -306,6 +303,10 @@ def set_nonbonded_interactions(system, gt, vl, lj_cutoff, qq_cutoff=None, tab_cu
         for n1, n2 in pairs:
             coul.setPotential(type1=sym2id[n1], type2=sym2id[n2], potential=pot_qq)
         system.addInteraction(coul, "coulomb")
+    if used["lj"]:
+        system.addInteraction(lj, "lj")
+    if used["tab"]:
+        system.addInteraction(tab, "lj-tab")
     return cr_observs, []
 
 

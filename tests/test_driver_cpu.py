@@ -338,7 +338,7 @@ def test_pccg_lj_driver_on_the_oracle_backend(tmp_path):
     reference driver (src/start_simulation.py:215-228) incl. `import espressopp` inside hooks.py and analysis.AngleDistribution."""
     import chemlab_b200.espressopp as es
     a = run_pccg_lj(str(tmp_path), "oracle", 600)
-    assert a["steps"] == 600 and a["names"][:2] == ["chem_fpl_reaction_1", "lj"] and "dyn_angles_0" in a["names"]
+    assert a["steps"] == 600 and a["names"][:3] == ["chem_fpl_reaction_1", "coulomb", "lj"] and "dyn_angles_0" in a["names"]
     assert len(a["bonds"]) >= 3
     assert any(f.endswith("_atrp_stats.dat") for f in a["files"])
     hist = np.loadtxt(os.path.join(a["dir"], "output_angle.csv"))           # hook_before_sim + hook_at_step + hook_end ran
