@@ -399,13 +399,15 @@ def _main(argv, rank, world):
                                  ("dihedrals", list(dyn_fql.values()) + list(static_fql), "getAllQuadruples")):
         tuple_rows.append((label, [t for lst in lists for t in getattr(lst, getter)()]))
     if rank == 0:
+        # :1008-1012 -- the input configuration with the folded end positions: title, atom and residue names as read (the current
+        # types are in _state.dat and _output_topol.top); velocities that the input file carried are written back unchanged,
+        # as GROFile.update_position(unfolded=False) of the reference leaves them (files_io.py:276-279)
         out_conf = files_io.GROFile("%s_confout.gro" % prefix)
-        out_conf.box = box
-        out_conf.title = "chemlab_b200 final configuration, step %d" % integrator.step
+        out_conf.box, out_conf.title = box, conf.title
         for k, pid in enumerate(ids):
-            a = conf.atoms[pid]
-            out_conf.atoms[pid] = a._replace(name=id2type.get(int(g["type"][k]), a.name), position=tuple(g["pos"][k]), velocity=None)
-        out_conf.write()
+            out_conf.atoms[pid] = conf.atoms[pid]._replace(position=tuple(g["pos"][k]))
+        out_conf.write(with_velocity=True)
+        print("Wrote end configuration to: %s_confout.gro" % prefix)
         np.savetxt("%s_state.dat" % prefix, np.column_stack([ids, g["type"], g["state"], g["res_id"]]), fmt="%d", header="id type state res_id")
         for i, bonds_i in enumerate(chem_bonds):
             np.savetxt("%s_bonds_chem_%d.dat" % (prefix, i), bonds_i, fmt="%d")

@@ -134,7 +134,12 @@ def test_driver_host_logic_on_the_oracle_backend(tmp_path, monkeypatch):
     stats = np.loadtxt(os.path.join("data", "cpc01_42_atrp_stats.dat"), ndmin=2)
     assert len(stats) >= 1 and (stats[:, 1] + stats[:, 2]).sum() > 0                     # the activator fired and changed some chain ends
     g = GROFile(os.path.join("data", "cpc01_42_confout.gro")); g.read()
-    assert len(g.atoms) == 6000 and {a.name for a in g.atoms.values()} >= {"MA", "ML", "FA", "PL"}      # activated trimers renamed
+    # the end configuration is the input file with new (folded) positions: same title, atom and residue names (:1008-1012)
+    g0 = GROFile(os.path.join(d, "conf.gro")); g0.read()
+    assert len(g.atoms) == 6000 and g.title == g0.title and all(g.atoms[k].name == g0.atoms[k].name and g.atoms[k].chain_name == g0.atoms[k].chain_name for k in g0.atoms)
+    assert all(0.0 <= x < 28.11442 + 1e-3 for k in (1, 3000, 6000) for x in g.atoms[k].position)
+    st = np.loadtxt(os.path.join("data", "cpc01_42_state.dat"))
+    assert st.shape == (6000, 4) and len(set(st[:, 1].astype(int))) >= 4                                  # current types live in _state.dat
     csv = open(os.path.join("data", "cpc01_energy_42.csv")).read().splitlines()
     # columns and rows of the reference's SystemMonitor (src/start_simulation.py:446-569,705): T, Ekin, the interactions sorted by
     # label, the conversion observers (cr_<type id>_<state> of maximum_conversion=PL(1):...), count_<k> per reaction list; the row
