@@ -198,20 +198,37 @@ class GROMACSTopologyFile:
     def _sec_molecules(self, c):
         self.molecules.append((c[0], int(c[1])))      # order matters
 
-    # ---- writing (final `_output_topol.top`: src/start_simulation.py:834-994, reduced to the sections we own)
+    # ---- writing (final `_output_topol.top`: src/start_simulation.py:834-994 + the section writers files_io.py:823-954)
     def write_system(self, path, atoms, bonds, angles, dihedrals, type_names):
+        """The whole system as ONE molecule `MOL` (nrexcl 3), with the force-field sections of the input topology -- atomtypes,
+        bondtypes, angletypes, dihedraltypes, nonbond_params, atomstate -- so that the file can be fed back to the driver.
+        Tuple rows are `ids [func parameters ; origin]` as in the _bonds/_angles/_dihedrals.dat files, sorted like the reference's
+        `_write_default`."""
+        d = dict({"nbfunc": 1, "combinationrule": 1, "gen-pairs": False, "fudgeLJ": 1.0, "fudgeQQ": 1.0}, **self.defaults)
+        out = ["[ defaults ]", "%s %s %s %s %s" % (d["nbfunc"], d["combinationrule"], "yes" if d["gen-pairs"] else "no", d["fudgeLJ"], d["fudgeQQ"]), ""]
+        out += ["[ atomtypes ]"] + ["%s %s %s %s %s %s" % (a["name"], a["mass"], a["charge"], a["type"], a["sigma"], a["epsilon"]) for a in self.atomtypes.values()] + [""]
+
+        def walk(node, prefix, depth):
+            if depth == 0:
+                yield prefix, node
+            else:
+                for k, v in node.items():
+                    yield from walk(v, prefix + [k], depth - 1)
+        for title, store, depth in (("bondtypes", self.bondtypes, 2), ("angletypes", self.angletypes, 3), ("dihedraltypes", self.dihedraltypes, 4)):
+            rows = ["%s %s %s" % (" ".join(names), p["func"], " ".join(str(x) for x in p["params"])) for names, p in walk(store, [], depth)]
+            if rows:
+                out += ["[ %s ]" % title] + rows + [""]
+        if self.nonbond_params:
+            out += ["[ nonbond_params ]"] + ["%s %s %s %s" % (k[0], k[1], p["func"], " ".join(str(x) for x in p["params"])) for k, p in self.nonbond_params.items()] + [""]
+        if self.atomstate:
+            out += ["[ atomstate ]"] + ["%s %s" % kv for kv in self.atomstate.items()] + [""]
+        out += ["[ moleculetype ]", "MOL 3", "", "[ atoms ]"]
+        for aid in sorted(atoms):
+            a = atoms[aid]
+            out.append("%s %s %s %s %s %s %s %s" % (aid, type_names[a["type_id"]], a["chain_idx"], a["chain_name"], a["name"], aid,
+                                                    a["charge"] if a.get("charge") is not None else "0.0", a["mass"] if a.get("mass") is not None else ""))
+        for title, rows in (("bonds", bonds), ("angles", angles), ("dihedrals", dihedrals)):
+            out += ["", "[ %s ]" % title] + [" ".join(str(x) for x in r) for r in sorted((list(r) for r in rows), key=lambda r: [x for x in r if isinstance(x, int)])]
+        out += ["", "[ pairs ]", "", "[ system ]", self.system_name or "system", "", "[ molecules ]", "MOL 1", ""]
         with open(path, "w") as f:
-            f.write("[ defaults ]\n%d %d\n\n" % (self.defaults.get("func", 1), self.defaults.get("combinationrule", 1)))
-            f.write("[ atomtypes ]\n")
-            for name, a in self.atomtypes.items():
-                f.write("%s %g %g %s %g %g\n" % (name, a["mass"], a["charge"], a["type"], a["sigma"], a["epsilon"]))
-            f.write("\n[ moleculetype ]\nSYSTEM 0\n\n[ atoms ]\n")
-            for aid in sorted(atoms):
-                a = atoms[aid]
-                f.write("%d %s %d %s %s %d %g %g\n" % (aid, type_names[a["type_id"]], a["chain_idx"], a["chain_name"], a["name"],
-                                                       aid, a["charge"], a["mass"]))
-            for title, rows in (("bonds", bonds), ("angles", angles), ("dihedrals", dihedrals)):
-                f.write("\n[ %s ]\n" % title)
-                for r in rows:
-                    f.write(" ".join(str(x) for x in r) + "\n")
-            f.write("\n[ system ]\n%s\n\n[ molecules ]\nSYSTEM 1\n" % (self.system_name or "system"))
+            f.write("\n".join(out))

@@ -389,15 +389,10 @@ def _main(argv, rank, world):
 
     # ---- outputs (:800-1081)
     e = system._ctx.require_engine()
-    g = e.get_particles(fields=("pos", "image", "type", "state", "res_id"))
+    g = e.get_particles(fields=("pos", "image", "type", "state", "res_id", "mass", "q"))
     ids = sorted(system._ctx.pid)
     id2type = {v: k for k, v in gt.atomsym_atomtype.items()}
     chem_bonds = [np.asarray(f.fpl.getAllBonds(), np.int64).reshape(-1, 2) for f in chem_fpls]
-    tuple_rows = []
-    for label, lists, getter in (("bonds", list(dyn_fpl.values()) + list(static_fpl), "getAllBonds"),
-                                 ("angles", list(dyn_ftl.values()) + list(static_ftl), "getAllTriples"),
-                                 ("dihedrals", list(dyn_fql.values()) + list(static_fql), "getAllQuadruples")):
-        tuple_rows.append((label, [t for lst in lists for t in getattr(lst, getter)()]))
     if rank == 0:
         # :1008-1012 -- the input configuration with the folded end positions: title, atom and residue names as read (the current
         # types are in _state.dat and _output_topol.top); velocities that the input file carried are written back unchanged,
@@ -419,7 +414,7 @@ def _main(argv, rank, world):
         def lookup(params, tup):
             key = tuple(type_of[x] for x in tup)
             return params.get(key) or params.get(key[::-1])
-        written = {}
+        tuple_lines = {}
         for label, getter, statics, dynamics, params in (("bonds", "getAllBonds", static_fpl, dyn_fpl, gt.bondparams), ("angles", "getAllTriples", static_ftl, dyn_ftl, gt.angleparams),
                                                          ("dihedrals", "getAllQuadruples", static_fql, dyn_fql, gt.dihedralparams)):
             lines = []
@@ -436,14 +431,16 @@ def _main(argv, rank, world):
                         q = lookup(params, t)
                         names = "-".join(name_of(x) for x in t)
                         lines.append([*t, ("%s %s ; chem %s" % (q["func"], " ".join(str(x) for x in q["params"]), names)) if q else ("; chem MISSING params type: %s" % names)])
-            written[label] = len(lines)
+            tuple_lines[label] = lines
             with open("%s_%s.dat" % (prefix, label), "w") as f:
                 f.writelines(" ".join(str(x) for x in row) + "\n" for row in lines)
-        # final topology (:834-994): current types, the static lists and everything the reactions added
-        top_atoms = {pid: dict(gt.atoms[pid], type_id=int(g["type"][k])) for k, pid in enumerate(ids) if pid in gt.atoms}
-        rows = dict(tuple_rows)
-        gt.gt.write_system("%s_output_topol.top" % prefix, top_atoms, list(rows["bonds"]) + [tuple(b_) for bb in chem_bonds for b_ in bb.tolist()],
-                           rows["angles"], rows["dihedrals"], {v: k_ for k_, v in gt.atomsym_atomtype.items()})
+        # final topology (:834-994): the force-field sections of the input, every particle with its current type, mass, charge and
+        # residue, and the tuple rows written above (static and type-dispatched lists, reaction bonds) with their parameters
+        top_atoms = {pid: dict(gt.atoms[pid], type_id=int(g["type"][k]), mass=float(g["mass"][k]), charge=float(g["q"][k]), chain_idx=int(g["res_id"][k]))
+                     for k, pid in enumerate(ids) if pid in gt.atoms}
+        gt.gt.write_system("%s_output_topol.top" % prefix, top_atoms, tuple_lines["bonds"], tuple_lines["angles"], tuple_lines["dihedrals"],
+                           {v: k_ for k_, v in gt.atomsym_atomtype.items()})
+        print("Write output topology: %s_output_topol.top" % prefix)
         if ar is not None:                                           # :1027-1036
             ar.save_reaction_counters("%s_reaction_counters" % prefix)
             with open("%s_reaction_counters" % prefix, "a") as f:

@@ -150,6 +150,18 @@ def test_driver_host_logic_on_the_oracle_backend(tmp_path, monkeypatch):
     assert open(os.path.join("data", "cpc01_42_benchmark.csv")).read().split()[:2] == ["1", "6000"]
     gt = GromacsTopology(os.path.join("data", "cpc01_42_output_topol.top")).read()
     assert len(gt.atoms) == 6000 and len(gt.bonds) >= 4000 and len(gt.angles) >= 2000
+    # the output topology carries the force-field sections of the input (files_io.py:540-575) and, with the end configuration,
+    # restarts the driver: the reaction bonds are now ordinary bonds, their generated angles ordinary angles, both excluded
+    sections = [l.strip() for l in open(os.path.join("data", "cpc01_42_output_topol.top")) if l.startswith("[")]
+    assert sections == ["[ defaults ]", "[ atomtypes ]", "[ bondtypes ]", "[ angletypes ]", "[ atomstate ]", "[ moleculetype ]",
+                        "[ atoms ]", "[ bonds ]", "[ angles ]", "[ dihedrals ]", "[ pairs ]", "[ system ]", "[ molecules ]"]
+    nb, na = len(gt.bonds), len(gt.angles)
+    shutil.copy(os.path.join("data", "cpc01_42_output_topol.top"), "restart.top")
+    shutil.copy(os.path.join("data", "cpc01_42_confout.gro"), "restart.gro")
+    r2 = S.main(["@params", "--rng_seed", "43", "--run", "100", "--top", "restart.top", "--conf", "restart.gro", "--exclusion_list", "none.list",
+                 "--reactions", "", "--energy_collect", "100", "--int_step", "100"])
+    assert r2["steps"] == 100 and (len(r2["topology"].bonds), len(r2["topology"].angles)) == (nb, na)
+    assert len(r2["system"]._ctx.engine.get_exclusions()) >= 6000 + (nb - 4000)
 
 
 def test_coulomb_label_for_neutral_systems():
