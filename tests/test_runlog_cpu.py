@@ -77,7 +77,10 @@ def test_geometry_density_and_counts(logged_run):
     assert _find(r"^Cell grid: (\(.*?\))", log) == _find(r"^Cell grid: (\(.*?\))", out) == "(6, 6, 6)"
     assert abs(_find(r"^Density: ([0-9.]+) kg", out, float) - _find(r"^Density: ([0-9.]+) kg", log, float)) < 1e-8      # 273.445308845
     assert _find(r"^Excluded pairs from LJ interaction: (\d+)", out, int) == _find(r"^Excluded pairs from LJ interaction: (\d+)", log, int) == 6000
-    assert _find(r"^Reads (\d+) particles", out, int) == _find(r"^Reads (\d+) particles", log, int)
+    assert _find(r"^(Reads \d+ particles with properties .*)$", out) == _find(r"^(Reads \d+ particles with properties .*)$", log)
+    assert _find(r"^(Using kB=.*)$", log) == "Using kB=0.0083144621 and mass-factor=1.6605402"
+    assert _find(r"^Boltzmann constant: (.*)$", out) == _find(r"^Boltzmann constant: (.*)$", log) == "0.0083144621"
+    assert _find(r"^Skin: (.*)$", out, float) == _find(r"^Skin: (.*)$", log, float) == 0.1
     assert _find(r"distribution T=343.0 \(([0-9.]+)\)", out, float) == _find(r"distribution T=343.0 \(([0-9.]+)\)", log, float)
     gt = r["topology"]
     assert (len(gt.bonds), len(gt.angles), len(gt.dihedrals)) == tuple(_find(r"^%s: (\d+)" % k, log, int) for k in ("Bonds", "Angles", "Dihedrals"))
