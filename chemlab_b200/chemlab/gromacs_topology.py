@@ -267,11 +267,13 @@ def set_nonbonded_interactions(system, gt, vl, lj_cutoff, qq_cutoff=None, tab_cu
                 key = (cr_type, cr_total, None)
                 if key not in cr_observs:
                     cr_observs[key] = espressopp.analysis.ChemicalConversion(system, cr_type, cr_total)
+                print("Set mixed tabulated potential %s-%s with conversion observable (U=x*%s + (1-x)*%s)" % (t1, t2, pot_table(pr[0]), pot_table(pr[1])))
                 mixed.setPotential(type1=t1, type2=t2, potential=espressopp.interaction.MixedTabulated(
                     itype=1, tab1=pot_table(pr[0]), tab2=pot_table(pr[1]), cr_observation=cr_observs[key], cutoff=tab_cutoff))
                 used["mixed"] = True
                 continue
             elif func == 12:     # tab1 tab2 mix_value
+                print("Set mixed tabulated potential %s-%s with static scaling x=%s (U=%s*%s+(1-%s)*%s)" % (t1, t2, pr[2], pr[2], pot_table(pr[0]), pr[2], pot_table(pr[1])))
                 mixed.setPotential(type1=t1, type2=t2, potential=espressopp.interaction.MixedTabulated(
                     itype=1, tab1=pot_table(pr[0]), tab2=pot_table(pr[1]), mix_value=float(pr[2]), cutoff=tab_cutoff))
                 used["mixed"] = True

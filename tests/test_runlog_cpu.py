@@ -154,3 +154,21 @@ def test_registered_angles_and_monitored_labels_match_the_log(logged_run):
     assert ours == sorted(ours)
     # the reaction list was called fpl_<group> when the log was written, chem_fpl_<group> in the shipped source (reaction_setup.py:467)
     assert sorted(l.replace("chem_fpl_", "fpl_") for l in ours) == logged_labels
+
+
+def test_force_field_assembly_matches_the_log(logged_run):
+    """Which table every type pair reads, which pairs are conversion-mixed, and the table number of every angle type tuple."""
+    r, out, log = logged_run
+    assert _find(r"^Number of non-bonded type pairs: (\d+)", out, int) == _find(r"^Number of non-bonded type pairs: (\d+)", log, int) == 28
+    tab = lambda text: {(frozenset(m.group(1).split("-")), m.group(2)) for m in re.finditer(r"^Set tab potential (\S+): (\S+)", text, re.M)}
+    assert tab(out) == tab(log) and len(tab(log)) == 24
+    mixed = lambda text: {frozenset(int(x) for x in m.group(1).split("-")) for m in re.finditer(r"^Set mixed tabulated potential (\d+-\d+) ", text, re.M)}
+    assert mixed(out) == mixed(log) == {frozenset((1, 6)), frozenset((0, 4))}
+    gt = r["topology"]
+    n = 0
+    for m in re.finditer(r"^\((\d+), (\d+), (\d+)\) \{'params': \['(\d+)', '([0-9.]+)'\], 'func': (\d+)\}", log, re.M):
+        key = tuple(int(m.group(k)) for k in (1, 2, 3))
+        p = gt.angleparams.get(key) or gt.angleparams.get(key[::-1])
+        assert p is not None and int(p["func"]) == int(m.group(6)) and [str(x) for x in p["params"]] == [m.group(4), m.group(5)], (key, p)
+        n += 1
+    assert n == 19
