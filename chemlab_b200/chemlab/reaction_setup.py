@@ -159,6 +159,8 @@ class SetupReactions:
             fpl.interaction = inter
             self.system.addInteraction(inter, "chem_fpl_%s" % group_name)     # reaction bonds come first (reaction_setup.py:467)
             per_reaction = collections.defaultdict(list)
+            to_integrator = []      # re-initialised for every group, as in the reference (:471): the integrator extensions (ATRPActivator)
+            #                         of the LAST group are the ones the driver adds
             for ext_name, ext_cfg in group["extensions"].items():
                 x = self.pp.setup(ext_cfg)
                 if x.ext_type == EXT_INTEGRATOR:
