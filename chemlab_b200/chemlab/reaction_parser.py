@@ -73,7 +73,7 @@ def process_reaction(items):
     r = dict(items)
     data = {"rate": float(r["rate"]), "intramolecular": _literal(r.get("intramolecular"), False),
             "intraresidual": _literal(r.get("intraresidual"), False), "virtual": _literal(r.get("virtual"), False),
-            "exclude_extensions": set(), "equation": r["reaction"], "active": _literal(r.get("active"), True)}
+            "exclude_extensions": [], "equation": r["reaction"], "active": _literal(r.get("active"), True)}
     if "exclude_extensions" in r:
         data["exclude_extensions"] = {s.strip() for s in r["exclude_extensions"].split(",")}
     kind = None
