@@ -32,16 +32,19 @@ class GROFile:
         self.box = np.array([float(x) for x in lines[n + 2].split()][:3])
         return self.atoms
 
-    def update_position(self, system, unfolded=True):
-        """Pulls current coordinates out of the engine (storage.getParticle(pid).pos / imageBox in the reference)."""
+    def update_position(self, system, unfolded=False):
+        """Current coordinates out of the engine, with the reference's semantics (files_io.py:261-279): unfolded=True stores
+        pos + imageBox * L AND the velocities; unfolded=False replaces the positions only (velocities stay what they were)."""
         ctx = system._ctx
         g = ctx.require_engine().get_particles(fields=("pos", "image", "vel"))
         pids = sorted(ctx.pid)
         box = np.asarray(ctx.box)
         for k, pid in enumerate(pids):
             if pid in self.atoms:
-                p = g["pos"][k] + (g["image"][k] * box if unfolded else 0.0)
-                self.atoms[pid] = self.atoms[pid]._replace(position=p, velocity=g["vel"][k])
+                if unfolded:
+                    self.atoms[pid] = self.atoms[pid]._replace(position=g["pos"][k] + g["image"][k] * box, velocity=g["vel"][k])
+                else:
+                    self.atoms[pid] = self.atoms[pid]._replace(position=g["pos"][k])
 
     def write(self, file_name=None, force=False, with_velocity=False):
         # the reference's own writer (files_io.py:216-257): title (default 'XXX of molecules'), '%d' atoms, fixed-width rows with
@@ -205,8 +208,8 @@ class GROMACSTopologyFile:
         Tuple rows are `ids [func parameters ; origin]` as in the _bonds/_angles/_dihedrals.dat files, sorted like the reference's
         `_write_default`."""
         d = dict({"nbfunc": 1, "combinationrule": 1, "gen-pairs": False, "fudgeLJ": 1.0, "fudgeQQ": 1.0}, **self.defaults)
-        out = ["[ defaults ]", "%s %s %s %s %s" % (d["nbfunc"], d["combinationrule"], "yes" if d["gen-pairs"] else "no", d["fudgeLJ"], d["fudgeQQ"]), ""]
-        out += ["[ atomtypes ]"] + ["%s %s %s %s %s %s" % (a["name"], a["mass"], a["charge"], a["type"], a["sigma"], a["epsilon"]) for a in self.atomtypes.values()] + [""]
+        sections = [("defaults", ["%s %s %s %s %s" % (d["nbfunc"], d["combinationrule"], "yes" if d["gen-pairs"] else "no", d["fudgeLJ"], d["fudgeQQ"])]),
+                    ("atomtypes", ["%s %s %s %s %s %s" % (a["name"], a["mass"], a["charge"], a["type"], a["sigma"], a["epsilon"]) for a in self.atomtypes.values()])]
 
         def walk(node, prefix, depth):
             if depth == 0:
@@ -217,18 +220,24 @@ class GROMACSTopologyFile:
         for title, store, depth in (("bondtypes", self.bondtypes, 2), ("angletypes", self.angletypes, 3), ("dihedraltypes", self.dihedraltypes, 4)):
             rows = ["%s %s %s" % (" ".join(names), p["func"], " ".join(str(x) for x in p["params"])) for names, p in walk(store, [], depth)]
             if rows:
-                out += ["[ %s ]" % title] + rows + [""]
+                sections.append((title, rows))
         if self.nonbond_params:
-            out += ["[ nonbond_params ]"] + ["%s %s %s %s" % (k[0], k[1], p["func"], " ".join(str(x) for x in p["params"])) for k, p in self.nonbond_params.items()] + [""]
+            sections.append(("nonbond_params", ["%s %s %s %s" % (k[0], k[1], p["func"], " ".join(str(x) for x in p["params"])) for k, p in self.nonbond_params.items()]))
         if self.atomstate:
-            out += ["[ atomstate ]"] + ["%s %s" % kv for kv in self.atomstate.items()] + [""]
-        out += ["[ moleculetype ]", "MOL 3", "", "[ atoms ]"]
+            sections.append(("atomstate", ["%s %s" % kv for kv in self.atomstate.items()]))
+        sections.append(("moleculetype", ["MOL 3"]))
+        rows = []
         for aid in sorted(atoms):
             a = atoms[aid]
-            out.append("%s %s %s %s %s %s %s %s" % (aid, type_names[a["type_id"]], a["chain_idx"], a["chain_name"], a["name"], aid,
-                                                    a["charge"] if a.get("charge") is not None else "0.0", a["mass"] if a.get("mass") is not None else ""))
-        for title, rows in (("bonds", bonds), ("angles", angles), ("dihedrals", dihedrals)):
-            out += ["", "[ %s ]" % title] + [" ".join(str(x) for x in r) for r in sorted((list(r) for r in rows), key=lambda r: [x for x in r if isinstance(x, int)])]
-        out += ["", "[ pairs ]", "", "[ system ]", self.system_name or "system", "", "[ molecules ]", "MOL 1", ""]
+            rows.append("%s %s %s %s %s %s %s %s" % (aid, type_names[a["type_id"]], a["chain_idx"], a["chain_name"], a["name"], aid,
+                                                     a["charge"] if a.get("charge") is not None else "0.0", a["mass"] if a.get("mass") is not None else ""))
+        sections.append(("atoms", rows))
+        for title, trows in (("bonds", bonds), ("angles", angles), ("dihedrals", dihedrals)):
+            sections.append((title, [" ".join(str(x) for x in r) for r in sorted((list(r) for r in trows), key=lambda r: [x for x in r if isinstance(x, int)])]))
+        sections += [("pairs", []), ("system", [self.system_name or "system"]), ("molecules", ["MOL 1"])]
+        # layout of GROMACSTopologyFile.write (files_io.py:576-604): an empty line, the section name, its rows, an empty line
         with open(path, "w") as f:
-            f.write("\n".join(out))
+            for title, rows in sections:
+                f.write("\n[ %s ]\n" % title)
+                f.writelines(r + "\n" for r in rows)
+                f.write("\n")

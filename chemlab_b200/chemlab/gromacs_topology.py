@@ -134,9 +134,12 @@ class GromacsTopology:
             for m in range(n_mols):
                 for k, v in per_atom.items():
                     self.atoms[offset + k + m * n_atoms] = v
+            # molecule by molecule, like `_replicate_lists` (:431-446); within the fixed lists the tuples then follow the
+            # insertion order of these dicts (the Python-2 reference walks them in the hash order of the id tuples, which no
+            # shipped artefact records)
             for name, store in (("bonds", self.bonds), ("angles", self.angles), ("dihedrals", self.dihedrals), ("pairs", self.pairs)):
-                for tup, params in gt.molecules_data[mol].get(name, {}).items():
-                    for m in range(n_mols):
+                for m in range(n_mols):
+                    for tup, params in gt.molecules_data[mol].get(name, {}).items():
                         store[tuple(offset + x + m * n_atoms for x in tup)] = params
             offset += n_mols * n_atoms
         for v in gt.nonbond_params.values():
@@ -379,22 +382,29 @@ def _set_tuple_interactions(arity, system, gt, dynamic_type_ids, change_types, s
     params = getattr(gt, K["params"])
     dyn_types = {}
     by_func = collections.defaultdict(list)
+    # The reference's rule, kept to the letter (:969-1011, :1102-1135, :1230-1264): the parameter dicts are keyed by type tuples in
+    # ONE orientation (bonds sorted, angles first <= last, dihedrals first >= last: _prepare_bondedparams), a bond is looked up by
+    # its sorted types, but an angle / dihedral by its types in the order the tuple is LISTED -- a tuple listed in the other
+    # orientation is therefore static (with the parameters of its line, or those of the reversed key) even when its types are
+    # dynamic.  examples/hyperbranched: the 1000 listed dihedrals `2 1 3 4 8 0.0 1.0` stay on table d0 whatever their types become.
     for pt, p in params.items():
         if not (set(pt) & set(dynamic_type_ids)) and tuple(pt) not in change_types:
             continue
-        dyn_types[_canon(pt)] = p
+        dyn_types[tuple(sorted(pt)) if arity == 2 else tuple(pt)] = p
         by_func[p["func"]].append((pt, p))
     dyn_tuples = collections.defaultdict(list)
     static = collections.defaultdict(lambda: collections.defaultdict(list))
     for tup, raw in getattr(gt, K["tuples"]).items():
-        pt = _canon(gt.atoms[x]["type_id"] for x in tup)
+        pt = tuple(gt.atoms[x]["type_id"] for x in tup)
+        if arity == 2:
+            pt = tuple(sorted(pt))
         if raw:
-            func, pr = int(raw[0]), tuple(raw[1:])
+            func, pr = int(raw[0]), tuple(float(x) for x in raw[1:])
         else:
             p = params.get(pt) or params.get(pt[::-1])
             if p is None:
                 raise RuntimeError("no %s parameters for types %s" % (K["label"], pt))
-            func, pr = int(p["func"]), tuple(p["params"])
+            func, pr = int(p["func"]), tuple(float(x) for x in p["params"])
         if pt in dyn_types and pt not in separate:
             dyn_tuples[func].append(tup)
         else:

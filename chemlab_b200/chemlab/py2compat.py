@@ -19,6 +19,14 @@ def py2_dict_order(keys):
     """Iteration order of a CPython-2.7 dict into which the str `keys` were inserted in this order (no deletions):
     open addressing with the perturbed probe sequence of Objects/dictobject.c, 8 slots at first, resize to the first power of two
     above 4 * used once two thirds are filled; iteration runs over the slots.  chemlab's type ids depend on it (see _prepare)."""
+    import os
+    if os.environ.get("CHEMLAB_PY2_ORDER", "1") == "0":      # insertion order: what the reference's code does when it runs under Python 3
+        seen, out = set(), []                              # (tests/test_reference_driver_cpu.py compares with exactly that)
+        for k in keys:
+            if k not in seen:
+                seen.add(k); out.append(k)
+        return out
+
     def insert(table, k, h):
         mask = len(table) - 1
         i, perturb = h & mask, h

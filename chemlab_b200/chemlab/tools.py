@@ -42,10 +42,31 @@ def get_maximum_conversion(args, system, chem_fpls, gt, cr_observs=None):
     return out
 
 
-def get_integrator_timers(system, integrator):
-    """per-interaction timer labels like the reference's f<i> buckets (src/tools.py:51-79)."""
-    e = system._ctx.engine
-    if e is None:
+def get_integrator_timers(alltimers, system):
+    """integrator.getTimers() = one list of (name, seconds) pairs per rank -> {label: seconds averaged over the ranks}; 'timeRun' is
+    skipped and 'f<i>' becomes the label of interaction i (src/tools.py:51-79)."""
+    if not alltimers or not alltimers[0]:
         return {}
-    t, c = e.timers()
-    return dict(t, **{"n_" + k: v for k, v in c.items()})
+    nprocs = len(alltimers)
+    timers = {k: 0.0 for k, _ in alltimers[0]}
+    for ntimer in alltimers:
+        for k, v in ntimer:
+            if k != "timeRun":
+                timers[k] += float(v)
+    for k in timers:
+        timers[k] /= nprocs
+    for k, v in sorted(timers.items()):
+        if k.startswith("f") and k[1:].isdigit():
+            timers[system.getNameOfInteraction(int(k[1:]))] = v
+            del timers[k]
+    return timers
+
+
+def average_timers(timer_list):
+    """list per rank of (name, value) pairs -> {name: mean over the ranks} (src/tools.py:82-99)"""
+    import collections
+    acc = collections.defaultdict(list)
+    for cpu_list in timer_list:
+        for k, v in cpu_list:
+            acc[k].append(v)
+    return {k: sum(v) / float(len(v)) for k, v in acc.items() if v}

@@ -85,15 +85,30 @@ class VelocityVerlet:
         self._wall += time.time() - t0
 
     def getTimers(self):
+        """One list of (name, seconds) pairs per rank, the structure src/tools.py:51-79 consumes: 'timeRun' (skipped there), one
+        'f<i>' per registered interaction (label = system.getNameOfInteraction(i)), communication, integration, resort and
+        reaction buckets.  The engine times pair and bonded forces as two buckets (clb_timers): the pair bucket is spread evenly
+        over the Verlet-list interactions, the bonded bucket over the fixed-list interactions."""
         e = self._ctx.engine
         if e is None:
-            return []
+            return [[]]
         t, c = e.timers()
-        return [t["total"], t["pair"], t["bonded"], t["neighbour"], t["integrate"], t["comm"], t["reaction"]]
+        g = lambda k: float(t.get(k, 0.0))
+        inters = [i for i, _ in self._ctx.interactions]
+        is_nb = [hasattr(i, "_vl") or type(i).__name__.startswith("VerletList") for i in inters]
+        n_nb, n_b = max(1, sum(is_nb)), max(1, len(inters) - sum(is_nb))
+        rows = [("timeRun", g("total"))]
+        rows += [("f%d" % k, g("pair") / n_nb if nb else g("bonded") / n_b) for k, nb in enumerate(is_nb)]
+        rows += [("timeComm1", g("comm")), ("timeInt1", 0.5 * g("integrate")), ("timeInt2", 0.5 * g("integrate")), ("timeResort", g("neighbour")),
+                 ("timeReaction", g("reaction"))]
+        return [rows]
 
 
 class LangevinThermostat:
     """LangevinThermostat(system): .temperature (= T*kB) .gamma .add_valid_types(types): src/start_simulation.py:330-336."""
+    def get_timers(self):
+        return []
+
     def __init__(self, system):
         self._system = system
         self.temperature = 1.0
@@ -259,7 +274,8 @@ class ChemicalReaction:
         e.reaction_general(int(enabled), self.interval, int(bool(self.nearest_mode)), int(self.max_per_interval or 0))
 
     def get_timers(self):
-        return {}
+        e = self._engine
+        return [[("timeReact", float(e.timers()[0].get("reaction", 0.0)))]] if e is not None else []
 
     def get_reaction_counters(self):
         if self._engine is None:
@@ -332,7 +348,7 @@ class TopologyManager:
         pass
 
     def get_timers(self):
-        return {}
+        return []       # list per rank of (name, seconds) pairs (src/start_simulation.py:1040-1048); the graph lives in the engine's reaction bucket
 
     def get_fixed_pair_list(self, t1, t2):
         return None
@@ -383,6 +399,9 @@ class TopologyManager:
 
 class ExtAnalyze:
     """integrator.ExtAnalyze(observable_or_monitor, interval): src/start_simulation.py:566-569."""
+    def get_timers(self):
+        return []
+
     def __init__(self, action, interval):
         self._action, self._interval = action, int(interval)
 
@@ -401,6 +420,9 @@ class ATRPActivator:
     The pass itself runs in the engine (clb_atrp_configure / clb_atrp_add_center / clb_atrp_now: candidate scan, counter-based
     random selection of num_particles centres, activation / deactivation draws, property change -- csrc/clb_react.cuh); this
     class holds the parameters, fires the pass every `interval` steps and writes the statistics file [EXT, U22]."""
+    def get_timers(self):
+        return []
+
     def __init__(self, system, interval, num_particles, ratio_activator, ratio_deactivator, delta_catalyst, k_activate, k_deactivate):
         self._ctx = system._ctx
         self.interval, self.num_particles = int(interval), int(num_particles)
@@ -444,6 +466,9 @@ class ATRPActivator:
 class CapForce:
     """integrator.CapForce(system, capForce): src/start_simulation.py:320-324 (--max_force).  Force vectors longer than capForce
     are scaled back to that length after every force evaluation, before the thermostat (clb_set_cap_force, U26)."""
+    def get_timers(self):
+        return []
+
     def __init__(self, system, capForce, **kw):
         self._system = system
         self.capForce = float(capForce)

@@ -7,9 +7,9 @@ def final_info(system, integrator, vl=None, start_time=None, end_time=None):
     if e is None:
         return
     t, c = e.timers()
-    print("steps=%d rebuilds=%d launches=%d" % (c["steps"], c["rebuilds"], c["launches"]))
+    print("steps=%d rebuilds=%d launches=%d" % (c.get("steps", 0), c.get("rebuilds", 0), c.get("launches", 0)))
     for k in ("pair", "bonded", "neighbour", "integrate", "comm", "reaction", "total"):
-        print("  %-10s %10.4f s" % (k, t[k]))
+        print("  %-10s %10.4f s" % (k, t.get(k, 0.0)))
 
 
 def info(system, integrator, per_atom=False):

@@ -300,8 +300,9 @@ def _main(argv, rank, world):
             type_name, state = ts.split(":")
             monitor.add_observable("st_%s_%d" % (type_name, int(state)),
                                    espressopp.analysis.ChemicalConversionTypeState(system, gt.atomsym_atomtype[type_name], int(state)))
-    # :565-569: data are collected every min(reaction interval | integrator step, energy_collect) steps
-    cr_interval = ar_interval if ar is not None else integrator_step
+    # :278, :565-569: cr_interval = min(integrator step, reaction interval) = the integrator step (itself capped by the reaction
+    # interval, :265-267); data are collected every min(cr_interval, energy_collect) steps
+    cr_interval = min(integrator_step, ar_interval) if ar is not None else integrator_step
     if args.energy_collect > 0:
         energy_collect = min(cr_interval, args.energy_collect)
         integrator.addExtension(espressopp.integrator.ExtAnalyze(monitor, energy_collect))
@@ -340,11 +341,11 @@ def _main(argv, rank, world):
             for ext in ext_to_integrator:
                 integrator.addExtension(ext)
             reactions_enabled = True
-            before = files_io.GROFile("%s_before_reaction_confout.gro" % prefix)      # :742-746 (written unconditionally, unfolded)
-            before.box, before.title, before.atoms = box, "before reaction, step %d" % integrator.step, dict(conf.atoms)
-            before.update_position(system, unfolded=True)
+            # :742-746 -- the INPUT configuration object is updated (unfolded positions + velocities) and written, unconditionally
+            print("Save configuration before start of the reaction, filename: %s_before_reaction_confout.gro" % prefix)
+            conf.update_position(system, unfolded=True)
             if rank == 0:
-                before.write(with_velocity=True)
+                conf.write("%s_before_reaction_confout.gro" % prefix, with_velocity=True)
             if "hook_init_reaction" in hooks:                    # :748-750
                 print("Processing hook_init_reaction")
                 if not hooks["hook_init_reaction"](system, integrator, ar, gt, args):
@@ -394,14 +395,13 @@ def _main(argv, rank, world):
     id2type = {v: k for k, v in gt.atomsym_atomtype.items()}
     chem_bonds = [np.asarray(f.fpl.getAllBonds(), np.int64).reshape(-1, 2) for f in chem_fpls]
     if rank == 0:
-        # :1008-1012 -- the input configuration with the folded end positions: title, atom and residue names as read (the current
-        # types are in _state.dat and _output_topol.top); velocities that the input file carried are written back unchanged,
-        # as GROFile.update_position(unfolded=False) of the reference leaves them (files_io.py:276-279)
-        out_conf = files_io.GROFile("%s_confout.gro" % prefix)
-        out_conf.box, out_conf.title = box, conf.title
+        # :1008-1012 -- the input configuration object with the folded end positions: title, atom and residue names as read (the
+        # current types are in _state.dat and _output_topol.top).  GROFile.update_position(unfolded=False) of the reference leaves
+        # the velocities alone (files_io.py:276-279): they are those of the input file, or those stored when the
+        # before-reaction file was written
         for k, pid in enumerate(ids):
-            out_conf.atoms[pid] = conf.atoms[pid]._replace(position=tuple(g["pos"][k]))
-        out_conf.write(with_velocity=True)
+            conf.atoms[pid] = conf.atoms[pid]._replace(position=tuple(g["pos"][k]))
+        conf.write("%s_confout.gro" % prefix, with_velocity=True)
         print("Wrote end configuration to: %s_confout.gro" % prefix)
         np.savetxt("%s_state.dat" % prefix, np.column_stack([ids, g["type"], g["state"], g["res_id"]]), fmt="%d", header="id type state res_id")
         for i, bonds_i in enumerate(chem_bonds):
@@ -457,17 +457,20 @@ def _main(argv, rank, world):
     for meth, pattern in tm_files:
         getattr(topology_manager, meth)(pattern % prefix if rank == 0 else os.devnull)
     if rank == 0:
-        import pickle                                               # :1062-1076 -- per-bucket timers of the run
+        import pickle                                               # :1040-1076 -- per-bucket timers of the run, averaged over the ranks
         ext_timers = {}
         for k_ in range(integrator.getNumberOfExtensions()):
             ext = integrator.getExtension(k_)
-            tmr = ext.get_timers() if hasattr(ext, "get_timers") else {}
+            tmr = tools.average_timers(ext.get_timers()) if hasattr(ext, "get_timers") else {}
             if tmr:
                 ext_timers["%s_%d" % (type(ext).__name__, id(ext))] = tmr
         with open("%s_benchmark.pck" % prefix, "wb") as f:
-            pickle.dump({"traj_timers": {}, "topol_timers": topology_manager.get_timers(), "integrator_timers": tools.get_integrator_timers(system, integrator),
-                         "extension_timers": ext_timers, "verlet_list": verletlist.get_timers()}, f)
-    timers = tools.get_integrator_timers(system, integrator)
+            pickle.dump({"traj_timers": {}, "topol_timers": tools.average_timers(topology_manager.get_timers()),
+                         "integrator_timers": tools.get_integrator_timers(integrator.getTimers(), system),
+                         "extension_timers": ext_timers, "verlet_list": tools.average_timers(verletlist.get_timers())}, f)
+    timers = tools.get_integrator_timers(integrator.getTimers(), system)
+    e_t, e_c = e.timers()
+    timers.update({"n_" + k: v for k, v in e_c.items()})
     print("final: steps=%d total=%.3fs integratorLoop=%.3fs (%.1f steps/s) setup=%.3fs" %
           (integrator.step, total_time, integrator_loop, integrator.step / max(integrator_loop, 1e-9), total_time0 - time0))
     print("engine timers/counters: %s" % {k: (round(v, 4) if isinstance(v, float) else v) for k, v in timers.items()})

@@ -49,6 +49,13 @@ class OracleEngine:
     def get_particles(self, ids=None, fields=("pos", "vel", "force", "type", "state", "mass", "image", "q", "res_id"), out=None):
         g = self.o.get()
         sel = slice(None) if ids is None else self._ix(ids)
+        # the oracle folds at rebuilds only: between two rebuilds a stored coordinate may sit just outside [0, L).  The engine
+        # always hands out the folded position with the matching image counter -- do the same here
+        shift = np.floor(g["pos"] / self.box)
+        folded = g["pos"] - shift * self.box
+        wrap = folded >= self.box                                    # x = -1e-17 -> x + L == L in floating point
+        folded[wrap] -= np.broadcast_to(self.box, folded.shape)[wrap]
+        shift[wrap] += 1
         out = {}
         for f in fields:
             if f == "q":
@@ -56,7 +63,9 @@ class OracleEngine:
             elif f == "res_id":
                 out[f] = self._resid[sel]
             elif f == "pos":
-                out[f] = (g["pos"] - g["image"] * self.box)[sel]     # folded, like the engine
+                out[f] = folded[sel]
+            elif f == "image":
+                out[f] = (g["image"] + shift.astype(g["image"].dtype))[sel]
             else:
                 out[f] = g[f][sel]
         return out
