@@ -30,6 +30,11 @@ CASES = {
     # 36 tabulated pair potentials (15 conversion-mixed), tabulated bonds / angles / dihedrals: the 1000 LISTED dihedrals are static in
     # the reference although their types are dynamic (they are listed in the non-canonical orientation)
     "hyperbranched": ["--run", "500", "--rng_seed", "5"],
+    # the optional observers and stop rules: tuple / type / type-state counters, monitor filter, Arrhenius rate update with its
+    # rate file, .gro trajectory, two conversion criteria with eq_steps, stop_ar
+    "atrp_lj+options": ["--run", "800", "--rng_seed", "42", "--start_ar", "200", "--energy_collect", "200", "--count_tuples", "True", "--count_types", "MA,FA",
+                        "--count_types_state", "PL:1,FA:2", "--system_monitor_filter", "lj,count", "--rate_arrhenius", "True", "--gro_trj_collect", "400",
+                        "--maximum_conversion", "MA:5000:6000,PL(1)+FA(7):2:2000", "--eq_steps", "16", "--stop_ar", "600"],
     # RestrictReaction (connectivity map), CapForce, exclusion list from file, tabulated angles of 45,000 rows
     "dacron_restrict": ["--run", "200", "--rng_seed", "7", "--t_hybrid_bond", "0", "--int_step", "100", "--energy_collect", "100"],
 }
@@ -53,6 +58,7 @@ def test_products_equal_those_of_the_reference_driver(example, tmp_path):
     sys.path.insert(0, ROOT)
     from chemlab_b200 import synthetic
     args = ["@params"] + CASES[example]
+    example = example.split("+")[0]
     d_ref = synthetic.prepare_example(os.path.join(GOLD, example), str(tmp_path / "ref"), example)
     d_our = synthetic.prepare_example(os.path.join(GOLD, example), str(tmp_path / "ours"), example)
     os.makedirs(os.path.join(d_ref, "data"), exist_ok=True)        # the reference expects the directory of output_prefix to exist
