@@ -125,8 +125,9 @@ def main(argv):
     sys.path.insert(0, os.path.join(tmp, "chemlab")); sys.path.insert(0, tmp)      # the reference's implicit relative imports
     import chemlab_b200.espressopp as es
     import chemlab_b200.espressopp._context as C
-    from oracle.engine_adapter import OracleEngine
-    C.Engine = OracleEngine
+    if os.environ.get("CHEMLAB_HARNESS_BACKEND", "oracle") != "gpu":      # "gpu": the CUDA engine itself (needs a B200 and the reference tree)
+        from oracle.engine_adapter import OracleEngine
+        C.Engine = OracleEngine
     sys.modules["espressopp"] = es
     for sub in ("analysis", "integrator", "interaction", "storage", "bc", "esutil", "io", "tools"):
         sys.modules["espressopp." + sub] = getattr(es, sub)
