@@ -80,3 +80,49 @@ def test_products_equal_those_of_the_reference_driver(example, tmp_path):
     # the run did something: the energy file has rows, and the reaction lists are not empty in the cases that react within the window
     energy = [k for k in a if "_energy_" in k]
     assert len(energy) == 1 and len(open(a[energy[0]]).read().splitlines()) >= 3
+
+
+def test_topology_preparation_equals_the_reference_code_on_every_shipped_topology(tmp_path):
+    """GromacsTopology(...).read() of the reference (src/chemlab/gromacs_topology.py, converted in memory) against ours on every
+    shipped .top: type ids, the replicated atoms with their parameters, bonds / angles / dihedrals / pairs with the parameters of
+    their lines, the parameter dictionaries keyed by type-id tuples, and the generated exclusions.  In a child process (the
+    reference module needs `espressopp` to be this repo's surface)."""
+    code = r'''
+import os, sys, glob, tempfile, io, contextlib
+os.environ["CHEMLAB_PY2_ORDER"] = "0"
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+import ref_driver_harness as H
+tmp = H.build(tempfile.mkdtemp(prefix="chemlab_ref_topology_"))
+sys.path.insert(0, os.path.join(tmp, "chemlab")); sys.path.insert(0, tmp)
+import chemlab_b200.espressopp as es
+sys.modules["espressopp"] = es
+for sub in ("analysis", "integrator", "interaction", "storage", "bc", "esutil", "io", "tools"):
+    sys.modules["espressopp." + sub] = getattr(es, sub)
+import gromacs_topology as ref_gt
+from chemlab_b200.chemlab import gromacs_topology as our_gt
+def norm(o):
+    if isinstance(o, dict): return {str(k): norm(v) for k, v in o.items()}
+    if isinstance(o, (set, frozenset)): return sorted(norm(v) for v in o)
+    if isinstance(o, (list, tuple)): return [norm(v) for v in o]
+    if isinstance(o, float): return round(o, 12)
+    return o
+n = 0
+for p in sorted(glob.glob("/root/reference/examples/**/*.top", recursive=True)) + ["/root/reference/src/tests/topol.top"]:
+    if p.endswith("atrp_activator/topol.top"):
+        continue                      # includes idd.itp, which the reference does not ship
+    os.chdir(os.path.dirname(p))
+    with contextlib.redirect_stdout(io.StringIO()):
+        a = ref_gt.GromacsTopology(os.path.basename(p)); a.read()
+        b = our_gt.GromacsTopology(os.path.basename(p), generate_exclusions=True).read()
+    for attr in ("atomsym_atomtype", "used_atomsym_atomtype", "atoms", "bonds", "angles", "dihedrals", "pairs", "bondparams", "angleparams", "dihedralparams", "exclusions"):
+        x, y = getattr(a, attr), getattr(b, attr)
+        if attr == "exclusions":
+            x, y = {tuple(sorted(t)) for t in x}, {tuple(sorted(t)) for t in y}
+        assert norm(x) == norm(y), (p, attr)
+    n += 1
+assert n >= 15
+import shutil; shutil.rmtree(tmp, ignore_errors=True)
+print("TOPOLOGY_OK", n)
+''' % (ROOT, HERE)
+    p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    assert "TOPOLOGY_OK" in p.stdout, p.stderr[-3000:]
