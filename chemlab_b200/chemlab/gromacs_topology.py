@@ -283,6 +283,9 @@ def set_nonbonded_interactions(system, gt, vl, lj_cutoff, qq_cutoff=None, tab_cu
                 continue
             elif func in (9, 13, 16, 17, 18):
                 raise NotImplementedError("nonbond_params func %d (multi/capped/scaled tables) is outside the scope of the B200 engine" % func)
+            elif func in (11, 14, 15):
+                raise NotImplementedError("nonbond_params func %d (dynamic-resolution / pair-scaled potentials of the AdResS-style machinery) is "
+                                          "outside the scope of the B200 engine (SURVEY E21)" % func)
             else:
                 raise RuntimeError("Functional %d not found" % func)
         elif n1 in tables and n2 in tables:
