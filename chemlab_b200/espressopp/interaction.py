@@ -106,6 +106,10 @@ class AngularHarmonic(_Pot):
 
 
 class Cosine(_Pot):
+    """Cosine(K, theta0): U = K (1 + cos(theta - theta0)) [EXT, U29].  chemlab passes the topology K unchanged (angletypes func 11,
+    gromacs_topology.py:1082); doc/topology.rst:99-104,160 writes 1/2 K with the footnote "internally divided by 2.0" -- the wording
+    it uses for the harmonic angle, whose K chemlab itself halves (:1073) -- so the documentation describes a halving the code
+    does not do.  The code path is followed."""
     kind = "Cosine"
 
     def __init__(self, K=1.0, theta0=0.0, **kw):
@@ -116,13 +120,16 @@ class Cosine(_Pot):
 
 
 class DihedralHarmonic(_Pot):
+    """DihedralHarmonic(K, phi0): U = 1/2 K (phi - phi0)^2 [EXT, U30] -- the formula of doc/topology.rst:123-129 for dihedraltypes
+    func 12, whose K chemlab passes unchanged (gromacs_topology.py:1199-1202; no "divided by 2" footnote in the table, :177).  The
+    engine's kind 8 evaluates K' (phi - phi0)^2 (include/chemlab_b200.h): K' = K / 2 is handed down."""
     kind = "DihedralHarmonic"
 
     def __init__(self, K=1.0, phi0=0.0, **kw):
         self.K, self.phi0 = float(K), float(phi0)
 
     def params(self):
-        return (self.K, self.phi0)
+        return (0.5 * self.K, self.phi0)
 
 
 # ------------------------------------------------------------------ non-bonded interactions over the Verlet list

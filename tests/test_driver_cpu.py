@@ -459,3 +459,51 @@ def test_driver_calls_bind_to_the_cuda_engine_signatures(tmp_path, monkeypatch):
         assert m is not None, "Engine has no method %s" % name
         for a, k in lst[:40]:
             inspect.signature(m).bind(None, *a, **k)
+
+
+def test_potentials_equal_the_formulas_of_the_reference_documentation():
+    """doc/topology.rst:7-129 states every analytic potential as a function of the parameters written in the topology file.  The
+    chain under test is the one a run uses: topology parameters -> this driver's conversion (`_bond_pot`, `_angle_pot`,
+    `_dihedral_pot`: K halved where chemlab halves it, degrees -> radians) -> the espressopp surface's parameter hand-down -> the
+    oracle's evaluation (which the CUDA kernels are tested against).  Cosine follows chemlab's CODE, which does not halve K although
+    the documentation says so (REFERENCE_UNVERIFIED U29)."""
+    import math
+    from oracle import pyoracle
+    from chemlab_b200.engine import POT
+    from chemlab_b200.chemlab import gromacs_topology as G
+
+    def energy(arity, pot, pos):
+        n = len(pos)
+        o = pyoracle.Oracle(n, [30.0, 30.0, 30.0], 2.5, 0.3, seed=1)
+        o.set_particles(np.asarray(pos, float) + 10.0, None, np.ones(n), None, np.zeros(n, np.int32), None, None)
+        lst = o.add_list(arity); o.list_add(lst, [list(range(n))])
+        h = o.add_bonded(lst, 0)
+        o.bonded_set_potential(h, (), POT[pot.kind], pot.params())
+        o.compute_forces()
+        return o.energy(h)
+
+    def angle_pos(theta):
+        return [[1.0, 0.0, 0.0], [0.0, 0.0, 0.0], [0.9 * math.cos(theta), 0.9 * math.sin(theta), 0.0]]
+
+    def dihedral_pos(phi):
+        return [[1.0, 1.0, 0.0], [1.0, 0.0, 0.0], [0.0, 0.0, 0.0], [0.0, math.cos(phi), math.sin(phi)]]
+    close = lambda a, b: abs(a - b) <= 1e-11 * max(1.0, abs(b))
+    for r in (0.8, 0.97, 1.3):
+        r0, K = 0.97, 60.0
+        assert close(energy(2, G._bond_pot(1, [str(r0), str(K)]), [[0, 0, 0], [r, 0, 0]]), 0.5 * K * (r - r0) ** 2)                    # eq1
+        b, K = 1.5, 30.0
+        fene = -0.5 * K * b * b * math.log(1.0 - r * r / (b * b))
+        assert close(energy(2, G._bond_pot(7, [str(b), str(K)]), [[0, 0, 0], [r, 0, 0]]), fene)                                         # eqFENE
+        sig, eps = 1.0, 1.2
+        lj = 4 * eps * ((sig / r) ** 12 - (sig / r) ** 6)
+        assert close(energy(2, G._bond_pot(9, [str(b), str(K), str(sig), str(eps)]), [[0, 0, 0], [r, 0, 0]]), fene + lj)                # eqFENELJ
+    for deg in (95.0, 120.0, 170.0):
+        th, th0, K = math.radians(deg), math.radians(110.0), 80.0
+        assert close(energy(3, G._angle_pot(1, ["110.0", str(K)]), angle_pos(th)), 0.5 * K * (th - th0) ** 2)                          # eq2
+        assert close(energy(3, G._angle_pot(11, ["110.0", str(K)]), angle_pos(th)), K * (1.0 + math.cos(th - th0)))                    # eq3 without its 1/2: U29
+    phi_of = None
+    for deg in (-150.0, -20.0, 75.0):
+        phi0, K = math.radians(30.0), 12.0
+        e = energy(4, G._dihedral_pot(12, ["30.0", str(K)]), dihedral_pos(math.radians(deg)))
+        # the sign convention of phi (U15) is not part of this test: the quadruple is built for +deg or -deg
+        assert any(close(e, 0.5 * K * (math.radians(s * deg) - phi0) ** 2) for s in (1.0, -1.0)), (deg, e)                             # eq7
