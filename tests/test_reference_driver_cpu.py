@@ -35,6 +35,12 @@ CASES = {
     "atrp_lj+options": ["--run", "800", "--rng_seed", "42", "--start_ar", "200", "--energy_collect", "200", "--count_tuples", "True", "--count_types", "MA,FA",
                         "--count_types_state", "PL:1,FA:2", "--system_monitor_filter", "lj,count", "--rate_arrhenius", "True", "--gro_trj_collect", "400",
                         "--maximum_conversion", "MA:5000:6000,PL(1)+FA(7):2:2000", "--eq_steps", "16", "--stop_ar", "600"],
+    # two reaction groups (their order!), 28 tabulated pair potentials, random partner selection, Akima reaction-bond tables
+    "rim135": ["--run", "1000", "--rng_seed", "11", "--start_ar", "500", "--energy_collect", "500"],
+    # network formation, intramolecular: 0 (molecule ids), state window up to 3
+    "mf": ["--run", "1000", "--rng_seed", "3", "--start_ar", "0"],
+    # p >= 1, nearest partner, virtual reactions
+    "chain_growth_catalytic": ["--run", "1000", "--rng_seed", "3", "--start_ar", "500"],
     # RestrictReaction (connectivity map), CapForce, exclusion list from file, tabulated angles of 45,000 rows
     "dacron_restrict": ["--run", "200", "--rng_seed", "7", "--t_hybrid_bond", "0", "--int_step", "100", "--energy_collect", "100"],
 }
