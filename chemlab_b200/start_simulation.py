@@ -40,12 +40,20 @@ def _load_hooks(path="hooks.py"):
             if hasattr(espressopp, sub):
                 sys.modules.setdefault("espressopp." + sub, getattr(espressopp, sub))
         with open(path) as f:
+            text = f.read()
+        try:
+            code = compile(text, path, "exec")
+        except SyntaxError:               # the hooks shipped with the reference's examples are Python-2 user code:
+            import re                     # print statements are rewritten, anything beyond that has to be ported by hand
+            fixed = "\n".join(re.sub(r"^(\s*)print (?!\()(.*)$", r"\1print(\2)", line) for line in text.split("\n"))
             try:
-                code = compile(f.read(), path, "exec")
-            except SyntaxError as e:      # the hooks shipped with the reference's examples are Python-2 user code
+                code = compile(fixed, path, "exec")
+                print("Note: %s uses Python-2 print statements; they were rewritten as calls" % path)
+            except SyntaxError as e:
                 raise RuntimeError("%s is not valid Python 3 (%s, line %s): port the hook file (print statements, "
                                    "random.sample on sets, ...)" % (path, e.msg, e.lineno)) from e
-            exec(code, ns)
+        ns.setdefault("xrange", range)
+        exec(code, ns)
         # the five hooks of the reference (:215-228) plus two names earlier versions of this driver accepted
         for name in ("hook_init_reaction", "hook_postsetup_reaction", "hook_at_step", "hook_before_sim", "hook_end",
                      "hook_postsetup_interaction", "hook_setup_interactions"):

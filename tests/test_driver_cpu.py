@@ -507,3 +507,27 @@ def test_potentials_equal_the_formulas_of_the_reference_documentation():
         e = energy(4, G._dihedral_pot(12, ["30.0", str(K)]), dihedral_pos(math.radians(deg)))
         # the sign convention of phi (U15) is not part of this test: the quadruple is built for +deg or -deg
         assert any(close(e, 0.5 * K * (math.radians(s * deg) - phi0) ** 2) for s in (1.0, -1.0)), (deg, e)                             # eq7
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/examples"), reason="reference examples are not mounted")
+def test_shipped_python2_hook_file_runs_unmodified(tmp_path, monkeypatch, capsys):
+    """examples/pccg_lj/chemical_reactions/hooks.py exactly as shipped (Python 2: a print statement; `import espressopp`; module-level
+    state shared by hook_before_sim / hook_at_step / hook_end through `global`): the driver rewrites the print statement, and the hook
+    file drives analysis.AngleDistribution and writes output_angle.csv."""
+    import shutil
+    import sys
+    sys.path.insert(0, HERE)
+    import chemlab_b200.espressopp._context as C
+    from oracle.engine_adapter import OracleEngine
+    from chemlab_b200 import start_simulation as S
+    d = str(tmp_path / "pccg")
+    shutil.copytree(os.path.join(GOLD, "pccg_lj"), d)
+    shutil.copy("/root/reference/examples/pccg_lj/chemical_reactions/hooks.py", os.path.join(d, "hooks.py"))
+    assert "print res_ids" in open(os.path.join(d, "hooks.py")).read()
+    monkeypatch.chdir(d)
+    monkeypatch.setattr(C, "Engine", OracleEngine)
+    r = S.main(["@params", "--rng_seed", "3", "--run", "400", "--energy_collect", "200"])
+    out = capsys.readouterr().out
+    assert r["steps"] == 400 and "Python-2 print statements" in out and "Activated 20 monomers" in out
+    hist = np.loadtxt("output_angle.csv")
+    assert hist.shape == (100, 2)
